@@ -1,0 +1,289 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (this container only).
+
+    python tests/golden/make_golden.py
+
+Every array stored here is either a seeded input or an output of reference code imported from
+/root/reference (Python modules) or compiled from it unmodified (setup/library.cpp ->
+oracle/_ref/).  The fixtures pin the oracle (tests/test_oracle_golden.py) and, on the GPU box,
+the CUDA path (tests/test_gpu_*.py); the GPU box never sees /root/reference.
+
+Reference entry points exercised (file:line):
+  models/modules.py:137 log_sinkhorn_iterations, :145 log_optimal_transport, :165 log_optimal_transport2
+  setup/library.cpp:47 resize (module tensor_resize)
+  utils/utils.py:152 split_patches, :189 get_result, :1179 Iterative_expand_matrix, :1300 origin_extract,
+                 :1343 Compute_imgs, :1527 Compute_positions_and_ranges
+  models/second_layer.py:137 merge_patches_old, :189 merge_patches_new
+  models/third_layer.py:184 Compute_result (+ the label test at :166-167, inline code restated verbatim)
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from ref_loader import load_reference  # noqa: E402
+
+warnings.filterwarnings("ignore")
+SEED = 18027  # configs/*.yaml `seed`
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()})
+    print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB  keys={list(arrs)}")
+
+
+def areas(g, *shape, span=16.0):
+    # exp(U(-ln span, ln span)): the range scale_proj produces (first_layer.py:107, third_layer.py:152)
+    return torch.exp((torch.rand(*shape, generator=g) * 2 - 1) * math.log(span))
+
+
+def planted_scores(g, b, gh, gw, sharp=6.0, noise=0.3, dust=None):
+    """Affinity of a smooth warp between two gh x gw grids -> peaked, spatially coherent plans
+    (what the trained network produces; random scores never grow a box in Iterative_expand_matrix)."""
+    n = gh * gw
+    ys, xs = torch.meshgrid(torch.arange(gh).float(), torch.arange(gw).float(), indexing="ij")
+    src = torch.stack([ys.reshape(-1), xs.reshape(-1)], 1)  # [n,2]
+    out = []
+    for _ in range(b):
+        A = torch.eye(2) * (0.6 + 0.8 * torch.rand(1, generator=g)) + 0.1 * torch.randn(2, 2, generator=g)
+        t = torch.randn(2, generator=g) * 1.5
+        ctr = torch.tensor([gh / 2.0, gw / 2.0])
+        warped = (src - ctr) @ A.T + ctr + t
+        d2 = ((warped[:, None, :] - src[None, :, :]) ** 2).sum(-1)
+        s = -d2 / sharp + noise * torch.randn(n, n, generator=g)
+        out.append(s)
+    return torch.stack(out)
+
+
+def gen_ot(ref):
+    g = torch.Generator().manual_seed(SEED)
+    M = ref.modules
+    d = {}
+    # a1 raw sinkhorn, non-square
+    Z = 0.5 * torch.randn(3, 9, 14, generator=g)
+    lmu = torch.log_softmax(torch.randn(3, 9, generator=g), 1)
+    lnu = torch.log_softmax(torch.randn(3, 14, generator=g), 1)
+    d.update(a1_Z=Z, a1_log_mu=lmu, a1_log_nu=lnu, a1_out_it100=M.log_sinkhorn_iterations(Z, lmu, lnu, 100),
+             a1_out_it3=M.log_sinkhorn_iterations(Z, lmu, lnu, 3))
+    # a2 augmenting transport: small, non-square, real L1 size
+    for tag, (b, m, n, alpha, scale) in {
+        "a2_small": (2, 12, 12, 1.0, 0.1),
+        "a2_rect": (2, 7, 11, 0.5, 1.0),
+        "a2_L1": (1, 300, 300, 1.0, 0.1),
+        "a2_L1_peaked": (1, 300, 300, 0.25, None),
+    }.items():
+        if scale is None:
+            s = 0.1 * planted_scores(g, b, 15, 20, sharp=0.6, noise=1.0)
+        else:
+            s = scale * torch.randn(b, m, n, generator=g)
+        ns = areas(g, b, 1, n)
+        a = torch.tensor(alpha)
+        d[tag + "_scores"], d[tag + "_ns"], d[tag + "_alpha"] = s, ns, a
+        d[tag + "_out"] = M.log_optimal_transport(s, a, ns, 100)
+    d["a2_small_out_it1"] = M.log_optimal_transport(d["a2_small_scores"], d["a2_small_alpha"], d["a2_small_ns"], 1)
+    # a3 dustbin-in-place transport: the real L2 / L3 shapes + a ragged one
+    for tag, (b, m, n, scale, span) in {
+        "a3_L2": (3, 145, 145, 0.1, 256.0),
+        "a3_L3": (8, 65, 65, 0.1, 16.0),
+        "a3_L3_wide": (4, 65, 65, 2.0, 16.0),
+        "a3_rect": (2, 10, 14, 0.7, 4.0),
+    }.items():
+        s = scale * torch.randn(b, m, n, generator=g)
+        ns = areas(g, b, 1, n - 1, span=span)
+        d[tag + "_scores"], d[tag + "_ns"] = s, ns
+        d[tag + "_out"] = M.log_optimal_transport2(s, torch.tensor(1.0), ns, 100)
+    save("ot", **d)
+
+
+def gen_resize(ref):
+    g = torch.Generator().manual_seed(SEED + 1)
+    src = torch.floor(torch.rand(2, 3, 200, 260, generator=g) * 256)
+    rows = []
+    for k in range(14):
+        img = k % 2
+        y0 = int(torch.randint(0, 150, (1,), generator=g))
+        x0 = int(torch.randint(0, 200, (1,), generator=g))
+        h = int(torch.randint(1, 200 - y0 + 1, (1,), generator=g))
+        w = int(torch.randint(1, 260 - x0 + 1, (1,), generator=g))
+        rows.append([y0, y0 + h, x0, x0 + w - 1, img * 10000 + k])
+    rows += [[5, 6, 7, 7, 0], [0, 200, 0, 259, 10001], [10, 106, 20, 115, 3], [3, 4, 0, 259, 10000], [0, 200, 9, 9, 7]]
+    bound = torch.tensor(rows, dtype=torch.long)
+    out = ref.tensor_resize.tensor_resize(src, bound)
+    # the real shape: right image padded by 128, one real-size crop and an up-scaling crop
+    g2 = torch.Generator().manual_seed(SEED + 2)
+    src2 = torch.floor(torch.rand(1, 3, 736, 896, generator=g2) * 256)
+    bound2 = torch.tensor([[79, 464, 143, 528, 0], [300, 330, 400, 447, 17], [0, 735, 0, 895, 299]], dtype=torch.long)
+    out2 = ref.tensor_resize.tensor_resize(src2, bound2)
+    save("resize", src=src.to(torch.uint8), bound=bound, out=out, src2_seed=np.int64(SEED + 2), bound2=bound2, out2=out2)
+
+
+def gen_extract_imgs_split(ref):
+    U = ref.utils
+    g = torch.Generator().manual_seed(SEED + 3)
+    d = {}
+    # a6 origin_extract: small patch scale, uint8 and f32
+    for tag, (B, h, w, ps, dt) in {"u8": (2, 4, 5, 8, torch.uint8), "f32": (1, 3, 3, 4, torch.float32)}.items():
+        left = torch.floor(torch.rand(B, 3, ps * (h + 2), ps * (w + 2), generator=g) * 256).to(dt)
+        d[f"ext_{tag}_left"] = left
+        d[f"ext_{tag}_out"] = U.origin_extract(left, ps, w, h)
+        d[f"ext_{tag}_dims"] = np.array([B, h, w, ps])
+    # a5 Compute_imgs on a 4x5-patch image (128x160), uint8 images as evaluate.py feeds them
+    h, w = 4, 5
+    tries = 0
+    while True:
+        tries += 1
+        left = torch.randint(0, 256, (2, 32 * h, 32 * w, 3), generator=g, dtype=torch.uint8)
+        right = torch.randint(0, 256, (2, 32 * h, 32 * w, 3), generator=g, dtype=torch.uint8)
+        xs = torch.exp((torch.rand(2, h * w, generator=g) * 2 - 1) * 1.2)
+        ys = torch.exp((torch.rand(2, h * w, generator=g) * 2 - 1) * 1.2)
+        avg = torch.rand(2, h * w, 2, generator=g) * torch.tensor([h + 1.0, w + 1.0]) - 0.5
+        nm = torch.rand(2, h * w, generator=g) < 0.6
+        try:
+            nl, nr, xsn, ysn, avn = U.Compute_imgs(xs, ys, avg, nm, left, right, width=w, height=h)
+            break
+        except RuntimeError:
+            continue
+    print("Compute_imgs tries:", tries, "matched:", int((~nm).sum()))
+    d.update(ci_left=left, ci_right=right, ci_x_scale=xs, ci_y_scale=ys, ci_avg=avg, ci_nm=nm, ci_new_left=nl,
+             ci_new_right=nr, ci_x_scale_new=xsn, ci_y_scale_new=ysn, ci_average_new=avn, ci_hw=np.array([h, w]))
+    # a7 split_patches
+    cases = []
+    for k, (hh, ww, frac, mx) in enumerate([(15, 20, 0.9, 40), (15, 20, 0.5, 40), (15, 20, 1.0, 512), (15, 20, 1.0, 40),
+                                            (15, 20, 0.05, 40), (32, 32, 0.8, 64), (6, 4, 0.7, 5), (15, 20, 0.97, 100)]):
+        m = torch.rand(hh * ww, generator=g) < frac
+        sc = torch.cumsum(m.int(), 0)
+        cn, s2, s3 = U.split_patches(sc, hh, ww, mx)
+        d[f"sp{k}_sum_cycle"] = sc
+        d[f"sp{k}_args"] = np.array([hh, ww, mx])
+        d[f"sp{k}_cycle_num"] = np.int64(cn)
+        d[f"sp{k}_second"] = np.array([[int(a), int(b)] for a, b in s2], dtype=np.int64)
+        d[f"sp{k}_third"] = np.array([[int(a), int(b)] for a, b in s3], dtype=np.int64)
+    d["sp_count"] = np.int64(8)
+    save("subdivide", **d)
+
+
+def gen_iem(ref):
+    U, M = ref.utils, ref.modules
+    g = torch.Generator().manual_seed(SEED + 4)
+    d = {}
+    # L1-like: one 15x20 plan, planted warp, iter 15, lower bound 1e-5 (first_layer.py:175-176)
+    s = 0.1 * planted_scores(g, 1, 15, 20, sharp=0.35, noise=2.0)
+    ns = areas(g, 1, 1, 300, span=4.0)
+    Z = M.log_optimal_transport(s, torch.tensor(1.0), ns, 100)
+    scale_src = torch.sqrt(Z[:, :-1, :-1].exp().sum(1) + 1e-8).reshape(1, -1, 1)  # first_layer.py:117-118,161
+    pos, rng = U.Compute_positions_and_ranges(15, 20, "cpu")
+    lim = torch.tensor([0, 15, 0, 20])
+    outs = U.Iterative_expand_matrix(Z.exp(), scale_src, scale_src, lim, rng, pos, height=15, width=20, iter_num=15,
+                                     lower_bound=1e-5)
+    d.update(L1_Z=Z, L1_scalex=scale_src, L1_scaley=scale_src)
+    for k, nme in enumerate(["whole_cost", "core_cost", "average_point", "x_scale", "y_scale", "bound"]):
+        d["L1_" + nme] = outs[k]
+    # L2-like: four 12x12 plans with dustbin in place, iter 8, lower bound 1e-3 (second_layer.py:255-257)
+    s2 = planted_scores(g, 4, 12, 12, sharp=2.0, noise=0.5) * 0.5
+    s2 = torch.cat([torch.cat([s2, torch.zeros(4, 144, 1)], 2), torch.zeros(4, 1, 145)], 1)
+    ns2x = areas(g, 4, 1, 144, span=3.0)
+    ns2y = areas(g, 4, 1, 144, span=3.0)
+    Z2 = M.log_optimal_transport2(s2, torch.tensor(1.0), ns2x * ns2y, 100)
+    Z2[:, :, -1] += math.log(2.0)  # second_layer.py:108-109 (outdoor)
+    Z2[:, -1, :] += math.log(2.0)
+    pos2, rng2 = U.Compute_positions_and_ranges(12, 12, "cpu")
+    lim2 = torch.tensor([0, 12, 0, 12])
+    outs2 = U.Iterative_expand_matrix(Z2.exp(), ns2x.reshape(4, -1, 1), ns2y.reshape(4, -1, 1), lim2, rng2, pos2, height=12,
+                                      width=12, iter_num=8, lower_bound=1e-3)
+    d.update(L2_Z=Z2, L2_scalex=ns2x.reshape(4, -1, 1), L2_scaley=ns2y.reshape(4, -1, 1))
+    for k, nme in enumerate(["whole_cost", "core_cost", "average_point", "x_scale", "y_scale", "bound"]):
+        d["L2_" + nme] = outs2[k]
+    # est_position's masks (first_layer.py:162-167; second_layer.py:244-249)
+    for tag, ZZ, dust in (("L1", Z, 300), ("L2", Z2, 144)):
+        max0, max1 = ZZ.max(2).indices[:, :-1], ZZ.max(1).indices[:, :-1]
+        d[tag + "_nm1"], d[tag + "_nm2"] = max0 == dust, max1 == dust
+    save("expand", **d)
+
+
+def gen_merge(ref):
+    SL = ref.second_layer.SecondLayer
+    g = torch.Generator().manual_seed(SEED + 5)
+    d = {}
+    h, w = 15, 20
+    for tag, merge_new in (("new", True), ("old", False)):
+        fn = SL.merge_patches_new if merge_new else SL.merge_patches_old
+        sb = torch.zeros(1, h * w, 16, 9).double()
+        # two consecutive chunks of one image, as models/pats.py:33-37 drives it (scores_back carried)
+        m_all = torch.rand(1, h * w, generator=g) < 0.8
+        csum = torch.cumsum(m_all.int(), 1)
+        half = int(csum[0, 8 * w - 1])
+        for c, (lo, hi) in enumerate([(0, half), (int(csum[0, 7 * w - 1]), int(csum[0, -1]))]):
+            nm1 = ~(m_all & (csum > lo) & (csum <= hi))
+            P = int((~nm1).sum())
+            # trust: mostly small with exact zeros (if_nomatching rows give whole_cost=1e-14) and some > 2
+            trust = torch.rand(P, 144, generator=g) ** 3 * 1.2
+            trust[torch.rand(P, 144, generator=g) < 0.05] = 1e-14
+            nm2 = torch.rand(P, 144, generator=g) < 0.35
+            d[f"{tag}{c}_trust"], d[f"{tag}{c}_nm1"], d[f"{tag}{c}_nm2"], d[f"{tag}{c}_sb_in"] = trust.clone(), nm1.clone(), nm2.clone(), sb.clone()
+            t_in, nm2_in, sb_in = trust.clone(), nm2.clone(), sb.clone()
+            out, sb = fn(None, P, t_in, [32 * h, 32 * w], nm1, nm2_in, sb_in)
+            d[f"{tag}{c}_out"], d[f"{tag}{c}_sb_out"] = out, sb
+            d[f"{tag}{c}_trust_after"], d[f"{tag}{c}_nm2_after"] = t_in, nm2_in
+    d["hw"] = np.array([h, w])
+    save("merge", **d)
+
+
+def gen_result(ref):
+    U = ref.utils
+    g = torch.Generator().manual_seed(SEED + 6)
+    h, w = 15, 20
+    nm0 = torch.rand(1, h * w, generator=g) < 0.9
+    P = int((~nm0).sum())
+    pt0 = torch.rand(1, h * w, 2, generator=g) * torch.tensor([h * 1.0, w * 1.0])
+    sc0 = torch.cat([torch.exp(torch.randn(1, h * w, 1, generator=g) * 0.4), torch.ones(1, h * w, 1)], 2)
+    nm1 = torch.rand(P, 2304, generator=g) < 0.97
+    pt1 = torch.rand(P, 2304, 2, generator=g) * 48
+    sc1 = sc0.reshape(-1, h * w, 2)[~nm0].reshape(-1, 1, 2).repeat(1, 2304, 1)  # models/pats.py:73
+    choice = [torch.ones(1).bool(), torch.ones(P).bool()]
+    # pt1 is stored as f16; run the reference on the rounded values so input and output agree exactly
+    pt1r = pt1.half().float()
+    ml, mr = U.get_result(1, [nm0, nm1], [pt0, pt1r], [sc0, sc1], [[32, h, w], [2, 48, 48]], choice)
+    save("result", nm0=nm0, pt0=pt0, sc0=sc0, nm1=nm1, pt1=pt1r.half(), sc1_first=sc1[:, 0], matches_l=ml, matches_r=mr)
+
+
+def gen_third(ref):
+    M = ref.modules
+    TL = ref.third_layer.ThirdLayer
+    g = torch.Generator().manual_seed(SEED + 7)
+    K = 12
+    s = planted_scores(g, K, 8, 8, sharp=1.0, noise=0.6) * 3.0
+    s = torch.cat([torch.cat([s, torch.full((K, 64, 1), -6.0)], 2), torch.full((K, 1, 65), -6.0)], 1)
+    s[:3, :, -1] += 8.0  # a few problems whose best match is the dustbin
+    scale = areas(g, K, 1, 64, span=16.0)
+    Z = M.log_optimal_transport2(s, torch.tensor(1.0), scale, 100)
+    scores = torch.exp(Z)
+    scale_x = (scale + 1e-8).sqrt()  # third_layer.py:153-154
+    scale_y = (scale + 1e-8).sqrt()
+    p_s = (torch.randint(0, 24, (K, 2), generator=g) * 4)  # mkpts0_c after snapping (:122)
+    p_t = (torch.randint(0, 25, (K, 2), generator=g) * 4)
+    me = types.SimpleNamespace(pad=torch.nn.ZeroPad2d(2), pad_1=torch.nn.ConstantPad2d(2, 1e-2))
+    m0, m1, _ = TL.Compute_result(me, scores, 8, 5, scale_x, scale_y, p_s, p_t, "cpu")
+    # label test, third_layer.py:166-167 (inline in forward; restated verbatim with W=8)
+    scores_used = scores[:, :-1, :].reshape(K, 8, 8, -1)[:, 2:6, 2:6, :].reshape(K, 16, -1) + 1e-8
+    if_matching1 = scores_used.max(2)[1] != 8 ** 2
+    save("third", Z=Z, scale=scale, p_s=p_s, p_t=p_t, mkpts0_f=m0, mkpts1_f=m1, if_matching1=if_matching1)
+
+
+if __name__ == "__main__":
+    ref = load_reference()
+    torch.set_num_threads(8)
+    gen_ot(ref)
+    gen_resize(ref)
+    gen_extract_imgs_split(ref)
+    gen_iem(ref)
+    gen_merge(ref)
+    gen_result(ref)
+    gen_third(ref)
