@@ -1,0 +1,127 @@
+/*
+ * pats_b200.h -- C ABI of the B200-native (sm_100a) PATS hot path.
+ *
+ * Drop-in boundary: plain pointers and sizes, no torch types.  Every entry point names the
+ * reference interface (zju3dv/pats, file:line) it replaces.  All `*_f32` functions compute in
+ * IEEE float32.  Unless the name ends in `_host`, every data pointer is a DEVICE pointer on the
+ * current CUDA device and the call only ENQUEUES work on `stream` (a cudaStream_t passed as
+ * void*; NULL = legacy default stream) -- no host synchronisation, usable under CUDA graphs.
+ * `_host` variants take HOST buffers, copy in, run, copy out and synchronise before returning.
+ *
+ * Return value: 0 on success, negative PATS_E_* on failure; pats_last_error() returns a
+ * thread-local description.  Outputs never alias inputs.
+ *
+ * There is no CPU implementation behind this header: if the library was built without a kernel
+ * for the device found at run time, the calls fail with PATS_E_CUDA.
+ */
+#ifndef PATS_B200_H
+#define PATS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PATS_B200_VERSION 100 /* 0.1.0 */
+
+enum {
+    PATS_OK = 0,
+    PATS_E_INVALID = -1,     /* bad argument (null pointer, non-positive size, unsupported shape) */
+    PATS_E_CUDA = -2,        /* CUDA runtime error (launch failure, no sm_100 device, out of memory) */
+    PATS_E_BAD_CROP = -3,    /* tensor_resize: a bound row the reference would reject (library.cpp:55-59 narrow) */
+    PATS_E_CAPACITY = -4     /* an output buffer is too small for the result */
+};
+
+int pats_version(void);
+const char *pats_last_error(void);
+/* Number of SMs of the current device, 0 if no CUDA device is usable. */
+int pats_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sinkhorn / optimal transport            (replaces models/modules.py:137-182)
+ * ------------------------------------------------------------------------------------------- */
+
+/* log_sinkhorn_iterations(Z, log_mu, log_nu, iters)         models/modules.py:137-143
+ *   Z [b,M,N], log_mu [b,M], log_nu [b,N]  ->  out [b,M,N]   (row-major, contiguous) */
+int pats_log_sinkhorn_iterations_f32(const float *Z, const float *log_mu, const float *log_nu, int b, int M, int N,
+                                     int iters, float *out, void *stream);
+
+/* log_optimal_transport(scores, alpha, ns, iters)           models/modules.py:145-162
+ *   scores [b,m,n], alpha: DEVICE pointer to one float (the reference passes a 0-dim tensor,
+ *   first_layer.py:114), ns [b,1,n]  ->  out [b,m+1,n+1]; dustbin row/column synthesised in-kernel. */
+int pats_log_optimal_transport_f32(const float *scores, const float *alpha, const float *ns, int b, int m, int n,
+                                   int iters, float *out, void *stream);
+
+/* log_optimal_transport2(scores, one, ns, iters)            models/modules.py:165-182
+ *   scores [b,m,n] (dustbin = last row / column), one: DEVICE pointer to one float,
+ *   ns [b,1,n-1]  ->  out [b,m,n] (fresh buffer: second_layer.py:108-112 mutates it in place). */
+int pats_log_optimal_transport2_f32(const float *scores, const float *one, const float *ns, int b, int m, int n,
+                                    int iters, float *out, void *stream);
+
+/* Which kernel family the dispatcher picks for a shape (0 = register-resident warp kernel,
+ * 1 = register-resident CTA kernel, 2 = generic log-domain kernel); for tests and the bench. */
+int pats_sinkhorn_kernel_kind(int M, int N);
+/* Force the generic log-domain kernel for every shape (tests: exercises the fallback path). */
+void pats_sinkhorn_force_generic(int on);
+/* Problems the register-resident kernels handed to the log-domain fallback since the last reset
+ * (device counter, read with a synchronising copy; tests / diagnostics only). */
+int pats_sinkhorn_fallback_count(int reset);
+
+/* HOST-buffer variants (end-to-end path: H2D, solve, D2H, synchronise). alpha / one by value. */
+int pats_log_optimal_transport_f32_host(const float *scores, float alpha, const float *ns, int b, int m, int n,
+                                        int iters, float *out);
+int pats_log_optimal_transport2_f32_host(const float *scores, float one, const float *ns, int b, int m, int n,
+                                         int iters, float *out);
+
+/* ---------------------------------------------------------------------------------------------
+ * Patch subdivision                        (replaces setup/library.cpp and utils/utils.py pieces)
+ * ------------------------------------------------------------------------------------------- */
+
+/* tensor_resize.tensor_resize(input, bound)                 setup/library.cpp:47-66, :92-93
+ *   input [B,C,Hp,Wp] f32, bound [K,5] i64 rows (y0,y1,x0,x1,img*10000+patch)
+ *   -> out [K,C,out_h,out_w] f32 (reference: 96x96).  Crop rows [y0,y1), cols [x0,x1], bilinear,
+ *   align_corners.  One launch, bounds read on the device.  `bad_rows` (DEVICE int*, may be NULL)
+ *   is incremented once per row the reference would reject; such rows are written as zeros. */
+int pats_tensor_resize_f32(const float *input, int B, int C, int Hp, int Wp, const int64_t *bound, int K, int out_h,
+                           int out_w, float *out, int *bad_rows, void *stream);
+/* Same kernel with an explicit rounding recipe for the lerp (0 = as compiled, 1/2 = the two FMA
+ * contractions, 3 = no contraction); used to pin bit-exactness against ATen's CUDA kernel. */
+int pats_tensor_resize_f32_variant(const float *input, int B, int C, int Hp, int Wp, const int64_t *bound, int K,
+                                   int out_h, int out_w, float *out, int *bad_rows, int variant, void *stream);
+int pats_tensor_resize_f32_host(const float *input, int B, int C, int Hp, int Wp, const int64_t *bound, int K,
+                                int out_h, int out_w, float *out);
+
+/* origin_extract(left, patch_scale, width, height)          utils/utils.py:1300-1318 (non-swap)
+ *   left [B,C,ps*(height+2),ps*(width+2)] of `elem` bytes per element
+ *   -> out [B,C,height*width,3ps,3ps]; window p=(i,j) starts at (ps*i, ps*j).  Pure copy. */
+int pats_origin_extract(const void *left, int elem, int B, int C, int height, int width, int ps, void *out,
+                        void *stream);
+
+/* Compute_imgs -- bound / scale arithmetic                   utils/utils.py:1357-1372,1380-1381
+ *   x_scale,y_scale [B,n], average_point [B,n,2], n = height*width
+ *   -> bound [B,n,4] i64, x_scale_new,y_scale_new [B,n,2], average_new [B,n,2] */
+int pats_compute_bounds_f32(const float *x_scale, const float *y_scale, const float *average_point, int B, int height,
+                            int width, int ps, int margin, int64_t *bound, float *x_scale_new, float *y_scale_new,
+                            float *average_new, void *stream);
+
+/* Compute_imgs -- fused subdivision                          utils/utils.py:1343-1393
+ *   left,right [B,H,W,3] (H = ps*height, W = ps*width) of uint8 (elem=1) or f32 (elem=4);
+ *   if_nomatching [B,n] u8.  Pads implicitly (zeros), extracts the left 3ps x 3ps windows
+ *   (origin_extract) and crop-resizes the right patches (tensor_resize) for the MATCHED patches
+ *   only, in row-major mask order:
+ *     new_left  [P,3ps,3ps,3] (same element type as left),  new_right [P,3,3ps,3ps] f32
+ *     (the reference hands out new_right as the NHWC *view* of this NCHW buffer, utils.py:1385),
+ *     bound5 [P,5] i64 (y0,y1,x0,x1,img*10000+patch), x_scale_new,y_scale_new,average_new [B,n,2].
+ *   `capacity` = rows available in new_left/new_right/bound5; `count` (DEVICE int*) receives P.
+ *   `bad_rows` as in pats_tensor_resize_f32. */
+int pats_compute_imgs(const float *x_scale, const float *y_scale, const float *average_point,
+                      const uint8_t *if_nomatching, const void *left, const void *right, int elem, int B, int height,
+                      int width, int ps, int margin, void *new_left, float *new_right, int64_t *bound5,
+                      float *x_scale_new, float *y_scale_new, float *average_new, int capacity, int *count,
+                      int *bad_rows, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PATS_B200_H */

@@ -1,0 +1,69 @@
+"""ctypes binding of libpats_b200.so (the C ABI declared in include/pats_b200.h).
+
+PyTorch is used by the callers for device memory and streams only; no torch type crosses
+this boundary.  There is NO fallback: if the library is missing or a call fails, a
+RuntimeError is raised (the reference raises RuntimeError from its C++ extension too).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libpats_b200.so")
+_lib = None
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+
+# name -> argtypes; every function returns int unless listed in _RESTYPE
+SIGNATURES = {
+    "pats_version": [],
+    "pats_last_error": [],
+    "pats_sm_count": [],
+    "pats_log_sinkhorn_iterations_f32": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "pats_log_optimal_transport_f32": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "pats_log_optimal_transport2_f32": [_P, _P, _P, _I, _I, _I, _I, _P, _P],
+    "pats_sinkhorn_kernel_kind": [_I, _I],
+    "pats_sinkhorn_force_generic": [_I],
+    "pats_sinkhorn_fallback_count": [_I],
+    "pats_log_optimal_transport_f32_host": [_P, _F, _P, _I, _I, _I, _I, _P],
+    "pats_log_optimal_transport2_f32_host": [_P, _F, _P, _I, _I, _I, _I, _P],
+    "pats_tensor_resize_f32": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P],
+    "pats_tensor_resize_f32_variant": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _I, _P],
+    "pats_tensor_resize_f32_host": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P],
+    "pats_origin_extract": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "pats_compute_bounds_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "pats_compute_imgs": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
+}
+_RESTYPE = {"pats_last_error": C.c_char_p, "pats_sinkhorn_force_generic": None}
+
+
+def library_path() -> str:
+    return _SO
+
+
+def load():
+    """Load the CUDA library (built by pats_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise RuntimeError(
+            f"pats_b200: {_SO} is missing. The hot path is CUDA-only (no CPU fallback); "
+            "build it with `python -m pats_b200.build` (needs nvcc)."
+        )
+    lib = C.CDLL(_SO)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, C.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pats_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"pats_b200.{what} failed (code {rc}): {msg}")

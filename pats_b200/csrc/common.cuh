@@ -1,0 +1,76 @@
+// Shared host/device helpers for the pats_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/pats_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "pats_b200 kernels are written for sm_100a (B200); build with -gencode arch=compute_100a,code=sm_100a"
+#endif
+
+#define PATS_API extern "C" __attribute__((visibility("default")))
+
+namespace pats {
+
+// ---- host side -------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+int invalid(const char *fmt, ...);
+int sm_count();
+
+#define PATS_CUDA_TRY(expr)                                            \
+    do {                                                               \
+        cudaError_t _e = (expr);                                       \
+        if (_e != cudaSuccess) return ::pats::cuda_fail(_e, #expr);    \
+    } while (0)
+
+#define PATS_LAUNCH_CHECK(name)                                        \
+    do {                                                               \
+        cudaError_t _e = cudaGetLastError();                           \
+        if (_e != cudaSuccess) return ::pats::cuda_fail(_e, name);     \
+    } while (0)
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- device side -----------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// exp / log on the SFU (MUFU.EX2 / MUFU.LG2): 2 ulp class, ample for the 1e-4 log-domain tolerance.
+__device__ __forceinline__ float fast_exp(float x) { return exp2f(x * kLog2e); }
+__device__ __forceinline__ float fast_log(float x) { return __log2f(x) * kLn2; }
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Packed FP32 pair arithmetic (Blackwell FFMA2 / FADD2 / FMUL2): one issue slot for two lanes of work.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long *>(&c);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace pats

@@ -1,0 +1,603 @@
+// Sinkhorn optimal transport for sm_100a -- replaces models/modules.py:137-182 of zju3dv/pats.
+//
+//   log_sinkhorn_iterations (:137-143), log_optimal_transport (:145-162), log_optimal_transport2 (:165-182)
+//
+// Design (see DESIGN.md "Sinkhorn kernels"):
+//   * The plan never leaves the chip between iterations.  Each problem is owned by one warp
+//     (<= 72 x 68, the level-3 65 x 65 problems) or one CTA (<= 160 x 160, the level-2 145 x 145
+//     problems); every thread keeps an RT x CT tile of the kernel matrix in REGISTERS.
+//   * Iteration 1 is done exactly in the log domain (row / column log-sum-exp, as the reference
+//     does).  Its potentials (u1, v1) are absorbed into the matrix, K = exp(Z + u1 + v1), so every
+//     entry is a probability <= 1 and the remaining iterations are plain scaling updates
+//        alpha_i = mu_i / sum_j K_ij beta_j ,   beta_j = nu_j / sum_i K_ij alpha_i
+//     (u first, then v with the new u: modules.py:141-142) -- two packed-FP32 FMAs (FFMA2) per
+//     element per iteration instead of two exp + two max passes.  Row sums reduce over the QC
+//     lanes that share a row with warp shuffles; column sums reduce over lanes with shuffles and
+//     over warps through a few hundred bytes of shared memory.
+//   * Result = Z + (u1 + ln alpha) + (v1 + ln beta) - norm, with Z re-read (L2 hit).
+//   * The scalings are monitored; a problem whose scalings leave [1e-13, 1e13] or whose potentials
+//     are not finite is re-solved by the same threads with the exact log-domain iteration
+//     (log_domain_solve), which is also the kernel for shapes that do not fit in registers.
+//     No CPU path exists.
+#include <mutex>
+
+#include "common.cuh"
+
+namespace pats {
+
+enum { MODE_RAW = 0, MODE_OT = 1, MODE_OT2 = 2 };
+
+struct SinkArgs {
+    const float *Z;       // raw/OT2: [b,M,N]; OT: un-augmented scores [b,M-1,N-1]
+    const float *log_mu;  // raw only [b,M]
+    const float *log_nu;  // raw only [b,N]
+    const float *alpha;   // OT: dustbin score (device scalar); OT2: `one` (device scalar)
+    const float *ns;      // OT/OT2: [b,N-1] target areas
+    float *out;           // [b,M,N]
+    int b, M, N, iters, mode;
+    int *fb_total;        // device counter: problems sent to the log-domain fallback
+};
+
+struct Marg {
+    float norm, lms, lnsum, fill;
+};
+
+__device__ __forceinline__ float z_at(const SinkArgs &a, const Marg &g, int p, int row, int col) {
+    if (a.mode == MODE_OT) {
+        const int zm = a.M - 1, zn = a.N - 1;  // couplings = [[scores, alpha],[alpha, alpha]]  (modules.py:152-156)
+        return (row < zm && col < zn) ? __ldg(a.Z + ((size_t)p * zm + row) * zn + col) : g.fill;
+    }
+    return __ldg(a.Z + ((size_t)p * a.M + row) * a.N + col);
+}
+
+__device__ __forceinline__ float lmu_at(const SinkArgs &a, const Marg &g, int p, int row) {
+    if (a.mode == MODE_RAW) return __ldg(a.log_mu + (size_t)p * a.M + row);
+    return row < a.M - 1 ? g.norm : g.lnsum + g.norm;  // modules.py:159 / :178
+}
+
+__device__ __forceinline__ float lnu_at(const SinkArgs &a, const Marg &g, int p, int col) {
+    if (a.mode == MODE_RAW) return __ldg(a.log_nu + (size_t)p * a.N + col);
+    return col < a.N - 1 ? logf(__ldg(a.ns + (size_t)p * (a.N - 1) + col)) + g.norm : g.lms + g.norm;  // :158 / :177
+}
+
+// Per-problem scalars of the marginals (modules.py:157 / :175).  Every warp computes them
+// redundantly in the same order, so all warps of a CTA hold bit-identical values.
+__device__ __forceinline__ Marg problem_marginals(const SinkArgs &a, int p, int lane) {
+    Marg g;
+    g.norm = 0.f, g.lms = 0.f, g.lnsum = 0.f, g.fill = 0.f;
+    if (a.mode != MODE_RAW) {
+        const int nr = a.N - 1;
+        float s = 0.f;
+        for (int j = lane; j < nr; j += 32) s += __ldg(a.ns + (size_t)p * nr + j);
+        s = warp_sum(s);
+        const float sc = __ldg(a.alpha);
+        const float ms = (a.mode == MODE_OT2) ? (float)(a.M - 1) * sc : (float)(a.M - 1);
+        g.norm = -logf(ms + s);
+        g.lms = logf(ms);
+        g.lnsum = logf(s);
+        g.fill = (a.mode == MODE_OT) ? sc : 0.f;
+    }
+    return g;
+}
+
+struct BlockSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+struct WarpSync {
+    __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Exact log-domain Sinkhorn by a group of GT threads (modules.py:137-143 as written: max-shifted
+// log-sum-exp for rows, then columns).  u[M], v[N] live in shared memory; `red` holds 2*GT floats.
+// Used (a) as the in-kernel fallback of the register kernels and (b) as the kernel for shapes
+// that do not fit in registers.
+// ---------------------------------------------------------------------------------------------
+template <int GT, class Sync>
+__device__ void log_domain_solve(const SinkArgs &a, const Marg &g, int p, float *u, float *v, float *red, int gtid,
+                                 Sync gsync) {
+    const int M = a.M, N = a.N;
+    const int lane = gtid & 31, warp = gtid >> 5;
+    constexpr int NW = GT / 32;
+    for (int j = gtid; j < N; j += GT) v[j] = 0.f;
+    for (int i = gtid; i < M; i += GT) u[i] = 0.f;
+    // column pass geometry: NP columns (padded to a warp multiple) x G row groups
+    const int NP = (N + 31) & ~31;
+    const int G = (NP <= GT) ? GT / NP : 1;
+    gsync();
+    for (int it = 0; it < a.iters; ++it) {
+        for (int i = warp; i < M; i += NW) {
+            float mx = -INFINITY;
+            for (int j = lane; j < N; j += 32) mx = fmaxf(mx, z_at(a, g, p, i, j) + v[j]);
+            mx = warp_max(mx);
+            const float mxs = (fabsf(mx) == INFINITY) ? 0.f : mx;
+            float s = 0.f;
+            for (int j = lane; j < N; j += 32) s += expf((z_at(a, g, p, i, j) + v[j]) - mxs);
+            s = warp_sum(s);
+            if (lane == 0) u[i] = lmu_at(a, g, p, i) - (logf(s) + mxs);
+        }
+        gsync();
+        if (G > 1) {
+            const int jj = gtid % NP, gi = gtid / NP;
+            float mx = -INFINITY, s = 0.f;
+            if (gi < G && jj < N) {
+                for (int i = gi; i < M; i += G) mx = fmaxf(mx, z_at(a, g, p, i, jj) + u[i]);
+                const float mxs = (fabsf(mx) == INFINITY) ? 0.f : mx;
+                for (int i = gi; i < M; i += G) s += expf((z_at(a, g, p, i, jj) + u[i]) - mxs);
+                red[2 * (gi * NP + jj)] = mx;
+                red[2 * (gi * NP + jj) + 1] = s;
+            }
+            gsync();
+            if (gi == 0 && jj < N) {
+                float m2 = -INFINITY;
+                for (int q = 0; q < G; ++q) m2 = fmaxf(m2, red[2 * (q * NP + jj)]);
+                const float m2s = (fabsf(m2) == INFINITY) ? 0.f : m2;
+                float s2 = 0.f;
+                for (int q = 0; q < G; ++q) {
+                    const float mq = red[2 * (q * NP + jj)];
+                    const float mqs = (fabsf(mq) == INFINITY) ? 0.f : mq;
+                    s2 += red[2 * (q * NP + jj) + 1] * expf(mqs - m2s);
+                }
+                v[jj] = lnu_at(a, g, p, jj) - (logf(s2) + m2s);
+            }
+        } else {
+            for (int j = gtid; j < N; j += GT) {
+                float mx = -INFINITY;
+                for (int i = 0; i < M; ++i) mx = fmaxf(mx, z_at(a, g, p, i, j) + u[i]);
+                const float mxs = (fabsf(mx) == INFINITY) ? 0.f : mx;
+                float s = 0.f;
+                for (int i = 0; i < M; ++i) s += expf((z_at(a, g, p, i, j) + u[i]) - mxs);
+                v[j] = lnu_at(a, g, p, j) - (logf(s) + mxs);
+            }
+        }
+        gsync();
+    }
+    const float shift = (a.mode == MODE_RAW) ? 0.f : g.norm;  // modules.py:161 / :181
+    float *o = a.out + (size_t)p * M * N;
+    for (int e = gtid; e < M * N; e += GT) {
+        const int i = e / N, j = e - i * N;
+        o[e] = ((z_at(a, g, p, i, j) + u[i]) + v[j]) - shift;
+    }
+}
+
+template <int GT>
+__global__ void __launch_bounds__(GT) sinkhorn_generic_kernel(SinkArgs a) {
+    extern __shared__ float sm[];
+    float *u = sm, *v = sm + a.M, *red = sm + a.M + a.N;
+    for (int p = blockIdx.x; p < a.b; p += gridDim.x) {
+        const Marg g = problem_marginals(a, p, threadIdx.x & 31);
+        log_domain_solve<GT>(a, g, p, u, v, red, threadIdx.x, BlockSync());
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Register-resident kernel.
+//   A problem is owned by WARPS warps.  Threads form a PR x QC grid (QC = 2^QC_LOG2 lanes along a
+//   row, PR = WARPS*32/QC row groups); thread (pr,qc) owns rows pr + PR*k (k < RT) and columns
+//   qc + QC*c (c < CT).  Capacity MAXM x MAXN = PR*RT x QC*CT; the padding holds K = 1 with zero
+//   marginals, which keeps every sum positive and every padded scaling exactly 0 (no NaN, no
+//   select in the loop).
+// ---------------------------------------------------------------------------------------------
+template <int WARPS_, int QC_LOG2_, int RT_, int CT_, int GROUPS_>
+struct RegCfg {
+    static constexpr int W = WARPS_, QCL = QC_LOG2_, RT = RT_, CT = CT_, GROUPS = GROUPS_;
+    static constexpr int GT = W * 32;       // threads per problem
+    static constexpr int QC = 1 << QCL;     // lanes along a row
+    static constexpr int PRW = 32 / QC;     // row groups per warp
+    static constexpr int PR = W * PRW;      // row groups per problem
+    static constexpr int MAXM = PR * RT, MAXN = QC * CT;
+    static constexpr int CT2 = CT / 2;
+    static constexpr bool ODD = (CT & 1) != 0;
+    static constexpr int THREADS = GT * GROUPS;
+    static_assert(W == 1 || GROUPS == 1, "multi-warp problems use __syncthreads: one problem per CTA");
+};
+
+template <class C>
+__device__ __forceinline__ float row_allreduce_sum(float v) {
+#pragma unroll
+    for (int o = 1; o < C::QC; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <class C>
+__device__ __forceinline__ float row_allreduce_max(float v) {
+#pragma unroll
+    for (int o = 1; o < C::QC; o <<= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+struct OpSum {
+    __device__ __forceinline__ float operator()(float x, float y) const { return x + y; }
+};
+struct OpMax {
+    __device__ __forceinline__ float operator()(float x, float y) const { return fmaxf(x, y); }
+};
+
+// Column all-reduce over every row group of the problem (lanes, then warps through smem).
+// SCALE: the reducing thread turns a total t of column j into s_nu[j] / t (the beta update).
+template <class C, bool SCALE, class Op>
+__device__ __forceinline__ void col_reduce(float (&v)[C::CT], Op op, float *s_part, float *s_tot, const float *s_nu,
+                                           int warp, int prw, int qc, int gtid) {
+#pragma unroll
+    for (int c = 0; c < C::CT; ++c) {
+#pragma unroll
+        for (int o = C::QC; o < 32; o <<= 1) v[c] = op(v[c], __shfl_xor_sync(0xffffffffu, v[c], o));
+    }
+    if (C::W == 1) {
+        if (SCALE) {
+#pragma unroll
+            for (int c = 0; c < C::CT; ++c) v[c] = s_nu[qc + C::QC * c] * fast_rcp(v[c]);
+        }
+        return;
+    }
+    if (prw == 0) {
+#pragma unroll
+        for (int c = 0; c < C::CT; ++c) s_part[warp * C::MAXN + qc + C::QC * c] = v[c];
+    }
+    __syncthreads();
+    for (int j = gtid; j < C::MAXN; j += C::GT) {
+        float t = s_part[j];
+#pragma unroll
+        for (int w = 1; w < C::W; ++w) t = op(t, s_part[w * C::MAXN + j]);
+        s_tot[j] = SCALE ? s_nu[j] * fast_rcp(t) : t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < C::CT; ++c) v[c] = s_tot[qc + C::QC * c];
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
+    constexpr int RT = C::RT, CT = C::CT, CT2 = C::CT2, QC = C::QC, PR = C::PR;
+    constexpr bool ODD = C::ODD;
+    __shared__ float s_mu[C::GROUPS][C::MAXM];  // exp-domain marginals; reused as u[] by the fallback
+    __shared__ float s_nu[C::GROUPS][C::MAXN];  //                        reused as v[] by the fallback
+    __shared__ float s_u1[C::GROUPS][C::MAXM];  // potentials of the exact first iteration
+    __shared__ float s_v1[C::GROUPS][C::MAXN];
+    __shared__ float s_part[C::W > 1 ? C::W * C::MAXN : 1];
+    __shared__ float s_tot[C::W > 1 ? C::MAXN : 1];
+    __shared__ float s_red[2 * C::GT * C::GROUPS];  // fallback scratch
+
+    const int group = threadIdx.x / C::GT, gtid = threadIdx.x % C::GT;
+    const int lane = gtid & 31, warp = gtid >> 5;
+    const int qc = lane & (QC - 1), prw = lane >> C::QCL;
+    const int pr = warp * C::PRW + prw;
+    const int p = blockIdx.x * C::GROUPS + group;
+    if (p >= a.b) return;  // warp-uniform; W>1 => GROUPS==1 so the whole CTA leaves together
+
+    const int M = a.M, N = a.N;
+    const Marg g = problem_marginals(a, p, lane);
+    float *mu_s = s_mu[group], *nu_s = s_nu[group], *u1_s = s_u1[group], *v1_s = s_v1[group];
+
+    // ---- load the tile (padding = -inf) --------------------------------------------------------
+    float z[RT][CT];
+#pragma unroll
+    for (int k = 0; k < RT; ++k) {
+        const int row = pr + PR * k;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const int col = qc + QC * c;
+            z[k][c] = (row < M && col < N) ? z_at(a, g, p, row, col) : -INFINITY;
+        }
+    }
+    // marginals to shared memory (each value written by its qc==0 / pr==0 owner)
+    if (qc == 0) {
+#pragma unroll
+        for (int k = 0; k < RT; ++k) {
+            const int row = pr + PR * k;
+            mu_s[row] = (row < M) ? expf(lmu_at(a, g, p, row)) : 0.f;
+        }
+    }
+    if (pr == 0) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const int col = qc + QC * c;
+            nu_s[col] = (col < N) ? expf(lnu_at(a, g, p, col)) : 0.f;
+        }
+    }
+
+    // ---- iteration 1, exact in the log domain; K = exp(Z + u1 + v1) ------------------------------
+    if (a.iters >= 1) {
+        float u1[RT];
+#pragma unroll
+        for (int k = 0; k < RT; ++k) {
+            const int row = pr + PR * k;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) mx = fmaxf(mx, z[k][c]);
+            mx = row_allreduce_max<C>(mx);
+            const float mxs = (fabsf(mx) == INFINITY) ? 0.f : mx;
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) s += fast_exp(z[k][c] - mxs);
+            s = row_allreduce_sum<C>(s);
+            u1[k] = (row < M) ? lmu_at(a, g, p, row) - (fast_log(s) + mxs) : 0.f;
+            if (qc == 0) u1_s[row] = u1[k];
+        }
+        float cm[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < RT; ++k) mx = fmaxf(mx, z[k][c] + u1[k]);
+            cm[c] = mx;
+        }
+        col_reduce<C, false>(cm, OpMax(), s_part, s_tot, nu_s, warp, prw, qc, gtid);
+        float cs[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            cm[c] = (fabsf(cm[c]) == INFINITY) ? 0.f : cm[c];
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < RT; ++k) s += fast_exp((z[k][c] + u1[k]) - cm[c]);
+            cs[c] = s;
+        }
+        col_reduce<C, false>(cs, OpSum(), s_part, s_tot, nu_s, warp, prw, qc, gtid);
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const int col = qc + QC * c;
+            const float v1 = (col < N) ? lnu_at(a, g, p, col) - (fast_log(cs[c]) + cm[c]) : 0.f;
+            if (pr == 0) v1_s[col] = v1;
+#pragma unroll
+            for (int k = 0; k < RT; ++k) {
+                const int row = pr + PR * k;
+                z[k][c] = (row < M && col < N) ? fast_exp((z[k][c] + u1[k]) + v1) : 1.0f;
+            }
+        }
+    }
+    if (C::W == 1) __syncwarp(); else __syncthreads();
+
+    // ---- iterations 2..iters: scaling updates on the register tile --------------------------------
+    float2 Kp[RT][CT2 > 0 ? CT2 : 1];
+    float Kl[RT];
+#pragma unroll
+    for (int k = 0; k < RT; ++k) {
+#pragma unroll
+        for (int h = 0; h < CT2; ++h) Kp[k][h] = make_float2(z[k][2 * h], z[k][2 * h + 1]);
+        Kl[k] = ODD ? z[k][CT - 1] : 0.f;
+    }
+    float bcol[CT], al[RT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) bcol[c] = (qc + QC * c < N) ? 1.f : 0.f;
+#pragma unroll
+    for (int k = 0; k < RT; ++k) al[k] = 1.f;
+    float lo = INFINITY, hi = 0.f;
+
+    for (int it = 1; it < a.iters; ++it) {
+        // alpha_i = mu_i / sum_j K_ij beta_j
+        float2 acc[RT];
+#pragma unroll
+        for (int k = 0; k < RT; ++k) acc[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < CT2; ++h) {
+            const float2 bp = make_float2(bcol[2 * h], bcol[2 * h + 1]);
+#pragma unroll
+            for (int k = 0; k < RT; ++k) acc[k] = ffma2(Kp[k][h], bp, acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < RT; ++k) {
+            float r = acc[k].x + acc[k].y;
+            if (ODD) r = fmaf(Kl[k], bcol[CT - 1], r);
+            r = row_allreduce_sum<C>(r);
+            al[k] = mu_s[pr + PR * k] * fast_rcp(r);
+        }
+        // beta_j = nu_j / sum_i K_ij alpha_i
+        float2 s2[CT2 > 0 ? CT2 : 1];
+        float sl = 0.f;
+#pragma unroll
+        for (int h = 0; h < CT2; ++h) s2[h] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < RT; ++k) {
+            const float2 ak = make_float2(al[k], al[k]);
+#pragma unroll
+            for (int h = 0; h < CT2; ++h) s2[h] = ffma2(Kp[k][h], ak, s2[h]);
+            if (ODD) sl = fmaf(Kl[k], al[k], sl);
+        }
+#pragma unroll
+        for (int h = 0; h < CT2; ++h) {
+            bcol[2 * h] = s2[h].x;
+            bcol[2 * h + 1] = s2[h].y;
+        }
+        if (ODD) bcol[CT - 1] = sl;
+        col_reduce<C, true>(bcol, OpSum(), s_part, s_tot, nu_s, warp, prw, qc, gtid);
+
+        if ((it & 7) == 0 || it == a.iters - 1) {  // range monitor (valid entries only)
+#pragma unroll
+            for (int k = 0; k < RT; ++k)
+                if (pr + PR * k < M) lo = fminf(lo, al[k]), hi = fmaxf(hi, al[k]);
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+                if (qc + QC * c < N) lo = fminf(lo, bcol[c]), hi = fmaxf(hi, bcol[c]);
+        }
+    }
+
+    // ---- potentials, health check, output ---------------------------------------------------------
+    const float shift = (a.mode == MODE_RAW) ? 0.f : g.norm;
+    float U[RT], V[CT];
+    bool bad = !(lo >= 1e-13f && hi <= 1e13f);
+#pragma unroll
+    for (int k = 0; k < RT; ++k) {
+        const int row = pr + PR * k;
+        float t = 0.f;
+        if (a.iters >= 1) t = u1_s[row];
+        if (a.iters >= 2) t += fast_log(al[k]);
+        U[k] = t;
+        if (row < M && !(fabsf(t) < INFINITY)) bad = true;
+    }
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        const int col = qc + QC * c;
+        float t = 0.f;
+        if (a.iters >= 1) t = v1_s[col];
+        if (a.iters >= 2) t += fast_log(bcol[c]);
+        if (col < N && !(fabsf(t) < INFINITY)) bad = true;
+        V[c] = t - shift;
+    }
+    const bool any_bad = (C::W == 1) ? (__any_sync(0xffffffffu, bad) != 0) : (__syncthreads_or(bad ? 1 : 0) != 0);
+    if (!any_bad) {
+        float *o = a.out + (size_t)p * M * N;
+#pragma unroll
+        for (int k = 0; k < RT; ++k) {
+            const int row = pr + PR * k;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                const int col = qc + QC * c;
+                if (row < M && col < N) o[(size_t)row * N + col] = (z_at(a, g, p, row, col) + U[k]) + V[c];
+            }
+        }
+    } else {
+        if (gtid == 0 && a.fb_total) atomicAdd(a.fb_total, 1);
+        if (C::W == 1)
+            log_domain_solve<C::GT>(a, g, p, mu_s, nu_s, s_red + 2 * C::GT * group, gtid, WarpSync());
+        else
+            log_domain_solve<C::GT>(a, g, p, mu_s, nu_s, s_red, gtid, BlockSync());
+    }
+}
+
+// ---- host dispatch ------------------------------------------------------------------------------
+using CfgTiny = RegCfg<1, 2, 4, 8, 4>;     // <= 32 x 32, one warp per problem, 4 problems per CTA
+using CfgWarp = RegCfg<1, 2, 9, 17, 4>;    // <= 72 x 68  (level 3: 65 x 65)
+using CfgCta = RegCfg<8, 4, 10, 10, 1>;    // <= 160 x 160 (level 2: 145 x 145), 16 x 16 threads
+
+static int g_force_generic = 0;
+static int *g_fb_total = nullptr;  // device counter
+static std::mutex g_mu;
+
+static int ensure_counter() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_fb_total) {
+        PATS_CUDA_TRY(cudaMalloc(&g_fb_total, sizeof(int)));
+        PATS_CUDA_TRY(cudaMemset(g_fb_total, 0, sizeof(int)));
+    }
+    return PATS_OK;
+}
+
+static int kernel_kind(int M, int N) {
+    if (g_force_generic) return 2;
+    if (M <= CfgWarp::MAXM && N <= CfgWarp::MAXN) return 0;
+    if (M <= CfgCta::MAXM && N <= CfgCta::MAXN) return 1;
+    return 2;
+}
+
+template <class C>
+static int launch_reg(const SinkArgs &a, cudaStream_t st) {
+    const int grid = (a.b + C::GROUPS - 1) / C::GROUPS;
+    sinkhorn_reg_kernel<C><<<grid, C::THREADS, 0, st>>>(a);
+    PATS_LAUNCH_CHECK("sinkhorn_reg_kernel");
+    return PATS_OK;
+}
+
+static int launch_generic(const SinkArgs &a, cudaStream_t st) {
+    constexpr int GT = 1024;
+    const size_t smem = sizeof(float) * ((size_t)a.M + a.N + 2 * GT);
+    if (smem > 200 * 1024) return invalid("sinkhorn: M+N = %d exceeds the shared-memory budget of the generic kernel", a.M + a.N);
+    if (smem > 48 * 1024) {
+        PATS_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_generic_kernel<GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    int grid = a.b;
+    const int cap = 4 * (sm_count() > 0 ? sm_count() : 148);
+    if (grid > cap) grid = cap;
+    sinkhorn_generic_kernel<GT><<<grid, GT, smem, st>>>(a);
+    PATS_LAUNCH_CHECK("sinkhorn_generic_kernel");
+    return PATS_OK;
+}
+
+static int run_sinkhorn(SinkArgs a, void *stream) {
+    if (a.b < 0 || a.M <= 0 || a.N <= 0 || a.iters < 0) return invalid("sinkhorn: bad sizes b=%d M=%d N=%d iters=%d", a.b, a.M, a.N, a.iters);
+    if (a.mode != MODE_RAW && (a.M < 2 || a.N < 2)) return invalid("optimal transport needs at least one real row and column");
+    if (a.b == 0) return PATS_OK;
+    if (!a.Z || !a.out) return invalid("sinkhorn: null pointer");
+    if ((long long)a.M * a.N > 0x7fffffffLL / 2) return invalid("sinkhorn: problem too large");
+    int rc = ensure_counter();
+    if (rc) return rc;
+    a.fb_total = g_fb_total;
+    cudaStream_t st = as_stream(stream);
+    switch (kernel_kind(a.M, a.N)) {
+        case 0:
+            if (a.M <= CfgTiny::MAXM && a.N <= CfgTiny::MAXN) return launch_reg<CfgTiny>(a, st);
+            return launch_reg<CfgWarp>(a, st);
+        case 1:
+            return launch_reg<CfgCta>(a, st);
+        default:
+            return launch_generic(a, st);
+    }
+}
+
+}  // namespace pats
+
+using namespace pats;
+
+PATS_API int pats_log_sinkhorn_iterations_f32(const float *Z, const float *log_mu, const float *log_nu, int b, int M, int N,
+                                              int iters, float *out, void *stream) {
+    if (b > 0 && (!log_mu || !log_nu)) return invalid("log_sinkhorn_iterations: null marginals");
+    SinkArgs a{Z, log_mu, log_nu, nullptr, nullptr, out, b, M, N, iters, MODE_RAW, nullptr};
+    return run_sinkhorn(a, stream);
+}
+
+PATS_API int pats_log_optimal_transport_f32(const float *scores, const float *alpha, const float *ns, int b, int m, int n,
+                                            int iters, float *out, void *stream) {
+    if (b > 0 && (!alpha || !ns)) return invalid("log_optimal_transport: null alpha / ns");
+    SinkArgs a{scores, nullptr, nullptr, alpha, ns, out, b, m + 1, n + 1, iters, MODE_OT, nullptr};
+    return run_sinkhorn(a, stream);
+}
+
+PATS_API int pats_log_optimal_transport2_f32(const float *scores, const float *one, const float *ns, int b, int m, int n,
+                                             int iters, float *out, void *stream) {
+    if (b > 0 && (!one || !ns)) return invalid("log_optimal_transport2: null one / ns");
+    SinkArgs a{scores, nullptr, nullptr, one, ns, out, b, m, n, iters, MODE_OT2, nullptr};
+    return run_sinkhorn(a, stream);
+}
+
+PATS_API int pats_sinkhorn_kernel_kind(int M, int N) { return kernel_kind(M, N); }
+PATS_API void pats_sinkhorn_force_generic(int on) { g_force_generic = on ? 1 : 0; }
+
+PATS_API int pats_sinkhorn_fallback_count(int reset) {
+    if (ensure_counter() != PATS_OK) return -1;
+    int v = 0;
+    if (cudaMemcpy(&v, g_fb_total, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (reset) cudaMemset(g_fb_total, 0, sizeof(int));
+    return v;
+}
+
+// ---- host-buffer (end-to-end) variants -------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess ? 0 : -1; }
+};
+
+int ot_host(int mode, const float *scores, float scalar, const float *ns, int b, int m, int n, int iters, float *out) {
+    if (b < 0 || m <= 0 || n <= 0) return invalid("optimal transport (host): bad sizes");
+    if (b == 0) return PATS_OK;
+    if (!scores || !ns || !out) return invalid("optimal transport (host): null pointer");
+    const int M = (mode == MODE_OT) ? m + 1 : m, N = (mode == MODE_OT) ? n + 1 : n;
+    const size_t nin = (size_t)b * m * n, nns = (size_t)b * (N - 1), nout = (size_t)b * M * N;
+    DevBuf d_in, d_ns, d_sc, d_out;
+    if (d_in.alloc(nin * 4) || d_ns.alloc(nns * 4) || d_sc.alloc(4) || d_out.alloc(nout * 4))
+        return cuda_fail(cudaGetLastError(), "cudaMalloc (host variant)");
+    cudaStream_t st = nullptr;
+    PATS_CUDA_TRY(cudaMemcpyAsync(d_in.p, scores, nin * 4, cudaMemcpyHostToDevice, st));
+    PATS_CUDA_TRY(cudaMemcpyAsync(d_ns.p, ns, nns * 4, cudaMemcpyHostToDevice, st));
+    PATS_CUDA_TRY(cudaMemcpyAsync(d_sc.p, &scalar, 4, cudaMemcpyHostToDevice, st));
+    int rc = (mode == MODE_OT)
+                 ? pats_log_optimal_transport_f32((const float *)d_in.p, (const float *)d_sc.p, (const float *)d_ns.p, b, m, n, iters, (float *)d_out.p, st)
+                 : pats_log_optimal_transport2_f32((const float *)d_in.p, (const float *)d_sc.p, (const float *)d_ns.p, b, m, n, iters, (float *)d_out.p, st);
+    if (rc) return rc;
+    PATS_CUDA_TRY(cudaMemcpyAsync(out, d_out.p, nout * 4, cudaMemcpyDeviceToHost, st));
+    PATS_CUDA_TRY(cudaStreamSynchronize(st));
+    return PATS_OK;
+}
+}  // namespace
+
+PATS_API int pats_log_optimal_transport_f32_host(const float *scores, float alpha, const float *ns, int b, int m, int n,
+                                                 int iters, float *out) {
+    return ot_host(MODE_OT, scores, alpha, ns, b, m, n, iters, out);
+}
+
+PATS_API int pats_log_optimal_transport2_f32_host(const float *scores, float one, const float *ns, int b, int m, int n,
+                                                  int iters, float *out) {
+    return ot_host(MODE_OT2, scores, one, ns, b, m, n, iters, out);
+}

@@ -1,0 +1,60 @@
+"""world_size-2 gloo test of the multi-GPU plumbing (pair sharding + gather of match lists)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pats_b200.dist import gather_match_lists, shard_range
+
+
+def test_shard_range_covers_everything_once():
+    for n in (0, 1, 7, 8, 1500):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = shard_range(n, r, world)
+                assert 0 <= lo <= hi <= n
+                seen += list(range(lo, hi))
+            assert seen == list(range(n))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_pairs):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_range(n_pairs, rank, world)
+        mine = []
+        for i in range(lo, hi):
+            g = torch.Generator().manual_seed(i)
+            k = int(torch.randint(0, 50, (1,), generator=g))
+            mine.append(torch.rand(k, 4, generator=g))
+        allm = gather_match_lists(mine)
+        assert len(allm) == world
+        flat = [m for per_rank in allm for m in per_rank]
+        assert len(flat) == n_pairs
+        for i, m in enumerate(flat):
+            g = torch.Generator().manual_seed(i)
+            k = int(torch.randint(0, 50, (1,), generator=g))
+            assert m.shape == (k, 4)
+            assert torch.equal(m, torch.rand(k, 4, generator=g))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_match_lists_gloo_world2():
+    mp.spawn(_worker, args=(2, _free_port(), 5), nprocs=2, join=True)
+
+
+def test_gather_match_lists_uneven_and_empty_rank():
+    mp.spawn(_worker, args=(2, _free_port(), 1), nprocs=2, join=True)

@@ -1,0 +1,242 @@
+"""GPU parity tests of the Sinkhorn / OT kernels, called through the reference-named wrappers (C ABI).
+
+Bar (BASELINE.json north_star): OT scores within 1e-4 (f32, log domain) of the reference, row/column
+argmax (match indices) identical.  Checked against (1) the committed outputs of the unmodified reference
+(tests/golden/ot.npz), (2) the CPU oracle on seeded inputs, (3) size-independent properties at full size.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def M():
+    from pats_b200 import modules
+
+    return modules
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pats_b200 import _lib
+
+    return _lib.load()
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def areas(g, b, n, span):
+    return torch.exp((torch.rand(b, 1, n, generator=g) * 2 - 1) * math.log(span))
+
+
+def assert_plan_equal(out, ref, tol=TOL):
+    assert out.shape == ref.shape
+    err = np.abs(out - ref).max()
+    assert err <= tol, f"max|err| = {err}"
+    assert (out.argmax(2) == ref.argmax(2)).all(), "row argmax (match index) differs"
+    assert (out.argmax(1) == ref.argmax(1)).all(), "column argmax (match index) differs"
+
+
+# ---- (1) golden vectors of the unmodified reference ------------------------------------------------------
+def test_golden_log_sinkhorn_iterations(M, dev):
+    g = load_golden("ot")
+    for tag, it in (("a1_out_it100", 100), ("a1_out_it3", 3)):
+        out = M.log_sinkhorn_iterations(T(g["a1_Z"], dev), T(g["a1_log_mu"], dev), T(g["a1_log_nu"], dev), it).cpu().numpy()
+        np.testing.assert_allclose(out, g[tag], atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("tag", ["a2_small", "a2_rect", "a2_L1", "a2_L1_peaked"])
+def test_golden_log_optimal_transport(M, dev, tag):
+    g = load_golden("ot")
+    out = M.log_optimal_transport(T(g[tag + "_scores"], dev), torch.tensor(float(g[tag + "_alpha"]), device=dev), T(g[tag + "_ns"], dev), 100)
+    assert out.is_contiguous() and out.dtype == torch.float32
+    assert_plan_equal(out.cpu().numpy(), g[tag + "_out"])
+
+
+def test_golden_single_iteration(M, dev):
+    g = load_golden("ot")
+    out = M.log_optimal_transport(T(g["a2_small_scores"], dev), float(g["a2_small_alpha"]), T(g["a2_small_ns"], dev), 1)
+    np.testing.assert_allclose(out.cpu().numpy(), g["a2_small_out_it1"], atol=TOL, rtol=0)
+
+
+@pytest.mark.parametrize("tag", ["a3_L2", "a3_L3", "a3_L3_wide", "a3_rect"])
+def test_golden_log_optimal_transport2(M, dev, tag):
+    g = load_golden("ot")
+    s = T(g[tag + "_scores"], dev)
+    s0 = s.clone()
+    out = M.log_optimal_transport2(s, torch.tensor(1.0, device=dev), T(g[tag + "_ns"], dev), 100)
+    assert torch.equal(s, s0), "input must not be modified"
+    assert out.data_ptr() != s.data_ptr()
+    assert_plan_equal(out.cpu().numpy(), g[tag + "_out"])
+
+
+# ---- (2) CPU oracle on seeded inputs -------------------------------------------------------------------
+@pytest.mark.parametrize("b,m,n,scale,span", [
+    (64, 65, 65, 0.1, 16.0),     # level 3 shape, warp kernel
+    (37, 65, 65, 1.5, 16.0),     # ragged batch (not a multiple of the 4 problems per CTA), wider scores
+    (12, 145, 145, 0.1, 256.0),  # level 2 shape, CTA kernel
+    (5, 145, 145, 1.0, 256.0),
+    (9, 33, 60, 0.5, 4.0),       # non-square, padded tile
+    (7, 72, 20, 0.5, 4.0),       # capacity edge of the warp kernel (72 rows)
+    (3, 2, 2, 1.0, 2.0),         # smallest legal transport2 problem
+    (5, 17, 31, 0.3, 8.0),       # tiny kernel
+    (4, 100, 160, 0.4, 8.0),     # CTA kernel, capacity edge (160 columns)
+    (3, 160, 73, 0.4, 8.0),      # CTA kernel, capacity edge (160 rows)
+    (2, 161, 90, 0.4, 8.0),      # first shape that needs the generic log-domain kernel
+])
+def test_transport2_vs_oracle(M, lib, dev, b, m, n, scale, span):
+    g = torch.Generator().manual_seed(1000 + b * 7 + m)
+    s = scale * torch.randn(b, m, n, generator=g)
+    ns = areas(g, b, n - 1, span)
+    out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), 100).cpu().numpy()
+    ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), 100)
+    assert_plan_equal(out, ref)
+
+
+@pytest.mark.parametrize("b,m,n,alpha", [(1, 300, 300, 1.0), (3, 64, 64, 0.7), (2, 20, 33, 0.0), (2, 144, 144, 2.0), (1, 160, 100, 1.0)])
+def test_transport_vs_oracle(M, dev, b, m, n, alpha):
+    g = torch.Generator().manual_seed(2000 + m)
+    s = 0.1 * torch.randn(b, m, n, generator=g)
+    ns = areas(g, b, n, 16.0)
+    out = M.log_optimal_transport(s.to(dev), torch.tensor(alpha, device=dev), ns.to(dev), 100)
+    assert out.shape == (b, m + 1, n + 1)
+    ref = oracle.log_optimal_transport(s.numpy(), alpha, ns.numpy(), 100)
+    assert_plan_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("iters", [0, 1, 2, 3, 9, 17])
+def test_iteration_counts(M, dev, iters):
+    g = torch.Generator().manual_seed(3000 + iters)
+    for (b, m, n) in ((6, 65, 65), (3, 145, 145)):
+        s = 0.3 * torch.randn(b, m, n, generator=g)
+        ns = areas(g, b, n - 1, 16.0)
+        out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), iters).cpu().numpy()
+        ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), iters)
+        np.testing.assert_allclose(out, ref, atol=TOL, rtol=0)
+
+
+def test_raw_sinkhorn_vs_oracle(M, dev):
+    g = torch.Generator().manual_seed(4000)
+    for (b, m, n) in ((5, 65, 65), (3, 40, 150), (2, 200, 180)):
+        Z = 0.5 * torch.randn(b, m, n, generator=g)
+        lmu = torch.log_softmax(torch.randn(b, m, generator=g), 1)
+        lnu = torch.log_softmax(torch.randn(b, n, generator=g), 1)
+        out = M.log_sinkhorn_iterations(Z.to(dev), lmu.to(dev), lnu.to(dev), 50).cpu().numpy()
+        ref = oracle.log_sinkhorn_iterations(Z.numpy(), lmu.numpy(), lnu.numpy(), 50)
+        np.testing.assert_allclose(out, ref, atol=TOL, rtol=0)
+
+
+def test_generic_kernel_matches_register_kernels(M, lib, dev):
+    """The log-domain kernel (fallback / large shapes) and the register kernels agree."""
+    g = torch.Generator().manual_seed(5000)
+    for (b, m, n) in ((8, 65, 65), (3, 145, 145)):
+        s = (0.2 * torch.randn(b, m, n, generator=g)).to(dev)
+        ns = areas(g, b, n - 1, 16.0).to(dev)
+        fast = M.log_optimal_transport2(s, 1.0, ns, 100)
+        lib.pats_sinkhorn_force_generic(1)
+        try:
+            assert lib.pats_sinkhorn_kernel_kind(m, n) == 2
+            slow = M.log_optimal_transport2(s, 1.0, ns, 100)
+        finally:
+            lib.pats_sinkhorn_force_generic(0)
+        assert (fast - slow).abs().max().item() <= TOL
+
+
+def test_extreme_dynamic_range_takes_the_log_domain_fallback(M, lib, dev):
+    """Scores with a huge spread drive the scaling form out of its safe range; those problems must be
+    re-solved in the log domain and still match the oracle."""
+    g = torch.Generator().manual_seed(6000)
+    b, m, n = 6, 65, 65
+    s = 0.1 * torch.randn(b, m, n, generator=g)
+    s[0] *= 400.0       # |Z| up to ~150: far outside anything the exp-domain form can hold
+    s[3, :, :5] -= 90.0
+    ns = areas(g, b, n - 1, 16.0)
+    lib.pats_sinkhorn_fallback_count(1)
+    out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), 100).cpu().numpy()
+    n_fb = lib.pats_sinkhorn_fallback_count(1)
+    ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), 100)
+    assert np.isfinite(out).all()
+    # large-magnitude entries: relative tolerance on top of the absolute one
+    np.testing.assert_allclose(out, ref, atol=TOL, rtol=2e-6)
+    assert n_fb >= 1, "expected at least one problem to use the fallback"
+    assert n_fb < b, "well-conditioned problems must stay on the fast path"
+
+
+def test_empty_batch(M, dev):
+    out = M.log_optimal_transport2(torch.zeros(0, 65, 65, device=dev), 1.0, torch.zeros(0, 1, 64, device=dev), 100)
+    assert out.shape == (0, 65, 65)
+    out = M.log_optimal_transport(torch.zeros(0, 30, 30, device=dev), 1.0, torch.zeros(0, 1, 30, device=dev), 100)
+    assert out.shape == (0, 31, 31)
+
+
+def test_rejects_cpu_tensors(M):
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        M.log_optimal_transport2(torch.zeros(1, 5, 5), 1.0, torch.ones(1, 1, 4), 10)
+
+
+# ---- (3) full-size, size-independent properties --------------------------------------------------------------
+def _torch_lse_sinkhorn(Z, lmu, lnu, iters):
+    u, v = torch.zeros_like(lmu), torch.zeros_like(lnu)
+    for _ in range(iters):
+        u = lmu - torch.logsumexp(Z + v[:, None, :], 2)
+        v = lnu - torch.logsumexp(Z + u[:, :, None], 1)
+    return Z + u[:, :, None] + v[:, None, :]
+
+
+@pytest.mark.parametrize("b,m,n,span", [(4800, 65, 65, 16.0), (300, 145, 145, 256.0)])
+def test_full_size_marginals_and_subset_parity(M, dev, b, m, n, span):
+    """BASELINE sizes (K=4800 level-3 problems / P=300 level-2 problems of one 640x480 pair):
+    the column marginals are met exactly after the last v-update, and a random subset equals the oracle."""
+    g = torch.Generator().manual_seed(7000 + m)
+    s = (0.1 * torch.randn(b, m, n, generator=g)).to(dev)
+    ns = areas(g, b, n - 1, span).to(dev)
+    out = M.log_optimal_transport2(s, 1.0, ns, 100)
+    ms = float(m - 1)
+    tot = ms + ns.sum(2)                                   # [b,1]
+    nu = torch.cat([ns.reshape(b, -1), torch.full((b, 1), ms, device=dev)], 1)   # column masses (x (m+sum ns) scaling)
+    col = torch.logsumexp(out, 1)                          # log of column sums of the scaled plan
+    assert (col - nu.log()).abs().max().item() < 2e-4
+    mu = torch.cat([torch.ones(b, m - 1, device=dev), ns.sum(2)], 1)
+    row = torch.logsumexp(out, 2)
+    assert (row - mu.log()).abs().max().item() < 0.2       # rows only approximately (not converged exactly)
+    assert abs(float(torch.exp(out).sum((1, 2)).mean() / tot.mean()) - 1.0) < 1e-3
+    idx = torch.randperm(b, generator=g)[:24]
+    ref = oracle.log_optimal_transport2(s[idx].cpu().numpy(), 1.0, ns[idx].cpu().numpy(), 100)
+    assert_plan_equal(out[idx].cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("N,iters", [(1536, 100), (1024, 100)])
+def test_large_plan_generic_kernel(M, lib, dev, N, iters):
+    """BASELINE.json's synthetic kernel sizes (N=1536) and the 1024x1024-pair coarse plan (1024 -> 1025):
+    generic log-domain kernel against a torch fp32 logsumexp restatement on the same device."""
+    g = torch.Generator().manual_seed(8000 + N)
+    b = 2
+    s = (0.1 * torch.randn(b, N, N, generator=g)).to(dev)
+    ns = areas(g, b, N, 16.0).to(dev)
+    alpha = torch.tensor(1.0, device=dev)
+    assert lib.pats_sinkhorn_kernel_kind(N + 1, N + 1) == 2
+    out = M.log_optimal_transport(s, alpha, ns, iters)
+    Z = torch.cat([torch.cat([s, alpha.expand(b, N, 1)], 2), alpha.expand(b, 1, N + 1)], 1)
+    nsum = ns.sum(2).reshape(b)
+    norm = -(N + nsum).log()
+    lnu = torch.cat([ns.reshape(b, N).log() + norm[:, None], (math.log(N) + norm)[:, None]], 1)
+    lmu = torch.cat([norm[:, None].expand(b, N), (nsum.log() + norm)[:, None]], 1)
+    ref = _torch_lse_sinkhorn(Z, lmu, lnu, iters) - norm[:, None, None]
+    assert (out - ref).abs().max().item() <= TOL
+    assert torch.equal(out.argmax(2), ref.argmax(2))
