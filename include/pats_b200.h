@@ -85,8 +85,9 @@ int pats_log_optimal_transport2_f32_host(const float *scores, float one, const f
  *   is incremented once per row the reference would reject; such rows are written as zeros. */
 int pats_tensor_resize_f32(const float *input, int B, int C, int Hp, int Wp, const int64_t *bound, int K, int out_h,
                            int out_w, float *out, int *bad_rows, void *stream);
-/* Same kernel with an explicit rounding recipe for the lerp (0 = as compiled, 1/2 = the two FMA
- * contractions, 3 = no contraction); used to pin bit-exactness against ATen's CUDA kernel. */
+/* Same kernel with an explicit rounding recipe for the lerp (0 = bare expression as compiled, 1..9 =
+ * (inner, outer) FMA contractions); used to pin bit-exactness against ATen's CUDA kernel.  The shipping
+ * recipe is 5, which is bit-identical to torch's upsample_bilinear2d on CUDA. */
 int pats_tensor_resize_f32_variant(const float *input, int B, int C, int Hp, int Wp, const int64_t *bound, int K,
                                    int out_h, int out_w, float *out, int *bad_rows, int variant, void *stream);
 int pats_tensor_resize_f32_host(const float *input, int B, int C, int Hp, int Wp, const int64_t *bound, int K,
@@ -120,6 +121,49 @@ int pats_compute_imgs(const float *x_scale, const float *y_scale, const float *a
                       int width, int ps, int margin, void *new_left, float *new_right, int64_t *bound5,
                       float *x_scale_new, float *y_scale_new, float *average_new, int capacity, int *count,
                       int *bad_rows, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Area expansion, regrouping, match assembly      (utils/utils.py, models/second_layer.py, third_layer.py)
+ * ------------------------------------------------------------------------------------------- */
+
+/* Iterative_expand_matrix(scores_in, scalex, scaley, limitation, ranges, positions, lower_bound, ..., iter_num)
+ *                                                           utils/utils.py:1179-1297 (+ Compute_scaling :1321-1340)
+ *   scores_in [b,m+1,n+1] = exp(Z), scalex,scaley [b,n], target grid grid_h x grid_w (n = grid_h*grid_w;
+ *   `limitation`, `ranges`, `positions` of the reference are functions of the grid and are not passed)
+ *   -> whole_cost, core_cost [b,m], average_point [b,m,2], x_scale,y_scale [b,m], bound [b,m,4] i64,
+ *      if_nomatching [b,m] u8 (may be NULL; the mask of utils.py:1194). */
+int pats_iterative_expand_matrix_f32(const float *scores_in, const float *scalex, const float *scaley, int b, int m,
+                                     int grid_h, int grid_w, float lower_bound, int iter_num, float *whole_cost,
+                                     float *core_cost, float *average_point, float *x_scale, float *y_scale,
+                                     int64_t *bound, uint8_t *if_nomatching, void *stream);
+
+/* est_position's masks                                      first_layer.py:162-167, second_layer.py:244-249
+ *   Z [b,M,N] -> nm1 [b,M-1] = (argmax_j Z[i,:] == dust), nm2 [b,N-1] = (argmax_i Z[:,j] == dust) */
+int pats_est_nomatching_f32(const float *Z, int b, int M, int N, int dust, uint8_t *nm1, uint8_t *nm2, void *stream);
+
+/* SecondLayer.merge_patches_new / merge_patches_old         models/second_layer.py:189-238 / :137-186
+ *   trust_score [P,144] f32 and nm_L2 [P,144] u8 are MUTATED in place exactly as the reference mutates its
+ *   arguments; nm_L1 [B,hw] u8; scores_back [B,hw,16,9] f64 in/out (carried across chunks for `new`, zeroed on
+ *   return for `old`); out [P,144] u8 = if_nomatching per window cell.  workspace: 2*B*hw+1 ints (device). */
+int pats_merge_patches(int merge_new, float *trust_score, const uint8_t *nm_L1, uint8_t *nm_L2, double *scores_back, int B,
+                       int height, int width, int P, uint8_t *out, int *workspace, void *stream);
+
+/* get_result(batch, if_nomatching, average_point, scale, patch_size, left_choice)   utils/utils.py:189-213
+ *   two levels, left_choice all true (models/pats.py:75-77).  Level 0: nm0 [B,n0] u8, pt0,sc0 [B,n0,2],
+ *   (ps0,h0,w0); level 1: nm1 [P,n1] u8, pt1,sc1 [P,n1,2], (ps1,h1,w1); P = matched level-0 patches.
+ *   -> matches_l, matches_r [capacity,2] f32 filled in row-major mask order; *total (DEVICE i64) = Kf.
+ *   workspace (device): 8*(P+1) + 4*(2*B*n0 + 1 + P) bytes, 8-byte aligned. */
+int pats_get_result_f32(const uint8_t *nm0, const float *pt0, const float *sc0, int B, int ps0, int h0, int w0,
+                        const uint8_t *nm1, const float *pt1, const float *sc1, int P, int ps1, int h1, int w1,
+                        float *matches_l, float *matches_r, long long capacity, long long *total, void *workspace,
+                        void *stream);
+
+/* ThirdLayer.Compute_result + the outdoor label test        models/third_layer.py:184-217, :166-167
+ *   scores = exp(Z) [K,65,65], scale_x,scale_y [K,64], p_s,p_t [K,2] i64 (x,y)
+ *   -> mkpts0_f, mkpts1_f [K,16,2] f32, if_matching1 [K,16] u8 */
+int pats_third_compute_result_f32(const float *scores, const float *scale_x, const float *scale_y, const int64_t *p_s,
+                                  const int64_t *p_t, int K, float *mkpts0_f, float *mkpts1_f, uint8_t *if_matching1,
+                                  void *stream);
 
 #ifdef __cplusplus
 }

@@ -15,12 +15,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 SO = os.path.join(HERE, "libpats_b200.so")
-SOURCES = ["api.cu", "sinkhorn.cu", "subdivide.cu", "regroup.cu"]
+OBJ_DIR = os.path.join(HERE, "build")
+# source -> extra flags.  regroup.cu is compiled without FMA contraction: its f32 expressions must round
+# exactly like the C oracle's (integer results hang off them).
+SOURCES = {"api.cu": [], "sinkhorn.cu": [], "subdivide.cu": [], "regroup.cu": ["-fmad=false"]}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
-    "-shared",
 ]
 
 
@@ -46,14 +48,27 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return SO
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", SO, *sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
     env = dict(os.environ)
     env.pop("CC", None)  # the image exports a CC that nvcc's host pass must not pick up
-    subprocess.run(cmd, check=True, env=env)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    deps_t = max(os.path.getmtime(d) for d in (os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "pats_b200.h")))
+    objs, procs = [], []
+    for src in sources():
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), deps_t):
+            continue
+        cmd = [_nvcc(), *NVCC_FLAGS, *SOURCES[os.path.basename(src)], *(["-Xptxas", "-v"] if verbose else []), "-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd, env=env)))
+    for cmd, pr in procs:
+        if pr.wait() != 0:
+            raise subprocess.CalledProcessError(pr.returncode, cmd)
+    link = [_nvcc(), "-shared", "-o", SO, *objs]
+    if verbose:
+        print(" ".join(link))
+    subprocess.run(link, check=True, env=env)
     return SO
 
 

@@ -1,0 +1,610 @@
+// Area expansion, window regrouping, match assembly and the third-layer result for sm_100a.
+// Replaces, from zju3dv/pats:
+//   utils/utils.py:1179-1297  Iterative_expand_matrix (+ :1321-1340 Compute_scaling, est_position's argmaxes)
+//   models/second_layer.py:137-238  merge_patches_old / merge_patches_new
+//   utils/utils.py:189-213    get_result
+//   models/third_layer.py:184-217, :166-167  ThirdLayer.Compute_result + the label test
+//
+// These kernels produce the integers (boxes, masks, match order) that define match-index parity, so they
+// are written to be bit-identical to the CPU oracle: short f32 sums run sequentially in the oracle's
+// order, long sums accumulate in f64, and this file is compiled with -fmad=false so every f32 expression
+// rounds exactly like the C restatement.  They are latency-bound index kernels; the work is spread over
+// (rows | window cells | matches) >> 148 SMs worth of warps.
+#include "common.cuh"
+
+namespace pats {
+
+// =================================================================================================
+// a8/a9  area expansion: one warp per (problem, source row)
+// =================================================================================================
+constexpr int EX_WARPS = 8;
+constexpr float kZero = 1e-14f;  // `zero` of utils/utils.py:1203
+
+struct ExpandArgs {
+    const float *scores;  // [b, m+1, n+1] = exp(Z)
+    const float *sx, *sy; // [b, n]
+    int b, m, n, grid_w, width, height, iters;
+    float lb;
+    float *whole, *core, *avg, *xs, *ys;
+    int64_t *bound;
+    uint8_t *nomatch;
+};
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(EX_WARPS * 32) area_expand_kernel(ExpandArgs a) {
+    extern __shared__ float sm[];
+    const int n = a.n, m = a.m, bb = blockIdx.y;
+    const int stride = n + 2;
+    float *O = sm, *SX = sm + stride, *SY = sm + 2 * stride;  // dustbin row, target scales (shared by the CTA)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *E = sm + (3 + warp) * stride;                      // this warp's source row (+ dustbin col, + zero slot)
+    const float *opp = a.scores + ((size_t)bb * (m + 1) + m) * (n + 1);
+    for (int j = threadIdx.x; j < stride; j += blockDim.x) {
+        O[j] = j < n ? opp[j] : kZero;
+        SX[j] = j < n ? a.sx[(size_t)bb * n + j] : 0.f;
+        SY[j] = j < n ? a.sy[(size_t)bb * n + j] : 0.f;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * EX_WARPS + warp;
+    if (i >= m) return;
+    const float *row = a.scores + ((size_t)bb * (m + 1) + i) * (n + 1);
+    for (int j = lane; j < stride; j += 32) E[j] = j <= n ? row[j] : kZero;
+    __syncwarp();
+    auto Sval = [&](long long idx) -> float { return idx < n ? SX[idx] * SY[idx] : kZero; };
+
+    // ---- argmax over real targets (first maximum), dustbin test (utils.py:1182,1194) ------------------------
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < n; j += 32) {
+        const float v = E[j];
+        if (v > bv || bi == 0x7fffffff) {
+            if (v > bv || bi == 0x7fffffff) bv = v, bi = j;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) bv = ov, bi = oi;
+    }
+    const int max0 = bi;
+    const int maxall = (E[n] > E[max0]) ? n : max0;
+    const bool nomatch = (maxall == m);
+
+    long long bd0, bd1, bd2, bd3, dy = 0, dx = 0, sdy = 0, sdx = 0;
+    bd0 = bd1 = max0 / a.grid_w;
+    bd2 = bd3 = max0 % a.grid_w;
+    const int width = a.width, height = a.height;
+    float last_sum = E[max0], last_nom = O[max0];
+
+    // ---- box growth (utils.py:1213-1243): lanes 0..11 = (direction, quantity), sequential over the strip -------
+    for (int it = 0; it < a.iters; ++it) {
+        sdy = dy, sdx = dx;
+        float acc = 0.f;
+        if (lane < 12) {
+            const int d = lane / 3, q = lane - 3 * d;
+            long long off;
+            if (d == 0) off = bd2 + bd0 * width - width;
+            else if (d == 1) off = bd2 + bd1 * width + width;
+            else if (d == 2) off = bd2 + bd0 * width - 1;
+            else off = bd3 + bd0 * width + 1;
+            const float foff = (float)off;
+            for (int t = 0; t < width; ++t) {
+                float rng;
+                if (d < 2) rng = (t <= dx) ? (float)t : 1e7f;
+                else rng = ((t <= dy) ? (float)t : 1e7f) * (float)width;
+                long long s = (long long)(rng + foff);
+                if (s < 0 || s > n - 1) s = n + 1;
+                const float e = E[s];
+                if (q == 0) acc += e;
+                else if (q == 1) acc += (e > a.lb) ? O[s] : kZero;
+                else acc += Sval(s);
+            }
+        }
+        float es0 = __shfl_sync(0xffffffffu, acc, 0), es1 = __shfl_sync(0xffffffffu, acc, 3);
+        float es2 = __shfl_sync(0xffffffffu, acc, 6), es3 = __shfl_sync(0xffffffffu, acc, 9);
+        if (bd0 == 0) es0 = kZero;
+        if (bd1 == height - 1) es1 = kZero;
+        if (bd2 == 0) es2 = kZero;
+        if (bd3 == width - 1) es3 = kZero;
+        int arg = 0;
+        float mx = es0;
+        if (es1 > mx) mx = es1, arg = 1;
+        if (es2 > mx) mx = es2, arg = 2;
+        if (es3 > mx) mx = es3, arg = 3;
+        const float en_arg = __shfl_sync(0xffffffffu, acc, arg * 3 + 1);
+        float add_sum = kZero, add_nom = kZero;
+        if (mx > a.lb) {
+            if (arg == 0) bd0 -= 1;
+            else if (arg == 1) bd1 += 1;
+            else if (arg == 2) bd2 -= 1;
+            else bd3 += 1;
+            add_sum = mx, add_nom = en_arg;
+        }
+        dy = bd1 - bd0, dx = bd3 - bd2;
+        last_sum += add_sum;
+        last_nom += add_nom;
+    }
+    const bool core_exist = (dy > 1) && (dx > 1);
+
+    // ---- border strips of the final box with the previous iteration's extents (utils.py:1245-1253) ------------
+    float acc = 0.f;
+    if (lane < 8) {
+        const int d = lane >> 1, q = lane & 1;
+        long long off;
+        if (d == 0) off = bd2 + bd0 * width;
+        else if (d == 1) off = bd2 + bd1 * width;
+        else if (d == 2) off = bd2 + bd0 * width;
+        else off = bd3 + bd0 * width;
+        const float foff = (float)off;
+        for (int t = 0; t < width; ++t) {
+            float rng;
+            if (d < 2) rng = (t <= sdx) ? (float)t : 1e7f;
+            else rng = ((t <= sdy) ? (float)t : 1e7f) * (float)width;
+            long long s = (long long)(rng + foff);
+            if (s < 0 || s > n - 1) s = n + 1;
+            acc += (q == 0) ? E[s] : Sval(s);
+        }
+    }
+    const float e0 = __shfl_sync(0xffffffffu, acc, 0), e1 = __shfl_sync(0xffffffffu, acc, 2);
+    const float e2 = __shfl_sync(0xffffffffu, acc, 4), e3 = __shfl_sync(0xffffffffu, acc, 6);
+    const float s0 = __shfl_sync(0xffffffffu, acc, 1), s1 = __shfl_sync(0xffffffffu, acc, 3);
+    const float s2 = __shfl_sync(0xffffffffu, acc, 5), s3 = __shfl_sync(0xffffffffu, acc, 7);
+    const float es4 = ((e0 + e1) + e2) + e3, ss4 = ((s0 + s1) + s2) + s3;
+
+    // ---- weighted mean position / area scale inside the box (utils.py:1254-1268, 1321-1340), f64 sums ----------
+    double wx = 0, wy = 0, sxs = 0, sys = 0, wsc = 0, psum = 0, ts = 0;
+    for (int p = lane; p < n; p += 32) {
+        const long long pr = p / a.grid_w, pc = p % a.grid_w;
+        const bool in = pr >= bd0 && pr <= bd1 && pc >= bd2 && pc <= bd3;
+        float ox = kZero, oy = kZero;
+        if (in) {
+            const float q = sqrtf(E[p] + 1e-7f);
+            ox = q / SX[p];
+            oy = q / SY[p];
+        }
+        wx += (double)(ox * (float)pc);
+        wy += (double)(oy * (float)pr);
+        sxs += (double)ox;
+        sys += (double)oy;
+        const float o = ox * oy;
+        wsc += (double)(o * (SX[p] * SY[p]));
+        psum += (double)o;
+    }
+    for (int j = lane; j <= n; j += 32) ts += (double)E[j];
+    wx = warp_sum_f64(wx), wy = warp_sum_f64(wy), sxs = warp_sum_f64(sxs), sys = warp_sum_f64(sys);
+    wsc = warp_sum_f64(wsc), psum = warp_sum_f64(psum), ts = warp_sum_f64(ts);
+
+    if (lane == 0) {
+        const size_t r = (size_t)bb * m + i;
+        a.avg[2 * r + 1] = (float)wx / (float)sxs + 0.5f;
+        a.avg[2 * r + 0] = (float)wy / (float)sys + 0.5f;
+        const float avg_scale = sqrtf((float)wsc / (float)psum);
+        a.xs[r] = 1.0f / (avg_scale / 1.0f);
+        a.ys[r] = 1.0f / (avg_scale * 1.0f);
+        long long cn[4] = {bd0 * width + bd2, bd0 * width + bd3, bd1 * width + bd2, bd1 * width + bd3};
+        float cps = 0.f, css = 0.f;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            if (cn[d] < 0 || cn[d] > n - 1) cn[d] = n + 1;
+            cps += E[cn[d]];
+            css += Sval(cn[d]);
+        }
+        const float the_scale = (float)ts;
+        const float core_scale_sum = (the_scale - ss4) + css;
+        const float core_sum = (last_sum - es4) + cps;
+        a.core[r] = (core_exist && !nomatch) ? fabsf((core_sum - core_scale_sum) / the_scale) : kZero;
+        a.whole[r] = nomatch ? kZero : (fabsf(the_scale - last_sum) + last_nom / 4.0f) / the_scale;
+        a.bound[4 * r + 0] = bd0, a.bound[4 * r + 1] = bd1, a.bound[4 * r + 2] = bd2, a.bound[4 * r + 3] = bd3;
+        if (a.nomatch) a.nomatch[r] = nomatch ? 1 : 0;
+    }
+}
+
+// est_position's masks (first_layer.py:162-167): row / column argmax of Z equals the dustbin index.
+__global__ void __launch_bounds__(256) est_nomatching_kernel(const float *__restrict__ Z, int M, int N, int dust,
+                                                             uint8_t *__restrict__ nm1, uint8_t *__restrict__ nm2) {
+    const int bb = blockIdx.x;
+    const float *z = Z + (size_t)bb * M * N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = warp; i < M - 1; i += nw) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int j = lane; j < N; j += 32) {
+            const float v = z[(size_t)i * N + j];
+            if (bi == 0x7fffffff || v > bv) bv = v, bi = j;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) bv = ov, bi = oi;
+        }
+        if (lane == 0) nm1[(size_t)bb * (M - 1) + i] = (bi == dust);
+    }
+    for (int j = threadIdx.x; j < N - 1; j += blockDim.x) {
+        float bv = z[j];
+        int bi = 0;
+        for (int i = 1; i < M; ++i) {
+            const float v = z[(size_t)i * N + j];
+            if (v > bv) bv = v, bi = i;
+        }
+        nm2[(size_t)bb * (N - 1) + j] = (bi == dust);
+    }
+}
+
+// =================================================================================================
+// a11  merge_patches_new / merge_patches_old
+// =================================================================================================
+// Ordered index maps between matched level-1 patches q (row-major over [B,hw]) and window numbers p.
+__global__ void __launch_bounds__(1024) window_maps_kernel(const uint8_t *__restrict__ nm_L1, int total, int *__restrict__ qmap,
+                                                           int *__restrict__ pmap, int capacity, int *count) {
+    __shared__ int warp_tot[32];
+    __shared__ int base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int start = 0; start < total; start += blockDim.x) {
+        const int q = start + threadIdx.x;
+        const bool matched = q < total && nm_L1[q] == 0;
+        const unsigned mm = __ballot_sync(0xffffffffu, matched);
+        if (lane == 0) warp_tot[warp] = __popc(mm);
+        __syncthreads();
+        int before = base;
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        const int pos = before + __popc(mm & ((1u << lane) - 1u));
+        if (q < total) pmap[q] = matched ? pos : -1;
+        if (matched && pos < capacity) qmap[pos] = q;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w];
+            base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
+// Pass 1 (per window cell): border-ring weighting and filtering (second_layer.py:190-201 / :138-149), scores into
+// scores_back (:210 / :157).
+__global__ void merge_rings_kernel(float *__restrict__ trust, uint8_t *__restrict__ nm_L2, double *__restrict__ scores_back,
+                                   const int *__restrict__ qmap, int P, int merge_new) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P * 144) return;
+    const int p = e / 144, cell = e - p * 144;
+    const int y = cell / 12, x = cell - 12 * y;
+    float t = trust[e];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        if (x < 3 - i || x > 7 + i || y < 3 - i || y > 7 + i) t *= 2.0f;
+    uint8_t f = nm_L2[e];
+    if (t > 2.0f) f = 1;
+    if (x < 1 || x > 10 || y < 1 || y > 10) f = 1;
+    if (merge_new && !f) t -= 10000.0f;
+    trust[e] = t;
+    nm_L2[e] = f;
+    const int a = y >> 2, r = y & 3, c = x >> 2, s = x & 3;
+    scores_back[((size_t)qmap[p] * 16 + r * 4 + s) * 9 + a * 3 + c] = (double)t;
+}
+
+// Pass 2 (per window cell): which of the <= 9 overlapping windows keeps the cell.  Gather formulation of the
+// reference's shift / argsort / scatter (see DESIGN.md "merge_regroup" for the derivation).
+__global__ void merge_select_kernel(const uint8_t *__restrict__ nm_L2, const double *__restrict__ scores_back,
+                                    const int *__restrict__ qmap, const int *__restrict__ pmap, int P, int height, int width,
+                                    int merge_new, uint8_t *__restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P * 144) return;
+    const int p = e / 144, cell = e - p * 144;
+    const int cy = cell / 12, cx = cell - 12 * cy;
+    const int a1 = cy >> 2, r = cy & 3, c1 = cx >> 2, s = cx & 3;
+    const int hw = height * width, H4 = 4 * height, W4 = 4 * width;
+    const int q = qmap[p], bb = q / hw, ij = q - bb * hw;
+    const int i1 = ij / width, j1 = ij - i1 * width;
+    const int Y = 4 * (i1 + a1 - 1) + r, X = 4 * (j1 + c1 - 1) + s;  // true fine-grid cell
+    uint8_t res = 1;
+    if (Y >= 0 && Y < H4 && X >= 0 && X < W4) {
+        int ks = 0;
+        double best = 0.0;
+        if (merge_new) {
+            // second_layer.py:225: argsort of the centre window's OWN nine scores (+1e5 where the neighbour is outside)
+            const double *sb = scores_back + ((size_t)(bb * hw + (Y >> 2) * width + (X >> 2)) * 16 + r * 4 + s) * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int yy = Y + 4 * (k / 3 - 1), xx = X + 4 * (k % 3 - 1);
+                double v = sb[k];
+                if (yy < 0 || yy >= H4 || xx < 0 || xx >= W4) v += 100000.0;
+                if (k == 0 || v < best) best = v, ks = k;
+            }
+            if (ks == (2 - a1) * 3 + (2 - c1)) res = nm_L2[e];
+        } else {
+            // second_layer.py:159-169: per-channel shifted scores (own value where the shift leaves the grid),
+            // -1e4 where that window matched the cell
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const int a = k / 3, c = k % 3;
+                int yy = Y - 4 * (a - 1), xx = X - 4 * (c - 1);
+                if (yy < 0 || yy >= H4 || xx < 0 || xx >= W4) yy = Y, xx = X;
+                const int qq = bb * hw + (yy >> 2) * width + (xx >> 2);
+                double v = scores_back[((size_t)qq * 16 + (yy & 3) * 4 + (xx & 3)) * 9 + k];
+                const int pp = pmap[qq];
+                if (pp >= 0 && nm_L2[(size_t)pp * 144 + (4 * a + (yy & 3)) * 12 + 4 * c + (xx & 3)] == 0) v -= 10000.0;
+                if (k == 0 || v < best) best = v, ks = k;
+            }
+            if (ks == a1 * 3 + c1) res = nm_L2[e];
+        }
+    }
+    out[e] = res;
+}
+
+// =================================================================================================
+// a14  get_result: two-level ordered compaction + affine composition
+// =================================================================================================
+__global__ void __launch_bounds__(256) count_rows_kernel(const uint8_t *__restrict__ nm1, int n1, int *__restrict__ cnt) {
+    __shared__ int part[8];
+    const int p = blockIdx.x;
+    int c = 0;
+    for (int e = threadIdx.x; e < n1; e += blockDim.x) c += nm1[(size_t)p * n1 + e] == 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+        cnt[p] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int *__restrict__ cnt, int P, long long *__restrict__ off,
+                                                              long long *total) {
+    __shared__ long long warp_tot[32];
+    __shared__ long long base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int start = 0; start < P; start += blockDim.x) {
+        const int p = start + threadIdx.x;
+        const long long v = p < P ? cnt[p] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        long long before = base;
+        for (int w = 0; w < warp; ++w) before += warp_tot[w];
+        if (p < P) off[p] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long t = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w];
+            base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = base;
+}
+
+struct ResultArgs {
+    const uint8_t *nm1;
+    const float *pt0, *sc0, *pt1, *sc1;
+    const int *qmap;
+    const long long *off;
+    int P, n0, w0, ps0, n1, w1, ps1;
+    long long capacity;
+    float *ml, *mr;
+};
+
+__global__ void __launch_bounds__(256) assemble_matches_kernel(ResultArgs a) {
+    __shared__ int warp_tot[8];
+    __shared__ long long base;
+    const int p = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = a.qmap[p], cell = q % a.n0;
+    // level 0 (utils.py:205-207)
+    float l0[2], r0[2];
+    const float pos0[2] = {(float)((cell / a.w0) * a.ps0), (float)((cell % a.w0) * a.ps0)};
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        const float dl = (pos0[d] + 0.5f * (float)a.ps0) - (1.5f * a.sc0[(size_t)q * 2 + 1]) * (float)a.ps0;
+        const float dr = (a.pt0[(size_t)q * 2 + d] - 1.5f * a.sc0[(size_t)q * 2 + 0]) * (float)a.ps0;
+        l0[d] = 0.f + dl;
+        r0[d] = 0.f + dr;
+    }
+    if (threadIdx.x == 0) base = a.off[p];
+    __syncthreads();
+    for (int start = 0; start < a.n1; start += blockDim.x) {
+        const int c1 = start + threadIdx.x;
+        const size_t e = (size_t)p * a.n1 + c1;
+        const bool matched = c1 < a.n1 && a.nm1[e] == 0;
+        const unsigned mm = __ballot_sync(0xffffffffu, matched);
+        if (lane == 0) warp_tot[warp] = __popc(mm);
+        __syncthreads();
+        long long pos = base;
+        for (int w = 0; w < warp; ++w) pos += warp_tot[w];
+        pos += __popc(mm & ((1u << lane) - 1u));
+        if (matched && pos < a.capacity) {
+            const float pos1[2] = {(float)((c1 / a.w1) * a.ps1), (float)((c1 % a.w1) * a.ps1)};
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                // last level (utils.py:209-210)
+                const float dl = (pos1[d] + 0.5f * (float)a.ps1) * a.sc1[e * 2 + 1];
+                const float dr = (a.pt1[e * 2 + d] * (float)a.ps1) * a.sc1[e * 2 + 0];
+                a.ml[pos * 2 + d] = l0[d] + dl;
+                a.mr[pos * 2 + d] = r0[d] + dr;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += warp_tot[w];
+            base += t;
+        }
+        __syncthreads();
+    }
+}
+
+// =================================================================================================
+// a13  ThirdLayer.Compute_result: one thread per (problem, inner source cell), rows staged in smem
+// =================================================================================================
+constexpr int TH_K = 8;  // problems per CTA
+
+__global__ void __launch_bounds__(TH_K * 16) third_result_kernel(const float *__restrict__ scores, const float *__restrict__ scale_x,
+                                                                 const float *__restrict__ scale_y, const int64_t *__restrict__ p_s,
+                                                                 const int64_t *__restrict__ p_t, int K, float *__restrict__ mk0,
+                                                                 float *__restrict__ mk1, uint8_t *__restrict__ if_matching1) {
+    constexpr int W = 8, T = 5, NN = 65;
+    __shared__ float rows[TH_K * 16][NN];
+    __shared__ float gx[TH_K][64], gy[TH_K][64];
+    const int k0 = blockIdx.x * TH_K;
+    for (int e = threadIdx.x; e < TH_K * 16 * NN; e += blockDim.x) {
+        const int rr = e / NN, j = e - rr * NN;
+        const int k = k0 + rr / 16, c16 = rr % 16;
+        const int srow = (2 + c16 / 4) * W + 2 + c16 % 4;  // inner 4x4 of the 8x8 source window (:186)
+        rows[rr][j] = k < K ? __ldg(scores + ((size_t)k * NN + srow) * NN + j) : 0.f;
+    }
+    for (int e = threadIdx.x; e < TH_K * 64; e += blockDim.x) {
+        const int k = k0 + e / 64;
+        gx[e / 64][e % 64] = k < K ? __ldg(scale_x + (size_t)k * 64 + e % 64) : 1.f;
+        gy[e / 64][e % 64] = k < K ? __ldg(scale_y + (size_t)k * 64 + e % 64) : 1.f;
+    }
+    __syncthreads();
+    const int kk = threadIdx.x / 16, c16 = threadIdx.x % 16, k = k0 + kk;
+    if (k >= K) return;
+    const float *row = rows[threadIdx.x];
+    int max0 = 0;
+    for (int j = 1; j < 64; ++j)
+        if (row[j] > row[max0]) max0 = j;
+    int mall = 0;
+    for (int j = 1; j < NN; ++j)
+        if (row[j] + 1e-8f > row[mall] + 1e-8f) mall = j;  // label test, third_layer.py:166-167
+    if_matching1[(size_t)k * 16 + c16] = (mall != W * W);
+    const int mx = max0 % W, my = max0 / W;
+    float wx = 0.f, wy = 0.f, sx = 0.f, sy = 0.f;
+    for (int ty = 0; ty < T; ++ty)
+        for (int tx = 0; tx < T; ++tx) {
+            const int iy = my + ty - 2, ix = mx + tx - 2;
+            const bool in = iy >= 0 && iy < W && ix >= 0 && ix < W;
+            const float sc = in ? row[iy * W + ix] : 0.f;       // ZeroPad2d(2)             (:185)
+            const float sgx = in ? gx[kk][iy * W + ix] : 1e-2f;  // ConstantPad2d(2, 1e-2)   (:195-196)
+            const float sgy = in ? gy[kk][iy * W + ix] : 1e-2f;
+            const float qv = sqrtf(sc + 1e-7f);
+            const float ux = qv / sgx, uy = qv / sgy;
+            wx += ux * (float)(tx * 2 - (T - 1));
+            wy += uy * (float)(ty * 2 - (T - 1));
+            sx += ux;
+            sy += uy;
+        }
+    float *o1 = mk1 + ((size_t)k * 16 + c16) * 2, *o0 = mk0 + ((size_t)k * 16 + c16) * 2;
+    o1[0] = (wx / sx + ((float)mx + 0.5f - (float)W / 2) * 2.0f) + (float)p_t[(size_t)k * 2 + 0];
+    o1[1] = (wy / sy + ((float)my + 0.5f - (float)W / 2) * 2.0f) + (float)p_t[(size_t)k * 2 + 1];
+    o0[0] = ((float)p_s[(size_t)k * 2 + 0] + (float)(c16 % 4) * 2.0f) - 3.0f;
+    o0[1] = ((float)p_s[(size_t)k * 2 + 1] + (float)(c16 / 4) * 2.0f) - 3.0f;
+}
+
+}  // namespace pats
+
+using namespace pats;
+
+PATS_API int pats_iterative_expand_matrix_f32(const float *scores_in, const float *scalex, const float *scaley, int b, int m,
+                                              int grid_h, int grid_w, float lower_bound, int iter_num, float *whole_cost,
+                                              float *core_cost, float *average_point, float *x_scale, float *y_scale,
+                                              int64_t *bound, uint8_t *if_nomatching, void *stream) {
+    const long long n = (long long)grid_h * grid_w;
+    if (b < 0 || m <= 0 || grid_h <= 0 || grid_w <= 0 || iter_num < 1) return invalid("iterative_expand_matrix: bad sizes");
+    if (b == 0) return PATS_OK;
+    if (!scores_in || !scalex || !scaley || !whole_cost || !core_cost || !average_point || !x_scale || !y_scale || !bound)
+        return invalid("iterative_expand_matrix: null pointer");
+    ExpandArgs a;
+    a.scores = scores_in, a.sx = scalex, a.sy = scaley;
+    a.b = b, a.m = m, a.n = (int)n, a.grid_w = grid_w;
+    a.width = grid_h > grid_w ? grid_h : grid_w;  // ranges.shape[0]   (utils.py:1181)
+    a.height = (int)(n / a.width);
+    a.iters = iter_num, a.lb = lower_bound;
+    a.whole = whole_cost, a.core = core_cost, a.avg = average_point, a.xs = x_scale, a.ys = y_scale;
+    a.bound = bound, a.nomatch = if_nomatching;
+    const size_t smem = sizeof(float) * (size_t)(3 + EX_WARPS) * (n + 2);
+    if (smem > 200 * 1024) return invalid("iterative_expand_matrix: grid of %lld cells exceeds the shared-memory budget", n);
+    if (smem > 48 * 1024)
+        PATS_CUDA_TRY(cudaFuncSetAttribute(area_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (b > 65535) return invalid("iterative_expand_matrix: batch %d exceeds gridDim.y", b);
+    dim3 grid((m + EX_WARPS - 1) / EX_WARPS, b);
+    area_expand_kernel<<<grid, EX_WARPS * 32, smem, as_stream(stream)>>>(a);
+    PATS_LAUNCH_CHECK("area_expand_kernel");
+    return PATS_OK;
+}
+
+PATS_API int pats_est_nomatching_f32(const float *Z, int b, int M, int N, int dust, uint8_t *nm1, uint8_t *nm2, void *stream) {
+    if (b < 0 || M < 2 || N < 2) return invalid("est_nomatching: bad sizes");
+    if (b == 0) return PATS_OK;
+    if (!Z || !nm1 || !nm2) return invalid("est_nomatching: null pointer");
+    est_nomatching_kernel<<<b, 256, 0, as_stream(stream)>>>(Z, M, N, dust, nm1, nm2);
+    PATS_LAUNCH_CHECK("est_nomatching_kernel");
+    return PATS_OK;
+}
+
+PATS_API int pats_merge_patches(int merge_new, float *trust_score, const uint8_t *nm_L1, uint8_t *nm_L2, double *scores_back, int B,
+                                int height, int width, int P, uint8_t *out, int *workspace, void *stream) {
+    if (B <= 0 || height <= 0 || width <= 0 || P < 0) return invalid("merge_patches: bad sizes");
+    if (!nm_L1 || !scores_back || !workspace) return invalid("merge_patches: null pointer");
+    if (P > 0 && (!trust_score || !nm_L2 || !out)) return invalid("merge_patches: null pointer");
+    cudaStream_t st = as_stream(stream);
+    const int total = B * height * width;
+    int *qmap = workspace, *pmap = workspace + total, *count = workspace + 2 * total;  // workspace: 2*B*hw+1 ints
+    window_maps_kernel<<<1, 1024, 0, st>>>(nm_L1, total, qmap, pmap, P, count);
+    PATS_LAUNCH_CHECK("window_maps_kernel");
+    if (P == 0) return PATS_OK;
+    const int cells = P * 144;
+    merge_rings_kernel<<<(cells + 255) / 256, 256, 0, st>>>(trust_score, nm_L2, scores_back, qmap, P, merge_new ? 1 : 0);
+    PATS_LAUNCH_CHECK("merge_rings_kernel");
+    merge_select_kernel<<<(cells + 255) / 256, 256, 0, st>>>(nm_L2, scores_back, qmap, pmap, P, height, width, merge_new ? 1 : 0, out);
+    PATS_LAUNCH_CHECK("merge_select_kernel");
+    if (!merge_new) PATS_CUDA_TRY(cudaMemsetAsync(scores_back, 0, sizeof(double) * (size_t)total * 144, st));  // second_layer.py:186
+    return PATS_OK;
+}
+
+PATS_API int pats_get_result_f32(const uint8_t *nm0, const float *pt0, const float *sc0, int B, int ps0, int h0, int w0,
+                                 const uint8_t *nm1, const float *pt1, const float *sc1, int P, int ps1, int h1, int w1,
+                                 float *matches_l, float *matches_r, long long capacity, long long *total, void *workspace,
+                                 void *stream) {
+    if (B <= 0 || h0 <= 0 || w0 <= 0 || h1 <= 0 || w1 <= 0 || P < 0 || capacity < 0) return invalid("get_result: bad sizes");
+    if (!nm0 || !pt0 || !sc0 || !total || !workspace) return invalid("get_result: null pointer");
+    cudaStream_t st = as_stream(stream);
+    const int n0 = h0 * w0, n1 = h1 * w1, tot0 = B * n0;
+    // workspace layout: off[P+1] (i64) | qmap[tot0] | pmap[tot0] | count | cnt[P]
+    long long *off = (long long *)workspace;
+    int *qmap = (int *)(off + P + 1), *pmap = qmap + tot0, *count = pmap + tot0, *cnt = count + 1;
+    window_maps_kernel<<<1, 1024, 0, st>>>(nm0, tot0, qmap, pmap, P, count);
+    PATS_LAUNCH_CHECK("window_maps_kernel");
+    if (P == 0) {
+        PATS_CUDA_TRY(cudaMemsetAsync(total, 0, sizeof(long long), st));
+        return PATS_OK;
+    }
+    if (!nm1 || !pt1 || !sc1 || !matches_l || !matches_r) return invalid("get_result: null pointer");
+    count_rows_kernel<<<P, 256, 0, st>>>(nm1, n1, cnt);
+    PATS_LAUNCH_CHECK("count_rows_kernel");
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(cnt, P, off, total);
+    PATS_LAUNCH_CHECK("exclusive_scan_kernel");
+    ResultArgs a{nm1, pt0, sc0, pt1, sc1, qmap, off, P, n0, w0, ps0, n1, w1, ps1, capacity, matches_l, matches_r};
+    assemble_matches_kernel<<<P, 256, 0, st>>>(a);
+    PATS_LAUNCH_CHECK("assemble_matches_kernel");
+    return PATS_OK;
+}
+
+PATS_API int pats_third_compute_result_f32(const float *scores, const float *scale_x, const float *scale_y, const int64_t *p_s,
+                                           const int64_t *p_t, int K, float *mkpts0_f, float *mkpts1_f, uint8_t *if_matching1,
+                                           void *stream) {
+    if (K < 0) return invalid("third_compute_result: bad sizes");
+    if (K == 0) return PATS_OK;
+    if (!scores || !scale_x || !scale_y || !p_s || !p_t || !mkpts0_f || !mkpts1_f || !if_matching1)
+        return invalid("third_compute_result: null pointer");
+    third_result_kernel<<<(K + TH_K - 1) / TH_K, TH_K * 16, 0, as_stream(stream)>>>(scores, scale_x, scale_y, p_s, p_t, K, mkpts0_f,
+                                                                                  mkpts1_f, if_matching1);
+    PATS_LAUNCH_CHECK("third_result_kernel");
+    return PATS_OK;
+}

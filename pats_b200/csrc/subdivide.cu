@@ -11,8 +11,10 @@ namespace pats {
 // ---- bilinear lerp with a selectable rounding recipe ------------------------------------------------
 // ATen's CUDA kernel (UpSampleBilinear2d.cu) evaluates
 //     h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d)
-// and lets nvcc contract it.  VARIANT 0 is the same expression compiled the same way; 1..9 spell out
-// every contraction (inner, outer in {none, fma on the first product, fma on the second product}).
+// and lets nvcc contract it.  Variants 1..9 spell out every contraction (inner, outer in {none, fma on the
+// first product, fma on the second product}); measured on B200 against torch 2.11 (tests/test_gpu_subdivide.py,
+// profiles/r01_resize_variants.json) variant 5 -- fma(h0, fma(w0, a, w1*b), h1*t2) -- is bit-identical to ATen
+// on 8.3 M outputs, so it is the shipping recipe (kShipVariant).  Variant 0 is the bare expression as compiled.
 template <int VARIANT>
 __device__ __forceinline__ float lerp2(float h0, float h1, float w0, float w1, float a, float b, float c, float d) {
     if (VARIANT == 0) {
@@ -35,6 +37,8 @@ __device__ __forceinline__ float lerp2(float h0, float h1, float w0, float w1, f
         return __fmaf_rn(h1, t2, __fmul_rn(h0, t1));
     }
 }
+
+constexpr int kShipVariant = 5;
 
 struct Crop {
     long long y0, x0, h, w, img;
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(256) right_patches_kernel(const T *__restrict_
             const float b = (vya && vxb) ? (float)__ldg(img + ((size_t)ya * W + xb) * 3 + ch) : 0.f;
             const float cc = (vyb && vxa) ? (float)__ldg(img + ((size_t)yb * W + xa) * 3 + ch) : 0.f;
             const float d = (vyb && vxb) ? (float)__ldg(img + ((size_t)yb * W + xb) * 3 + ch) : 0.f;
-            dst[(size_t)ch * total + e] = lerp2<0>(ay.l0, ay.l1, ax.l0, ax.l1, a, b, cc, d);
+            dst[(size_t)ch * total + e] = lerp2<kShipVariant>(ay.l0, ay.l1, ax.l0, ax.l1, a, b, cc, d);
         }
     }
 }
@@ -304,7 +308,7 @@ PATS_API int pats_tensor_resize_f32_variant(const float *input, int B, int C, in
 
 PATS_API int pats_tensor_resize_f32(const float *input, int B, int C, int Hp, int Wp, const int64_t *bound, int K, int out_h,
                                     int out_w, float *out, int *bad_rows, void *stream) {
-    return pats_tensor_resize_f32_variant(input, B, C, Hp, Wp, bound, K, out_h, out_w, out, bad_rows, 0, stream);
+    return pats_tensor_resize_f32_variant(input, B, C, Hp, Wp, bound, K, out_h, out_w, out, bad_rows, kShipVariant, stream);
 }
 
 PATS_API int pats_tensor_resize_f32_host(const float *input, int B, int C, int Hp, int Wp, const int64_t *bound, int K,
@@ -388,9 +392,10 @@ PATS_API int pats_compute_imgs(const float *x_scale, const float *y_scale, const
     if (B <= 0 || height <= 0 || width <= 0 || ps <= 0 || margin < 0 || capacity < 0) return invalid("compute_imgs: bad sizes");
     if (elem != 1 && elem != 4) return invalid("compute_imgs: images must be uint8 (elem=1) or float32 (elem=4)");
     if (width * height >= 10000) return invalid("compute_imgs: more than 9999 patches per image cannot be encoded (img*10000+patch)");
-    if (!x_scale || !y_scale || !average_point || !if_nomatching || !left || !right || !new_left || !new_right || !bound5 ||
-        !x_scale_new || !y_scale_new || !average_new || !count)
+    if (!x_scale || !y_scale || !average_point || !if_nomatching || !left || !right || !x_scale_new || !y_scale_new ||
+        !average_new || !count)
         return invalid("compute_imgs: null pointer");
+    if (capacity > 0 && (!new_left || !new_right || !bound5)) return invalid("compute_imgs: null output pointer");
     if (((size_t)ps * 3 * elem) % 16 != 0 || ((uintptr_t)left | (uintptr_t)new_left) % 16 != 0)
         return invalid("compute_imgs: patch rows must be 16-byte multiples and images 16-byte aligned");
     cudaStream_t st = as_stream(stream);

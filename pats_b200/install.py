@@ -15,6 +15,7 @@ from __future__ import annotations
 import importlib
 import sys
 
+from . import layers as _layers
 from . import modules as _modules
 from . import tensor_resize as _tensor_resize
 from . import utils as _utils
@@ -27,10 +28,18 @@ _OT = {
 }
 _TABLE = {
     "models.modules": dict(_OT),
-    "models.first_layer": {**_OT, "Compute_imgs": _utils.Compute_imgs},
-    "models.second_layer": dict(_OT),
+    "models.first_layer": {**_OT, "Compute_imgs": _utils.Compute_imgs, "Iterative_expand_matrix": _utils.Iterative_expand_matrix},
+    "models.second_layer": {**_OT, "Iterative_expand_matrix": _utils.Iterative_expand_matrix},
     "models.third_layer": dict(_OT),
-    "utils.utils": {"tensor_resize": _tensor_resize, "origin_extract": _utils.origin_extract, "Compute_imgs": _utils.Compute_imgs},
+    "models.pats": {"get_result": _utils.get_result},
+    "utils.utils": {"tensor_resize": _tensor_resize, "origin_extract": _utils.origin_extract, "Compute_imgs": _utils.Compute_imgs,
+                    "Iterative_expand_matrix": _utils.Iterative_expand_matrix, "get_result": _utils.get_result},
+}
+# (reference module, class, method) -> replacement: bound methods the layers call through `self`
+_METHODS = {
+    ("models.second_layer", "SecondLayer", "merge_patches_new"): _layers.merge_patches_new,
+    ("models.second_layer", "SecondLayer", "merge_patches_old"): _layers.merge_patches_old,
+    ("models.third_layer", "ThirdLayer", "Compute_result"): _layers.Compute_result,
 }
 _saved: dict = {}
 
@@ -51,6 +60,15 @@ def install(only=None) -> list:
                 _saved.setdefault((modname, name), getattr(mod, name))
                 setattr(mod, name, repl)
                 done.append((modname, name))
+    for (modname, clsname, meth), repl in _METHODS.items():
+        if only is not None and meth not in only:
+            continue
+        mod = sys.modules.get(modname)
+        cls = getattr(mod, clsname, None) if mod is not None else None
+        if cls is not None and hasattr(cls, meth):
+            _saved.setdefault((modname, clsname + "." + meth), getattr(cls, meth))
+            setattr(cls, meth, repl)
+            done.append((modname, clsname + "." + meth))
     return done
 
 
@@ -58,5 +76,9 @@ def uninstall() -> None:
     for (modname, name), orig in list(_saved.items()):
         mod = sys.modules.get(modname)
         if mod is not None:
-            setattr(mod, name, orig)
+            if "." in name:
+                clsname, meth = name.split(".")
+                setattr(getattr(mod, clsname), meth, orig)
+            else:
+                setattr(mod, name, orig)
         del _saved[(modname, name)]

@@ -1,0 +1,81 @@
+"""Layer-level pieces of the hot path with the reference's method names.
+
+    merge_patches_new / merge_patches_old      models/second_layer.py:189-238 / :137-186   (SecondLayer methods)
+    Compute_result                             models/third_layer.py:184-217               (ThirdLayer method)
+They take `self` first so they can be bound over the reference's methods (pats_b200.install).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._torchutil import cuda_f32, stream_ptr
+
+__all__ = ["merge_patches_new", "merge_patches_old", "Compute_result", "third_compute_result"]
+
+
+def _merge(merge_new, patch_num, trust_score, original_image_shape, if_nomatching1_L1, if_nomatching1_L2, scores_back):
+    dev = trust_score.device
+    if not trust_score.is_cuda:
+        raise RuntimeError("merge_patches: tensors are on the CPU; pats_b200 is CUDA-only (no CPU fallback)")
+    height, width = int(original_image_shape[0]) // 32, int(original_image_shape[1]) // 32
+    B = if_nomatching1_L1.shape[0]
+    P = int(if_nomatching1_L2.shape[0])
+    # the reference mutates trust_score / if_nomatching1_L2 / scores_back in place: work on the caller's storage
+    t = trust_score if (trust_score.is_contiguous() and trust_score.dtype == torch.float32) else trust_score.float().contiguous()
+    f = if_nomatching1_L2 if (if_nomatching1_L2.is_contiguous() and if_nomatching1_L2.dtype == torch.bool) else if_nomatching1_L2.bool().contiguous()
+    sb = scores_back if (scores_back.is_contiguous() and scores_back.dtype == torch.float64) else scores_back.double().contiguous()
+    nm1 = if_nomatching1_L1.to(torch.uint8).contiguous()
+    out = torch.empty((P, 144), dtype=torch.bool, device=dev)
+    ws = torch.empty(2 * B * height * width + 1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pats_merge_patches(1 if merge_new else 0, t.data_ptr(), nm1.data_ptr(), f.data_ptr(), sb.data_ptr(), B, height, width, P,
+                                            out.data_ptr(), ws.data_ptr(), stream_ptr(dev))
+    _lib.check(rc, "merge_patches")
+    if t is not trust_score:
+        trust_score.copy_(t)
+    if f is not if_nomatching1_L2:
+        if_nomatching1_L2.copy_(f)
+    if sb is not scores_back:
+        scores_back.copy_(sb)
+    return out, sb
+
+
+def merge_patches_new(self, patch_num, trust_score, original_image_shape, if_nomatching1_L1, if_nomatching1_L2, scores_back):
+    """models/second_layer.py:189-238; scores_back is carried across chunks."""
+    return _merge(True, patch_num, trust_score, original_image_shape, if_nomatching1_L1, if_nomatching1_L2, scores_back)
+
+
+def merge_patches_old(self, patch_num, trust_score, original_image_shape, if_nomatching1_L1, if_nomatching1_L2, scores_back):
+    """models/second_layer.py:137-186; returns zeroed scores_back."""
+    return _merge(False, patch_num, trust_score, original_image_shape, if_nomatching1_L1, if_nomatching1_L2, scores_back)
+
+
+def third_compute_result(scores, scale_x, scale_y, p_s, p_t):
+    """(mkpts0_f, mkpts1_f, if_matching1) for K level-3 problems: third_layer.py:184-217 and the label test :166-167."""
+    scores = cuda_f32(scores, "scores")
+    K = scores.shape[0]
+    if scores.shape[1:] != (65, 65):
+        raise ValueError(f"third layer plans are [K,65,65] (W=8), got {tuple(scores.shape)}")
+    dev = scores.device
+    sx = cuda_f32(scale_x, "scale_x").reshape(K, 64)
+    sy = cuda_f32(scale_y, "scale_y").reshape(K, 64)
+    ps = p_s.to(device=dev, dtype=torch.int64).contiguous()
+    pt = p_t.to(device=dev, dtype=torch.int64).contiguous()
+    m0 = torch.empty((K, 16, 2), dtype=torch.float32, device=dev)
+    m1 = torch.empty_like(m0)
+    im = torch.empty((K, 16), dtype=torch.bool, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pats_third_compute_result_f32(scores.data_ptr(), sx.data_ptr(), sy.data_ptr(), ps.data_ptr(), pt.data_ptr(), K, m0.data_ptr(),
+                                                       m1.data_ptr(), im.data_ptr(), stream_ptr(dev))
+    _lib.check(rc, "Compute_result")
+    return m0, m1, im
+
+
+def Compute_result(self, scores, W, T, scale_x, scale_y, p_s, p_t, device):
+    """ThirdLayer.Compute_result (third_layer.py:184-217).  whole_loss, the third return value, is discarded by the only
+    caller (third_layer.py:160) and is returned as zeros."""
+    if W != 8 or T != 5:
+        raise NotImplementedError("Compute_result: the reference fixes W=8, T=5 (third_layer.py:107-110)")
+    m0, m1, _ = third_compute_result(scores, scale_x, scale_y, p_s, p_t)
+    return m0, m1, torch.zeros((scores.shape[0], 16), dtype=torch.float32, device=scores.device)

@@ -103,3 +103,97 @@ def Compute_imgs(x_scale, y_scale, average_point, if_nomatching, left, right, se
             raise RuntimeError(f"Compute_imgs: {nbad} matched patch(es) have an empty or out-of-range crop")
     out = (new_left, new_right.permute(0, 2, 3, 1), xs, ys, avg)
     return out + (bound5,) if return_bound else out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# area expansion / match assembly
+# ---------------------------------------------------------------------------------------------------------
+def _grid_dims(limitation, ranges, positions, width, height):
+    """The reference rebuilds the grid from `ranges` / `positions` (utils.py:1181) and reads limitation[3] on the
+    device; both callers also pass the true grid as keywords (first_layer.py:175-176, second_layer.py:255-257),
+    which avoids a host sync.  Fall back to reading `limitation` when the keywords do not describe the tensors."""
+    n = positions.shape[0]
+    if width * height == n and ranges.shape[0] == max(width, height):
+        return int(height), int(width)
+    lim = [int(v) for v in limitation.tolist()]
+    return lim[1], lim[3]
+
+
+def Iterative_expand_matrix(scores_in, scalex, scaley, limitation, ranges, positions, lower_bound=1e-3, upper_bound=1e7, iter_num=15,
+                            width=20, height=15, type="distance", *, return_nomatching=False):
+    """Grow the matched area box around every source patch's best target cell (utils/utils.py:1179-1297).
+
+    scores_in [b,m+1,n+1] = exp(Z); scalex, scaley [b,n,1].  Returns (whole_cost [b,m], core_cost [b,m],
+    average_point [b,m,2], x_scale [b,m], y_scale [b,m], bound [b,m,4] int64).
+    """
+    scores_in = cuda_f32(scores_in, "scores_in")
+    b, M, N = scores_in.shape
+    m, n = M - 1, N - 1
+    grid_h, grid_w = _grid_dims(limitation, ranges, positions, width, height)
+    if grid_h * grid_w != n:
+        raise ValueError(f"grid {grid_h}x{grid_w} does not match {n} target cells")
+    sx = cuda_f32(scalex, "scalex").reshape(b, n)
+    sy = cuda_f32(scaley, "scaley").reshape(b, n)
+    dev = scores_in.device
+    whole = torch.empty((b, m), dtype=torch.float32, device=dev)
+    core = torch.empty_like(whole)
+    avg = torch.empty((b, m, 2), dtype=torch.float32, device=dev)
+    xs = torch.empty_like(whole)
+    ys = torch.empty_like(whole)
+    bound = torch.empty((b, m, 4), dtype=torch.int64, device=dev)
+    nm = torch.empty((b, m), dtype=torch.bool, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pats_iterative_expand_matrix_f32(scores_in.data_ptr(), sx.data_ptr(), sy.data_ptr(), b, m, grid_h, grid_w,
+                                                          float(lower_bound), int(iter_num), whole.data_ptr(), core.data_ptr(), avg.data_ptr(),
+                                                          xs.data_ptr(), ys.data_ptr(), bound.data_ptr(), nm.data_ptr(), stream_ptr(dev))
+    _lib.check(rc, "Iterative_expand_matrix")
+    out = (whole, core, avg, xs, ys, bound)
+    return out + (nm,) if return_nomatching else out
+
+
+def est_nomatching(scores, dust: int):
+    """The two masks of est_position (first_layer.py:162-167): (argmax over columns == dust)[:, :-1], (argmax over rows == dust)[:, :-1]."""
+    scores = cuda_f32(scores, "scores")
+    b, M, N = scores.shape
+    nm1 = torch.empty((b, M - 1), dtype=torch.bool, device=scores.device)
+    nm2 = torch.empty((b, N - 1), dtype=torch.bool, device=scores.device)
+    with torch.cuda.device(scores.device):
+        rc = _lib.load().pats_est_nomatching_f32(scores.data_ptr(), b, M, N, int(dust), nm1.data_ptr(), nm2.data_ptr(), stream_ptr(scores.device))
+    _lib.check(rc, "est_nomatching")
+    return nm1, nm2
+
+
+def get_result(batch_size, if_nomatching, average_point, scale, patch_size, left_choice, layer_num=2):
+    """Compose level-0 patch geometry with level-1 cell positions into absolute matches (utils/utils.py:189-213).
+
+    Two levels with left_choice all True, as models/pats.py:72-78 calls it.  Returns (matches_l, matches_r) [Kf,2] f32 in the
+    row-major order of the reference's boolean-mask indexing.
+    """
+    if layer_num != 2 or len(if_nomatching) != 2:
+        raise NotImplementedError("get_result: the hot path uses exactly two levels (models/pats.py:72-78)")
+    nm0 = _require_cuda(if_nomatching[0], "if_nomatching[0]")
+    dev = nm0.device
+    nm0 = nm0.to(torch.uint8)
+    nm1 = _require_cuda(if_nomatching[1], "if_nomatching[1]").to(torch.uint8)
+    pt0, pt1 = cuda_f32(average_point[0], "average_point[0]"), cuda_f32(average_point[1], "average_point[1]")
+    sc0, sc1 = cuda_f32(scale[0], "scale[0]"), cuda_f32(scale[1], "scale[1]")
+    (ps0, h0, w0), (ps1, h1, w1) = [[int(v) for v in s] for s in patch_size]
+    B, n0 = nm0.shape
+    P, n1 = nm1.shape
+    if n0 != h0 * w0 or n1 != h1 * w1:
+        raise ValueError("get_result: mask shapes do not match patch_size")
+    cap = P * n1
+    ml = torch.empty((max(cap, 1), 2), dtype=torch.float32, device=dev)
+    mr = torch.empty_like(ml)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = torch.empty(8 * (P + 1) + 4 * (2 * B * n0 + 1 + P) + 8, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pats_get_result_f32(nm0.data_ptr(), pt0.data_ptr(), sc0.data_ptr(), B, ps0, h0, w0, nm1.data_ptr(), pt1.data_ptr(),
+                                             sc1.data_ptr(), P, ps1, h1, w1, ml.data_ptr(), mr.data_ptr(), cap, total.data_ptr(),
+                                             ws.data_ptr(), stream_ptr(dev))
+    _lib.check(rc, "get_result")
+    kf = int(total.item())  # the reference synchronises here too (boolean-mask indexing)
+    return ml[:kf], mr[:kf]
+
+
+__all__ += ["Iterative_expand_matrix", "est_nomatching", "get_result"]

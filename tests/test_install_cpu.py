@@ -1,0 +1,39 @@
+"""install() rebinds the hot-path names inside the reference's caller modules (needs /root/reference; CPU only,
+no compute is executed -- the replaced functions are CUDA-only)."""
+import os
+import sys
+
+import pytest
+
+from conftest import REPO
+
+sys.path.insert(0, os.path.join(REPO, "tests", "golden"))
+import ref_loader  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not present (GPU box)")
+
+
+def test_install_rebinds_callers_and_uninstall_restores():
+    ref = ref_loader.load_reference()
+    from pats_b200 import install as inst
+    from pats_b200 import layers, modules, utils
+
+    orig = ref.first_layer.log_optimal_transport
+    orig_merge = ref.second_layer.SecondLayer.merge_patches_new
+    done = inst.install()
+    try:
+        assert ("models.first_layer", "log_optimal_transport") in done
+        assert ref.first_layer.log_optimal_transport is modules.log_optimal_transport
+        assert ref.second_layer.log_optimal_transport2 is modules.log_optimal_transport2
+        assert ref.third_layer.log_optimal_transport2 is modules.log_optimal_transport2
+        assert ref.first_layer.Compute_imgs is utils.Compute_imgs
+        assert ref.first_layer.Iterative_expand_matrix is utils.Iterative_expand_matrix
+        assert ref.second_layer.Iterative_expand_matrix is utils.Iterative_expand_matrix
+        assert ref.pats.get_result is utils.get_result
+        assert ref.utils.tensor_resize.tensor_resize.__module__ == "pats_b200.tensor_resize"
+        assert ref.second_layer.SecondLayer.merge_patches_new is layers.merge_patches_new
+        assert ref.third_layer.ThirdLayer.Compute_result is layers.Compute_result
+    finally:
+        inst.uninstall()
+    assert ref.first_layer.log_optimal_transport is orig
+    assert ref.second_layer.SecondLayer.merge_patches_new is orig_merge
