@@ -59,8 +59,8 @@ int pats_log_optimal_transport_f32(const float *scores, const float *alpha, cons
 int pats_log_optimal_transport2_f32(const float *scores, const float *one, const float *ns, int b, int m, int n,
                                     int iters, float *out, void *stream);
 
-/* Which kernel family the dispatcher picks for a shape (0 = register-resident warp kernel,
- * 1 = register-resident CTA kernel, 2 = generic log-domain kernel); for tests and the bench. */
+/* Which kernel family the dispatcher picks for a shape (0 = register-resident warp kernel, 1 = register-resident
+ * CTA kernel, 3 = register-resident 8-CTA cluster kernel, 2 = generic log-domain kernel); for tests and the bench. */
 int pats_sinkhorn_kernel_kind(int M, int N);
 /* Force the generic log-domain kernel for every shape (tests: exercises the fallback path). */
 void pats_sinkhorn_force_generic(int on);

@@ -4,8 +4,10 @@
 //
 // Design (see DESIGN.md "Sinkhorn kernels"):
 //   * The plan never leaves the chip between iterations.  Each problem is owned by one warp
-//     (<= 72 x 68, the level-3 65 x 65 problems) or one CTA (<= 160 x 160, the level-2 145 x 145
-//     problems); every thread keeps an RT x CT tile of the kernel matrix in REGISTERS.
+//     (<= 72 x 68, the level-3 65 x 65 problems), one CTA (<= 160 x 160, the level-2 145 x 145
+//     problems) or one thread-block CLUSTER of 8 CTAs (<= 320 x 320 / 512 x 512, the level-1
+//     301 x 301 problem; column sums cross CTAs through distributed shared memory); every thread
+//     keeps an RT x CT tile of the kernel matrix in REGISTERS.
 //   * Iteration 1 is done exactly in the log domain (row / column log-sum-exp, as the reference
 //     does).  Its potentials (u1, v1) are absorbed into the matrix, K = exp(Z + u1 + v1), so every
 //     entry is a probability <= 1 and the remaining iterations are plain scaling updates
@@ -19,9 +21,13 @@
 //     are not finite is re-solved by the same threads with the exact log-domain iteration
 //     (log_domain_solve), which is also the kernel for shapes that do not fit in registers.
 //     No CPU path exists.
+#include <cooperative_groups.h>
+
 #include <mutex>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pats {
 
@@ -179,18 +185,40 @@ __global__ void __launch_bounds__(GT) sinkhorn_generic_kernel(SinkArgs a) {
 //   marginals, which keeps every sum positive and every padded scaling exactly 0 (no NaN, no
 //   select in the loop).
 // ---------------------------------------------------------------------------------------------
-template <int WARPS_, int QC_LOG2_, int RT_, int CT_, int GROUPS_>
+//   With CL > 1 the problem is split by rows over the CL CTAs of a cluster: CTA `rank` owns rows
+//   rank*PR*RT + pr + PR*k.  Row sums stay inside a CTA; column sums are pushed into every CTA's shared
+//   memory (DSMEM), one cluster barrier per reduction, double-buffered by call parity.
+template <int WARPS_, int QC_LOG2_, int RT_, int CT_, int GROUPS_, int CL_ = 1>
 struct RegCfg {
-    static constexpr int W = WARPS_, QCL = QC_LOG2_, RT = RT_, CT = CT_, GROUPS = GROUPS_;
-    static constexpr int GT = W * 32;       // threads per problem
+    static constexpr int W = WARPS_, QCL = QC_LOG2_, RT = RT_, CT = CT_, GROUPS = GROUPS_, CL = CL_;
+    static constexpr int GT = W * 32;       // threads per CTA working on the problem
     static constexpr int QC = 1 << QCL;     // lanes along a row
     static constexpr int PRW = 32 / QC;     // row groups per warp
-    static constexpr int PR = W * PRW;      // row groups per problem
-    static constexpr int MAXM = PR * RT, MAXN = QC * CT;
+    static constexpr int PR = W * PRW;      // row groups per CTA
+    static constexpr int ROWS = PR * RT;    // rows per CTA
+    static constexpr int MAXM = CL * ROWS, MAXN = QC * CT;
     static constexpr int CT2 = CT / 2;
     static constexpr bool ODD = (CT & 1) != 0;
     static constexpr int THREADS = GT * GROUPS;
-    static_assert(W == 1 || GROUPS == 1, "multi-warp problems use __syncthreads: one problem per CTA");
+    static constexpr bool BLOCK = (W > 1) || (CL > 1);  // reductions need block-level synchronisation
+    static_assert(!BLOCK || GROUPS == 1, "multi-warp problems use __syncthreads: one problem per CTA");
+};
+
+// Shared-memory carve-up of one CTA (dynamic shared memory; sizes in floats).
+template <class C>
+struct Smem {
+    static constexpr int MU = 0;                                   // [GROUPS][ROWS]  exp-domain row marginals
+    static constexpr int NU = MU + C::GROUPS * C::ROWS;            // [GROUPS][MAXN]
+    static constexpr int U1 = NU + C::GROUPS * C::MAXN;            // [GROUPS][ROWS]  potentials of iteration 1
+    static constexpr int V1 = U1 + C::GROUPS * C::ROWS;            // [GROUPS][MAXN]
+    static constexpr int PART = V1 + C::GROUPS * C::MAXN;          // [W][MAXN]       per-warp column partials
+    static constexpr int TOT = PART + (C::BLOCK ? C::W * C::MAXN : 0);   // [MAXN]
+    static constexpr int XBUF = TOT + (C::BLOCK ? C::MAXN : 0);          // [2][CL][MAXN]   cluster exchange
+    static constexpr int XFLAG = XBUF + (C::CL > 1 ? 2 * C::CL * C::MAXN : 0);  // [CL]
+    static constexpr int FB = XFLAG + (C::CL > 1 ? C::CL : 0);     // fallback scratch: u[MAXM], v[MAXN], red[2*GT] per group
+    static constexpr int FB_PER = C::MAXM + C::MAXN + 2 * C::GT;
+    static constexpr int FLOATS = FB + C::GROUPS * FB_PER;
+    static constexpr size_t BYTES = sizeof(float) * (size_t)FLOATS;
 };
 
 template <class C>
@@ -213,33 +241,56 @@ struct OpMax {
     __device__ __forceinline__ float operator()(float x, float y) const { return fmaxf(x, y); }
 };
 
-// Column all-reduce over every row group of the problem (lanes, then warps through smem).
-// SCALE: the reducing thread turns a total t of column j into s_nu[j] / t (the beta update).
+// Column all-reduce over every row group of the problem (lanes, then warps through smem, then the CTAs
+// of the cluster through DSMEM).  SCALE: the reducing thread turns a total t of column j into
+// nu[j] / t (the beta update).  Every CTA sums the same CL partials in the same order, so all CTAs
+// hold bit-identical results.
 template <class C, bool SCALE, class Op>
-__device__ __forceinline__ void col_reduce(float (&v)[C::CT], Op op, float *s_part, float *s_tot, const float *s_nu,
-                                           int warp, int prw, int qc, int gtid) {
+__device__ __forceinline__ void col_reduce(float (&v)[C::CT], Op op, float *sm, const float *s_nu, int warp, int prw, int qc,
+                                           int gtid, unsigned rank, int &parity) {
 #pragma unroll
     for (int c = 0; c < C::CT; ++c) {
 #pragma unroll
         for (int o = C::QC; o < 32; o <<= 1) v[c] = op(v[c], __shfl_xor_sync(0xffffffffu, v[c], o));
     }
-    if (C::W == 1) {
+    if (!C::BLOCK) {
         if (SCALE) {
 #pragma unroll
             for (int c = 0; c < C::CT; ++c) v[c] = s_nu[qc + C::QC * c] * fast_rcp(v[c]);
         }
         return;
     }
+    float *s_part = sm + Smem<C>::PART, *s_tot = sm + Smem<C>::TOT;
     if (prw == 0) {
 #pragma unroll
         for (int c = 0; c < C::CT; ++c) s_part[warp * C::MAXN + qc + C::QC * c] = v[c];
     }
     __syncthreads();
-    for (int j = gtid; j < C::MAXN; j += C::GT) {
-        float t = s_part[j];
+    if (C::CL == 1) {
+        for (int j = gtid; j < C::MAXN; j += C::GT) {
+            float t = s_part[j];
 #pragma unroll
-        for (int w = 1; w < C::W; ++w) t = op(t, s_part[w * C::MAXN + j]);
-        s_tot[j] = SCALE ? s_nu[j] * fast_rcp(t) : t;
+            for (int w = 1; w < C::W; ++w) t = op(t, s_part[w * C::MAXN + j]);
+            s_tot[j] = SCALE ? s_nu[j] * fast_rcp(t) : t;
+        }
+    } else {
+        cg::cluster_group cluster = cg::this_cluster();
+        float *xb = sm + Smem<C>::XBUF + parity * C::CL * C::MAXN;
+        for (int j = gtid; j < C::MAXN; j += C::GT) {
+            float t = s_part[j];
+#pragma unroll
+            for (int w = 1; w < C::W; ++w) t = op(t, s_part[w * C::MAXN + j]);
+#pragma unroll
+            for (int r = 0; r < C::CL; ++r) cluster.map_shared_rank(xb, r)[rank * C::MAXN + j] = t;
+        }
+        cluster.sync();
+        for (int j = gtid; j < C::MAXN; j += C::GT) {
+            float t = xb[j];
+#pragma unroll
+            for (int r = 1; r < C::CL; ++r) t = op(t, xb[r * C::MAXN + j]);
+            s_tot[j] = SCALE ? s_nu[j] * fast_rcp(t) : t;
+        }
+        parity ^= 1;
     }
     __syncthreads();
 #pragma unroll
@@ -250,30 +301,29 @@ template <class C>
 __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
     constexpr int RT = C::RT, CT = C::CT, CT2 = C::CT2, QC = C::QC, PR = C::PR;
     constexpr bool ODD = C::ODD;
-    __shared__ float s_mu[C::GROUPS][C::MAXM];  // exp-domain marginals; reused as u[] by the fallback
-    __shared__ float s_nu[C::GROUPS][C::MAXN];  //                        reused as v[] by the fallback
-    __shared__ float s_u1[C::GROUPS][C::MAXM];  // potentials of the exact first iteration
-    __shared__ float s_v1[C::GROUPS][C::MAXN];
-    __shared__ float s_part[C::W > 1 ? C::W * C::MAXN : 1];
-    __shared__ float s_tot[C::W > 1 ? C::MAXN : 1];
-    __shared__ float s_red[2 * C::GT * C::GROUPS];  // fallback scratch
+    extern __shared__ __align__(16) float sm[];
 
     const int group = threadIdx.x / C::GT, gtid = threadIdx.x % C::GT;
     const int lane = gtid & 31, warp = gtid >> 5;
     const int qc = lane & (QC - 1), prw = lane >> C::QCL;
     const int pr = warp * C::PRW + prw;
-    const int p = blockIdx.x * C::GROUPS + group;
-    if (p >= a.b) return;  // warp-uniform; W>1 => GROUPS==1 so the whole CTA leaves together
+    unsigned rank = 0;
+    if (C::CL > 1) rank = cg::this_cluster().block_rank();
+    const int p = (C::CL > 1) ? (int)(blockIdx.x / C::CL) : (int)(blockIdx.x * C::GROUPS + group);
+    if (p >= a.b) return;  // warp-uniform; block/cluster kernels have GROUPS==1 and exact grids, so nobody is left waiting
 
     const int M = a.M, N = a.N;
+    const int row0 = (int)rank * C::ROWS;  // first row of this CTA's slab
     const Marg g = problem_marginals(a, p, lane);
-    float *mu_s = s_mu[group], *nu_s = s_nu[group], *u1_s = s_u1[group], *v1_s = s_v1[group];
+    float *mu_s = sm + Smem<C>::MU + group * C::ROWS, *nu_s = sm + Smem<C>::NU + group * C::MAXN;
+    float *u1_s = sm + Smem<C>::U1 + group * C::ROWS, *v1_s = sm + Smem<C>::V1 + group * C::MAXN;
+    int parity = 0;
 
     // ---- load the tile (padding = -inf) --------------------------------------------------------
     float z[RT][CT];
 #pragma unroll
     for (int k = 0; k < RT; ++k) {
-        const int row = pr + PR * k;
+        const int row = row0 + pr + PR * k;
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
             const int col = qc + QC * c;
@@ -284,8 +334,8 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
     if (qc == 0) {
 #pragma unroll
         for (int k = 0; k < RT; ++k) {
-            const int row = pr + PR * k;
-            mu_s[row] = (row < M) ? expf(lmu_at(a, g, p, row)) : 0.f;
+            const int row = row0 + pr + PR * k;
+            mu_s[pr + PR * k] = (row < M) ? expf(lmu_at(a, g, p, row)) : 0.f;
         }
     }
     if (pr == 0) {
@@ -301,7 +351,7 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
         float u1[RT];
 #pragma unroll
         for (int k = 0; k < RT; ++k) {
-            const int row = pr + PR * k;
+            const int row = row0 + pr + PR * k;
             float mx = -INFINITY;
 #pragma unroll
             for (int c = 0; c < CT; ++c) mx = fmaxf(mx, z[k][c]);
@@ -312,7 +362,7 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
             for (int c = 0; c < CT; ++c) s += fast_exp(z[k][c] - mxs);
             s = row_allreduce_sum<C>(s);
             u1[k] = (row < M) ? lmu_at(a, g, p, row) - (fast_log(s) + mxs) : 0.f;
-            if (qc == 0) u1_s[row] = u1[k];
+            if (qc == 0) u1_s[pr + PR * k] = u1[k];
         }
         float cm[CT];
 #pragma unroll
@@ -322,7 +372,7 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
             for (int k = 0; k < RT; ++k) mx = fmaxf(mx, z[k][c] + u1[k]);
             cm[c] = mx;
         }
-        col_reduce<C, false>(cm, OpMax(), s_part, s_tot, nu_s, warp, prw, qc, gtid);
+        col_reduce<C, false>(cm, OpMax(), sm, nu_s, warp, prw, qc, gtid, rank, parity);
         float cs[CT];
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
@@ -332,7 +382,7 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
             for (int k = 0; k < RT; ++k) s += fast_exp((z[k][c] + u1[k]) - cm[c]);
             cs[c] = s;
         }
-        col_reduce<C, false>(cs, OpSum(), s_part, s_tot, nu_s, warp, prw, qc, gtid);
+        col_reduce<C, false>(cs, OpSum(), sm, nu_s, warp, prw, qc, gtid, rank, parity);
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
             const int col = qc + QC * c;
@@ -340,12 +390,12 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
             if (pr == 0) v1_s[col] = v1;
 #pragma unroll
             for (int k = 0; k < RT; ++k) {
-                const int row = pr + PR * k;
+                const int row = row0 + pr + PR * k;
                 z[k][c] = (row < M && col < N) ? fast_exp((z[k][c] + u1[k]) + v1) : 1.0f;
             }
         }
     }
-    if (C::W == 1) __syncwarp(); else __syncthreads();
+    if (C::BLOCK) __syncthreads(); else __syncwarp();
 
     // ---- iterations 2..iters: scaling updates on the register tile --------------------------------
     float2 Kp[RT][CT2 > 0 ? CT2 : 1];
@@ -399,12 +449,12 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
             bcol[2 * h + 1] = s2[h].y;
         }
         if (ODD) bcol[CT - 1] = sl;
-        col_reduce<C, true>(bcol, OpSum(), s_part, s_tot, nu_s, warp, prw, qc, gtid);
+        col_reduce<C, true>(bcol, OpSum(), sm, nu_s, warp, prw, qc, gtid, rank, parity);
 
         if ((it & 7) == 0 || it == a.iters - 1) {  // range monitor (valid entries only)
 #pragma unroll
             for (int k = 0; k < RT; ++k)
-                if (pr + PR * k < M) lo = fminf(lo, al[k]), hi = fmaxf(hi, al[k]);
+                if (row0 + pr + PR * k < M) lo = fminf(lo, al[k]), hi = fmaxf(hi, al[k]);
 #pragma unroll
             for (int c = 0; c < CT; ++c)
                 if (qc + QC * c < N) lo = fminf(lo, bcol[c]), hi = fmaxf(hi, bcol[c]);
@@ -417,9 +467,9 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
     bool bad = !(lo >= 1e-13f && hi <= 1e13f);
 #pragma unroll
     for (int k = 0; k < RT; ++k) {
-        const int row = pr + PR * k;
+        const int row = row0 + pr + PR * k;
         float t = 0.f;
-        if (a.iters >= 1) t = u1_s[row];
+        if (a.iters >= 1) t = u1_s[pr + PR * k];
         if (a.iters >= 2) t += fast_log(al[k]);
         U[k] = t;
         if (row < M && !(fabsf(t) < INFINITY)) bad = true;
@@ -433,12 +483,27 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
         if (col < N && !(fabsf(t) < INFINITY)) bad = true;
         V[c] = t - shift;
     }
-    const bool any_bad = (C::W == 1) ? (__any_sync(0xffffffffu, bad) != 0) : (__syncthreads_or(bad ? 1 : 0) != 0);
+    bool any_bad;
+    if (!C::BLOCK) {
+        any_bad = __any_sync(0xffffffffu, bad) != 0;
+    } else {
+        any_bad = __syncthreads_or(bad ? 1 : 0) != 0;
+        if (C::CL > 1) {  // agree across the cluster
+            cg::cluster_group cluster = cg::this_cluster();
+            float *xf = sm + Smem<C>::XFLAG;
+            if (gtid < C::CL) cluster.map_shared_rank(xf, gtid)[rank] = any_bad ? 1.f : 0.f;
+            cluster.sync();
+            bool t = false;
+#pragma unroll
+            for (int r = 0; r < C::CL; ++r) t = t || (xf[r] != 0.f);
+            any_bad = t;
+        }
+    }
     if (!any_bad) {
         float *o = a.out + (size_t)p * M * N;
 #pragma unroll
         for (int k = 0; k < RT; ++k) {
-            const int row = pr + PR * k;
+            const int row = row0 + pr + PR * k;
 #pragma unroll
             for (int c = 0; c < CT; ++c) {
                 const int col = qc + QC * c;
@@ -446,18 +511,23 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
             }
         }
     } else {
+        // exact log-domain re-solve by this CTA (rank 0 of a cluster; the other CTAs are done)
+        if (rank != 0) return;
         if (gtid == 0 && a.fb_total) atomicAdd(a.fb_total, 1);
-        if (C::W == 1)
-            log_domain_solve<C::GT>(a, g, p, mu_s, nu_s, s_red + 2 * C::GT * group, gtid, WarpSync());
+        float *fb = sm + Smem<C>::FB + group * Smem<C>::FB_PER;
+        if (!C::BLOCK)
+            log_domain_solve<C::GT>(a, g, p, fb, fb + C::MAXM, fb + C::MAXM + C::MAXN, gtid, WarpSync());
         else
-            log_domain_solve<C::GT>(a, g, p, mu_s, nu_s, s_red, gtid, BlockSync());
+            log_domain_solve<C::GT>(a, g, p, fb, fb + C::MAXM, fb + C::MAXM + C::MAXN, gtid, BlockSync());
     }
 }
 
 // ---- host dispatch ------------------------------------------------------------------------------
-using CfgTiny = RegCfg<1, 2, 4, 8, 4>;     // <= 32 x 32, one warp per problem, 4 problems per CTA
-using CfgWarp = RegCfg<1, 2, 9, 17, 4>;    // <= 72 x 68  (level 3: 65 x 65)
-using CfgCta = RegCfg<8, 4, 10, 10, 1>;    // <= 160 x 160 (level 2: 145 x 145), 16 x 16 threads
+using CfgTiny = RegCfg<1, 2, 4, 8, 4>;         // <= 32 x 32, one warp per problem, 4 problems per CTA
+using CfgWarp = RegCfg<1, 2, 9, 17, 4>;        // <= 72 x 68  (level 3: 65 x 65)
+using CfgCta = RegCfg<8, 4, 10, 10, 1>;        // <= 160 x 160 (level 2: 145 x 145), 16 x 16 threads
+using CfgCl320 = RegCfg<8, 5, 5, 10, 1, 8>;    // <= 320 x 320 (level 1: 301 x 301), cluster of 8 CTAs x 256 threads
+using CfgCl512 = RegCfg<16, 5, 4, 16, 1, 8>;   // <= 512 x 512, cluster of 8 CTAs x 512 threads
 
 static int g_force_generic = 0;
 static int *g_fb_total = nullptr;  // device counter
@@ -476,14 +546,38 @@ static int kernel_kind(int M, int N) {
     if (g_force_generic) return 2;
     if (M <= CfgWarp::MAXM && N <= CfgWarp::MAXN) return 0;
     if (M <= CfgCta::MAXM && N <= CfgCta::MAXN) return 1;
+    if (M <= CfgCl512::MAXM && N <= CfgCl512::MAXN) return 3;
     return 2;
 }
 
 template <class C>
 static int launch_reg(const SinkArgs &a, cudaStream_t st) {
-    const int grid = (a.b + C::GROUPS - 1) / C::GROUPS;
-    sinkhorn_reg_kernel<C><<<grid, C::THREADS, 0, st>>>(a);
-    PATS_LAUNCH_CHECK("sinkhorn_reg_kernel");
+    constexpr size_t smem = Smem<C>::BYTES;
+    static_assert(smem <= 200 * 1024, "shared-memory layout too large");
+    if (smem > 48 * 1024) {
+        static bool configured = false;  // per kernel instantiation
+        if (!configured) {
+            PATS_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_reg_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = true;
+        }
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (C::CL > 1) {
+        cfg.gridDim = dim3((unsigned)a.b * C::CL);
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C::CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    } else {
+        cfg.gridDim = dim3((unsigned)((a.b + C::GROUPS - 1) / C::GROUPS));
+    }
+    PATS_CUDA_TRY(cudaLaunchKernelEx(&cfg, sinkhorn_reg_kernel<C>, a));
     return PATS_OK;
 }
 
@@ -518,6 +612,9 @@ static int run_sinkhorn(SinkArgs a, void *stream) {
             return launch_reg<CfgWarp>(a, st);
         case 1:
             return launch_reg<CfgCta>(a, st);
+        case 3:
+            if (a.M <= CfgCl320::MAXM && a.N <= CfgCl320::MAXN) return launch_reg<CfgCl320>(a, st);
+            return launch_reg<CfgCl512>(a, st);
         default:
             return launch_generic(a, st);
     }

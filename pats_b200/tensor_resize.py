@@ -19,7 +19,7 @@ CHECK_BOUNDS = True
 OUT_HW = (96, 96)  # library.cpp:50-52: patch_shape * 3
 
 
-def tensor_resize(input_tensor: torch.Tensor, bound: torch.Tensor, *, variant: int = 0) -> torch.Tensor:
+def tensor_resize(input_tensor: torch.Tensor, bound: torch.Tensor, *, variant: int | None = None) -> torch.Tensor:
     """feature resize"""
     inp = cuda_f32(input_tensor, "input_tensor")
     if inp.dim() != 4:
@@ -31,10 +31,14 @@ def tensor_resize(input_tensor: torch.Tensor, bound: torch.Tensor, *, variant: i
     K = bound.shape[0]
     out = torch.empty((K, Cc, OUT_HW[0], OUT_HW[1]), dtype=torch.float32, device=inp.device)
     bad = torch.zeros(1, dtype=torch.int32, device=inp.device) if CHECK_BOUNDS else None
+    bad_ptr = bad.data_ptr() if bad is not None else None
     with torch.cuda.device(inp.device):
-        rc = _lib.load().pats_tensor_resize_f32_variant(inp.data_ptr(), B, Cc, Hp, Wp, bound.data_ptr(), K, OUT_HW[0], OUT_HW[1],
-                                                        out.data_ptr(), bad.data_ptr() if bad is not None else None, int(variant),
-                                                        stream_ptr(inp.device))
+        if variant is None:  # shipping lerp recipe (bit-identical to ATen's CUDA bilinear kernel)
+            rc = _lib.load().pats_tensor_resize_f32(inp.data_ptr(), B, Cc, Hp, Wp, bound.data_ptr(), K, OUT_HW[0], OUT_HW[1], out.data_ptr(),
+                                                    bad_ptr, stream_ptr(inp.device))
+        else:  # explicit rounding recipe, tests only
+            rc = _lib.load().pats_tensor_resize_f32_variant(inp.data_ptr(), B, Cc, Hp, Wp, bound.data_ptr(), K, OUT_HW[0], OUT_HW[1],
+                                                            out.data_ptr(), bad_ptr, int(variant), stream_ptr(inp.device))
     _lib.check(rc, "tensor_resize")
     if bad is not None and K > 0:
         nbad = int(bad.item())

@@ -98,7 +98,13 @@ def test_golden_log_optimal_transport2(M, dev, tag):
     (5, 17, 31, 0.3, 8.0),       # tiny kernel
     (4, 100, 160, 0.4, 8.0),     # CTA kernel, capacity edge (160 columns)
     (3, 160, 73, 0.4, 8.0),      # CTA kernel, capacity edge (160 rows)
-    (2, 161, 90, 0.4, 8.0),      # first shape that needs the generic log-domain kernel
+    (2, 161, 90, 0.4, 8.0),      # first shape that needs the cluster kernel
+    (3, 301, 301, 0.1, 16.0),    # level-1 size with the dustbin in place, 8-CTA cluster (320 x 320 capacity)
+    (2, 320, 320, 0.3, 16.0),    # capacity edge of the 320 cluster
+    (2, 321, 200, 0.3, 16.0),    # needs the 512 cluster
+    (1, 512, 512, 0.2, 16.0),    # capacity edge of the 512 cluster
+    (5, 200, 500, 0.2, 16.0),    # ragged: most CTAs of the cluster own no valid rows
+    (1, 513, 40, 0.3, 4.0),      # first shape that needs the generic log-domain kernel
 ])
 def test_transport2_vs_oracle(M, lib, dev, b, m, n, scale, span):
     g = torch.Generator().manual_seed(1000 + b * 7 + m)
@@ -123,7 +129,7 @@ def test_transport_vs_oracle(M, dev, b, m, n, alpha):
 @pytest.mark.parametrize("iters", [0, 1, 2, 3, 9, 17])
 def test_iteration_counts(M, dev, iters):
     g = torch.Generator().manual_seed(3000 + iters)
-    for (b, m, n) in ((6, 65, 65), (3, 145, 145)):
+    for (b, m, n) in ((6, 65, 65), (3, 145, 145), (2, 301, 301)):
         s = 0.3 * torch.randn(b, m, n, generator=g)
         ns = areas(g, b, n - 1, 16.0)
         out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), iters).cpu().numpy()
@@ -145,7 +151,7 @@ def test_raw_sinkhorn_vs_oracle(M, dev):
 def test_generic_kernel_matches_register_kernels(M, lib, dev):
     """The log-domain kernel (fallback / large shapes) and the register kernels agree."""
     g = torch.Generator().manual_seed(5000)
-    for (b, m, n) in ((8, 65, 65), (3, 145, 145)):
+    for (b, m, n) in ((8, 65, 65), (3, 145, 145), (2, 301, 301)):
         s = (0.2 * torch.randn(b, m, n, generator=g)).to(dev)
         ns = areas(g, b, n - 1, 16.0).to(dev)
         fast = M.log_optimal_transport2(s, 1.0, ns, 100)
@@ -176,6 +182,21 @@ def test_extreme_dynamic_range_takes_the_log_domain_fallback(M, lib, dev):
     np.testing.assert_allclose(out, ref, atol=TOL, rtol=2e-6)
     assert n_fb >= 1, "expected at least one problem to use the fallback"
     assert n_fb < b, "well-conditioned problems must stay on the fast path"
+
+
+def test_cluster_kernel_fallback(M, lib, dev):
+    """Same as above for the 8-CTA cluster kernel: the cluster must agree on the verdict and rank 0 re-solves."""
+    g = torch.Generator().manual_seed(6100)
+    b, m, n = 3, 301, 301
+    s = 0.1 * torch.randn(b, m, n, generator=g)
+    s[1] *= 300.0
+    ns = areas(g, b, n - 1, 16.0)
+    lib.pats_sinkhorn_fallback_count(1)
+    out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), 30).cpu().numpy()
+    n_fb = lib.pats_sinkhorn_fallback_count(1)
+    ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), 30)
+    np.testing.assert_allclose(out, ref, atol=TOL, rtol=2e-6)
+    assert n_fb == 1
 
 
 def test_empty_batch(M, dev):

@@ -43,6 +43,8 @@ def test_kernel_dispatch_table():
     lib = _lib.load()
     assert lib.pats_sinkhorn_kernel_kind(65, 65) == 0      # level 3: one warp per problem
     assert lib.pats_sinkhorn_kernel_kind(145, 145) == 1    # level 2: one CTA per problem
+    assert lib.pats_sinkhorn_kernel_kind(301, 301) == 3    # level 1: one 8-CTA cluster per problem
+    assert lib.pats_sinkhorn_kernel_kind(512, 512) == 3
     assert lib.pats_sinkhorn_kernel_kind(1537, 1537) == 2  # generic log-domain kernel
 
 
