@@ -141,6 +141,16 @@ int pats_iterative_expand_matrix_f32(const float *scores_in, const float *scalex
  *   Z [b,M,N] -> nm1 [b,M-1] = (argmax_j Z[i,:] == dust), nm2 [b,N-1] = (argmax_i Z[:,j] == dust) */
 int pats_est_nomatching_f32(const float *Z, int b, int M, int N, int dust, uint8_t *nm1, uint8_t *nm2, void *stream);
 
+/* FirstLayer.est_position / SecondLayer.est_position, fused   first_layer.py:159-178, second_layer.py:240-259
+ *   Z [b,n+1,n+1] LOG-domain plan (square, n = grid_h*grid_w), scalex,scaley [b,n].  exp() is applied while the
+ *   rows are staged (the reference materialises scores.exp()); the two argmax masks and the area expansion run
+ *   back to back.  -> trust_score (= whole_cost), x_scale, y_scale [b,n]; average_point [b,n,2];
+ *   if_nomatching1, if_nomatching2 [b,n] u8; core_cost [b,n]; bound [b,n,4] i64. */
+int pats_est_position_f32(const float *Z, const float *scalex, const float *scaley, int b, int grid_h, int grid_w,
+                          float lower_bound, int iter_num, float *trust_score, float *average_point, float *x_scale,
+                          float *y_scale, uint8_t *if_nomatching1, uint8_t *if_nomatching2, float *core_cost,
+                          int64_t *bound, void *stream);
+
 /* SecondLayer.merge_patches_new / merge_patches_old         models/second_layer.py:189-238 / :137-186
  *   trust_score [P,144] f32 and nm_L2 [P,144] u8 are MUTATED in place exactly as the reference mutates its
  *   arguments; nm_L1 [B,hw] u8; scores_back [B,hw,16,9] f64 in/out (carried across chunks for `new`, zeroed on
@@ -164,6 +174,11 @@ int pats_get_result_f32(const uint8_t *nm0, const float *pt0, const float *sc0, 
 int pats_third_compute_result_f32(const float *scores, const float *scale_x, const float *scale_y, const int64_t *p_s,
                                   const int64_t *p_t, int K, float *mkpts0_f, float *mkpts1_f, uint8_t *if_matching1,
                                   void *stream);
+
+/* Same, taking the LOG-domain plan Z (third_layer.py:158-160: scores = exp(scores_origin) fused into the load). */
+int pats_third_result_from_log_f32(const float *Z, const float *scale_x, const float *scale_y, const int64_t *p_s,
+                                   const int64_t *p_t, int K, float *mkpts0_f, float *mkpts1_f, uint8_t *if_matching1,
+                                   void *stream);
 
 #ifdef __cplusplus
 }

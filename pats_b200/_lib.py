@@ -41,6 +41,8 @@ SIGNATURES = {
     "pats_merge_patches": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
     "pats_get_result_f32": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, C.c_longlong, _P, _P, _P],
     "pats_third_compute_result_f32": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
+    "pats_third_result_from_log_f32": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
+    "pats_est_position_f32": [_P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }
 _RESTYPE = {"pats_last_error": C.c_char_p, "pats_sinkhorn_force_generic": None}
 

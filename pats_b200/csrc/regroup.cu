@@ -23,7 +23,7 @@ constexpr float kZero = 1e-14f;  // `zero` of utils/utils.py:1203
 struct ExpandArgs {
     const float *scores;  // [b, m+1, n+1] = exp(Z)
     const float *sx, *sy; // [b, n]
-    int b, m, n, grid_w, width, height, iters;
+    int b, m, n, grid_w, width, height, iters, log_input;  // log_input: scores hold Z, exp() applied on load
     float lb;
     float *whole, *core, *avg, *xs, *ys;
     int64_t *bound;
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) area_expand_kernel(ExpandArgs a
     float *E = sm + (3 + warp) * stride;                      // this warp's source row (+ dustbin col, + zero slot)
     const float *opp = a.scores + ((size_t)bb * (m + 1) + m) * (n + 1);
     for (int j = threadIdx.x; j < stride; j += blockDim.x) {
-        O[j] = j < n ? opp[j] : kZero;
+        O[j] = j < n ? (a.log_input ? expf(opp[j]) : opp[j]) : kZero;
         SX[j] = j < n ? a.sx[(size_t)bb * n + j] : 0.f;
         SY[j] = j < n ? a.sy[(size_t)bb * n + j] : 0.f;
     }
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) area_expand_kernel(ExpandArgs a
     const int i = blockIdx.x * EX_WARPS + warp;
     if (i >= m) return;
     const float *row = a.scores + ((size_t)bb * (m + 1) + i) * (n + 1);
-    for (int j = lane; j < stride; j += 32) E[j] = j <= n ? row[j] : kZero;
+    for (int j = lane; j < stride; j += 32) E[j] = j <= n ? (a.log_input ? expf(row[j]) : row[j]) : kZero;
     __syncwarp();
     auto Sval = [&](long long idx) -> float { return idx < n ? SX[idx] * SY[idx] : kZero; };
 
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) est_nomatching_kernel(const float *__rest
     const int bb = blockIdx.x;
     const float *z = Z + (size_t)bb * M * N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int i = warp; i < M - 1; i += nw) {
+    for (int i = warp; nm1 != nullptr && i < M - 1; i += nw) {
         float bv = -INFINITY;
         int bi = 0x7fffffff;
         for (int j = lane; j < N; j += 32) {
@@ -456,8 +456,9 @@ constexpr int TH_K = 8;  // problems per CTA
 
 __global__ void __launch_bounds__(TH_K * 16) third_result_kernel(const float *__restrict__ scores, const float *__restrict__ scale_x,
                                                                  const float *__restrict__ scale_y, const int64_t *__restrict__ p_s,
-                                                                 const int64_t *__restrict__ p_t, int K, float *__restrict__ mk0,
-                                                                 float *__restrict__ mk1, uint8_t *__restrict__ if_matching1) {
+                                                                 const int64_t *__restrict__ p_t, int K, int log_input,
+                                                                 float *__restrict__ mk0, float *__restrict__ mk1,
+                                                                 uint8_t *__restrict__ if_matching1) {
     constexpr int W = 8, T = 5, NN = 65;
     __shared__ float rows[TH_K * 16][NN];
     __shared__ float gx[TH_K][64], gy[TH_K][64];
@@ -466,7 +467,8 @@ __global__ void __launch_bounds__(TH_K * 16) third_result_kernel(const float *__
         const int rr = e / NN, j = e - rr * NN;
         const int k = k0 + rr / 16, c16 = rr % 16;
         const int srow = (2 + c16 / 4) * W + 2 + c16 % 4;  // inner 4x4 of the 8x8 source window (:186)
-        rows[rr][j] = k < K ? __ldg(scores + ((size_t)k * NN + srow) * NN + j) : 0.f;
+        const float v = k < K ? __ldg(scores + ((size_t)k * NN + srow) * NN + j) : 0.f;
+        rows[rr][j] = (log_input && k < K) ? expf(v) : v;  // third_layer.py:159 scores = exp(scores_origin)
     }
     for (int e = threadIdx.x; e < TH_K * 64; e += blockDim.x) {
         const int k = k0 + e / 64;
@@ -525,7 +527,7 @@ PATS_API int pats_iterative_expand_matrix_f32(const float *scores_in, const floa
     a.b = b, a.m = m, a.n = (int)n, a.grid_w = grid_w;
     a.width = grid_h > grid_w ? grid_h : grid_w;  // ranges.shape[0]   (utils.py:1181)
     a.height = (int)(n / a.width);
-    a.iters = iter_num, a.lb = lower_bound;
+    a.iters = iter_num, a.lb = lower_bound, a.log_input = 0;
     a.whole = whole_cost, a.core = core_cost, a.avg = average_point, a.xs = x_scale, a.ys = y_scale;
     a.bound = bound, a.nomatch = if_nomatching;
     const size_t smem = sizeof(float) * (size_t)(3 + EX_WARPS) * (n + 2);
@@ -603,8 +605,54 @@ PATS_API int pats_third_compute_result_f32(const float *scores, const float *sca
     if (K == 0) return PATS_OK;
     if (!scores || !scale_x || !scale_y || !p_s || !p_t || !mkpts0_f || !mkpts1_f || !if_matching1)
         return invalid("third_compute_result: null pointer");
-    third_result_kernel<<<(K + TH_K - 1) / TH_K, TH_K * 16, 0, as_stream(stream)>>>(scores, scale_x, scale_y, p_s, p_t, K, mkpts0_f,
+    third_result_kernel<<<(K + TH_K - 1) / TH_K, TH_K * 16, 0, as_stream(stream)>>>(scores, scale_x, scale_y, p_s, p_t, K, 0, mkpts0_f,
                                                                                   mkpts1_f, if_matching1);
     PATS_LAUNCH_CHECK("third_result_kernel");
+    return PATS_OK;
+}
+
+PATS_API int pats_third_result_from_log_f32(const float *Z, const float *scale_x, const float *scale_y, const int64_t *p_s,
+                                            const int64_t *p_t, int K, float *mkpts0_f, float *mkpts1_f, uint8_t *if_matching1,
+                                            void *stream) {
+    if (K < 0) return invalid("third_result_from_log: bad sizes");
+    if (K == 0) return PATS_OK;
+    if (!Z || !scale_x || !scale_y || !p_s || !p_t || !mkpts0_f || !mkpts1_f || !if_matching1)
+        return invalid("third_result_from_log: null pointer");
+    third_result_kernel<<<(K + TH_K - 1) / TH_K, TH_K * 16, 0, as_stream(stream)>>>(Z, scale_x, scale_y, p_s, p_t, K, 1, mkpts0_f,
+                                                                                  mkpts1_f, if_matching1);
+    PATS_LAUNCH_CHECK("third_result_kernel");
+    return PATS_OK;
+}
+
+PATS_API int pats_est_position_f32(const float *Z, const float *scalex, const float *scaley, int b, int grid_h, int grid_w,
+                                   float lower_bound, int iter_num, float *trust_score, float *average_point, float *x_scale,
+                                   float *y_scale, uint8_t *if_nomatching1, uint8_t *if_nomatching2, float *core_cost,
+                                   int64_t *bound, void *stream) {
+    const long long n = (long long)grid_h * grid_w;
+    if (b < 0 || grid_h <= 0 || grid_w <= 0 || iter_num < 1) return invalid("est_position: bad sizes");
+    if (b == 0) return PATS_OK;
+    if (!Z || !scalex || !scaley || !trust_score || !average_point || !x_scale || !y_scale || !if_nomatching1 || !if_nomatching2 ||
+        !core_cost || !bound)
+        return invalid("est_position: null pointer");
+    // square plan [b, n+1, n+1]: row argmax == n is exactly the mask the expansion computes (utils.py:1194 with m == n)
+    ExpandArgs a;
+    a.scores = Z, a.sx = scalex, a.sy = scaley;
+    a.b = b, a.m = (int)n, a.n = (int)n, a.grid_w = grid_w;
+    a.width = grid_h > grid_w ? grid_h : grid_w;
+    a.height = (int)(n / a.width);
+    a.iters = iter_num, a.lb = lower_bound, a.log_input = 1;
+    a.whole = trust_score, a.core = core_cost, a.avg = average_point, a.xs = x_scale, a.ys = y_scale;
+    a.bound = bound, a.nomatch = if_nomatching1;
+    const size_t smem = sizeof(float) * (size_t)(3 + EX_WARPS) * (n + 2);
+    if (smem > 200 * 1024) return invalid("est_position: grid of %lld cells exceeds the shared-memory budget", n);
+    if (smem > 48 * 1024)
+        PATS_CUDA_TRY(cudaFuncSetAttribute(area_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (b > 65535) return invalid("est_position: batch %d exceeds gridDim.y", b);
+    cudaStream_t st = as_stream(stream);
+    est_nomatching_kernel<<<b, 256, 0, st>>>(Z, (int)n + 1, (int)n + 1, (int)n, nullptr, if_nomatching2);
+    PATS_LAUNCH_CHECK("est_nomatching_kernel");
+    dim3 grid(((int)n + EX_WARPS - 1) / EX_WARPS, b);
+    area_expand_kernel<<<grid, EX_WARPS * 32, smem, st>>>(a);
+    PATS_LAUNCH_CHECK("area_expand_kernel");
     return PATS_OK;
 }

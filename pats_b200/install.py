@@ -40,6 +40,8 @@ _METHODS = {
     ("models.second_layer", "SecondLayer", "merge_patches_new"): _layers.merge_patches_new,
     ("models.second_layer", "SecondLayer", "merge_patches_old"): _layers.merge_patches_old,
     ("models.third_layer", "ThirdLayer", "Compute_result"): _layers.Compute_result,
+    ("models.first_layer", "FirstLayer", "est_position"): _layers.first_layer_est_position,
+    ("models.second_layer", "SecondLayer", "est_position"): _layers.second_layer_est_position,
 }
 _saved: dict = {}
 

@@ -79,3 +79,66 @@ def Compute_result(self, scores, W, T, scale_x, scale_y, p_s, p_t, device):
         raise NotImplementedError("Compute_result: the reference fixes W=8, T=5 (third_layer.py:107-110)")
     m0, m1, _ = third_compute_result(scores, scale_x, scale_y, p_s, p_t)
     return m0, m1, torch.zeros((scores.shape[0], 16), dtype=torch.float32, device=scores.device)
+
+
+def est_position(scores, scale_x, scale_y, grid_h: int, grid_w: int, iter_num: int, lower_bound: float, *, return_extra=False):
+    """Fused est_position (first_layer.py:159-178 with scale_x = scale_y = scale_src, iter_num=15, lower_bound=1e-5;
+    second_layer.py:240-259 with iter_num=8, lower_bound=1e-3) from the LOG-domain plan `scores` [b,n+1,n+1].
+
+    Returns (trust_score [b,n], average_point [b,n,2], x_scale [b,n], y_scale [b,n], if_nomatching1 [b,n], if_nomatching2 [b,n]).
+    """
+    scores = cuda_f32(scores, "scores")
+    b, M, N = scores.shape
+    n = grid_h * grid_w
+    if M != n + 1 or N != n + 1:
+        raise ValueError(f"est_position: plan {tuple(scores.shape)} is not [b,{n + 1},{n + 1}] for a {grid_h}x{grid_w} grid")
+    dev = scores.device
+    sx = cuda_f32(scale_x, "scale_x").reshape(b, n)
+    sy = cuda_f32(scale_y, "scale_y").reshape(b, n)
+    trust = torch.empty((b, n), dtype=torch.float32, device=dev)
+    avg = torch.empty((b, n, 2), dtype=torch.float32, device=dev)
+    xs, ys, core = torch.empty_like(trust), torch.empty_like(trust), torch.empty_like(trust)
+    nm1 = torch.empty((b, n), dtype=torch.bool, device=dev)
+    nm2 = torch.empty_like(nm1)
+    bound = torch.empty((b, n, 4), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pats_est_position_f32(scores.data_ptr(), sx.data_ptr(), sy.data_ptr(), b, grid_h, grid_w, float(lower_bound), int(iter_num),
+                                               trust.data_ptr(), avg.data_ptr(), xs.data_ptr(), ys.data_ptr(), nm1.data_ptr(), nm2.data_ptr(),
+                                               core.data_ptr(), bound.data_ptr(), stream_ptr(dev))
+    _lib.check(rc, "est_position")
+    out = (trust, avg, xs, ys, nm1, nm2)
+    return out + (core, bound) if return_extra else out
+
+
+def first_layer_est_position(self, scores, scale_src, image_shape, patch_scale):
+    """FirstLayer.est_position (first_layer.py:159-178)."""
+    H, W = image_shape
+    return est_position(scores, scale_src, scale_src, H // patch_scale, W // patch_scale, 15, 1e-5)
+
+
+def second_layer_est_position(self, scores, scale_x, scale_y, image_shape, patch_scale):
+    """SecondLayer.est_position (second_layer.py:240-259)."""
+    H, W = image_shape
+    return est_position(scores, scale_x, scale_y, H // patch_scale, W // patch_scale, 8, 1e-3)
+
+
+def third_result_from_log(Z, scale_x, scale_y, p_s, p_t):
+    """third_compute_result on the log-domain plan (exp fused into the load; third_layer.py:158-160)."""
+    Z = cuda_f32(Z, "Z")
+    K = Z.shape[0]
+    dev = Z.device
+    sx = cuda_f32(scale_x, "scale_x").reshape(K, 64)
+    sy = cuda_f32(scale_y, "scale_y").reshape(K, 64)
+    ps = p_s.to(device=dev, dtype=torch.int64).contiguous()
+    pt = p_t.to(device=dev, dtype=torch.int64).contiguous()
+    m0 = torch.empty((K, 16, 2), dtype=torch.float32, device=dev)
+    m1 = torch.empty_like(m0)
+    im = torch.empty((K, 16), dtype=torch.bool, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pats_third_result_from_log_f32(Z.data_ptr(), sx.data_ptr(), sy.data_ptr(), ps.data_ptr(), pt.data_ptr(), K, m0.data_ptr(),
+                                                        m1.data_ptr(), im.data_ptr(), stream_ptr(dev))
+    _lib.check(rc, "third_result_from_log")
+    return m0, m1, im
+
+
+__all__ += ["est_position", "first_layer_est_position", "second_layer_est_position", "third_result_from_log"]

@@ -192,3 +192,36 @@ def test_third_compute_result_golden_and_oracle(dev):
     assert np.array_equal(im.cpu().numpy(), oim) and 0.05 < oim.mean() < 0.95
     assert np.array_equal(m0.cpu().numpy(), o0)
     assert np.array_equal(m1.cpu().numpy(), o1)
+
+
+@pytest.mark.parametrize("tag,gh,gw,lb,it", [("L1", 15, 20, 1e-5, 15), ("L2", 12, 12, 1e-3, 8)])
+def test_fused_est_position_equals_unfused(dev, tag, gh, gw, lb, it):
+    """est_position from the log-domain plan (exp fused into the row staging) == masks + Iterative_expand_matrix on
+    torch's scores.exp() -- and both equal the reference's golden outputs."""
+    from pats_b200 import layers as L
+    from pats_b200 import utils as U
+
+    g = load_golden("expand")
+    Z = T(g[tag + "_Z"], dev)
+    sx, sy = T(g[tag + "_scalex"], dev), T(g[tag + "_scaley"], dev)
+    trust, avg, xs, ys, nm1, nm2, core, bound = L.est_position(Z, sx, sy, gh, gw, it, lb, return_extra=True)
+    rng, pos = _ranges_positions(gh, gw, dev)
+    ref = U.Iterative_expand_matrix(Z.exp(), sx, sy, torch.tensor([0, gh, 0, gw], device=dev), rng, pos, height=gh, width=gw, iter_num=it,
+                                    lower_bound=lb)
+    assert torch.equal(bound, ref[5]) and np.array_equal(bound.cpu().numpy(), g[tag + "_bound"])
+    assert torch.equal(trust, ref[0]) and torch.equal(core, ref[1]) and torch.equal(avg, ref[2])
+    assert torch.equal(xs, ref[3]) and torch.equal(ys, ref[4])
+    assert np.array_equal(nm1.cpu().numpy(), g[tag + "_nm1"]) and np.array_equal(nm2.cpu().numpy(), g[tag + "_nm2"])
+
+
+def test_third_result_from_log_equals_exp_then_result(dev):
+    from pats_b200 import layers as L
+
+    g = load_golden("third")
+    sx = T(np.sqrt(g["scale"] + np.float32(1e-8)), dev)
+    Z = T(g["Z"], dev)
+    a = L.third_result_from_log(Z, sx, sx, T(g["p_s"], dev), T(g["p_t"], dev))
+    b = L.third_compute_result(Z.exp(), sx, sx, T(g["p_s"], dev), T(g["p_t"], dev))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert np.array_equal(a[2].cpu().numpy(), g["if_matching1"])
