@@ -345,7 +345,7 @@ def run_reference(args):
     oracle.set_num_threads(cores)
     torch.set_num_threads(cores)
     host = make_inputs(torch, 1, SEED)
-    frac3, frac2 = 1.0 / 16, 1.0 / 8
+    frac3, frac2 = 1.0 / 8, 1.0 / 4
     for _ in range(min(args.warmup, 1)):
         cpu_sample_step(torch, host, frac3 / 4, frac2 / 4)
     times = []
@@ -483,7 +483,7 @@ def main():
             cores = os.cpu_count() or 1
             oracle.set_num_threads(cores)
             torch.set_num_threads(cores)
-            secs, desc, parts = cpu_sample_step(torch, make_inputs(torch, 1, SEED), 1.0 / 16, 1.0 / 8)
+            secs, desc, parts = cpu_sample_step(torch, make_inputs(torch, 1, SEED), 1.0 / 4, 1.0 / 2)
             cpu = {"value": 1.0 / secs, "unit": "pairs/s", "cores": oracle.num_threads(), "kind": "port", "sample": desc,
                    "seconds_per_pair": secs, "parts_s": {k: round(v, 4) for k, v in parts.items()}}
         line = {
