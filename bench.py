@@ -149,14 +149,14 @@ class DeviceStep:
         # ---- level 1 ----------------------------------------------------------------------------------------
         c(L.pats_log_optimal_transport_f32(p(i["l1_scores"]), p(i["alpha"]), p(i["l1_ns"]), B, N1, N1, ITERS, p(o["l1_Z"]), stream_ptr), "ot1"); n += 1
         c(L.pats_est_position_f32(p(o["l1_Z"]), p(i["l1_ns"]), p(i["l1_ns"]), B, GH, GW, 1e-5, 15, p(o["l1_trust"]), p(o["l1_avg"]), p(o["l1_xs"]),
-                                  p(o["l1_ys"]), p(o["l1_nm1"]), p(o["l1_nm2"]), p(o["l1_core"]), p(o["l1_bound"]), stream_ptr), "est1"); n += 2
+                                  p(o["l1_ys"]), p(o["l1_nm1"]), p(o["l1_nm2"]), p(o["l1_core"]), p(o["l1_bound"]), stream_ptr), "est1"); n += 1
         c(L.pats_compute_imgs(p(i["ci_xs"]), p(i["ci_ys"]), p(i["ci_avg"]), p(i["ci_nm"]), p(i["left"]), p(i["right"]), 1, B, GH, GW, PS, 128,
                               p(o["new_left"]), p(o["new_right"]), p(o["bound5"]), p(o["ci_xs_new"]), p(o["ci_ys_new"]), p(o["ci_avg_new"]), B * N1,
                               p(o["ci_meta"]), p(o["ci_meta"]) + 4, stream_ptr), "imgs"); n += 3
         # ---- level 2 ----------------------------------------------------------------------------------------
         c(L.pats_log_optimal_transport2_f32(p(i["l2_scores"]), p(i["one"]), p(i["l2_ns"]), B * P2, 145, 145, ITERS, p(o["l2_Z"]), stream_ptr), "ot2"); n += 1
         c(L.pats_est_position_f32(p(o["l2_Z"]), p(i["l2_sx"]), p(i["l2_sy"]), B * P2, 12, 12, 1e-3, 8, p(o["l2_trust"]), p(o["l2_avg"]), p(o["l2_xs"]),
-                                  p(o["l2_ys"]), p(o["l2_nm1"]), p(o["l2_nm2"]), p(o["l2_core"]), p(o["l2_bound"]), stream_ptr), "est2"); n += 2
+                                  p(o["l2_ys"]), p(o["l2_nm1"]), p(o["l2_nm2"]), p(o["l2_core"]), p(o["l2_bound"]), stream_ptr), "est2"); n += 1
         c(L.pats_merge_patches(1, p(o["l2_trust"]), p(i["nm1_L1"]), p(o["l2_nm1"]), p(o["scores_back"]), B, GH, GW, B * P2, p(o["merge_out"]),
                                p(o["merge_ws"]), stream_ptr), "merge"); n += 3
         # ---- level 3 ----------------------------------------------------------------------------------------
@@ -278,41 +278,51 @@ def cpu_sample_step(torch, host_inputs, frac_l3: float, frac_l2: float):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / throttle reasons sampled through NVML every ~5 ms during the timed region (B200_PROFILING.md)."""
 
     def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.stop_flag, self.thread, self.err = gpu_index, [], False, None, None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nm in enumerate(names):
-                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        # nvidia-smi samples include idle gaps; the median of the upper half approximates "under load"
-        load = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx[0] if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+            def pump():
+                while not self.stop_flag:
+                    try:
+                        self.rows.append((time.perf_counter(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                          int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                    except Exception as e:  # noqa: BLE001
+                        self.err = repr(e)
+                        return
+                    time.sleep(0.004)
+
+            self.thread = threading.Thread(target=pump, daemon=True)
+            self.thread.start()
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def stop(self, t0=None, t1=None):
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        rows = [r for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)] or self.rows
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable: %s" % self.err], "samples": 0}
+        sm = sorted(r[1] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(v for k, v in names.items() if bits & k),
+                "samples": len(rows)}
 
 
 def peaks():
@@ -351,7 +361,7 @@ def run_reference(args):
     times = []
     desc = ""
     t_wall = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(min(args.steps, 20)):
         s, desc, _ = cpu_sample_step(torch, host, frac3, frac2)
         times.append(s)
         if time.perf_counter() - t_wall > 150:  # keep the whole run within a few minutes
@@ -373,8 +383,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--pairs-per-step", type=int, default=1)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -420,6 +430,7 @@ def main():
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_wall0 = time.perf_counter()
     e0.record()
     launches = 0
     for s in range(args.steps):
@@ -430,11 +441,12 @@ def main():
         gather_match_lists([torch.cat([step.o["ml"][:kf], step.o["mr"][:kf]], 1)])
     e1.record()
     barrier()
+    t_wall1 = time.perf_counter()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     value = world * B * args.steps / (total_ms * 1e-3)
     l3_ms = sorted(a.elapsed_time(b) for a, b in l3_events)
     l3_avg = sum(l3_ms) / len(l3_ms)
@@ -465,9 +477,9 @@ def main():
         achieved = alg_bytes / (l3_avg * 1e-3) / 1e9
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         fma_lane_peak = 148 * 128 * sm_mhz * 1e6                # FP32 FMA lanes/s
-        fma_done = b3 * 72 * 68 * 2 * (ITERS - 1)               # padded 72 x 68 tile, two passes per iteration
+        fma_done = b3 * 65 * 65 * 2 * (ITERS - 1)               # two FMA passes over the plan per iteration
         roofline = {
-            "kernel": "sinkhorn_reg_kernel<warp, 72x68 tile> (level-3 OT, 65x65 x %d problems)" % b3,
+            "kernel": "sinkhorn_w65_kernel (level-3 OT, one warp per 65x65 problem, %d problems)" % b3,
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
             "peak_source": peak_src, "ms_per_launch": l3_avg, "algorithmic_bytes": alg_bytes,
             "note": "plan is register-resident: HBM moves only the compulsory read+write, so the streaming-model fraction exceeds 1; "

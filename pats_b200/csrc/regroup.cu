@@ -10,64 +10,124 @@
 // order, long sums accumulate in f64, and this file is compiled with -fmad=false so every f32 expression
 // rounds exactly like the C restatement.  They are latency-bound index kernels; the work is spread over
 // (rows | window cells | matches) >> 148 SMs worth of warps.
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace pats {
 
+// Per-stream scratch (grown on demand, never shrunk).  Calls on one stream are ordered, so a stream's buffer is
+// never used by two launches at once.
+static void *stream_workspace(cudaStream_t st, size_t bytes) {
+    static std::mutex mu;
+    static std::map<cudaStream_t, std::pair<void *, size_t>> pool;
+    std::lock_guard<std::mutex> lk(mu);
+    auto &e = pool[st];
+    if (e.second < bytes) {
+        if (e.first) {
+            cudaStreamSynchronize(st);
+            cudaFree(e.first);
+        }
+        size_t cap = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
+        if (cudaMalloc(&e.first, cap) != cudaSuccess) {
+            e.first = nullptr, e.second = 0;
+            return nullptr;
+        }
+        e.second = cap;
+    }
+    return e.first;
+}
+
 // =================================================================================================
-// a8/a9  area expansion: one warp per (problem, source row)
+// a8/a9  area expansion: one half-warp (16 lanes) per (problem, source row), 16 rows per CTA
 // =================================================================================================
-constexpr int EX_WARPS = 8;
+constexpr int EX_ROWS = 16;      // rows (half-warps) per CTA
 constexpr float kZero = 1e-14f;  // `zero` of utils/utils.py:1203
 
 struct ExpandArgs {
-    const float *scores;  // [b, m+1, n+1] = exp(Z)
+    const float *scores;  // [b, m+1, n+1] = exp(Z)  (or Z when log_input)
     const float *sx, *sy; // [b, n]
     int b, m, n, grid_w, width, height, iters, log_input;  // log_input: scores hold Z, exp() applied on load
     float lb;
     float *whole, *core, *avg, *xs, *ys;
     int64_t *bound;
     uint8_t *nomatch;
+    // fused column-argmax mask of est_position (log_input only): nm2[j] = (argmax_i Z[i][j] == dustbin row)
+    uint8_t *nm2;
+    unsigned *colmax;   // [b, n] order-preserving encoding of max_i<m Z[i][j], zero-initialised
+    unsigned *counter;  // [b] CTAs finished, zero-initialised
 };
 
-__device__ __forceinline__ double warp_sum_f64(double v) {
+// monotone map float -> unsigned (atomicMax on floats of either sign); every key is > 0
+__device__ __forceinline__ unsigned enc_f32(float f) {
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__device__ __forceinline__ double half_sum_f64(double v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-__global__ void __launch_bounds__(EX_WARPS * 32) area_expand_kernel(ExpandArgs a) {
+__global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a) {
     extern __shared__ float sm[];
+    __shared__ bool s_last;
     const int n = a.n, m = a.m, bb = blockIdx.y;
     const int stride = n + 2;
     float *O = sm, *SX = sm + stride, *SY = sm + 2 * stride;  // dustbin row, target scales (shared by the CTA)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *E = sm + (3 + warp) * stride;                      // this warp's source row (+ dustbin col, + zero slot)
+    unsigned *CM = reinterpret_cast<unsigned *>(sm + 3 * stride);  // per-CTA column maxima (encoded)
+    const int hl = threadIdx.x & 15, half = threadIdx.x >> 4;      // lane within the half-warp, row slot
+    const int hbase = threadIdx.x & 16;                            // first lane of this half inside its warp
+    float *E = sm + (4 + half) * stride;                           // this row (+ dustbin col, + zero slot)
     const float *opp = a.scores + ((size_t)bb * (m + 1) + m) * (n + 1);
     for (int j = threadIdx.x; j < stride; j += blockDim.x) {
         O[j] = j < n ? (a.log_input ? expf(opp[j]) : opp[j]) : kZero;
         SX[j] = j < n ? a.sx[(size_t)bb * n + j] : 0.f;
         SY[j] = j < n ? a.sy[(size_t)bb * n + j] : 0.f;
+        CM[j] = 0u;
     }
     __syncthreads();
-    const int i = blockIdx.x * EX_WARPS + warp;
-    if (i >= m) return;
+    const int i_raw = blockIdx.x * EX_ROWS + half;
+    const bool row_ok = i_raw < m;
+    const int i = row_ok ? i_raw : m - 1;  // surplus half-warps recompute the last row and discard it (keeps shuffles full)
     const float *row = a.scores + ((size_t)bb * (m + 1) + i) * (n + 1);
-    for (int j = lane; j < stride; j += 32) E[j] = j <= n ? (a.log_input ? expf(row[j]) : row[j]) : kZero;
-    __syncwarp();
-    auto Sval = [&](long long idx) -> float { return idx < n ? SX[idx] * SY[idx] : kZero; };
+    for (int j = hl; j < stride; j += 16) {
+        float v = kZero;
+        if (j <= n) {
+            v = row[j];
+            if (a.nm2 && j < n && row_ok) atomicMax(&CM[j], enc_f32(v));
+            if (a.log_input) v = expf(v);
+        }
+        E[j] = v;
+    }
+    __syncthreads();
+    if (a.nm2) {  // publish this CTA's column maxima; the last CTA of the problem writes the mask
+        for (int j = threadIdx.x; j < n; j += blockDim.x) atomicMax(&a.colmax[(size_t)bb * n + j], CM[j]);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(&a.counter[bb], 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            for (int j = threadIdx.x; j < n; j += blockDim.x) {
+                const unsigned best = *reinterpret_cast<volatile unsigned *>(&a.colmax[(size_t)bb * n + j]);
+                a.nm2[(size_t)bb * n + j] = enc_f32(opp[j]) > best;  // strictly larger: ties go to the first (real) row
+            }
+        }
+    }
+    auto Sval = [&](int idx) -> float { return idx < n ? SX[idx] * SY[idx] : kZero; };
 
     // ---- argmax over real targets (first maximum), dustbin test (utils.py:1182,1194) ------------------------
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    for (int j = lane; j < n; j += 32) {
+    for (int j = hl; j < n; j += 16) {
         const float v = E[j];
-        if (v > bv || bi == 0x7fffffff) {
-            if (v > bv || bi == 0x7fffffff) bv = v, bi = j;
-        }
+        if (bi == 0x7fffffff || v > bv) bv = v, bi = j;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 8; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) bv = ov, bi = oi;
@@ -76,38 +136,41 @@ __global__ void __launch_bounds__(EX_WARPS * 32) area_expand_kernel(ExpandArgs a
     const int maxall = (E[n] > E[max0]) ? n : max0;
     const bool nomatch = (maxall == m);
 
-    long long bd0, bd1, bd2, bd3, dy = 0, dx = 0, sdy = 0, sdx = 0;
+    int bd0, bd1, bd2, bd3, dy = 0, dx = 0, sdy = 0, sdx = 0;
     bd0 = bd1 = max0 / a.grid_w;
     bd2 = bd3 = max0 % a.grid_w;
     const int width = a.width, height = a.height;
+    const float fwidth = (float)width;
     float last_sum = E[max0], last_nom = O[max0];
 
-    // ---- box growth (utils.py:1213-1243): lanes 0..11 = (direction, quantity), sequential over the strip -------
+    // ---- box growth (utils.py:1213-1243): lanes 0..11 of the half = (direction, quantity); the strip is summed
+    //      sequentially in the reference's order ------------------------------------------------------------------
+    const int d12 = hl / 3, q12 = hl - 3 * d12;
     for (int it = 0; it < a.iters; ++it) {
         sdy = dy, sdx = dx;
         float acc = 0.f;
-        if (lane < 12) {
-            const int d = lane / 3, q = lane - 3 * d;
-            long long off;
-            if (d == 0) off = bd2 + bd0 * width - width;
-            else if (d == 1) off = bd2 + bd1 * width + width;
-            else if (d == 2) off = bd2 + bd0 * width - 1;
-            else off = bd3 + bd0 * width + 1;
-            const float foff = (float)off;
+        if (hl < 12) {
+            int off, lim;
+            if (d12 == 0) off = bd2 + bd0 * width - width, lim = dx;
+            else if (d12 == 1) off = bd2 + bd1 * width + width, lim = dx;
+            else if (d12 == 2) off = bd2 + bd0 * width - 1, lim = dy;
+            else off = bd3 + bd0 * width + 1, lim = dy;
+            const float foff = (float)off, step = (d12 < 2) ? 1.0f : fwidth;
+#pragma unroll 4
             for (int t = 0; t < width; ++t) {
-                float rng;
-                if (d < 2) rng = (t <= dx) ? (float)t : 1e7f;
-                else rng = ((t <= dy) ? (float)t : 1e7f) * (float)width;
-                long long s = (long long)(rng + foff);
+                const float rng = ((t <= lim) ? (float)t : 1e7f) * step;  // ranges row, x width for the side strips
+                int s = (int)(rng + foff);                                 // f32 add then truncation, as torch does it
                 if (s < 0 || s > n - 1) s = n + 1;
                 const float e = E[s];
-                if (q == 0) acc += e;
-                else if (q == 1) acc += (e > a.lb) ? O[s] : kZero;
-                else acc += Sval(s);
+                float term;
+                if (q12 == 0) term = e;
+                else if (q12 == 1) term = (e > a.lb) ? O[s] : kZero;
+                else term = Sval(s);
+                acc += term;
             }
         }
-        float es0 = __shfl_sync(0xffffffffu, acc, 0), es1 = __shfl_sync(0xffffffffu, acc, 3);
-        float es2 = __shfl_sync(0xffffffffu, acc, 6), es3 = __shfl_sync(0xffffffffu, acc, 9);
+        float es0 = __shfl_sync(0xffffffffu, acc, hbase + 0), es1 = __shfl_sync(0xffffffffu, acc, hbase + 3);
+        float es2 = __shfl_sync(0xffffffffu, acc, hbase + 6), es3 = __shfl_sync(0xffffffffu, acc, hbase + 9);
         if (bd0 == 0) es0 = kZero;
         if (bd1 == height - 1) es1 = kZero;
         if (bd2 == 0) es2 = kZero;
@@ -117,7 +180,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) area_expand_kernel(ExpandArgs a
         if (es1 > mx) mx = es1, arg = 1;
         if (es2 > mx) mx = es2, arg = 2;
         if (es3 > mx) mx = es3, arg = 3;
-        const float en_arg = __shfl_sync(0xffffffffu, acc, arg * 3 + 1);
+        const float en_arg = __shfl_sync(0xffffffffu, acc, hbase + arg * 3 + 1);
         float add_sum = kZero, add_nom = kZero;
         if (mx > a.lb) {
             if (arg == 0) bd0 -= 1;
@@ -134,33 +197,32 @@ __global__ void __launch_bounds__(EX_WARPS * 32) area_expand_kernel(ExpandArgs a
 
     // ---- border strips of the final box with the previous iteration's extents (utils.py:1245-1253) ------------
     float acc = 0.f;
-    if (lane < 8) {
-        const int d = lane >> 1, q = lane & 1;
-        long long off;
-        if (d == 0) off = bd2 + bd0 * width;
-        else if (d == 1) off = bd2 + bd1 * width;
-        else if (d == 2) off = bd2 + bd0 * width;
-        else off = bd3 + bd0 * width;
-        const float foff = (float)off;
+    if (hl < 8) {
+        const int d = hl >> 1, q = hl & 1;
+        int off, lim;
+        if (d == 0) off = bd2 + bd0 * width, lim = sdx;
+        else if (d == 1) off = bd2 + bd1 * width, lim = sdx;
+        else if (d == 2) off = bd2 + bd0 * width, lim = sdy;
+        else off = bd3 + bd0 * width, lim = sdy;
+        const float foff = (float)off, step = (d < 2) ? 1.0f : fwidth;
+#pragma unroll 4
         for (int t = 0; t < width; ++t) {
-            float rng;
-            if (d < 2) rng = (t <= sdx) ? (float)t : 1e7f;
-            else rng = ((t <= sdy) ? (float)t : 1e7f) * (float)width;
-            long long s = (long long)(rng + foff);
+            const float rng = ((t <= lim) ? (float)t : 1e7f) * step;
+            int s = (int)(rng + foff);
             if (s < 0 || s > n - 1) s = n + 1;
             acc += (q == 0) ? E[s] : Sval(s);
         }
     }
-    const float e0 = __shfl_sync(0xffffffffu, acc, 0), e1 = __shfl_sync(0xffffffffu, acc, 2);
-    const float e2 = __shfl_sync(0xffffffffu, acc, 4), e3 = __shfl_sync(0xffffffffu, acc, 6);
-    const float s0 = __shfl_sync(0xffffffffu, acc, 1), s1 = __shfl_sync(0xffffffffu, acc, 3);
-    const float s2 = __shfl_sync(0xffffffffu, acc, 5), s3 = __shfl_sync(0xffffffffu, acc, 7);
+    const float e0 = __shfl_sync(0xffffffffu, acc, hbase + 0), e1 = __shfl_sync(0xffffffffu, acc, hbase + 2);
+    const float e2 = __shfl_sync(0xffffffffu, acc, hbase + 4), e3 = __shfl_sync(0xffffffffu, acc, hbase + 6);
+    const float s0 = __shfl_sync(0xffffffffu, acc, hbase + 1), s1 = __shfl_sync(0xffffffffu, acc, hbase + 3);
+    const float s2 = __shfl_sync(0xffffffffu, acc, hbase + 5), s3 = __shfl_sync(0xffffffffu, acc, hbase + 7);
     const float es4 = ((e0 + e1) + e2) + e3, ss4 = ((s0 + s1) + s2) + s3;
 
     // ---- weighted mean position / area scale inside the box (utils.py:1254-1268, 1321-1340), f64 sums ----------
     double wx = 0, wy = 0, sxs = 0, sys = 0, wsc = 0, psum = 0, ts = 0;
-    for (int p = lane; p < n; p += 32) {
-        const long long pr = p / a.grid_w, pc = p % a.grid_w;
+    for (int p = hl; p < n; p += 16) {
+        const int pr = p / a.grid_w, pc = p - pr * a.grid_w;
         const bool in = pr >= bd0 && pr <= bd1 && pc >= bd2 && pc <= bd3;
         float ox = kZero, oy = kZero;
         if (in) {
@@ -176,18 +238,18 @@ __global__ void __launch_bounds__(EX_WARPS * 32) area_expand_kernel(ExpandArgs a
         wsc += (double)(o * (SX[p] * SY[p]));
         psum += (double)o;
     }
-    for (int j = lane; j <= n; j += 32) ts += (double)E[j];
-    wx = warp_sum_f64(wx), wy = warp_sum_f64(wy), sxs = warp_sum_f64(sxs), sys = warp_sum_f64(sys);
-    wsc = warp_sum_f64(wsc), psum = warp_sum_f64(psum), ts = warp_sum_f64(ts);
+    for (int j = hl; j <= n; j += 16) ts += (double)E[j];
+    wx = half_sum_f64(wx), wy = half_sum_f64(wy), sxs = half_sum_f64(sxs), sys = half_sum_f64(sys);
+    wsc = half_sum_f64(wsc), psum = half_sum_f64(psum), ts = half_sum_f64(ts);
 
-    if (lane == 0) {
+    if (hl == 0 && row_ok) {
         const size_t r = (size_t)bb * m + i;
         a.avg[2 * r + 1] = (float)wx / (float)sxs + 0.5f;
         a.avg[2 * r + 0] = (float)wy / (float)sys + 0.5f;
         const float avg_scale = sqrtf((float)wsc / (float)psum);
         a.xs[r] = 1.0f / (avg_scale / 1.0f);
         a.ys[r] = 1.0f / (avg_scale * 1.0f);
-        long long cn[4] = {bd0 * width + bd2, bd0 * width + bd3, bd1 * width + bd2, bd1 * width + bd3};
+        int cn[4] = {bd0 * width + bd2, bd0 * width + bd3, bd1 * width + bd2, bd1 * width + bd3};
         float cps = 0.f, css = 0.f;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
@@ -206,8 +268,11 @@ __global__ void __launch_bounds__(EX_WARPS * 32) area_expand_kernel(ExpandArgs a
 }
 
 // est_position's masks (first_layer.py:162-167): row / column argmax of Z equals the dustbin index.
+// grid (b): warps take rows for nm1; for nm2 every warp scans a slab of rows for all columns (coalesced) and the
+// per-warp (max, first index) pairs are combined in shared memory.
 __global__ void __launch_bounds__(256) est_nomatching_kernel(const float *__restrict__ Z, int M, int N, int dust,
                                                              uint8_t *__restrict__ nm1, uint8_t *__restrict__ nm2) {
+    extern __shared__ float sm[];  // [8][N] max, [8][N] index
     const int bb = blockIdx.x;
     const float *z = Z + (size_t)bb * M * N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -226,12 +291,26 @@ __global__ void __launch_bounds__(256) est_nomatching_kernel(const float *__rest
         }
         if (lane == 0) nm1[(size_t)bb * (M - 1) + i] = (bi == dust);
     }
-    for (int j = threadIdx.x; j < N - 1; j += blockDim.x) {
-        float bv = z[j];
-        int bi = 0;
-        for (int i = 1; i < M; ++i) {
+    float *pmax = sm;
+    int *pidx = reinterpret_cast<int *>(sm + (size_t)nw * N);
+    const int rows_per = (M + nw - 1) / nw, r0 = warp * rows_per, r1 = min(M, r0 + rows_per);
+    for (int j = lane; j < N - 1; j += 32) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int i = r0; i < r1; ++i) {
             const float v = z[(size_t)i * N + j];
-            if (v > bv) bv = v, bi = i;
+            if (bi == 0x7fffffff || v > bv) bv = v, bi = i;
+        }
+        pmax[warp * N + j] = bv, pidx[warp * N + j] = bi;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < N - 1; j += blockDim.x) {
+        float bv = pmax[j];
+        int bi = pidx[j];
+        for (int w = 1; w < nw; ++w) {
+            const float ov = pmax[w * N + j];
+            const int oi = pidx[w * N + j];
+            if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv)) bv = ov, bi = oi;  // slabs are in row order: ties keep the earlier
         }
         nm2[(size_t)bb * (N - 1) + j] = (bi == dust);
     }
@@ -530,13 +609,14 @@ PATS_API int pats_iterative_expand_matrix_f32(const float *scores_in, const floa
     a.iters = iter_num, a.lb = lower_bound, a.log_input = 0;
     a.whole = whole_cost, a.core = core_cost, a.avg = average_point, a.xs = x_scale, a.ys = y_scale;
     a.bound = bound, a.nomatch = if_nomatching;
-    const size_t smem = sizeof(float) * (size_t)(3 + EX_WARPS) * (n + 2);
+    a.nm2 = nullptr, a.colmax = nullptr, a.counter = nullptr;
+    const size_t smem = sizeof(float) * (size_t)(4 + EX_ROWS) * (n + 2);
     if (smem > 200 * 1024) return invalid("iterative_expand_matrix: grid of %lld cells exceeds the shared-memory budget", n);
     if (smem > 48 * 1024)
         PATS_CUDA_TRY(cudaFuncSetAttribute(area_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (b > 65535) return invalid("iterative_expand_matrix: batch %d exceeds gridDim.y", b);
-    dim3 grid((m + EX_WARPS - 1) / EX_WARPS, b);
-    area_expand_kernel<<<grid, EX_WARPS * 32, smem, as_stream(stream)>>>(a);
+    dim3 grid((m + EX_ROWS - 1) / EX_ROWS, b);
+    area_expand_kernel<<<grid, EX_ROWS * 16, smem, as_stream(stream)>>>(a);
     PATS_LAUNCH_CHECK("area_expand_kernel");
     return PATS_OK;
 }
@@ -545,7 +625,11 @@ PATS_API int pats_est_nomatching_f32(const float *Z, int b, int M, int N, int du
     if (b < 0 || M < 2 || N < 2) return invalid("est_nomatching: bad sizes");
     if (b == 0) return PATS_OK;
     if (!Z || !nm1 || !nm2) return invalid("est_nomatching: null pointer");
-    est_nomatching_kernel<<<b, 256, 0, as_stream(stream)>>>(Z, M, N, dust, nm1, nm2);
+    const size_t smem = sizeof(float) * 2 * 8 * (size_t)N;
+    if (smem > 200 * 1024) return invalid("est_nomatching: N = %d exceeds the shared-memory budget", N);
+    if (smem > 48 * 1024)
+        PATS_CUDA_TRY(cudaFuncSetAttribute(est_nomatching_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    est_nomatching_kernel<<<b, 256, smem, as_stream(stream)>>>(Z, M, N, dust, nm1, nm2);
     PATS_LAUNCH_CHECK("est_nomatching_kernel");
     return PATS_OK;
 }
@@ -643,16 +727,20 @@ PATS_API int pats_est_position_f32(const float *Z, const float *scalex, const fl
     a.iters = iter_num, a.lb = lower_bound, a.log_input = 1;
     a.whole = trust_score, a.core = core_cost, a.avg = average_point, a.xs = x_scale, a.ys = y_scale;
     a.bound = bound, a.nomatch = if_nomatching1;
-    const size_t smem = sizeof(float) * (size_t)(3 + EX_WARPS) * (n + 2);
+    const size_t smem = sizeof(float) * (size_t)(4 + EX_ROWS) * (n + 2);
     if (smem > 200 * 1024) return invalid("est_position: grid of %lld cells exceeds the shared-memory budget", n);
     if (smem > 48 * 1024)
         PATS_CUDA_TRY(cudaFuncSetAttribute(area_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (b > 65535) return invalid("est_position: batch %d exceeds gridDim.y", b);
     cudaStream_t st = as_stream(stream);
-    est_nomatching_kernel<<<b, 256, 0, st>>>(Z, (int)n + 1, (int)n + 1, (int)n, nullptr, if_nomatching2);
-    PATS_LAUNCH_CHECK("est_nomatching_kernel");
-    dim3 grid(((int)n + EX_WARPS - 1) / EX_WARPS, b);
-    area_expand_kernel<<<grid, EX_WARPS * 32, smem, st>>>(a);
+    // column-argmax mask fused into the expansion kernel: encoded column maxima + per-problem arrival counters
+    const size_t ws_bytes = sizeof(unsigned) * ((size_t)b * n + b);
+    unsigned *ws = static_cast<unsigned *>(stream_workspace(st, ws_bytes));
+    if (!ws) return cuda_fail(cudaGetLastError(), "est_position workspace");
+    PATS_CUDA_TRY(cudaMemsetAsync(ws, 0, ws_bytes, st));
+    a.nm2 = if_nomatching2, a.colmax = ws, a.counter = ws + (size_t)b * n;
+    dim3 grid(((int)n + EX_ROWS - 1) / EX_ROWS, b);
+    area_expand_kernel<<<grid, EX_ROWS * 16, smem, st>>>(a);
     PATS_LAUNCH_CHECK("area_expand_kernel");
     return PATS_OK;
 }

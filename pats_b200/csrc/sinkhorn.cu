@@ -522,6 +522,266 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Level-3 kernel: exactly 65 x 65 (64 x 64 real cells + dustbin row / column), one warp per problem.
+//
+//   Lane (pr = lane>>2, qc = lane&3) keeps an 8 x 16 tile of the 64 x 64 core (128 registers, no padding).
+//   Row slot k of a lane holds logical row pr + 8*(k ^ rmask(qc)); column slot c holds logical column
+//   qc + 4*(c ^ cmask(pr)).  With these lane-dependent slot permutations the recursive-halving
+//   reduce-scatter ("keep slots [0,h), send slots [h,2h)") and the mirror all-gather need no selects:
+//       reduce:  v[t] += shfl_xor(v[t+h], bit)        gather:  v[t+h] = shfl_xor(v[t], bit)
+//   After a reduce every lane owns 2 complete row (column) sums, computes 2 scalings (2 MUFU.RCP instead of
+//   8 / 16 redundant ones) and the gather hands every lane the 8 (16) scalings of its tile.
+//   The dustbin row / column (129 values) are spread 2+2 per lane over the lanes that own the matching
+//   row / column sums; their own sums are two 5-step warp all-reduces per iteration, issued early so their
+//   latency hides under the FFMA2 stream.
+// ---------------------------------------------------------------------------------------------
+constexpr int W65_WARPS = 4;  // problems per CTA
+
+__device__ __forceinline__ void rs_rows(float (&v)[8]) {  // reduce-scatter over qc (lane bits 0,1): 8 -> 2
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] += __shfl_xor_sync(0xffffffffu, v[t + 4], 1);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) v[t] += __shfl_xor_sync(0xffffffffu, v[t + 2], 2);
+}
+__device__ __forceinline__ void ag_rows(float (&v)[8]) {  // all-gather over qc: 2 -> 8
+#pragma unroll
+    for (int t = 0; t < 2; ++t) v[t + 2] = __shfl_xor_sync(0xffffffffu, v[t], 2);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t + 4] = __shfl_xor_sync(0xffffffffu, v[t], 1);
+}
+__device__ __forceinline__ void rs_cols(float (&v)[16]) {  // reduce-scatter over pr (lane bits 2,3,4): 16 -> 2
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] += __shfl_xor_sync(0xffffffffu, v[t + 8], 4);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] += __shfl_xor_sync(0xffffffffu, v[t + 4], 8);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) v[t] += __shfl_xor_sync(0xffffffffu, v[t + 2], 16);
+}
+__device__ __forceinline__ void ag_cols(float (&v)[16]) {  // all-gather over pr: 2 -> 16
+#pragma unroll
+    for (int t = 0; t < 2; ++t) v[t + 2] = __shfl_xor_sync(0xffffffffu, v[t], 16);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t + 4] = __shfl_xor_sync(0xffffffffu, v[t], 8);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t + 8] = __shfl_xor_sync(0xffffffffu, v[t], 4);
+}
+__device__ __forceinline__ float max_over_qc(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float sum_over_qc(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+__device__ __forceinline__ float max_over_pr(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+}
+__device__ __forceinline__ float sum_over_pr(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    return v + __shfl_xor_sync(0xffffffffu, v, 16);
+}
+__device__ __forceinline__ float finite_or_zero(float m) { return (fabsf(m) == INFINITY) ? 0.f : m; }
+
+__global__ void __launch_bounds__(W65_WARPS * 32) sinkhorn_w65_kernel(SinkArgs a) {
+    constexpr int D = 64;  // dustbin index; M = N = 65
+    __shared__ float s_fb[W65_WARPS][65 + 65 + 64];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int p = blockIdx.x * W65_WARPS + wib;
+    if (p >= a.b) return;
+    const int pr = lane >> 2, qc = lane & 3;
+    const int rmask = ((qc & 1) << 2) | ((qc >> 1) << 1);
+    const int cmask = ((pr & 1) << 3) | (((pr >> 1) & 1) << 2) | ((pr >> 2) << 1);
+    const Marg g = problem_marginals(a, p, lane);
+#define LROW(k) (pr + 8 * ((k) ^ rmask))
+#define LCOL(c) (qc + 4 * ((c) ^ cmask))
+
+    // ---- load: core tile, dustbin column for my 8 rows, dustbin row for my 16 columns, corner ----------------------
+    float z[8][16], zc[8], zr[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) z[k][c] = z_at(a, g, p, LROW(k), LCOL(c));
+        zc[k] = z_at(a, g, p, LROW(k), D);
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) zr[c] = z_at(a, g, p, D, LCOL(c));
+    const float zcorner = z_at(a, g, p, D, D);
+
+    // owned rows / columns (slots 0,1 after a reduce-scatter) and their marginals
+    float mu2[2], nu2[2], u1o[2] = {0.f, 0.f}, v1o[2] = {0.f, 0.f}, u1d = 0.f, v1d = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        mu2[t] = expf(lmu_at(a, g, p, LROW(t)));
+        nu2[t] = expf(lnu_at(a, g, p, LCOL(t)));
+    }
+    const float mud = expf(lmu_at(a, g, p, D)), nud = expf(lnu_at(a, g, p, D));
+    float Dc[2] = {0.f, 0.f}, Dr[2] = {0.f, 0.f}, corner = 0.f;
+
+    // ---- iteration 1, exact in the log domain; K = exp(Z + u1 + v1) -----------------------------------------------
+    if (a.iters >= 1) {
+        float u1[8], v1[16];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // rows of the core (+ their dustbin-column entry)
+            float mx = zc[k];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) mx = fmaxf(mx, z[k][c]);
+            mx = finite_or_zero(max_over_qc(mx));
+            float sacc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) sacc += fast_exp(z[k][c] - mx);
+            sacc = sum_over_qc(sacc) + fast_exp(zc[k] - mx);
+            u1[k] = lmu_at(a, g, p, LROW(k)) - (fast_log(sacc) + mx);
+        }
+        {  // dustbin row: my 16 columns x the 4 qc lanes cover all 64 columns
+            float mx = zcorner;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) mx = fmaxf(mx, zr[c]);
+            mx = finite_or_zero(max_over_qc(mx));
+            float sacc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) sacc += fast_exp(zr[c] - mx);
+            sacc = sum_over_qc(sacc) + fast_exp(zcorner - mx);
+            u1d = lmu_at(a, g, p, D) - (fast_log(sacc) + mx);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {  // columns of the core (+ their dustbin-row entry)
+            float mx = zr[c] + u1d;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mx = fmaxf(mx, z[k][c] + u1[k]);
+            mx = finite_or_zero(max_over_pr(mx));
+            float sacc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sacc += fast_exp((z[k][c] + u1[k]) - mx);
+            sacc = sum_over_pr(sacc) + fast_exp((zr[c] + u1d) - mx);
+            v1[c] = lnu_at(a, g, p, LCOL(c)) - (fast_log(sacc) + mx);
+        }
+        {  // dustbin column: my 8 rows x the 8 pr lanes cover all 64 rows
+            float mx = zcorner + u1d;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mx = fmaxf(mx, zc[k] + u1[k]);
+            mx = finite_or_zero(max_over_pr(mx));
+            float sacc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sacc += fast_exp((zc[k] + u1[k]) - mx);
+            sacc = sum_over_pr(sacc) + fast_exp((zcorner + u1d) - mx);
+            v1d = lnu_at(a, g, p, D) - (fast_log(sacc) + mx);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) z[k][c] = fast_exp((z[k][c] + u1[k]) + v1[c]);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            Dc[t] = fast_exp((zc[t] + u1[t]) + v1d);
+            Dr[t] = fast_exp((zr[t] + u1d) + v1[t]);
+            u1o[t] = u1[t], v1o[t] = v1[t];
+        }
+        corner = fast_exp((zcorner + u1d) + v1d);
+    }
+
+    // ---- iterations 2..iters on the register tile -------------------------------------------------------------------
+    float2 Kp[8][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int h = 0; h < 8; ++h) Kp[k][h] = make_float2(z[k][2 * h], z[k][2 * h + 1]);
+    float be[16], al[8];  // beta of my 16 column slots, alpha of my 8 row slots
+#pragma unroll
+    for (int c = 0; c < 16; ++c) be[c] = 1.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) al[k] = 1.f;
+    float ald = 1.f, bed = 1.f;
+    float Sr = warp_sum(Dr[0] + Dr[1]);  // sum_j K[D][j] beta_j with beta = 1
+    float lo = INFINITY, hi = 0.f;
+
+    for (int it = 1; it < a.iters; ++it) {
+        // alpha_i = mu_i / sum_j K_ij beta_j
+        float2 acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const float2 bp = make_float2(be[2 * h], be[2 * h + 1]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = ffma2(Kp[k][h], bp, acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) al[k] = acc[k].x + acc[k].y;
+        rs_rows(al);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) al[t] = mu2[t] * fast_rcp(fmaf(Dc[t], bed, al[t]));
+        ald = mud * fast_rcp(fmaf(corner, bed, Sr));
+        float Sc = warp_sum(fmaf(Dc[0], al[0], Dc[1] * al[1]));  // sum_i K[i][D] alpha_i (hidden under the column pass)
+        const float al0 = al[0], al1 = al[1];
+        ag_rows(al);
+        // beta_j = nu_j / sum_i K_ij alpha_i
+        float2 s2[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) s2[h] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float2 ak = make_float2(al[k], al[k]);
+#pragma unroll
+            for (int h = 0; h < 8; ++h) s2[h] = ffma2(Kp[k][h], ak, s2[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < 8; ++h) be[2 * h] = s2[h].x, be[2 * h + 1] = s2[h].y;
+        rs_cols(be);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) be[t] = nu2[t] * fast_rcp(fmaf(Dr[t], ald, be[t]));
+        bed = nud * fast_rcp(fmaf(corner, ald, Sc));
+        Sr = warp_sum(fmaf(Dr[0], be[0], Dr[1] * be[1]));
+        if ((it & 7) == 0 || it == a.iters - 1) {
+            lo = fminf(fminf(fminf(lo, al0), fminf(al1, ald)), fminf(fminf(be[0], be[1]), bed));
+            hi = fmaxf(fmaxf(fmaxf(hi, al0), fmaxf(al1, ald)), fmaxf(fmaxf(be[0], be[1]), bed));
+        }
+        if (it == a.iters - 1) al[0] = al0, al[1] = al1;  // keep the owned alphas in slots 0,1 for the epilogue
+        ag_cols(be);
+    }
+
+    // ---- potentials, health check, output ------------------------------------------------------------------------------
+    const float shift = (a.mode == MODE_RAW) ? 0.f : g.norm;
+    float U[8], V[16], Ud = 0.f, Vd = -shift;
+    bool bad = !(lo >= 1e-13f && hi <= 1e13f);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        float tu = 0.f, tv = 0.f;
+        if (a.iters >= 1) tu = u1o[t], tv = v1o[t];
+        if (a.iters >= 2) tu += fast_log(al[t]), tv += fast_log(be[t]);
+        if (!(fabsf(tu) < INFINITY) || !(fabsf(tv) < INFINITY)) bad = true;
+        U[t] = tu, V[t] = tv - shift;
+    }
+    if (a.iters >= 1) Ud = u1d, Vd = v1d - shift;
+    if (a.iters >= 2) Ud += fast_log(ald), Vd += fast_log(bed);
+    if (!(fabsf(Ud) < INFINITY) || !(fabsf(Vd) < INFINITY)) bad = true;
+    if (__any_sync(0xffffffffu, bad)) {
+        if (lane == 0 && a.fb_total) atomicAdd(a.fb_total, 1);
+        log_domain_solve<32>(a, g, p, s_fb[wib], s_fb[wib] + 65, s_fb[wib] + 130, lane, WarpSync());
+        return;
+    }
+    ag_rows(U);
+    ag_cols(V);
+    float *o = a.out + (size_t)p * 65 * 65;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int row = LROW(k);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[row * 65 + LCOL(c)] = (z_at(a, g, p, row, LCOL(c)) + U[k]) + V[c];
+        if (qc == 0) o[row * 65 + D] = (z_at(a, g, p, row, D) + U[k]) + Vd;
+    }
+    if (pr == 0) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) o[D * 65 + LCOL(c)] = (z_at(a, g, p, D, LCOL(c)) + Ud) + V[c];
+    }
+    if (lane == 0) o[D * 65 + D] = (z_at(a, g, p, D, D) + Ud) + Vd;
+#undef LROW
+#undef LCOL
+}
+
 // ---- host dispatch ------------------------------------------------------------------------------
 using CfgTiny = RegCfg<1, 2, 4, 8, 4>;         // <= 32 x 32, one warp per problem, 4 problems per CTA
 using CfgWarp = RegCfg<1, 2, 9, 17, 4>;        // <= 72 x 68  (level 3: 65 x 65)
@@ -530,6 +790,7 @@ using CfgCl320 = RegCfg<8, 5, 5, 10, 1, 8>;    // <= 320 x 320 (level 1: 301 x 3
 using CfgCl512 = RegCfg<16, 5, 4, 16, 1, 8>;   // <= 512 x 512, cluster of 8 CTAs x 512 threads
 
 static int g_force_generic = 0;
+static int g_disable_w65 = 0;  // tests: route 65 x 65 through the padded warp kernel instead
 static int *g_fb_total = nullptr;  // device counter
 static std::mutex g_mu;
 
@@ -608,6 +869,11 @@ static int run_sinkhorn(SinkArgs a, void *stream) {
     cudaStream_t st = as_stream(stream);
     switch (kernel_kind(a.M, a.N)) {
         case 0:
+            if (a.M == 65 && a.N == 65 && !g_disable_w65) {
+                sinkhorn_w65_kernel<<<(a.b + W65_WARPS - 1) / W65_WARPS, W65_WARPS * 32, 0, st>>>(a);
+                PATS_LAUNCH_CHECK("sinkhorn_w65_kernel");
+                return PATS_OK;
+            }
             if (a.M <= CfgTiny::MAXM && a.N <= CfgTiny::MAXN) return launch_reg<CfgTiny>(a, st);
             return launch_reg<CfgWarp>(a, st);
         case 1:
@@ -647,6 +913,7 @@ PATS_API int pats_log_optimal_transport2_f32(const float *scores, const float *o
 
 PATS_API int pats_sinkhorn_kernel_kind(int M, int N) { return kernel_kind(M, N); }
 PATS_API void pats_sinkhorn_force_generic(int on) { g_force_generic = on ? 1 : 0; }
+PATS_API void pats_sinkhorn_disable_w65(int on) { g_disable_w65 = on ? 1 : 0; }
 
 PATS_API int pats_sinkhorn_fallback_count(int reset) {
     if (ensure_counter() != PATS_OK) return -1;

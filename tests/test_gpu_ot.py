@@ -184,6 +184,34 @@ def test_extreme_dynamic_range_takes_the_log_domain_fallback(M, lib, dev):
     assert n_fb < b, "well-conditioned problems must stay on the fast path"
 
 
+def test_padded_warp_kernel_still_matches_on_65x65(M, lib, dev):
+    """65 x 65 normally runs on the specialised level-3 kernel; the padded 72 x 68 warp kernel must agree with it
+    (and with the oracle) on the same problems, for every entry point that can produce a 65 x 65 plan."""
+    g = torch.Generator().manual_seed(6200)
+    b = 21
+    s = (0.3 * torch.randn(b, 65, 65, generator=g))
+    ns = areas(g, b, 64, 16.0)
+    ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), 100)
+    fast = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), 100)
+    lib.pats_sinkhorn_disable_w65(1)
+    try:
+        padded = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), 100)
+    finally:
+        lib.pats_sinkhorn_disable_w65(0)
+    assert_plan_equal(fast.cpu().numpy(), ref)
+    assert_plan_equal(padded.cpu().numpy(), ref)
+    # augmenting transport with m = n = 64 and the raw iteration also land on the 65 x 65 kernel
+    s64 = 0.2 * torch.randn(5, 64, 64, generator=g)
+    ns64 = areas(g, 5, 64, 16.0)
+    out = M.log_optimal_transport(s64.to(dev), 0.8, ns64.to(dev), 100).cpu().numpy()
+    assert_plan_equal(out, oracle.log_optimal_transport(s64.numpy(), 0.8, ns64.numpy(), 100))
+    Z = 0.5 * torch.randn(4, 65, 65, generator=g)
+    lmu = torch.log_softmax(torch.randn(4, 65, generator=g), 1)
+    lnu = torch.log_softmax(torch.randn(4, 65, generator=g), 1)
+    out = M.log_sinkhorn_iterations(Z.to(dev), lmu.to(dev), lnu.to(dev), 37).cpu().numpy()
+    np.testing.assert_allclose(out, oracle.log_sinkhorn_iterations(Z.numpy(), lmu.numpy(), lnu.numpy(), 37), atol=TOL, rtol=0)
+
+
 def test_cluster_kernel_fallback(M, lib, dev):
     """Same as above for the 8-CTA cluster kernel: the cluster must agree on the verdict and rank 0 re-solves."""
     g = torch.Generator().manual_seed(6100)
