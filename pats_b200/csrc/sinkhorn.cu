@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(GT) sinkhorn_generic_kernel(SinkArgs a) {
 // ---------------------------------------------------------------------------------------------
 //   With CL > 1 the problem is split by rows over the CL CTAs of a cluster: CTA `rank` owns rows
 //   rank*PR*RT + pr + PR*k.  Row sums stay inside a CTA; column sums are pushed into every CTA's shared
-//   memory (DSMEM), one cluster barrier per reduction, double-buffered by call parity.
+//   memory (DSMEM) as a reduce-scatter + broadcast over the cluster (two cluster barriers per reduction).
 template <int WARPS_, int QC_LOG2_, int RT_, int CT_, int GROUPS_, int CL_ = 1>
 struct RegCfg {
     static constexpr int W = WARPS_, QCL = QC_LOG2_, RT = RT_, CT = CT_, GROUPS = GROUPS_, CL = CL_;
@@ -213,8 +213,8 @@ struct Smem {
     static constexpr int V1 = U1 + C::GROUPS * C::ROWS;            // [GROUPS][MAXN]
     static constexpr int PART = V1 + C::GROUPS * C::MAXN;          // [W][MAXN]       per-warp column partials
     static constexpr int TOT = PART + (C::BLOCK ? C::W * C::MAXN : 0);   // [MAXN]
-    static constexpr int XBUF = TOT + (C::BLOCK ? C::MAXN : 0);          // [2][CL][MAXN]   cluster exchange
-    static constexpr int XFLAG = XBUF + (C::CL > 1 ? 2 * C::CL * C::MAXN : 0);  // [CL]
+    static constexpr int XBUF = TOT + (C::BLOCK ? C::MAXN : 0);          // [CL][MAXN/CL]   cluster exchange (slice partials)
+    static constexpr int XFLAG = XBUF + (C::CL > 1 ? C::MAXN : 0);  // [CL]
     static constexpr int FB = XFLAG + (C::CL > 1 ? C::CL : 0);     // fallback scratch: u[MAXM], v[MAXN], red[2*GT] per group
     static constexpr int FB_PER = C::MAXM + C::MAXN + 2 * C::GT;
     static constexpr int FLOATS = FB + C::GROUPS * FB_PER;
@@ -274,23 +274,36 @@ __device__ __forceinline__ void col_reduce(float (&v)[C::CT], Op op, float *sm, 
             s_tot[j] = SCALE ? s_nu[j] * fast_rcp(t) : t;
         }
     } else {
+        // reduce-scatter + broadcast across the cluster: CTA r owns the column slice [r*SL, (r+1)*SL).
+        //   1. every CTA sends its partial sums of slice r to CTA r              (MAXN remote stores per CTA)
+        //   2. CTA r adds the CL partials of its slice in rank order, applies the scaling, and
+        //   3. writes the finished slice into every CTA's s_tot                  (MAXN remote stores per CTA)
+        // Two cluster barriers order (1)->(2) and (3)->readers; they also fence buffer reuse between calls.
         cg::cluster_group cluster = cg::this_cluster();
-        float *xb = sm + Smem<C>::XBUF + parity * C::CL * C::MAXN;
+        constexpr int SL = C::MAXN / C::CL;
+        static_assert(SL * C::CL == C::MAXN, "column slices must tile the padded width");
+        float *xb = sm + Smem<C>::XBUF;
         for (int j = gtid; j < C::MAXN; j += C::GT) {
             float t = s_part[j];
 #pragma unroll
             for (int w = 1; w < C::W; ++w) t = op(t, s_part[w * C::MAXN + j]);
-#pragma unroll
-            for (int r = 0; r < C::CL; ++r) cluster.map_shared_rank(xb, r)[rank * C::MAXN + j] = t;
+            const int dst = j / SL;
+            cluster.map_shared_rank(xb, dst)[rank * SL + (j - dst * SL)] = t;
         }
         cluster.sync();
-        for (int j = gtid; j < C::MAXN; j += C::GT) {
-            float t = xb[j];
+        for (int jj = gtid; jj < SL; jj += C::GT) {
+            float t = xb[jj];
 #pragma unroll
-            for (int r = 1; r < C::CL; ++r) t = op(t, xb[r * C::MAXN + j]);
-            s_tot[j] = SCALE ? s_nu[j] * fast_rcp(t) : t;
+            for (int r = 1; r < C::CL; ++r) t = op(t, xb[r * SL + jj]);
+            const int col = (int)rank * SL + jj;
+            const float val = SCALE ? s_nu[col] * fast_rcp(t) : t;
+#pragma unroll
+            for (int r = 0; r < C::CL; ++r) cluster.map_shared_rank(s_tot, r)[col] = val;
         }
-        parity ^= 1;
+        cluster.sync();
+#pragma unroll
+        for (int c = 0; c < C::CT; ++c) v[c] = s_tot[qc + C::QC * c];
+        return;
     }
     __syncthreads();
 #pragma unroll
@@ -538,26 +551,30 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
 // ---------------------------------------------------------------------------------------------
 constexpr int W65_WARPS = 4;  // problems per CTA
 
-__device__ __forceinline__ void rs_rows(float (&v)[8]) {  // reduce-scatter over qc (lane bits 0,1): 8 -> 2
+template <class Op>
+__device__ __forceinline__ void rs_rows_op(float (&v)[8], Op op) {  // reduce-scatter over qc (lane bits 0,1): 8 -> 2
 #pragma unroll
-    for (int t = 0; t < 4; ++t) v[t] += __shfl_xor_sync(0xffffffffu, v[t + 4], 1);
+    for (int t = 0; t < 4; ++t) v[t] = op(v[t], __shfl_xor_sync(0xffffffffu, v[t + 4], 1));
 #pragma unroll
-    for (int t = 0; t < 2; ++t) v[t] += __shfl_xor_sync(0xffffffffu, v[t + 2], 2);
+    for (int t = 0; t < 2; ++t) v[t] = op(v[t], __shfl_xor_sync(0xffffffffu, v[t + 2], 2));
 }
+__device__ __forceinline__ void rs_rows(float (&v)[8]) { rs_rows_op(v, OpSum()); }
 __device__ __forceinline__ void ag_rows(float (&v)[8]) {  // all-gather over qc: 2 -> 8
 #pragma unroll
     for (int t = 0; t < 2; ++t) v[t + 2] = __shfl_xor_sync(0xffffffffu, v[t], 2);
 #pragma unroll
     for (int t = 0; t < 4; ++t) v[t + 4] = __shfl_xor_sync(0xffffffffu, v[t], 1);
 }
-__device__ __forceinline__ void rs_cols(float (&v)[16]) {  // reduce-scatter over pr (lane bits 2,3,4): 16 -> 2
+template <class Op>
+__device__ __forceinline__ void rs_cols_op(float (&v)[16], Op op) {  // reduce-scatter over pr (lane bits 2,3,4): 16 -> 2
 #pragma unroll
-    for (int t = 0; t < 8; ++t) v[t] += __shfl_xor_sync(0xffffffffu, v[t + 8], 4);
+    for (int t = 0; t < 8; ++t) v[t] = op(v[t], __shfl_xor_sync(0xffffffffu, v[t + 8], 4));
 #pragma unroll
-    for (int t = 0; t < 4; ++t) v[t] += __shfl_xor_sync(0xffffffffu, v[t + 4], 8);
+    for (int t = 0; t < 4; ++t) v[t] = op(v[t], __shfl_xor_sync(0xffffffffu, v[t + 4], 8));
 #pragma unroll
-    for (int t = 0; t < 2; ++t) v[t] += __shfl_xor_sync(0xffffffffu, v[t + 2], 16);
+    for (int t = 0; t < 2; ++t) v[t] = op(v[t], __shfl_xor_sync(0xffffffffu, v[t + 2], 16));
 }
+__device__ __forceinline__ void rs_cols(float (&v)[16]) { rs_cols_op(v, OpSum()); }
 __device__ __forceinline__ void ag_cols(float (&v)[16]) {  // all-gather over pr: 2 -> 16
 #pragma unroll
     for (int t = 0; t < 2; ++t) v[t + 2] = __shfl_xor_sync(0xffffffffu, v[t], 16);
@@ -565,24 +582,6 @@ __device__ __forceinline__ void ag_cols(float (&v)[16]) {  // all-gather over pr
     for (int t = 0; t < 4; ++t) v[t + 4] = __shfl_xor_sync(0xffffffffu, v[t], 8);
 #pragma unroll
     for (int t = 0; t < 8; ++t) v[t + 8] = __shfl_xor_sync(0xffffffffu, v[t], 4);
-}
-__device__ __forceinline__ float max_over_qc(float v) {
-    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
-    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
-}
-__device__ __forceinline__ float sum_over_qc(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    return v + __shfl_xor_sync(0xffffffffu, v, 2);
-}
-__device__ __forceinline__ float max_over_pr(float v) {
-    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
-    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
-    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
-}
-__device__ __forceinline__ float sum_over_pr(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    return v + __shfl_xor_sync(0xffffffffu, v, 16);
 }
 __device__ __forceinline__ float finite_or_zero(float m) { return (fabsf(m) == INFINITY) ? 0.f : m; }
 
@@ -599,16 +598,20 @@ __global__ void __launch_bounds__(W65_WARPS * 32) sinkhorn_w65_kernel(SinkArgs a
 #define LROW(k) (pr + 8 * ((k) ^ rmask))
 #define LCOL(c) (qc + 4 * ((c) ^ cmask))
 
-    // ---- load: core tile, dustbin column for my 8 rows, dustbin row for my 16 columns, corner ----------------------
-    float z[8][16], zc[8], zr[16];
+    // ---- load: core tile; dustbin column / row entries of the 2 rows / 2 columns this lane owns; corner --------------
+    // (slots 0,1 are the rows / columns whose complete sums land on this lane after a reduce-scatter; over the warp they
+    //  cover all 64 rows / columns exactly once)
+    float z[8][16], zc[2], zr[2];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) z[k][c] = z_at(a, g, p, LROW(k), LCOL(c));
-        zc[k] = z_at(a, g, p, LROW(k), D);
     }
 #pragma unroll
-    for (int c = 0; c < 16; ++c) zr[c] = z_at(a, g, p, D, LCOL(c));
+    for (int t = 0; t < 2; ++t) {
+        zc[t] = z_at(a, g, p, LROW(t), D);
+        zr[t] = z_at(a, g, p, D, LCOL(t));
+    }
     const float zcorner = z_at(a, g, p, D, D);
 
     // owned rows / columns (slots 0,1 after a reduce-scatter) and their marginals
@@ -623,52 +626,72 @@ __global__ void __launch_bounds__(W65_WARPS * 32) sinkhorn_w65_kernel(SinkArgs a
 
     // ---- iteration 1, exact in the log domain; K = exp(Z + u1 + v1) -----------------------------------------------
     if (a.iters >= 1) {
+        // NOTE: slot k of different lanes holds different logical rows, so every cross-lane combination goes through
+        // the slot-aware reduce-scatter / all-gather (never a plain same-slot butterfly).
         float u1[8], v1[16];
+        {  // rows: u1_i = log mu_i - LSE_j Z_ij
+            float mx[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // rows of the core (+ their dustbin-column entry)
-            float mx = zc[k];
+            for (int k = 0; k < 8; ++k) {
+                float m = z[k][0];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) mx = fmaxf(mx, z[k][c]);
-            mx = finite_or_zero(max_over_qc(mx));
-            float sacc = 0.f;
+                for (int c = 1; c < 16; ++c) m = fmaxf(m, z[k][c]);
+                mx[k] = m;
+            }
+            rs_rows_op(mx, OpMax());
 #pragma unroll
-            for (int c = 0; c < 16; ++c) sacc += fast_exp(z[k][c] - mx);
-            sacc = sum_over_qc(sacc) + fast_exp(zc[k] - mx);
-            u1[k] = lmu_at(a, g, p, LROW(k)) - (fast_log(sacc) + mx);
+            for (int t = 0; t < 2; ++t) mx[t] = finite_or_zero(fmaxf(mx[t], zc[t]));
+            ag_rows(mx);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 16; ++c) sacc += fast_exp(z[k][c] - mx[k]);
+                u1[k] = sacc;
+            }
+            rs_rows(u1);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const float sacc = u1[t] + fast_exp(zc[t] - mx[t]);
+                u1[t] = lmu_at(a, g, p, LROW(t)) - (fast_log(sacc) + mx[t]);
+            }
+            ag_rows(u1);
+            // dustbin row: every column is owned (slot 0/1) by exactly one lane
+            const float m = finite_or_zero(fmaxf(warp_max(fmaxf(zr[0], zr[1])), zcorner));
+            const float sacc = warp_sum(fast_exp(zr[0] - m) + fast_exp(zr[1] - m)) + fast_exp(zcorner - m);
+            u1d = lmu_at(a, g, p, D) - (fast_log(sacc) + m);
         }
-        {  // dustbin row: my 16 columns x the 4 qc lanes cover all 64 columns
-            float mx = zcorner;
+        {  // columns: v1_j = log nu_j - LSE_i (Z_ij + u1_i)
+            float mx[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) mx = fmaxf(mx, zr[c]);
-            mx = finite_or_zero(max_over_qc(mx));
-            float sacc = 0.f;
+            for (int c = 0; c < 16; ++c) {
+                float m = z[0][c] + u1[0];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) sacc += fast_exp(zr[c] - mx);
-            sacc = sum_over_qc(sacc) + fast_exp(zcorner - mx);
-            u1d = lmu_at(a, g, p, D) - (fast_log(sacc) + mx);
-        }
+                for (int k = 1; k < 8; ++k) m = fmaxf(m, z[k][c] + u1[k]);
+                mx[c] = m;
+            }
+            rs_cols_op(mx, OpMax());
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {  // columns of the core (+ their dustbin-row entry)
-            float mx = zr[c] + u1d;
+            for (int t = 0; t < 2; ++t) mx[t] = finite_or_zero(fmaxf(mx[t], zr[t] + u1d));
+            ag_cols(mx);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) mx = fmaxf(mx, z[k][c] + u1[k]);
-            mx = finite_or_zero(max_over_pr(mx));
-            float sacc = 0.f;
+            for (int c = 0; c < 16; ++c) {
+                float sacc = 0.f;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sacc += fast_exp((z[k][c] + u1[k]) - mx);
-            sacc = sum_over_pr(sacc) + fast_exp((zr[c] + u1d) - mx);
-            v1[c] = lnu_at(a, g, p, LCOL(c)) - (fast_log(sacc) + mx);
-        }
-        {  // dustbin column: my 8 rows x the 8 pr lanes cover all 64 rows
-            float mx = zcorner + u1d;
+                for (int k = 0; k < 8; ++k) sacc += fast_exp((z[k][c] + u1[k]) - mx[c]);
+                v1[c] = sacc;
+            }
+            rs_cols(v1);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) mx = fmaxf(mx, zc[k] + u1[k]);
-            mx = finite_or_zero(max_over_pr(mx));
-            float sacc = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) sacc += fast_exp((zc[k] + u1[k]) - mx);
-            sacc = sum_over_pr(sacc) + fast_exp((zcorner + u1d) - mx);
-            v1d = lnu_at(a, g, p, D) - (fast_log(sacc) + mx);
+            for (int t = 0; t < 2; ++t) {
+                const float sacc = v1[t] + fast_exp((zr[t] + u1d) - mx[t]);
+                v1[t] = lnu_at(a, g, p, LCOL(t)) - (fast_log(sacc) + mx[t]);
+            }
+            ag_cols(v1);
+            // dustbin column: every row is owned by exactly one lane
+            const float m = finite_or_zero(fmaxf(warp_max(fmaxf(zc[0] + u1[0], zc[1] + u1[1])), zcorner + u1d));
+            const float sacc = warp_sum(fast_exp((zc[0] + u1[0]) - m) + fast_exp((zc[1] + u1[1]) - m)) + fast_exp((zcorner + u1d) - m);
+            v1d = lnu_at(a, g, p, D) - (fast_log(sacc) + m);
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k)
