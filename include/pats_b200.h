@@ -64,8 +64,9 @@ int pats_log_optimal_transport2_f32(const float *scores, const float *one, const
 int pats_sinkhorn_kernel_kind(int M, int N);
 /* Force the generic log-domain kernel for every shape (tests: exercises the fallback path). */
 void pats_sinkhorn_force_generic(int on);
-/* Route 65 x 65 problems through the padded 72 x 68 warp kernel instead of the specialised 65 x 65 kernel (tests). */
-void pats_sinkhorn_disable_w65(int on);
+/* Routing of 65 x 65 problems (tests / A-B timing): 0 = two warps per problem (default), 1 = padded 72 x 68 warp
+ * kernel, 2 = one-warp 65 x 65 kernel. */
+void pats_sinkhorn_disable_w65(int mode);
 /* Problems the register-resident kernels handed to the log-domain fallback since the last reset
  * (device counter, read with a synchronising copy; tests / diagnostics only). */
 int pats_sinkhorn_fallback_count(int reset);

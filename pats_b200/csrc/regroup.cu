@@ -156,10 +156,10 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
             else if (d12 == 2) off = bd2 + bd0 * width - 1, lim = dy;
             else off = bd3 + bd0 * width + 1, lim = dy;
             const float foff = (float)off, step = (d12 < 2) ? 1.0f : fwidth;
-#pragma unroll 4
-            for (int t = 0; t < width; ++t) {
-                const float rng = ((t <= lim) ? (float)t : 1e7f) * step;  // ranges row, x width for the side strips
-                int s = (int)(rng + foff);                                 // f32 add then truncation, as torch does it
+            const int live = min(lim + 1, width);  // strip cells inside the current extent
+#pragma unroll 2
+            for (int t = 0; t < live; ++t) {
+                int s = (int)((float)t * step + foff);  // f32 multiply-add in two roundings, then truncation, as torch does it
                 if (s < 0 || s > n - 1) s = n + 1;
                 const float e = E[s];
                 float term;
@@ -168,6 +168,9 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
                 else term = Sval(s);
                 acc += term;
             }
+            // beyond the extent ranges[] holds 1e7 -> index n+1 -> every quantity contributes exactly `zero`
+            // (E = 1e-14 is never > lower_bound); keep the reference's additions, one FADD each
+            for (int t = live; t < width; ++t) acc += kZero;
         }
         float es0 = __shfl_sync(0xffffffffu, acc, hbase + 0), es1 = __shfl_sync(0xffffffffu, acc, hbase + 3);
         float es2 = __shfl_sync(0xffffffffu, acc, hbase + 6), es3 = __shfl_sync(0xffffffffu, acc, hbase + 9);
@@ -205,13 +208,14 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
         else if (d == 2) off = bd2 + bd0 * width, lim = sdy;
         else off = bd3 + bd0 * width, lim = sdy;
         const float foff = (float)off, step = (d < 2) ? 1.0f : fwidth;
-#pragma unroll 4
-        for (int t = 0; t < width; ++t) {
-            const float rng = ((t <= lim) ? (float)t : 1e7f) * step;
-            int s = (int)(rng + foff);
+        const int live = min(lim + 1, width);
+#pragma unroll 2
+        for (int t = 0; t < live; ++t) {
+            int s = (int)((float)t * step + foff);
             if (s < 0 || s > n - 1) s = n + 1;
             acc += (q == 0) ? E[s] : Sval(s);
         }
+        for (int t = live; t < width; ++t) acc += kZero;
     }
     const float e0 = __shfl_sync(0xffffffffu, acc, hbase + 0), e1 = __shfl_sync(0xffffffffu, acc, hbase + 2);
     const float e2 = __shfl_sync(0xffffffffu, acc, hbase + 4), e3 = __shfl_sync(0xffffffffu, acc, hbase + 6);
@@ -221,8 +225,9 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
 
     // ---- weighted mean position / area scale inside the box (utils.py:1254-1268, 1321-1340), f64 sums ----------
     double wx = 0, wy = 0, sxs = 0, sys = 0, wsc = 0, psum = 0, ts = 0;
-    for (int p = hl; p < n; p += 16) {
-        const int pr = p / a.grid_w, pc = p - pr * a.grid_w;
+    int pr = hl / a.grid_w, pc = hl - pr * a.grid_w;
+    for (int p = hl; p < n; p += 16, pc += 16) {
+        while (pc >= a.grid_w) pc -= a.grid_w, ++pr;
         const bool in = pr >= bd0 && pr <= bd1 && pc >= bd2 && pc <= bd3;
         float ox = kZero, oy = kZero;
         if (in) {

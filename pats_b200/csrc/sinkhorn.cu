@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(GT) sinkhorn_generic_kernel(SinkArgs a) {
 // ---------------------------------------------------------------------------------------------
 //   With CL > 1 the problem is split by rows over the CL CTAs of a cluster: CTA `rank` owns rows
 //   rank*PR*RT + pr + PR*k.  Row sums stay inside a CTA; column sums are pushed into every CTA's shared
-//   memory (DSMEM) as a reduce-scatter + broadcast over the cluster (two cluster barriers per reduction).
+//   memory (DSMEM) as a reduce-scatter + broadcast over the cluster: st.async stores that complete bytes on the
+//   receiver's mbarrier (no cluster barrier, no MEMBAR in the iteration loop).
 template <int WARPS_, int QC_LOG2_, int RT_, int CT_, int GROUPS_, int CL_ = 1>
 struct RegCfg {
     static constexpr int W = WARPS_, QCL = QC_LOG2_, RT = RT_, CT = CT_, GROUPS = GROUPS_, CL = CL_;
@@ -213,8 +214,10 @@ struct Smem {
     static constexpr int V1 = U1 + C::GROUPS * C::ROWS;            // [GROUPS][MAXN]
     static constexpr int PART = V1 + C::GROUPS * C::MAXN;          // [W][MAXN]       per-warp column partials
     static constexpr int TOT = PART + (C::BLOCK ? C::W * C::MAXN : 0);   // [MAXN]
-    static constexpr int XBUF = TOT + (C::BLOCK ? C::MAXN : 0);          // [CL][MAXN/CL]   cluster exchange (slice partials)
-    static constexpr int XFLAG = XBUF + (C::CL > 1 ? C::MAXN : 0);  // [CL]
+    static constexpr int XBUF = TOT + (C::BLOCK ? C::MAXN : 0);          // [2][CL][MAXN/CL] cluster exchange: slice partials
+    static constexpr int TOTB = XBUF + (C::CL > 1 ? 2 * C::MAXN : 0);    // [2][MAXN]        cluster exchange: finished values
+    static constexpr int MBAR = (TOTB + (C::CL > 1 ? 2 * C::MAXN : 0) + 3) & ~3;  // 4 mbarriers (8 B each), 16-B aligned
+    static constexpr int XFLAG = MBAR + (C::CL > 1 ? 8 : 0);       // [CL]
     static constexpr int FB = XFLAG + (C::CL > 1 ? C::CL : 0);     // fallback scratch: u[MAXM], v[MAXN], red[2*GT] per group
     static constexpr int FB_PER = C::MAXM + C::MAXN + 2 * C::GT;
     static constexpr int FLOATS = FB + C::GROUPS * FB_PER;
@@ -240,6 +243,39 @@ struct OpSum {
 struct OpMax {
     __device__ __forceinline__ float operator()(float x, float y) const { return fmaxf(x, y); }
 };
+
+// ---- DSMEM exchange primitives: st.async (SASS STAS) completes bytes on the RECEIVER's mbarrier, so the steady state
+//      needs no cluster barrier and no MEMBAR (cooperative_groups' cluster.sync() costs MEMBAR.ALL.GPU + CCTL.IVALL). ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_f32(unsigned remote_addr, float v, unsigned remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "r"(__float_as_uint(v)), "r"(remote_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned mb, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mb, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mb, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(mb),
+        "r"(parity)
+        : "memory");
+}
 
 // Column all-reduce over every row group of the problem (lanes, then warps through smem, then the CTAs
 // of the cluster through DSMEM).  SCALE: the reducing thread turns a total t of column j into
@@ -274,35 +310,48 @@ __device__ __forceinline__ void col_reduce(float (&v)[C::CT], Op op, float *sm, 
             s_tot[j] = SCALE ? s_nu[j] * fast_rcp(t) : t;
         }
     } else {
-        // reduce-scatter + broadcast across the cluster: CTA r owns the column slice [r*SL, (r+1)*SL).
-        //   1. every CTA sends its partial sums of slice r to CTA r              (MAXN remote stores per CTA)
-        //   2. CTA r adds the CL partials of its slice in rank order, applies the scaling, and
-        //   3. writes the finished slice into every CTA's s_tot                  (MAXN remote stores per CTA)
-        // Two cluster barriers order (1)->(2) and (3)->readers; they also fence buffer reuse between calls.
-        cg::cluster_group cluster = cg::this_cluster();
+        // reduce-scatter + broadcast across the cluster over DSMEM, synchronised by mbarriers (no cluster barrier):
+        //   1. every CTA st.async's its partial sums of column slice r to CTA r      -> completes bytes on r's mb_x
+        //   2. CTA r waits on mb_x, adds the CL partials of its slice in rank order, applies the scaling and
+        //      st.async's the finished slice into every CTA's tot buffer             -> completes bytes on their mb_t
+        //   3. every thread waits on mb_t and reads its columns.
+        // Buffers and barriers are double-buffered by call parity; a CTA cannot run two calls ahead of any other
+        // (step 3 of call n+1 needs every CTA's step 2 of call n+1), which orders all buffer reuse.
         constexpr int SL = C::MAXN / C::CL;
         static_assert(SL * C::CL == C::MAXN, "column slices must tile the padded width");
-        float *xb = sm + Smem<C>::XBUF;
+        const int q = parity & 1;
+        const unsigned phase = (unsigned)(parity >> 1) & 1u;
+        float *xb = sm + Smem<C>::XBUF + q * C::MAXN;     // [CL][SL] partials of my slice, one row per sender
+        float *tb = sm + Smem<C>::TOTB + q * C::MAXN;     // [MAXN] finished values
+        const unsigned mb_x = smem_u32(sm + Smem<C>::MBAR) + 16u * q, mb_t = mb_x + 8u;
+        if (gtid == 0) {
+            mbar_expect_tx(mb_x, (unsigned)(C::MAXN * sizeof(float)));
+            mbar_expect_tx(mb_t, (unsigned)(C::MAXN * sizeof(float)));
+        }
         for (int j = gtid; j < C::MAXN; j += C::GT) {
             float t = s_part[j];
 #pragma unroll
             for (int w = 1; w < C::W; ++w) t = op(t, s_part[w * C::MAXN + j]);
-            const int dst = j / SL;
-            cluster.map_shared_rank(xb, dst)[rank * SL + (j - dst * SL)] = t;
+            const unsigned dst = (unsigned)(j / SL);
+            st_async_f32(mapa_u32(smem_u32(xb + rank * SL + (j - (int)dst * SL)), dst), t, mapa_u32(mb_x, dst));
         }
-        cluster.sync();
-        for (int jj = gtid; jj < SL; jj += C::GT) {
-            float t = xb[jj];
+        if (gtid < SL) {
+            mbar_wait(mb_x, phase);
+            for (int jj = gtid; jj < SL; jj += C::GT) {
+                float t = xb[jj];
 #pragma unroll
-            for (int r = 1; r < C::CL; ++r) t = op(t, xb[r * SL + jj]);
-            const int col = (int)rank * SL + jj;
-            const float val = SCALE ? s_nu[col] * fast_rcp(t) : t;
+                for (int r = 1; r < C::CL; ++r) t = op(t, xb[r * SL + jj]);
+                const int col = (int)rank * SL + jj;
+                const float val = SCALE ? s_nu[col] * fast_rcp(t) : t;
+                const unsigned a_loc = smem_u32(tb + col);
 #pragma unroll
-            for (int r = 0; r < C::CL; ++r) cluster.map_shared_rank(s_tot, r)[col] = val;
+                for (unsigned r = 0; r < (unsigned)C::CL; ++r) st_async_f32(mapa_u32(a_loc, r), val, mapa_u32(mb_t, r));
+            }
         }
-        cluster.sync();
+        mbar_wait(mb_t, phase);
 #pragma unroll
-        for (int c = 0; c < C::CT; ++c) v[c] = s_tot[qc + C::QC * c];
+        for (int c = 0; c < C::CT; ++c) v[c] = tb[qc + C::QC * c];
+        parity += 1;
         return;
     }
     __syncthreads();
@@ -330,7 +379,16 @@ __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
     const Marg g = problem_marginals(a, p, lane);
     float *mu_s = sm + Smem<C>::MU + group * C::ROWS, *nu_s = sm + Smem<C>::NU + group * C::MAXN;
     float *u1_s = sm + Smem<C>::U1 + group * C::ROWS, *v1_s = sm + Smem<C>::V1 + group * C::MAXN;
-    int parity = 0;
+    int parity = 0;  // number of cluster column reductions done so far (buffer / mbarrier parity and phase)
+    if (C::CL > 1) {
+        if (gtid == 0) {
+            const unsigned mb0 = smem_u32(sm + Smem<C>::MBAR);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mbar_init(mb0 + 8u * i, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cg::this_cluster().sync();  // once: every CTA's mbarriers exist before any remote completion can arrive
+    }
 
     // ---- load the tile (padding = -inf) --------------------------------------------------------
     float z[RT][CT];
@@ -805,6 +863,275 @@ __global__ void __launch_bounds__(W65_WARPS * 32) sinkhorn_w65_kernel(SinkArgs a
 #undef LCOL
 }
 
+// ---------------------------------------------------------------------------------------------
+// Level-3 kernel, two warps per problem (the default for 65 x 65).
+//   Warp w of the pair keeps columns [32w, 32w+32) of the 64 x 64 core: an 8 x 8 tile per lane (64 registers),
+//   so four warps per scheduler stay resident and each iteration's dependency chain is half as long as in the
+//   one-warp kernel.  Column sums are complete inside a warp; the partial ROW sums of the two warps meet through
+//   128 floats of shared memory and one 64-thread named barrier per iteration (double-buffered by parity).
+//   Both warps then compute bit-identical alphas (a + b == b + a).  Slot permutations as in sinkhorn_w65_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int X2_PAIRS = 2;  // problems per CTA (4 warps)
+
+struct PairSync {
+    int id;
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+};
+
+template <class Op>
+__device__ __forceinline__ void rs_cols8_op(float (&v)[8], Op op) {  // reduce-scatter over pr (lane bits 2,3,4): 8 -> 1
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] = op(v[t], __shfl_xor_sync(0xffffffffu, v[t + 4], 4));
+#pragma unroll
+    for (int t = 0; t < 2; ++t) v[t] = op(v[t], __shfl_xor_sync(0xffffffffu, v[t + 2], 8));
+    v[0] = op(v[0], __shfl_xor_sync(0xffffffffu, v[1], 16));
+}
+__device__ __forceinline__ void ag_cols8(float (&v)[8]) {  // all-gather over pr: 1 -> 8
+    v[1] = __shfl_xor_sync(0xffffffffu, v[0], 16);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) v[t + 2] = __shfl_xor_sync(0xffffffffu, v[t], 8);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t + 4] = __shfl_xor_sync(0xffffffffu, v[t], 4);
+}
+
+__global__ void __launch_bounds__(X2_PAIRS * 64, 4) sinkhorn_w65x2_kernel(SinkArgs a) {
+    constexpr int D = 64;
+    __shared__ float s_x[X2_PAIRS][2][2][68];  // [pair][parity][warp]: 64 owned-row values + scalars
+    __shared__ float s_fb[X2_PAIRS][65 + 65 + 128];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int pair = wib >> 1, w = wib & 1;
+    const int p = blockIdx.x * X2_PAIRS + pair;
+    if (p >= a.b) return;  // uniform over the pair; the named barrier below involves this pair only
+    const PairSync psync{1 + pair};
+    const int pr = lane >> 2, qc = lane & 3;
+    const int rmask = ((qc & 1) << 2) | ((qc >> 1) << 1);
+    const int cmask = ((pr & 1) << 2) | (((pr >> 1) & 1) << 1) | (pr >> 2);
+    const Marg g = problem_marginals(a, p, lane);
+#define LROW(k) (pr + 8 * ((k) ^ rmask))
+#define LCOL(c) (32 * w + qc + 4 * ((c) ^ cmask))
+    int par = 0;
+    // exchange the two owned-row values and one scalar with the partner warp
+#define PAIR_XCHG(v0, v1, sc, o0, o1, osc)                               \
+    do {                                                                 \
+        float *mine_ = s_x[pair][par][w], *oth_ = s_x[pair][par][w ^ 1]; \
+        mine_[LROW(0)] = (v0);                                           \
+        mine_[LROW(1)] = (v1);                                           \
+        if (lane == 0) mine_[64] = (sc);                                 \
+        psync();                                                         \
+        (o0) = oth_[LROW(0)];                                            \
+        (o1) = oth_[LROW(1)];                                            \
+        (osc) = oth_[64];                                                \
+        par ^= 1;                                                        \
+    } while (0)
+
+    // ---- load ------------------------------------------------------------------------------------------------------
+    float z[8][8], zc[2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) z[k][c] = z_at(a, g, p, LROW(k), LCOL(c));
+#pragma unroll
+    for (int t = 0; t < 2; ++t) zc[t] = z_at(a, g, p, LROW(t), D);
+    const float zr = z_at(a, g, p, D, LCOL(0));  // dustbin-row entry of the one column this lane owns
+    const float zcorner = z_at(a, g, p, D, D);
+    float mu2[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) mu2[t] = expf(lmu_at(a, g, p, LROW(t)));
+    const float nu1 = expf(lnu_at(a, g, p, LCOL(0)));
+    const float mud = expf(lmu_at(a, g, p, D)), nud = expf(lnu_at(a, g, p, D));
+    float u1o[2] = {0.f, 0.f}, v1o = 0.f, u1d = 0.f, v1d = 0.f;
+    float Dc[2] = {0.f, 0.f}, Dr = 0.f, corner = 0.f;
+
+    // ---- iteration 1, exact in the log domain ---------------------------------------------------------------------
+    if (a.iters >= 1) {
+        float u1[8], v1[8];
+        {
+            float mx[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float m = z[k][0];
+#pragma unroll
+                for (int c = 1; c < 8; ++c) m = fmaxf(m, z[k][c]);
+                mx[k] = m;
+            }
+            rs_rows_op(mx, OpMax());
+            float o0, o1, osc;
+            const float drm_part = warp_max(zr);
+            PAIR_XCHG(mx[0], mx[1], drm_part, o0, o1, osc);
+            mx[0] = finite_or_zero(fmaxf(fmaxf(mx[0], o0), zc[0]));
+            mx[1] = finite_or_zero(fmaxf(fmaxf(mx[1], o1), zc[1]));
+            const float drm = finite_or_zero(fmaxf(fmaxf(drm_part, osc), zcorner));
+            ag_rows(mx);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) sacc += fast_exp(z[k][c] - mx[k]);
+                u1[k] = sacc;
+            }
+            rs_rows(u1);
+            const float drs_part = warp_sum(fast_exp(zr - drm));
+            PAIR_XCHG(u1[0], u1[1], drs_part, o0, o1, osc);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const float sacc = (u1[t] + (t == 0 ? o0 : o1)) + fast_exp(zc[t] - mx[t]);
+                u1[t] = lmu_at(a, g, p, LROW(t)) - (fast_log(sacc) + mx[t]);
+            }
+            u1d = lmu_at(a, g, p, D) - (fast_log((drs_part + osc) + fast_exp(zcorner - drm)) + drm);
+            ag_rows(u1);
+        }
+        {
+            float mx[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float m = z[0][c] + u1[0];
+#pragma unroll
+                for (int k = 1; k < 8; ++k) m = fmaxf(m, z[k][c] + u1[k]);
+                mx[c] = m;
+            }
+            rs_cols8_op(mx, OpMax());
+            mx[0] = finite_or_zero(fmaxf(mx[0], zr + u1d));
+            ag_cols8(mx);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sacc += fast_exp((z[k][c] + u1[k]) - mx[c]);
+                v1[c] = sacc;
+            }
+            rs_cols8_op(v1, OpSum());
+            v1[0] = lnu_at(a, g, p, LCOL(0)) - (fast_log(v1[0] + fast_exp((zr + u1d) - mx[0])) + mx[0]);
+            ag_cols8(v1);
+            const float m = finite_or_zero(fmaxf(warp_max(fmaxf(zc[0] + u1[0], zc[1] + u1[1])), zcorner + u1d));
+            const float sacc = warp_sum(fast_exp((zc[0] + u1[0]) - m) + fast_exp((zc[1] + u1[1]) - m)) + fast_exp((zcorner + u1d) - m);
+            v1d = lnu_at(a, g, p, D) - (fast_log(sacc) + m);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) z[k][c] = fast_exp((z[k][c] + u1[k]) + v1[c]);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            Dc[t] = fast_exp((zc[t] + u1[t]) + v1d);
+            u1o[t] = u1[t];
+        }
+        Dr = fast_exp((zr + u1d) + v1[0]);
+        v1o = v1[0];
+        corner = fast_exp((zcorner + u1d) + v1d);
+    }
+
+    // ---- iterations 2..iters ------------------------------------------------------------------------------------------
+    float2 Kp[8][4];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) Kp[k][h] = make_float2(z[k][2 * h], z[k][2 * h + 1]);
+    float be[8], al[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) be[c] = 1.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) al[k] = 1.f;
+    float ald = 1.f, bed = 1.f;
+    float Srp = warp_sum(Dr);  // this warp's half of sum_j K[D][j] beta_j
+    float lo = INFINITY, hi = 0.f;
+
+    for (int it = 1; it < a.iters; ++it) {
+        float2 acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const float2 bp = make_float2(be[2 * h], be[2 * h + 1]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = ffma2(Kp[k][h], bp, acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) al[k] = acc[k].x + acc[k].y;
+        rs_rows(al);
+        float o0, o1, oS;
+        PAIR_XCHG(al[0], al[1], Srp, o0, o1, oS);
+        al[0] = mu2[0] * fast_rcp(fmaf(Dc[0], bed, al[0] + o0));
+        al[1] = mu2[1] * fast_rcp(fmaf(Dc[1], bed, al[1] + o1));
+        ald = mud * fast_rcp(fmaf(corner, bed, Srp + oS));
+        const float Sc = warp_sum(fmaf(Dc[0], al[0], Dc[1] * al[1]));
+        ag_rows(al);
+        float2 s2[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) s2[h] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float2 ak = make_float2(al[k], al[k]);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) s2[h] = ffma2(Kp[k][h], ak, s2[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) be[2 * h] = s2[h].x, be[2 * h + 1] = s2[h].y;
+        rs_cols8_op(be, OpSum());
+        be[0] = nu1 * fast_rcp(fmaf(Dr, ald, be[0]));
+        bed = nud * fast_rcp(fmaf(corner, ald, Sc));
+        Srp = warp_sum(Dr * be[0]);
+        if ((it & 7) == 0 || it == a.iters - 1) {
+            lo = fminf(fminf(fminf(lo, al[0]), fminf(al[1], ald)), fminf(be[0], bed));
+            hi = fmaxf(fmaxf(fmaxf(hi, al[0]), fmaxf(al[1], ald)), fmaxf(be[0], bed));
+        }
+        ag_cols8(be);
+    }
+
+    // ---- potentials, health check (agreed over the pair), output -----------------------------------------------------------
+    const float shift = (a.mode == MODE_RAW) ? 0.f : g.norm;
+    float U[8], V[8], Ud = 0.f, Vd = -shift;
+    bool bad = !(lo >= 1e-13f && hi <= 1e13f);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        float tu = 0.f;
+        if (a.iters >= 1) tu = u1o[t];
+        if (a.iters >= 2) tu += fast_log(al[t]);
+        if (!(fabsf(tu) < INFINITY)) bad = true;
+        U[t] = tu;
+    }
+    {
+        float tv = 0.f;
+        if (a.iters >= 1) tv = v1o;
+        if (a.iters >= 2) tv += fast_log(be[0]);
+        if (!(fabsf(tv) < INFINITY)) bad = true;
+        V[0] = tv - shift;
+    }
+    if (a.iters >= 1) Ud = u1d, Vd = v1d - shift;
+    if (a.iters >= 2) Ud += fast_log(ald), Vd += fast_log(bed);
+    if (!(fabsf(Ud) < INFINITY) || !(fabsf(Vd) < INFINITY)) bad = true;
+    {
+        const float mine = __any_sync(0xffffffffu, bad) ? 1.f : 0.f;
+        float d0, d1, other;
+        PAIR_XCHG(0.f, 0.f, mine, d0, d1, other);
+        (void)d0, (void)d1;
+        bad = (mine != 0.f) || (other != 0.f);
+    }
+    if (bad) {
+        if (w == 0 && lane == 0 && a.fb_total) atomicAdd(a.fb_total, 1);
+        psync();  // everybody is done with s_x before the scratch is reused
+        log_domain_solve<64>(a, g, p, s_fb[pair], s_fb[pair] + 65, s_fb[pair] + 130, w * 32 + lane, psync);
+        return;
+    }
+    ag_rows(U);
+    ag_cols8(V);
+    float *o = a.out + (size_t)p * 65 * 65;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int row = LROW(k);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[row * 65 + LCOL(c)] = (z_at(a, g, p, row, LCOL(c)) + U[k]) + V[c];
+        if (w == 0 && qc == 0) o[row * 65 + D] = (z_at(a, g, p, row, D) + U[k]) + Vd;
+    }
+    if (pr == 0) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[D * 65 + LCOL(c)] = (z_at(a, g, p, D, LCOL(c)) + Ud) + V[c];
+    }
+    if (w == 0 && lane == 0) o[D * 65 + D] = (z_at(a, g, p, D, D) + Ud) + Vd;
+#undef PAIR_XCHG
+#undef LROW
+#undef LCOL
+}
+
 // ---- host dispatch ------------------------------------------------------------------------------
 using CfgTiny = RegCfg<1, 2, 4, 8, 4>;         // <= 32 x 32, one warp per problem, 4 problems per CTA
 using CfgWarp = RegCfg<1, 2, 9, 17, 4>;        // <= 72 x 68  (level 3: 65 x 65)
@@ -813,7 +1140,8 @@ using CfgCl320 = RegCfg<8, 5, 5, 10, 1, 8>;    // <= 320 x 320 (level 1: 301 x 3
 using CfgCl512 = RegCfg<16, 5, 4, 16, 1, 8>;   // <= 512 x 512, cluster of 8 CTAs x 512 threads
 
 static int g_force_generic = 0;
-static int g_disable_w65 = 0;  // tests: route 65 x 65 through the padded warp kernel instead
+static int g_disable_w65 = 0;  // 65 x 65 routing: 0 = two warps per problem (default), 1 = padded 72 x 68 warp kernel,
+                               //                  2 = one-warp 65 x 65 kernel (tests / A-B timing)
 static int *g_fb_total = nullptr;  // device counter
 static std::mutex g_mu;
 
@@ -892,7 +1220,12 @@ static int run_sinkhorn(SinkArgs a, void *stream) {
     cudaStream_t st = as_stream(stream);
     switch (kernel_kind(a.M, a.N)) {
         case 0:
-            if (a.M == 65 && a.N == 65 && !g_disable_w65) {
+            if (a.M == 65 && a.N == 65 && g_disable_w65 == 0) {
+                sinkhorn_w65x2_kernel<<<(a.b + X2_PAIRS - 1) / X2_PAIRS, X2_PAIRS * 64, 0, st>>>(a);
+                PATS_LAUNCH_CHECK("sinkhorn_w65x2_kernel");
+                return PATS_OK;
+            }
+            if (a.M == 65 && a.N == 65 && g_disable_w65 == 2) {
                 sinkhorn_w65_kernel<<<(a.b + W65_WARPS - 1) / W65_WARPS, W65_WARPS * 32, 0, st>>>(a);
                 PATS_LAUNCH_CHECK("sinkhorn_w65_kernel");
                 return PATS_OK;
@@ -936,7 +1269,7 @@ PATS_API int pats_log_optimal_transport2_f32(const float *scores, const float *o
 
 PATS_API int pats_sinkhorn_kernel_kind(int M, int N) { return kernel_kind(M, N); }
 PATS_API void pats_sinkhorn_force_generic(int on) { g_force_generic = on ? 1 : 0; }
-PATS_API void pats_sinkhorn_disable_w65(int on) { g_disable_w65 = on ? 1 : 0; }
+PATS_API void pats_sinkhorn_disable_w65(int mode) { g_disable_w65 = (mode >= 0 && mode <= 2) ? mode : 0; }
 
 PATS_API int pats_sinkhorn_fallback_count(int reset) {
     if (ensure_counter() != PATS_OK) return -1;

@@ -184,22 +184,27 @@ def test_extreme_dynamic_range_takes_the_log_domain_fallback(M, lib, dev):
     assert n_fb < b, "well-conditioned problems must stay on the fast path"
 
 
-def test_padded_warp_kernel_still_matches_on_65x65(M, lib, dev):
-    """65 x 65 normally runs on the specialised level-3 kernel; the padded 72 x 68 warp kernel must agree with it
-    (and with the oracle) on the same problems, for every entry point that can produce a 65 x 65 plan."""
+def test_all_three_65x65_kernels_agree(M, lib, dev):
+    """65 x 65 normally runs on the two-warps-per-problem kernel; the one-warp 65 x 65 kernel (mode 2) and the padded
+    72 x 68 warp kernel (mode 1) must agree with it and with the oracle on the same problems, including an odd batch,
+    a wide score range that needs the fallback, and every iteration-count edge."""
     g = torch.Generator().manual_seed(6200)
     b = 21
     s = (0.3 * torch.randn(b, 65, 65, generator=g))
+    s[4] *= 300.0
     ns = areas(g, b, 64, 16.0)
-    ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), 100)
-    fast = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), 100)
-    lib.pats_sinkhorn_disable_w65(1)
-    try:
-        padded = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), 100)
-    finally:
-        lib.pats_sinkhorn_disable_w65(0)
-    assert_plan_equal(fast.cpu().numpy(), ref)
-    assert_plan_equal(padded.cpu().numpy(), ref)
+    for iters in (100, 0, 1, 2, 9):
+        ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), iters)
+        for mode in (0, 1, 2):
+            lib.pats_sinkhorn_disable_w65(mode)
+            try:
+                out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), iters).cpu().numpy()
+            finally:
+                lib.pats_sinkhorn_disable_w65(0)
+            np.testing.assert_allclose(out, ref, atol=TOL, rtol=2e-6, err_msg=f"mode {mode} iters {iters}")
+            if iters == 100:
+                keep = [i for i in range(b) if i != 4]
+                assert (out[keep].argmax(2) == ref[keep].argmax(2)).all() and (out[keep].argmax(1) == ref[keep].argmax(1)).all()
     # augmenting transport with m = n = 64 and the raw iteration also land on the 65 x 65 kernel
     s64 = 0.2 * torch.randn(5, 64, 64, generator=g)
     ns64 = areas(g, 5, 64, 16.0)
