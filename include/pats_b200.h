@@ -67,6 +67,8 @@ void pats_sinkhorn_force_generic(int on);
 /* Routing of 65 x 65 problems (tests / A-B timing): 0 = two warps per problem (default), 1 = padded 72 x 68 warp
  * kernel, 2 = one-warp 65 x 65 kernel. */
 void pats_sinkhorn_disable_w65(int mode);
+/* Route 145 x 145 problems through the padded 160 x 160 CTA kernel instead of the dedicated 9-warp kernel (tests). */
+void pats_sinkhorn_disable_c145(int on);
 /* Problems the register-resident kernels handed to the log-domain fallback since the last reset
  * (device counter, read with a synchronising copy; tests / diagnostics only). */
 int pats_sinkhorn_fallback_count(int reset);

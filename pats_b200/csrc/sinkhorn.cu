@@ -1132,6 +1132,291 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, 4) sinkhorn_w65x2_kernel(SinkAr
 #undef LCOL
 }
 
+// ---------------------------------------------------------------------------------------------
+// Level-2 kernel: exactly 145 x 145 (144 x 144 real cells + dustbin row / column), one CTA of 9 warps per problem.
+//   Warp w keeps the 16-column slab [16w, 16w+16) of the core; lane (pr = lane>>1, qc = lane&1) holds a 9 x 8 tile
+//   (rows pr + 16k, columns 16w + qc + 2*(c ^ cmask(pr))): 72 registers, two CTAs per SM.
+//   Column sums are complete inside a warp (select-free reduce-scatter over pr, as in the level-3 kernels); the row
+//   partials of the 9 warps meet in shared memory, where thread t < 144 finishes row t (its dustbin-column entry,
+//   marginal and first-iteration potential live in that thread's registers).  Two CTA barriers per iteration.
+// ---------------------------------------------------------------------------------------------
+constexpr int C145_W = 9, C145_T = 288;
+
+template <class Op>
+__device__ __forceinline__ void rs_c145(float (&v)[8], Op op) {  // over pr (lane bits 1..4): 8 -> 1 (twins pr, pr^8 both hold it)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t] = op(v[t], __shfl_xor_sync(0xffffffffu, v[t + 4], 2));
+#pragma unroll
+    for (int t = 0; t < 2; ++t) v[t] = op(v[t], __shfl_xor_sync(0xffffffffu, v[t + 2], 4));
+    v[0] = op(v[0], __shfl_xor_sync(0xffffffffu, v[1], 8));
+    v[0] = op(v[0], __shfl_xor_sync(0xffffffffu, v[0], 16));
+}
+__device__ __forceinline__ void ag_c145(float (&v)[8]) {  // 1 -> 8
+    v[1] = __shfl_xor_sync(0xffffffffu, v[0], 8);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) v[t + 2] = __shfl_xor_sync(0xffffffffu, v[t], 4);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) v[t + 4] = __shfl_xor_sync(0xffffffffu, v[t], 2);
+}
+
+__global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 threads x 112 regs: two CTAs per SM
+    constexpr int D = 144;
+    __shared__ float s_part[C145_W][144];  // per-warp row partials
+    __shared__ float s_row[144];           // per-row values handed back to the tiles
+    __shared__ float s_red[2][16];         // [0][w]: dustbin-row partial of warp w (9); [1][w]: dustbin-column partial (warps 0..4)
+    __shared__ float s_fb[145 + 145 + 2 * C145_T];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int p = blockIdx.x;
+    if (p >= a.b) return;
+    const int pr = lane >> 1, qc = lane & 1;
+    const int cmask = ((pr & 1) << 2) | (((pr >> 1) & 1) << 1) | ((pr >> 2) & 1);
+    const bool col_owner = (pr & 8) == 0;  // of the twins (pr, pr^8) that own a column, this one counts it
+    const bool row_thread = tid < 144;     // thread t finishes row t
+    const Marg g = problem_marginals(a, p, lane);
+#define LROW(k) (pr + 16 * (k))
+#define LCOL(c) (16 * w + qc + 2 * ((c) ^ cmask))
+    auto red9 = [&](int which) {  // fixed-order sum of the per-warp partials
+        float t = s_red[which][0];
+        const int n = which == 0 ? 9 : 5;
+        for (int i = 1; i < n; ++i) t += s_red[which][i];
+        return t;
+    };
+    auto max9 = [&](int which) {
+        float t = s_red[which][0];
+        const int n = which == 0 ? 9 : 5;
+        for (int i = 1; i < n; ++i) t = fmaxf(t, s_red[which][i]);
+        return t;
+    };
+
+    // ---- load ------------------------------------------------------------------------------------------------------
+    float z[9][8];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) z[k][c] = z_at(a, g, p, LROW(k), LCOL(c));
+    const float zr = z_at(a, g, p, D, LCOL(0));                  // dustbin-row entry of my owned column
+    const float zc = row_thread ? z_at(a, g, p, tid, D) : 0.f;   // dustbin-column entry of row t
+    const float zcorner = z_at(a, g, p, D, D);
+    const float mu_t = row_thread ? expf(lmu_at(a, g, p, tid)) : 0.f;
+    const float nu_o = expf(lnu_at(a, g, p, LCOL(0)));
+    const float mud = expf(lmu_at(a, g, p, D)), nud = expf(lnu_at(a, g, p, D));
+    float u1_t = 0.f, v1_o = 0.f, u1d = 0.f, v1d = 0.f, Dc = 0.f, Dr = 0.f, corner = 0.f;
+
+    // ---- iteration 1, exact in the log domain ---------------------------------------------------------------------
+    if (a.iters >= 1) {
+        float u1[9], v1[8];
+        {  // row maxima
+            float mx[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                float m = z[k][0];
+#pragma unroll
+                for (int c = 1; c < 8; ++c) m = fmaxf(m, z[k][c]);
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                if (qc == 0) s_part[w][LROW(k)] = m;
+            }
+            const float drm_w = warp_max(zr);
+            if (lane == 0) s_red[0][w] = drm_w;
+            __syncthreads();
+            float rm = 0.f;
+            if (row_thread) {
+                rm = s_part[0][tid];
+#pragma unroll
+                for (int i = 1; i < C145_W; ++i) rm = fmaxf(rm, s_part[i][tid]);
+                rm = finite_or_zero(fmaxf(rm, zc));
+                s_row[tid] = rm;
+            }
+            const float drm = finite_or_zero(fmaxf(max9(0), zcorner));
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 9; ++k) mx[k] = s_row[LROW(k)];
+            // row sums
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) sacc += fast_exp(z[k][c] - mx[k]);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                u1[k] = sacc;
+            }
+            __syncthreads();  // everybody has read s_row (maxima) and s_red[0]
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                if (qc == 0) s_part[w][LROW(k)] = u1[k];
+            const float drs_w = warp_sum(col_owner ? fast_exp(zr - drm) : 0.f);
+            if (lane == 0) s_red[0][w] = drs_w;
+            __syncthreads();
+            if (row_thread) {
+                float sacc = s_part[0][tid];
+#pragma unroll
+                for (int i = 1; i < C145_W; ++i) sacc += s_part[i][tid];
+                sacc += fast_exp(zc - rm);
+                u1_t = lmu_at(a, g, p, tid) - (fast_log(sacc) + rm);
+                s_row[tid] = u1_t;
+            }
+            u1d = lmu_at(a, g, p, D) - (fast_log(red9(0) + fast_exp(zcorner - drm)) + drm);
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 9; ++k) u1[k] = s_row[LROW(k)];
+        }
+        {  // columns (inside the warp) and the dustbin column (row threads)
+            float mx[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float m = z[0][c] + u1[0];
+#pragma unroll
+                for (int k = 1; k < 9; ++k) m = fmaxf(m, z[k][c] + u1[k]);
+                mx[c] = m;
+            }
+            rs_c145(mx, OpMax());
+            mx[0] = finite_or_zero(fmaxf(mx[0], zr + u1d));
+            ag_c145(mx);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) sacc += fast_exp((z[k][c] + u1[k]) - mx[c]);
+                v1[c] = sacc;
+            }
+            rs_c145(v1, OpSum());
+            v1[0] = lnu_at(a, g, p, LCOL(0)) - (fast_log(v1[0] + fast_exp((zr + u1d) - mx[0])) + mx[0]);
+            ag_c145(v1);
+            const float dcm_w = warp_max(row_thread ? zc + u1_t : -INFINITY);
+            if (lane == 0 && w < 5) s_red[1][w] = dcm_w;
+            __syncthreads();
+            const float dcm = finite_or_zero(fmaxf(max9(1), zcorner + u1d));
+            __syncthreads();
+            const float dcs_w = warp_sum(row_thread ? fast_exp((zc + u1_t) - dcm) : 0.f);
+            if (lane == 0 && w < 5) s_red[1][w] = dcs_w;
+            __syncthreads();
+            v1d = lnu_at(a, g, p, D) - (fast_log(red9(1) + fast_exp((zcorner + u1d) - dcm)) + dcm);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) z[k][c] = fast_exp((z[k][c] + u1[k]) + v1[c]);
+        Dc = row_thread ? fast_exp((zc + u1_t) + v1d) : 0.f;
+        Dr = fast_exp((zr + u1d) + v1[0]);
+        v1_o = v1[0];
+        corner = fast_exp((zcorner + u1d) + v1d);
+    }
+    __syncthreads();
+
+    // ---- iterations 2..iters ------------------------------------------------------------------------------------------
+    float2 Kp[9][4];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) Kp[k][h] = make_float2(z[k][2 * h], z[k][2 * h + 1]);
+    float be[8], al[9];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) be[c] = 1.f;
+    float al_t = 1.f, ald = 1.f, bed = 1.f;
+    {
+        const float srp = warp_sum(col_owner ? Dr : 0.f);
+        if (lane == 0) s_red[0][w] = srp;
+    }
+    float lo = INFINITY, hi = 0.f;
+
+    for (int it = 1; it < a.iters; ++it) {
+        float2 acc[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const float2 bp = make_float2(be[2 * h], be[2 * h + 1]);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[k] = ffma2(Kp[k][h], bp, acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            float r = acc[k].x + acc[k].y;
+            r += __shfl_xor_sync(0xffffffffu, r, 1);
+            if (qc == 0) s_part[w][LROW(k)] = r;
+        }
+        __syncthreads();  // B1: row partials and the dustbin-row partials of the previous column pass are visible
+        ald = mud * fast_rcp(fmaf(corner, bed, red9(0)));
+        float scp = 0.f;
+        if (row_thread) {
+            float r = s_part[0][tid];
+#pragma unroll
+            for (int i = 1; i < C145_W; ++i) r += s_part[i][tid];
+            al_t = mu_t * fast_rcp(fmaf(Dc, bed, r));
+            s_row[tid] = al_t;
+            scp = Dc * al_t;
+        }
+        if (w < 5) {
+            scp = warp_sum(scp);
+            if (lane == 0) s_red[1][w] = scp;
+        }
+        __syncthreads();  // B2: alphas and dustbin-column partials visible
+#pragma unroll
+        for (int k = 0; k < 9; ++k) al[k] = s_row[LROW(k)];
+        const float Sc = red9(1);
+        float2 s2[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) s2[h] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float2 ak = make_float2(al[k], al[k]);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) s2[h] = ffma2(Kp[k][h], ak, s2[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) be[2 * h] = s2[h].x, be[2 * h + 1] = s2[h].y;
+        rs_c145(be, OpSum());
+        be[0] = nu_o * fast_rcp(fmaf(Dr, ald, be[0]));
+        bed = nud * fast_rcp(fmaf(corner, ald, Sc));
+        {
+            const float srp = warp_sum(col_owner ? Dr * be[0] : 0.f);
+            if (lane == 0) s_red[0][w] = srp;  // read after the next B1
+        }
+        if ((it & 7) == 0 || it == a.iters - 1) {
+            const float at = row_thread ? al_t : ald;
+            lo = fminf(fminf(lo, at), fminf(fminf(ald, be[0]), bed));
+            hi = fmaxf(fmaxf(hi, at), fmaxf(fmaxf(ald, be[0]), bed));
+        }
+        ag_c145(be);
+    }
+
+    // ---- potentials, health check, output ------------------------------------------------------------------------------
+    const float shift = (a.mode == MODE_RAW) ? 0.f : g.norm;
+    bool bad = !(lo >= 1e-13f && hi <= 1e13f);
+    float U_t = 0.f, Ud = 0.f, Vd = -shift, V[8], U[9];
+    if (a.iters >= 1) U_t = u1_t, Ud = u1d, Vd = v1d - shift;
+    if (a.iters >= 2) U_t += fast_log(al_t), Ud += fast_log(ald), Vd += fast_log(bed);
+    if (row_thread && !(fabsf(U_t) < INFINITY)) bad = true;
+    if (!(fabsf(Ud) < INFINITY) || !(fabsf(Vd) < INFINITY)) bad = true;
+    {
+        float tv = 0.f;
+        if (a.iters >= 1) tv = v1_o;
+        if (a.iters >= 2) tv += fast_log(be[0]);
+        if (!(fabsf(tv) < INFINITY)) bad = true;
+        V[0] = tv - shift;
+    }
+    if (row_thread) s_row[tid] = U_t;
+    if (__syncthreads_or(bad ? 1 : 0)) {
+        if (tid == 0 && a.fb_total) atomicAdd(a.fb_total, 1);
+        log_domain_solve<C145_T>(a, g, p, s_fb, s_fb + 145, s_fb + 290, tid, BlockSync());
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) U[k] = s_row[LROW(k)];
+    ag_c145(V);
+    float *o = a.out + (size_t)p * 145 * 145;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int row = LROW(k);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[row * 145 + LCOL(c)] = (z_at(a, g, p, row, LCOL(c)) + U[k]) + V[c];
+    }
+    if (row_thread) o[tid * 145 + D] = (z_at(a, g, p, tid, D) + U_t) + Vd;
+    if (col_owner) o[D * 145 + LCOL(0)] = (z_at(a, g, p, D, LCOL(0)) + Ud) + V[0];
+    if (tid == 0) o[D * 145 + D] = (z_at(a, g, p, D, D) + Ud) + Vd;
+#undef LROW
+#undef LCOL
+}
+
 // ---- host dispatch ------------------------------------------------------------------------------
 using CfgTiny = RegCfg<1, 2, 4, 8, 4>;         // <= 32 x 32, one warp per problem, 4 problems per CTA
 using CfgWarp = RegCfg<1, 2, 9, 17, 4>;        // <= 72 x 68  (level 3: 65 x 65)
@@ -1140,6 +1425,7 @@ using CfgCl320 = RegCfg<8, 5, 5, 10, 1, 8>;    // <= 320 x 320 (level 1: 301 x 3
 using CfgCl512 = RegCfg<16, 5, 4, 16, 1, 8>;   // <= 512 x 512, cluster of 8 CTAs x 512 threads
 
 static int g_force_generic = 0;
+static int g_disable_c145 = 0;  // 145 x 145 routing: 0 = dedicated 9-warp kernel (default), 1 = padded 160 x 160 CTA kernel
 static int g_disable_w65 = 0;  // 65 x 65 routing: 0 = two warps per problem (default), 1 = padded 72 x 68 warp kernel,
                                //                  2 = one-warp 65 x 65 kernel (tests / A-B timing)
 static int *g_fb_total = nullptr;  // device counter
@@ -1233,6 +1519,11 @@ static int run_sinkhorn(SinkArgs a, void *stream) {
             if (a.M <= CfgTiny::MAXM && a.N <= CfgTiny::MAXN) return launch_reg<CfgTiny>(a, st);
             return launch_reg<CfgWarp>(a, st);
         case 1:
+            if (a.M == 145 && a.N == 145 && !g_disable_c145) {
+                sinkhorn_c145_kernel<<<a.b, C145_T, 0, st>>>(a);
+                PATS_LAUNCH_CHECK("sinkhorn_c145_kernel");
+                return PATS_OK;
+            }
             return launch_reg<CfgCta>(a, st);
         case 3:
             if (a.M <= CfgCl320::MAXM && a.N <= CfgCl320::MAXN) return launch_reg<CfgCl320>(a, st);
@@ -1269,6 +1560,7 @@ PATS_API int pats_log_optimal_transport2_f32(const float *scores, const float *o
 
 PATS_API int pats_sinkhorn_kernel_kind(int M, int N) { return kernel_kind(M, N); }
 PATS_API void pats_sinkhorn_force_generic(int on) { g_force_generic = on ? 1 : 0; }
+PATS_API void pats_sinkhorn_disable_c145(int on) { g_disable_c145 = on ? 1 : 0; }
 PATS_API void pats_sinkhorn_disable_w65(int mode) { g_disable_w65 = (mode >= 0 && mode <= 2) ? mode : 0; }
 
 PATS_API int pats_sinkhorn_fallback_count(int reset) {
