@@ -69,6 +69,8 @@ void pats_sinkhorn_force_generic(int on);
 void pats_sinkhorn_disable_w65(int mode);
 /* Route 145 x 145 problems through the padded 160 x 160 CTA kernel instead of the dedicated 9-warp kernel (tests). */
 void pats_sinkhorn_disable_c145(int on);
+/* Cluster shape for plans up to 320 x 320 (A-B timing): 0 = 8 CTAs x 256 threads (default), 1 = 4 CTAs x 512 threads. */
+void pats_sinkhorn_cluster_variant(int v);
 /* Problems the register-resident kernels handed to the log-domain fallback since the last reset
  * (device counter, read with a synchronising copy; tests / diagnostics only). */
 int pats_sinkhorn_fallback_count(int reset);

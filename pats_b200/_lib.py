@@ -29,6 +29,7 @@ SIGNATURES = {
     "pats_sinkhorn_force_generic": [_I],
     "pats_sinkhorn_disable_w65": [_I],
     "pats_sinkhorn_disable_c145": [_I],
+    "pats_sinkhorn_cluster_variant": [_I],
     "pats_sinkhorn_fallback_count": [_I],
     "pats_log_optimal_transport_f32_host": [_P, _F, _P, _I, _I, _I, _I, _P],
     "pats_log_optimal_transport2_f32_host": [_P, _F, _P, _I, _I, _I, _I, _P],
@@ -46,7 +47,7 @@ SIGNATURES = {
     "pats_third_result_from_log_f32": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
     "pats_est_position_f32": [_P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
 }
-_RESTYPE = {"pats_last_error": C.c_char_p, "pats_sinkhorn_force_generic": None, "pats_sinkhorn_disable_w65": None, "pats_sinkhorn_disable_c145": None}
+_RESTYPE = {"pats_last_error": C.c_char_p, "pats_sinkhorn_force_generic": None, "pats_sinkhorn_disable_w65": None, "pats_sinkhorn_disable_c145": None, "pats_sinkhorn_cluster_variant": None}
 
 
 def library_path() -> str:

@@ -1159,11 +1159,12 @@ __device__ __forceinline__ void ag_c145(float (&v)[8]) {  // 1 -> 8
     for (int t = 0; t < 4; ++t) v[t + 4] = __shfl_xor_sync(0xffffffffu, v[t], 2);
 }
 
-__global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 threads x 112 regs: two CTAs per SM
+__global__ void __launch_bounds__(C145_T) sinkhorn_c145_kernel(SinkArgs a) {  // 9 warps; register allocation granularity allows one CTA per SM
     constexpr int D = 144;
     __shared__ float s_part[C145_W][144];  // per-warp row partials
     __shared__ float s_row[144];           // per-row values handed back to the tiles
-    __shared__ float s_red[2][16];         // [0][w]: dustbin-row partial of warp w (9); [1][w]: dustbin-column partial (warps 0..4)
+    __shared__ float s_red[2][16];         // [0][w]: dustbin-row partial of warp w; [1][w]: dustbin-column partial of warp w
+    __shared__ float s_keep[2][144];       // per-row first-iteration potential / final alpha (kept out of registers)
     __shared__ float s_fb[145 + 145 + 2 * C145_T];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int p = blockIdx.x;
@@ -1171,20 +1172,22 @@ __global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 thre
     const int pr = lane >> 1, qc = lane & 1;
     const int cmask = ((pr & 1) << 2) | (((pr >> 1) & 1) << 1) | ((pr >> 2) & 1);
     const bool col_owner = (pr & 8) == 0;  // of the twins (pr, pr^8) that own a column, this one counts it
-    const bool row_thread = tid < 144;     // thread t finishes row t
+    // row finishing is spread over all warps: the qc==0 lane (w, pr) finishes row 16w + pr (144 rows = 9 warps x 16)
+    const bool row_thread = qc == 0;
+    const int myrow = 16 * w + pr;
     const Marg g = problem_marginals(a, p, lane);
 #define LROW(k) (pr + 16 * (k))
 #define LCOL(c) (16 * w + qc + 2 * ((c) ^ cmask))
-    auto red9 = [&](int which) {  // fixed-order sum of the per-warp partials
+    auto red9 = [&](int which) {  // fixed-order sum of the 9 per-warp partials
         float t = s_red[which][0];
-        const int n = which == 0 ? 9 : 5;
-        for (int i = 1; i < n; ++i) t += s_red[which][i];
+#pragma unroll
+        for (int i = 1; i < C145_W; ++i) t += s_red[which][i];
         return t;
     };
     auto max9 = [&](int which) {
         float t = s_red[which][0];
-        const int n = which == 0 ? 9 : 5;
-        for (int i = 1; i < n; ++i) t = fmaxf(t, s_red[which][i]);
+#pragma unroll
+        for (int i = 1; i < C145_W; ++i) t = fmaxf(t, s_red[which][i]);
         return t;
     };
 
@@ -1194,17 +1197,17 @@ __global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 thre
     for (int k = 0; k < 9; ++k)
 #pragma unroll
         for (int c = 0; c < 8; ++c) z[k][c] = z_at(a, g, p, LROW(k), LCOL(c));
-    const float zr = z_at(a, g, p, D, LCOL(0));                  // dustbin-row entry of my owned column
-    const float zc = row_thread ? z_at(a, g, p, tid, D) : 0.f;   // dustbin-column entry of row t
+    const float zr = z_at(a, g, p, D, LCOL(0));                    // dustbin-row entry of my owned column
+    const float zc = row_thread ? z_at(a, g, p, myrow, D) : 0.f;   // dustbin-column entry of my row
     const float zcorner = z_at(a, g, p, D, D);
-    const float mu_t = row_thread ? expf(lmu_at(a, g, p, tid)) : 0.f;
+    const float mu_t = row_thread ? expf(lmu_at(a, g, p, myrow)) : 0.f;
     const float nu_o = expf(lnu_at(a, g, p, LCOL(0)));
     const float mud = expf(lmu_at(a, g, p, D)), nud = expf(lnu_at(a, g, p, D));
-    float u1_t = 0.f, v1_o = 0.f, u1d = 0.f, v1d = 0.f, Dc = 0.f, Dr = 0.f, corner = 0.f;
+    float v1_o = 0.f, u1d = 0.f, v1d = 0.f, Dc = 0.f, Dr = 0.f, corner = 0.f;
 
     // ---- iteration 1, exact in the log domain ---------------------------------------------------------------------
     if (a.iters >= 1) {
-        float u1[9], v1[8];
+        float u1[9], v1[8], u1_t = 0.f;
         {  // row maxima
             float mx[9];
 #pragma unroll
@@ -1220,17 +1223,16 @@ __global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 thre
             __syncthreads();
             float rm = 0.f;
             if (row_thread) {
-                rm = s_part[0][tid];
+                rm = s_part[0][myrow];
 #pragma unroll
-                for (int i = 1; i < C145_W; ++i) rm = fmaxf(rm, s_part[i][tid]);
+                for (int i = 1; i < C145_W; ++i) rm = fmaxf(rm, s_part[i][myrow]);
                 rm = finite_or_zero(fmaxf(rm, zc));
-                s_row[tid] = rm;
+                s_row[myrow] = rm;
             }
             const float drm = finite_or_zero(fmaxf(max9(0), zcorner));
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < 9; ++k) mx[k] = s_row[LROW(k)];
-            // row sums
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
                 float sacc = 0.f;
@@ -1247,12 +1249,13 @@ __global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 thre
             if (lane == 0) s_red[0][w] = drs_w;
             __syncthreads();
             if (row_thread) {
-                float sacc = s_part[0][tid];
+                float sacc = s_part[0][myrow];
 #pragma unroll
-                for (int i = 1; i < C145_W; ++i) sacc += s_part[i][tid];
+                for (int i = 1; i < C145_W; ++i) sacc += s_part[i][myrow];
                 sacc += fast_exp(zc - rm);
-                u1_t = lmu_at(a, g, p, tid) - (fast_log(sacc) + rm);
-                s_row[tid] = u1_t;
+                u1_t = lmu_at(a, g, p, myrow) - (fast_log(sacc) + rm);
+                s_row[myrow] = u1_t;
+                s_keep[0][myrow] = u1_t;
             }
             u1d = lmu_at(a, g, p, D) - (fast_log(red9(0) + fast_exp(zcorner - drm)) + drm);
             __syncthreads();
@@ -1282,12 +1285,12 @@ __global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 thre
             v1[0] = lnu_at(a, g, p, LCOL(0)) - (fast_log(v1[0] + fast_exp((zr + u1d) - mx[0])) + mx[0]);
             ag_c145(v1);
             const float dcm_w = warp_max(row_thread ? zc + u1_t : -INFINITY);
-            if (lane == 0 && w < 5) s_red[1][w] = dcm_w;
+            if (lane == 0) s_red[1][w] = dcm_w;
             __syncthreads();
             const float dcm = finite_or_zero(fmaxf(max9(1), zcorner + u1d));
             __syncthreads();
             const float dcs_w = warp_sum(row_thread ? fast_exp((zc + u1_t) - dcm) : 0.f);
-            if (lane == 0 && w < 5) s_red[1][w] = dcs_w;
+            if (lane == 0) s_red[1][w] = dcs_w;
             __syncthreads();
             v1d = lnu_at(a, g, p, D) - (fast_log(red9(1) + fast_exp((zcorner + u1d) - dcm)) + dcm);
         }
@@ -1303,6 +1306,9 @@ __global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 thre
     __syncthreads();
 
     // ---- iterations 2..iters ------------------------------------------------------------------------------------------
+    // Per iteration: [row partials] B1 [finish rows: alpha] B2 [column pass: beta].  The two dustbin sums
+    //   Sr = sum_j K[D][j] beta_j  and  Sc = sum_i K[i][D] alpha_i  are produced as per-warp partials AFTER B2 and consumed
+    //   after the next B1, so their 5-step warp reductions overlap the FFMA2 stream instead of sitting between the barriers.
     float2 Kp[9][4];
 #pragma unroll
     for (int k = 0; k < 9; ++k)
@@ -1334,25 +1340,23 @@ __global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 thre
             r += __shfl_xor_sync(0xffffffffu, r, 1);
             if (qc == 0) s_part[w][LROW(k)] = r;
         }
-        __syncthreads();  // B1: row partials and the dustbin-row partials of the previous column pass are visible
+        __syncthreads();  // B1: row partials + both dustbin partials of the previous iteration are visible
+        if (it > 1) bed = nud * fast_rcp(fmaf(corner, ald, red9(1)));  // beta_D of the previous iteration (Sc arrived late)
         ald = mud * fast_rcp(fmaf(corner, bed, red9(0)));
-        float scp = 0.f;
         if (row_thread) {
-            float r = s_part[0][tid];
+            float r = s_part[0][myrow];
 #pragma unroll
-            for (int i = 1; i < C145_W; ++i) r += s_part[i][tid];
+            for (int i = 1; i < C145_W; ++i) r += s_part[i][myrow];
             al_t = mu_t * fast_rcp(fmaf(Dc, bed, r));
-            s_row[tid] = al_t;
-            scp = Dc * al_t;
+            s_row[myrow] = al_t;
         }
-        if (w < 5) {
-            scp = warp_sum(scp);
-            if (lane == 0) s_red[1][w] = scp;
-        }
-        __syncthreads();  // B2: alphas and dustbin-column partials visible
+        __syncthreads();  // B2: alphas visible
 #pragma unroll
         for (int k = 0; k < 9; ++k) al[k] = s_row[LROW(k)];
-        const float Sc = red9(1);
+        {
+            const float scp = warp_sum(row_thread ? Dc * al_t : 0.f);
+            if (lane == 0) s_red[1][w] = scp;  // read after the next B1
+        }
         float2 s2[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) s2[h] = make_float2(0.f, 0.f);
@@ -1366,7 +1370,6 @@ __global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 thre
         for (int h = 0; h < 4; ++h) be[2 * h] = s2[h].x, be[2 * h + 1] = s2[h].y;
         rs_c145(be, OpSum());
         be[0] = nu_o * fast_rcp(fmaf(Dr, ald, be[0]));
-        bed = nud * fast_rcp(fmaf(corner, ald, Sc));
         {
             const float srp = warp_sum(col_owner ? Dr * be[0] : 0.f);
             if (lane == 0) s_red[0][w] = srp;  // read after the next B1
@@ -1378,12 +1381,14 @@ __global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 thre
         }
         ag_c145(be);
     }
+    __syncthreads();
+    if (a.iters >= 2) bed = nud * fast_rcp(fmaf(corner, ald, red9(1)));  // beta_D of the last iteration
 
     // ---- potentials, health check, output ------------------------------------------------------------------------------
     const float shift = (a.mode == MODE_RAW) ? 0.f : g.norm;
-    bool bad = !(lo >= 1e-13f && hi <= 1e13f);
+    bool bad = !(lo >= 1e-13f && hi <= 1e13f) || (a.iters >= 2 && !(bed >= 1e-13f && bed <= 1e13f));
     float U_t = 0.f, Ud = 0.f, Vd = -shift, V[8], U[9];
-    if (a.iters >= 1) U_t = u1_t, Ud = u1d, Vd = v1d - shift;
+    if (a.iters >= 1) U_t = row_thread ? s_keep[0][myrow] : 0.f, Ud = u1d, Vd = v1d - shift;
     if (a.iters >= 2) U_t += fast_log(al_t), Ud += fast_log(ald), Vd += fast_log(bed);
     if (row_thread && !(fabsf(U_t) < INFINITY)) bad = true;
     if (!(fabsf(Ud) < INFINITY) || !(fabsf(Vd) < INFINITY)) bad = true;
@@ -1394,7 +1399,7 @@ __global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 thre
         if (!(fabsf(tv) < INFINITY)) bad = true;
         V[0] = tv - shift;
     }
-    if (row_thread) s_row[tid] = U_t;
+    if (row_thread) s_row[myrow] = U_t;
     if (__syncthreads_or(bad ? 1 : 0)) {
         if (tid == 0 && a.fb_total) atomicAdd(a.fb_total, 1);
         log_domain_solve<C145_T>(a, g, p, s_fb, s_fb + 145, s_fb + 290, tid, BlockSync());
@@ -1410,7 +1415,7 @@ __global__ void __maxnreg__(112) sinkhorn_c145_kernel(SinkArgs a) {  // 288 thre
 #pragma unroll
         for (int c = 0; c < 8; ++c) o[row * 145 + LCOL(c)] = (z_at(a, g, p, row, LCOL(c)) + U[k]) + V[c];
     }
-    if (row_thread) o[tid * 145 + D] = (z_at(a, g, p, tid, D) + U_t) + Vd;
+    if (row_thread) o[myrow * 145 + D] = (z_at(a, g, p, myrow, D) + U_t) + Vd;
     if (col_owner) o[D * 145 + LCOL(0)] = (z_at(a, g, p, D, LCOL(0)) + Ud) + V[0];
     if (tid == 0) o[D * 145 + D] = (z_at(a, g, p, D, D) + Ud) + Vd;
 #undef LROW
@@ -1422,9 +1427,11 @@ using CfgTiny = RegCfg<1, 2, 4, 8, 4>;         // <= 32 x 32, one warp per probl
 using CfgWarp = RegCfg<1, 2, 9, 17, 4>;        // <= 72 x 68  (level 3: 65 x 65)
 using CfgCta = RegCfg<8, 4, 10, 10, 1>;        // <= 160 x 160 (level 2: 145 x 145), 16 x 16 threads
 using CfgCl320 = RegCfg<8, 5, 5, 10, 1, 8>;    // <= 320 x 320 (level 1: 301 x 301), cluster of 8 CTAs x 256 threads
+using CfgCl320b = RegCfg<16, 5, 5, 10, 1, 4>;  // <= 320 x 320, cluster of 4 CTAs x 512 threads (A/B variant)
 using CfgCl512 = RegCfg<16, 5, 4, 16, 1, 8>;   // <= 512 x 512, cluster of 8 CTAs x 512 threads
 
 static int g_force_generic = 0;
+static int g_cluster_variant = 0;  // <= 320 x 320 plans: 0 = 8 CTAs x 256 threads, 1 = 4 CTAs x 512 threads
 static int g_disable_c145 = 0;  // 145 x 145 routing: 0 = dedicated 9-warp kernel (default), 1 = padded 160 x 160 CTA kernel
 static int g_disable_w65 = 0;  // 65 x 65 routing: 0 = two warps per problem (default), 1 = padded 72 x 68 warp kernel,
                                //                  2 = one-warp 65 x 65 kernel (tests / A-B timing)
@@ -1526,7 +1533,8 @@ static int run_sinkhorn(SinkArgs a, void *stream) {
             }
             return launch_reg<CfgCta>(a, st);
         case 3:
-            if (a.M <= CfgCl320::MAXM && a.N <= CfgCl320::MAXN) return launch_reg<CfgCl320>(a, st);
+            if (a.M <= CfgCl320::MAXM && a.N <= CfgCl320::MAXN)
+                return g_cluster_variant == 1 ? launch_reg<CfgCl320b>(a, st) : launch_reg<CfgCl320>(a, st);
             return launch_reg<CfgCl512>(a, st);
         default:
             return launch_generic(a, st);
@@ -1560,6 +1568,7 @@ PATS_API int pats_log_optimal_transport2_f32(const float *scores, const float *o
 
 PATS_API int pats_sinkhorn_kernel_kind(int M, int N) { return kernel_kind(M, N); }
 PATS_API void pats_sinkhorn_force_generic(int on) { g_force_generic = on ? 1 : 0; }
+PATS_API void pats_sinkhorn_cluster_variant(int v) { g_cluster_variant = v == 1 ? 1 : 0; }
 PATS_API void pats_sinkhorn_disable_c145(int on) { g_disable_c145 = on ? 1 : 0; }
 PATS_API void pats_sinkhorn_disable_w65(int mode) { g_disable_w65 = (mode >= 0 && mode <= 2) ? mode : 0; }
 

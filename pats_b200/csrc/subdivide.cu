@@ -242,20 +242,24 @@ template <class T>
 __global__ void __launch_bounds__(256) right_patches_kernel(const T *__restrict__ right, float *__restrict__ out,
                                                             const int64_t *__restrict__ bound5, const int *__restrict__ count,
                                                             int B, int H, int W, int margin, int oh, int ow, int *bad_rows) {
+    // grid (P, bands): each CTA produces a band of output rows of one patch (P alone would leave most SMs idle)
     const int p = blockIdx.x;
     if (p >= *count) return;
     const int Hp = H + 2 * margin, Wp = W + 2 * margin;
     const Crop c = read_crop(bound5, p, B, Hp, Wp);
     float *dst = out + (size_t)p * 3 * oh * ow;
     const int total = oh * ow;
+    const int rows_per = (oh + gridDim.y - 1) / gridDim.y;
+    const int e0 = blockIdx.y * rows_per * ow, e1 = min(total, e0 + rows_per * ow);
     if (!c.ok) {
-        for (int e = threadIdx.x; e < 3 * total; e += blockDim.x) dst[e] = 0.f;
-        if (threadIdx.x == 0 && bad_rows) atomicAdd(bad_rows, 1);
+        for (int ch = 0; ch < 3; ++ch)
+            for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) dst[(size_t)ch * total + e] = 0.f;
+        if (blockIdx.y == 0 && threadIdx.x == 0 && bad_rows) atomicAdd(bad_rows, 1);
         return;
     }
     const T *img = right + (size_t)c.img * H * W * 3;
     const float sh = axis_scale(c.h, oh), sw = axis_scale(c.w, ow);
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
         const int oy = e / ow, ox = e - oy * ow;
         const Axis ay = axis_coord(sh, oy, c.h), ax = axis_coord(sw, ox, c.w);
         const int ya = (int)c.y0 + ay.i0 - margin, yb = (int)c.y0 + ay.i1 - margin;
@@ -408,12 +412,13 @@ PATS_API int pats_compute_imgs(const float *x_scale, const float *y_scale, const
     const int seg_v = (int)((size_t)ps * 3 * elem / 16);
     left_windows_kernel<uint4><<<grid, 256, 0, st>>>((const uint4 *)left, (uint4 *)new_left, bound5, count, H, W, ps, width, seg_v);
     PATS_LAUNCH_CHECK("left_windows_kernel");
+    const dim3 rgrid(grid, 8);
     if (elem == 1)
-        right_patches_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t *)right, new_right, bound5, count, B, H, W, margin, 3 * ps,
-                                                          3 * ps, bad_rows);
+        right_patches_kernel<uint8_t><<<rgrid, 256, 0, st>>>((const uint8_t *)right, new_right, bound5, count, B, H, W, margin, 3 * ps,
+                                                           3 * ps, bad_rows);
     else
-        right_patches_kernel<float><<<grid, 256, 0, st>>>((const float *)right, new_right, bound5, count, B, H, W, margin, 3 * ps, 3 * ps,
-                                                        bad_rows);
+        right_patches_kernel<float><<<rgrid, 256, 0, st>>>((const float *)right, new_right, bound5, count, B, H, W, margin, 3 * ps, 3 * ps,
+                                                         bad_rows);
     PATS_LAUNCH_CHECK("right_patches_kernel");
     return PATS_OK;
 }

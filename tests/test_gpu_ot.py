@@ -217,6 +217,33 @@ def test_all_three_65x65_kernels_agree(M, lib, dev):
     np.testing.assert_allclose(out, oracle.log_sinkhorn_iterations(Z.numpy(), lmu.numpy(), lnu.numpy(), 37), atol=TOL, rtol=0)
 
 
+def test_kernel_variants_145_and_cluster(M, lib, dev):
+    """145 x 145: dedicated 9-warp kernel vs the padded 160 x 160 CTA kernel; 301 x 301: both cluster shapes."""
+    g = torch.Generator().manual_seed(6300)
+    s = 0.3 * torch.randn(7, 145, 145, generator=g)
+    s[2] *= 250.0  # one problem that needs the log-domain fallback
+    ns = areas(g, 7, 144, 256.0)
+    for iters in (100, 0, 1, 2, 10):
+        ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), iters)
+        for off in (0, 1):
+            lib.pats_sinkhorn_disable_c145(off)
+            try:
+                out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), iters).cpu().numpy()
+            finally:
+                lib.pats_sinkhorn_disable_c145(0)
+            np.testing.assert_allclose(out, ref, atol=TOL, rtol=2e-6, err_msg=f"c145 off={off} iters={iters}")
+    s = 0.1 * torch.randn(2, 300, 300, generator=g)
+    ns = areas(g, 2, 300, 16.0)
+    ref = oracle.log_optimal_transport(s.numpy(), 1.0, ns.numpy(), 100)
+    for v in (0, 1):
+        lib.pats_sinkhorn_cluster_variant(v)
+        try:
+            out = M.log_optimal_transport(s.to(dev), 1.0, ns.to(dev), 100).cpu().numpy()
+        finally:
+            lib.pats_sinkhorn_cluster_variant(0)
+        assert_plan_equal(out, ref)
+
+
 def test_cluster_kernel_fallback(M, lib, dev):
     """Same as above for the 8-CTA cluster kernel: the cluster must agree on the verdict and rank 0 re-solves."""
     g = torch.Generator().manual_seed(6100)

@@ -57,6 +57,19 @@ for name, (b, m, n) in {"L3_4800x65": (4800, 65, 65), "L3_30000x65": (30000, 65,
                                                  torch.cuda.current_stream().cuda_stream)
         assert rc == 0
 
+    if m == 65:
+        for mode in (1, 2):
+            lib.pats_sinkhorn_disable_w65(mode)
+            tv = timeit(run)
+            res[f"{name}_w65mode{mode}"] = tv
+            print(name, "w65 mode", mode, tv["median_ms"], flush=True)
+        lib.pats_sinkhorn_disable_w65(0)
+    if m == 145:
+        lib.pats_sinkhorn_disable_c145(1)
+        tv = timeit(run)
+        res[f"{name}_paddedcta"] = tv
+        print(name, "padded cta", tv["median_ms"], flush=True)
+        lib.pats_sinkhorn_disable_c145(0)
     t = timeit(run)
     t["us_per_problem"] = 1e3 * t["median_ms"] / b
     t["alg_GBps"] = b * m * n * 4 * 102 / (t["median_ms"] * 1e-3) / 1e9
@@ -73,9 +86,12 @@ for name, (b, m, n) in {"L3_4800x65": (4800, 65, 65), "L3_30000x65": (30000, 65,
 for name, (b, m) in {"L1_1x300": (1, 300), "L1_32x300": (32, 300)}.items():
     s = (0.1 * torch.randn(b, m, m, generator=g)).to(dev)
     ns = torch.exp((torch.rand(b, 1, m, generator=g) * 2 - 1) * 2.77).to(dev)
-    t = timeit(lambda: modules.log_optimal_transport(s, one, ns, 100), reps=10)
-    res[name] = t
-    print(name, t, flush=True)
+    for v in (0, 1):
+        lib.pats_sinkhorn_cluster_variant(v)
+        t = timeit(lambda: modules.log_optimal_transport(s, one, ns, 100), reps=10)
+        res[f"{name}_cluster_variant{v}"] = t
+        print(name, "cluster variant", v, t, flush=True)
+    lib.pats_sinkhorn_cluster_variant(0)
 
 src = torch.floor(torch.rand(1, 3, 736, 896, generator=g) * 256).to(dev)
 rows = []
