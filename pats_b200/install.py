@@ -28,7 +28,8 @@ _OT = {
 }
 _TABLE = {
     "models.modules": dict(_OT),
-    "models.first_layer": {**_OT, "Compute_imgs": _utils.Compute_imgs, "Iterative_expand_matrix": _utils.Iterative_expand_matrix},
+    "models.first_layer": {**_OT, "Compute_imgs": _utils.Compute_imgs, "Iterative_expand_matrix": _utils.Iterative_expand_matrix,
+                           "split_patches": _utils.split_patches},
     "models.second_layer": {**_OT, "Iterative_expand_matrix": _utils.Iterative_expand_matrix},
     "models.third_layer": dict(_OT),
     "models.pats": {"get_result": _utils.get_result},

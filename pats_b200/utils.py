@@ -197,3 +197,34 @@ def get_result(batch_size, if_nomatching, average_point, scale, patch_size, left
 
 
 __all__ += ["Iterative_expand_matrix", "est_nomatching", "get_result"]
+
+
+def split_patches(sum_cycle, height, width, max_once_used=350):
+    """Row-aligned chunking of the matched coarse patches (utils/utils.py:152-181; called at first_layer.py:135).
+
+    Host integer logic in the reference too -- a Python loop that compares 0-dim CUDA tensors (one device sync per
+    row).  Here `sum_cycle` (inclusive cumsum of the matched mask) is copied to the host ONCE and the same decisions
+    are taken on plain ints; the returned sets hold ints, which every consumer accepts (tensor comparisons at
+    first_layer.py:138-139, `!= 0` and negative slicing at models/pats.py:38-39).  Python's negative indexing of the
+    reference (`sum_cycle[i*width-1]` with i == 0 reads the last element) is kept.
+    """
+    sc = [int(v) for v in sum_cycle.detach().reshape(-1).tolist()]
+    cycle_num, second_layer_set, third_layer_set = 0, [], []
+    last_second_line = last_third_line = 0
+    for i in range(height):
+        num = sc[(i + 1) * width - 1]
+        if num > max_once_used * (cycle_num + 1):
+            origin_num = 0 if last_second_line == 0 else sc[last_second_line * width - 1]
+            cycle_num += 1
+            second_layer_set.append([origin_num, num])
+            third_layer_set.append([sc[last_third_line * width] - origin_num, num - sc[i * width - 1]])
+            last_second_line, last_third_line = i, i + 1
+    origin_num = 0 if last_second_line == 0 else sc[last_second_line * width - 1]
+    cycle_num += 1
+    second_layer_set.append([origin_num, height * width])
+    end_num = origin_num if last_third_line == height else sc[last_third_line * width]
+    third_layer_set.append([end_num - origin_num, 0])
+    return cycle_num, second_layer_set, third_layer_set
+
+
+__all__ += ["split_patches"]
