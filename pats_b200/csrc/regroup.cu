@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
     const float *opp = a.scores + ((size_t)bb * (m + 1) + m) * (n + 1);
     for (int j = threadIdx.x; j < stride; j += blockDim.x) {
         O[j] = j < n ? (a.log_input ? expf(opp[j]) : opp[j]) : kZero;
-        SX[j] = j < n ? a.sx[(size_t)bb * n + j] : 0.f;
-        SY[j] = j < n ? a.sy[(size_t)bb * n + j] : 0.f;
+        SX[j] = j < n ? a.sx[(size_t)bb * n + j] : kZero;  // slots n, n+1: SX*SY == 1e-14 exactly (the `zero` padding of
+        SY[j] = j < n ? a.sy[(size_t)bb * n + j] : 1.0f;   // expand_scale, utils.py:1208-1209)
         CM[j] = 0u;
     }
     __syncthreads();
@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
             }
         }
     }
-    auto Sval = [&](int idx) -> float { return idx < n ? SX[idx] * SY[idx] : kZero; };
+    auto Sval = [&](int idx) -> float { return SX[idx] * SY[idx]; };
+    const float lbv = a.lb;
 
     // ---- argmax over real targets (first maximum), dustbin test (utils.py:1182,1194) ------------------------
     float bv = -INFINITY;
@@ -145,32 +146,29 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
 
     // ---- box growth (utils.py:1213-1243): lanes 0..11 of the half = (direction, quantity); the strip is summed
     //      sequentially in the reference's order ------------------------------------------------------------------
-    const int d12 = hl / 3, q12 = hl - 3 * d12;
+    const int d12 = (hl / 3) & 3, q12 = hl - 3 * (hl / 3);  // lanes 12..15: d12 wraps to 0 (discarded)
     for (int it = 0; it < a.iters; ++it) {
         sdy = dy, sdx = dx;
         float acc = 0.f;
-        if (hl < 12) {
+        {
+            // Every lane runs the same instruction stream (lanes 12..15 of the half compute a discarded copy of lane 0..3).
+            // Inside the extent (t <= lim) ranges[] holds t, so the f32 index arithmetic of the reference is exact and
+            // equals off + t*step in integers; beyond it ranges[] holds 1e7 -> slot n+1 -> every quantity adds `zero`.
             int off, lim;
             if (d12 == 0) off = bd2 + bd0 * width - width, lim = dx;
             else if (d12 == 1) off = bd2 + bd1 * width + width, lim = dx;
             else if (d12 == 2) off = bd2 + bd0 * width - 1, lim = dy;
             else off = bd3 + bd0 * width + 1, lim = dy;
-            const float foff = (float)off, step = (d12 < 2) ? 1.0f : fwidth;
-            const int live = min(lim + 1, width);  // strip cells inside the current extent
-#pragma unroll 2
-            for (int t = 0; t < live; ++t) {
-                int s = (int)((float)t * step + foff);  // f32 multiply-add in two roundings, then truncation, as torch does it
-                if (s < 0 || s > n - 1) s = n + 1;
-                const float e = E[s];
-                float term;
-                if (q12 == 0) term = e;
-                else if (q12 == 1) term = (e > a.lb) ? O[s] : kZero;
-                else term = Sval(s);
-                acc += term;
+            const int stepi = (d12 < 2) ? 1 : width;
+            const int tmax = min(max(dx, dy) + 1, width);  // uniform over the half-warp
+            for (int t = 0; t < tmax; ++t) {
+                int sidx = off + t * stepi;
+                if (sidx < 0 || sidx > n - 1 || t > lim) sidx = n + 1;
+                const float e = E[sidx], o = O[sidx], sv = SX[sidx] * SY[sidx];
+                const float t1 = (e > lbv) ? o : kZero;
+                acc += (q12 == 0) ? e : ((q12 == 1) ? t1 : sv);
             }
-            // beyond the extent ranges[] holds 1e7 -> index n+1 -> every quantity contributes exactly `zero`
-            // (E = 1e-14 is never > lower_bound); keep the reference's additions, one FADD each
-            for (int t = live; t < width; ++t) acc += kZero;
+            for (int t = tmax; t < width; ++t) acc += kZero;
         }
         float es0 = __shfl_sync(0xffffffffu, acc, hbase + 0), es1 = __shfl_sync(0xffffffffu, acc, hbase + 3);
         float es2 = __shfl_sync(0xffffffffu, acc, hbase + 6), es3 = __shfl_sync(0xffffffffu, acc, hbase + 9);
@@ -200,22 +198,22 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
 
     // ---- border strips of the final box with the previous iteration's extents (utils.py:1245-1253) ------------
     float acc = 0.f;
-    if (hl < 8) {
-        const int d = hl >> 1, q = hl & 1;
+    {
+        const int d = (hl >> 1) & 3, q = hl & 1;
         int off, lim;
         if (d == 0) off = bd2 + bd0 * width, lim = sdx;
         else if (d == 1) off = bd2 + bd1 * width, lim = sdx;
         else if (d == 2) off = bd2 + bd0 * width, lim = sdy;
         else off = bd3 + bd0 * width, lim = sdy;
-        const float foff = (float)off, step = (d < 2) ? 1.0f : fwidth;
-        const int live = min(lim + 1, width);
-#pragma unroll 2
-        for (int t = 0; t < live; ++t) {
-            int s = (int)((float)t * step + foff);
-            if (s < 0 || s > n - 1) s = n + 1;
-            acc += (q == 0) ? E[s] : Sval(s);
+        const int stepi = (d < 2) ? 1 : width;
+        const int tmax = min(max(sdx, sdy) + 1, width);
+        for (int t = 0; t < tmax; ++t) {
+            int sidx = off + t * stepi;
+            if (sidx < 0 || sidx > n - 1 || t > lim) sidx = n + 1;
+            const float e = E[sidx], sv = SX[sidx] * SY[sidx];
+            acc += (q == 0) ? e : sv;
         }
-        for (int t = live; t < width; ++t) acc += kZero;
+        for (int t = tmax; t < width; ++t) acc += kZero;
     }
     const float e0 = __shfl_sync(0xffffffffu, acc, hbase + 0), e1 = __shfl_sync(0xffffffffu, acc, hbase + 2);
     const float e2 = __shfl_sync(0xffffffffu, acc, hbase + 4), e3 = __shfl_sync(0xffffffffu, acc, hbase + 6);
