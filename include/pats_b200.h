@@ -187,6 +187,24 @@ int pats_third_result_from_log_f32(const float *Z, const float *scale_x, const f
                                    const int64_t *p_t, int K, float *mkpts0_f, float *mkpts1_f, uint8_t *if_matching1,
                                    void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Feature gathers next to the path                  (models/second_layer.py:71-80, models/third_layer.py:119-146)
+ * ------------------------------------------------------------------------------------------- */
+
+/* 12x12 grid sampling of the three stem maps (AvgPool2d(2,1,1) of levels 0/1 fused into the gather)
+ *   f0 [N,C0,4R,4R], f1 [N,C1,2R,2R], f2 [N,C2,R,R] (R = row_num = 12) -> out [N,C0+C1+C2,R*R]      second_layer.py:71-80 */
+int pats_grid_sample12_f32(const float *f0, const float *f1, const float *f2, int N, int C0, int C1, int C2, int row_num,
+                           float *out, void *stream);
+
+/* Third-layer 8x8 window unfold + positional add + rubbish token                                 third_layer.py:119-146
+ *   feat [P,C,M,M], mkpts_c [K,2] f32 (x,y; snapped to the 4-grid inside; clamp96 = right-image clamp of :127-128),
+ *   b_ids [K] f32, kenc [C,64], rubbish [P,C,144], mkpts0_c [K,2] (left points: choose the rubbish token)
+ *   -> out [K,C,65].  `bad_index` (DEVICE int*) counts windows whose flat gather index leaves the tensor
+ *   (torch.gather would raise). */
+int pats_third_unfold_f32(const float *feat, int P, int C, int M, const float *mkpts_c, const float *b_ids, int K, int clamp96,
+                          const float *kenc, const float *rubbish, const float *mkpts0_c, float *out, int *bad_index,
+                          void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -142,3 +142,45 @@ def third_result_from_log(Z, scale_x, scale_y, p_s, p_t):
 
 
 __all__ += ["est_position", "first_layer_est_position", "second_layer_est_position", "third_result_from_log"]
+
+
+def grid_sample12(maps, row_num: int = 12):
+    """second_layer.py:71-80: sample the three stem maps [N,64,48,48], [N,64,24,24], [N,128,12,12] on the 12x12 grid
+    (levels 0/1 through AvgPool2d(2, stride=1, padding=1)) and concatenate along channels -> [N,256,144]."""
+    f0, f1, f2 = (cuda_f32(m, f"maps[{i}]") for i, m in enumerate(maps))
+    N = f0.shape[0]
+    R = row_num
+    if f0.shape[2:] != (4 * R, 4 * R) or f1.shape[2:] != (2 * R, 2 * R) or f2.shape[2:] != (R, R):
+        raise ValueError("grid_sample12: maps must be [N,C0,4R,4R], [N,C1,2R,2R], [N,C2,R,R]")
+    out = torch.empty((N, f0.shape[1] + f1.shape[1] + f2.shape[1], R * R), dtype=torch.float32, device=f0.device)
+    with torch.cuda.device(f0.device):
+        rc = _lib.load().pats_grid_sample12_f32(f0.data_ptr(), f1.data_ptr(), f2.data_ptr(), N, f0.shape[1], f1.shape[1], f2.shape[1], R,
+                                                out.data_ptr(), stream_ptr(f0.device))
+    _lib.check(rc, "grid_sample12")
+    return out
+
+
+def third_unfold(feat, mkpts_c, b_ids, kenc_out, rubbish, mkpts0_c, clamp96: bool, *, check: bool = True):
+    """third_layer.py:119-146 for one image side: 8x8 window features around every point + kenc(kpts) + rubbish token
+    -> [K,C,65] (the GNN input).  mkpts_c / mkpts0_c are the raw (x,y) points of third_layer.forward's arguments."""
+    feat = cuda_f32(feat, "feat")
+    P, Cc, M, M2 = feat.shape
+    dev = feat.device
+    mk = cuda_f32(mkpts_c, "mkpts_c").reshape(-1, 2)
+    K = mk.shape[0]
+    mk0 = cuda_f32(mkpts0_c, "mkpts0_c").reshape(K, 2)
+    b = cuda_f32(b_ids, "b_ids").reshape(K)
+    kenc = cuda_f32(kenc_out, "kenc_out").reshape(Cc, 64)
+    rub = cuda_f32(rubbish, "rubbish").reshape(P, Cc, 144)
+    out = torch.empty((K, Cc, 65), dtype=torch.float32, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pats_third_unfold_f32(feat.data_ptr(), P, Cc, M, mk.data_ptr(), b.data_ptr(), K, 1 if clamp96 else 0, kenc.data_ptr(),
+                                               rub.data_ptr(), mk0.data_ptr(), out.data_ptr(), bad.data_ptr(), stream_ptr(dev))
+    _lib.check(rc, "third_unfold")
+    if check and K > 0 and int(bad.item()):
+        raise IndexError("third_unfold: a window's gather index lies outside the feature tensor")
+    return out
+
+
+__all__ += ["grid_sample12", "third_unfold"]

@@ -277,6 +277,79 @@ def gen_third(ref):
     save("third", Z=Z, scale=scale, p_s=p_s, p_t=p_t, mkpts0_f=m0, mkpts1_f=m1, if_matching1=if_matching1)
 
 
+def gen_gathers(ref):
+    """a10 / a12 are inline code inside SecondLayer.forward / ThirdLayer.forward; the statements are restated verbatim
+    (same torch ops, same order) on seeded CPU tensors -- second_layer.py:71-80 and third_layer.py:119-146."""
+    g = torch.Generator().manual_seed(SEED + 8)
+    d = {}
+    # ---- a10: second_layer.py:71-80 -------------------------------------------------------------------------------
+    N, row_num = 2, 12
+    gF = torch.Generator().manual_seed(SEED + 80)  # the big feature maps are regenerated from this seed by the tests
+    maps = [torch.randn(N, 64, 48, 48, generator=gF), torch.randn(N, 64, 24, 24, generator=gF), torch.randn(N, 128, 12, 12, generator=gF)]
+    cols = torch.arange(0, row_num).reshape(row_num, 1).repeat(1, row_num).reshape(144)
+    rows = torch.arange(0, row_num).reshape(1, row_num).repeat(row_num, 1).reshape(144)
+    positions = torch.zeros((144, 2))
+    positions[:, 0] = cols
+    positions[:, 1] = rows
+    avgpool = torch.nn.AvgPool2d(2, stride=1, padding=1)
+    desc = []
+    for i, feat in enumerate(maps):
+        stride = int(8.0 / torch.pow(torch.tensor(2.0), i + 1))
+        if i <= 1:
+            feat = avgpool(feat)
+        index = ((positions.reshape(row_num, row_num, 2) + 0.5) * stride).long()
+        index = (index[:, :, 0] * feat.shape[3] + index[:, :, 1]).reshape(1, 1, -1).repeat(feat.shape[0], feat.shape[1], 1)
+        desc.append(torch.gather(feat.reshape(feat.shape[0], feat.shape[1], -1), 2, index))
+    desc = torch.cat(desc, dim=1)
+    d.update(gs_seed=np.int64(SEED + 80), gs_N=np.int64(N))
+    # regenerate from the f16-rounded maps so the stored inputs reproduce the stored output exactly
+    maps = [m.half().float() for m in maps]
+    desc = []
+    for i, feat in enumerate(maps):
+        stride = int(8.0 / torch.pow(torch.tensor(2.0), i + 1))
+        if i <= 1:
+            feat = avgpool(feat)
+        index = ((positions.reshape(row_num, row_num, 2) + 0.5) * stride).long()
+        index = (index[:, :, 0] * feat.shape[3] + index[:, :, 1]).reshape(1, 1, -1).repeat(feat.shape[0], feat.shape[1], 1)
+        desc.append(torch.gather(feat.reshape(feat.shape[0], feat.shape[1], -1), 2, index))
+    d["gs_out"] = torch.cat(desc, dim=1)
+    # ---- a12: third_layer.py:119-146 ------------------------------------------------------------------------------
+    P, K, W, M = 3, 24, 8, 52
+    feat_f0 = torch.randn(P, 128, M, M, generator=gF).half().float()
+    feat_f1 = torch.randn(P, 128, M, M, generator=gF).half().float()
+    rubbish = torch.randn(P, 128, 144, generator=g)
+    kenc_out = torch.randn(1, 128, 64, generator=g)
+    # matched level-2 cells never lie on the outer ring of the 12x12 window (merge_patches drops it, second_layer.py:193-200)
+    seq = (torch.randint(1, 11, (K,), generator=g) * 12 + torch.randint(1, 11, (K,), generator=g))
+    mkpts0_in = torch.stack([seq % 12 * 4 + 2, seq // 12 * 4 + 2], 1).float() * 2          # pats.py:57-61 (x,y), times 2
+    mkpts1_in = (torch.rand(K, 2, generator=g) * 110 - 7)                                      # predictions, some outside [0,96]
+    mkpts1_in[:6] = torch.tensor([[2., 50.], [94., 96.], [6., 6.], [10., 14.], [97.5, 40.], [48., -3.]])[:6] if K >= 6 else mkpts1_in[:6]
+    mkpts1_in[:, 1] = mkpts1_in[:, 1].clamp(8, 88)    # keep rows inside so the flat index of the reference's gather stays valid
+    mkpts1_in[:, 0] = mkpts1_in[:, 0].clamp(-7, 103)
+    b_ids = torch.randint(0, P, (K,), generator=g).float()
+    b_ids[mkpts1_in[:, 0] < 6] = b_ids[mkpts1_in[:, 0] < 6].clamp(min=1)   # a wrapped window must still land inside the tensor
+    b = b_ids.reshape(-1, 1).repeat(1, W * W)
+    mkpts0_c = torch.round(mkpts0_in / 4.0).long() * 4
+    x0 = (mkpts0_c[:, 0] // 2).reshape(-1, 1).expand(-1, W * W) + torch.arange(W).reshape(1, 1, W).repeat(K, W, 1).reshape(-1, W * W) - W / 2 + 2
+    y0 = (mkpts0_c[:, 1] // 2).reshape(-1, 1).expand(-1, W * W) + torch.arange(W).reshape(1, W, 1).repeat(K, 1, W).reshape(-1, W * W) - W / 2 + 2
+    index0 = (b * M * M + y0 * M + x0).long().reshape(-1, 1).expand(-1, 128)
+    mkpts1_c = torch.where(mkpts1_in >= 96, torch.tensor(96).float(), mkpts1_in)
+    mkpts1_c = torch.where(mkpts1_c <= 0, torch.tensor(0).float(), mkpts1_c)
+    mkpts1_c = torch.round(mkpts1_c / 4.0).long() * 4
+    x1 = (mkpts1_c[:, 0] // 2).reshape(-1, 1).expand(-1, W * W) + torch.arange(W).reshape(1, 1, W).repeat(K, W, 1).reshape(-1, W * W) - W / 2 + 2
+    y1 = (mkpts1_c[:, 1] // 2).reshape(-1, 1).expand(-1, W * W) + torch.arange(W).reshape(1, W, 1).repeat(K, 1, W).reshape(-1, W * W) - W / 2 + 2
+    index1 = (b * M * M + y1 * M + x1).long().reshape(-1, 1).expand(-1, 128)
+    f0u = torch.gather(feat_f0.permute(0, 2, 3, 1).reshape(-1, 128), 0, index0).reshape(-1, W * W, 128).permute(0, 2, 1) + kenc_out
+    f1u = torch.gather(feat_f1.permute(0, 2, 3, 1).reshape(-1, 128), 0, index1).reshape(-1, W * W, 128).permute(0, 2, 1) + kenc_out
+    x2 = torch.round(mkpts0_c[:, 0] / 8.0).long()
+    y2 = torch.round(mkpts0_c[:, 1] / 8.0).long()
+    index2 = (b_ids * 12 * 12 + y2 * 12 + x2).long().reshape(-1, 1).expand(-1, 128)
+    rub = torch.gather(rubbish.permute(0, 2, 1).reshape(-1, 128), 0, index2).reshape(-1, 128, 1)
+    d.update(un_P=np.int64(P), un_rubbish=rubbish, un_kenc=kenc_out, un_mk0=mkpts0_in, un_mk1=mkpts1_in,
+             un_b=b_ids, un_out0=torch.cat([f0u, rub], 2), un_out1=torch.cat([f1u, rub], 2))
+    save("gathers", **d)
+
+
 if __name__ == "__main__":
     ref = load_reference()
     torch.set_num_threads(8)
@@ -287,3 +360,4 @@ if __name__ == "__main__":
     gen_merge(ref)
     gen_result(ref)
     gen_third(ref)
+    gen_gathers(ref)

@@ -225,3 +225,39 @@ def test_third_result_from_log_equals_exp_then_result(dev):
     for x, y in zip(a, b):
         assert torch.equal(x, y)
     assert np.array_equal(a[2].cpu().numpy(), g["if_matching1"])
+
+
+def test_grid_sample12_and_third_unfold_golden(dev):
+    """a10 / a12: bit-exact against the reference statements (tests/golden/gathers.npz) and the oracle at real sizes."""
+    from conftest import gathers_inputs
+    from pats_b200 import layers as L
+
+    g, maps, feat0, feat1 = gathers_inputs()
+    out = L.grid_sample12([m.to(dev) for m in maps])
+    assert np.array_equal(out.cpu().numpy(), g["gs_out"])
+    kenc = T(g["un_kenc"], dev)
+    o0 = L.third_unfold(feat0.to(dev), T(g["un_mk0"], dev), T(g["un_b"], dev), kenc, T(g["un_rubbish"], dev), T(g["un_mk0"], dev), False)
+    o1 = L.third_unfold(feat1.to(dev), T(g["un_mk1"], dev), T(g["un_b"], dev), kenc, T(g["un_rubbish"], dev), T(g["un_mk0"], dev), True)
+    assert np.array_equal(o0.cpu().numpy(), g["un_out0"]) and np.array_equal(o1.cpu().numpy(), g["un_out1"])
+    with pytest.raises(IndexError):
+        L.third_unfold(feat1.to(dev), torch.zeros(1, 2, device=dev), torch.zeros(1, device=dev), kenc, T(g["un_rubbish"], dev),
+                       T(g["un_mk0"][:1], dev), True)
+    # real sizes: 2P = 600 windows (a10), K = 4800 points over P = 300 windows (a12)
+    gen = torch.Generator().manual_seed(90)
+    big = [torch.randn(600, 64, 48, 48, generator=gen), torch.randn(600, 64, 24, 24, generator=gen), torch.randn(600, 128, 12, 12, generator=gen)]
+    outb = L.grid_sample12([m.to(dev) for m in big]).cpu().numpy()
+    sel = [0, 299, 599]
+    ref = oracle.grid_sample12(big[0][sel].numpy(), big[1][sel].numpy(), big[2][sel].numpy())
+    assert np.array_equal(outb[sel], ref)
+    P, K = 300, 4800
+    feat = torch.randn(P, 128, 52, 52, generator=gen)
+    rub = torch.randn(P, 128, 144, generator=gen)
+    kk = torch.randn(128, 64, generator=gen)
+    cell = torch.randint(1, 11, (K, 2), generator=gen)
+    mk0 = (cell * 4 + 2).float() * 2
+    mk1 = (torch.rand(K, 2, generator=gen) * 80 + 8)
+    b = torch.randint(0, P, (K,), generator=gen).float()
+    o = L.third_unfold(feat.to(dev), mk1.to(dev), b.to(dev), kk.to(dev), rub.to(dev), mk0.to(dev), True).cpu().numpy()
+    idx = torch.randperm(K, generator=gen)[:64]
+    r = oracle.third_unfold(feat.numpy(), mk1[idx].numpy(), b[idx].numpy(), kk.numpy(), rub.numpy(), mk0[idx].numpy(), True)
+    assert np.array_equal(o[idx.numpy()], r)

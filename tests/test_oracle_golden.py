@@ -154,3 +154,24 @@ def test_a13_third_compute_result():
     assert (~im).any() and im.any()
     assert np.array_equal(m0, g["mkpts0_f"])
     np.testing.assert_allclose(m1, g["mkpts1_f"], rtol=1e-5, atol=2e-5)
+
+
+def test_a10_grid_sample12():
+    from conftest import gathers_inputs
+
+    g, maps, _, _ = gathers_inputs()
+    out = oracle.grid_sample12(maps[0].numpy(), maps[1].numpy(), maps[2].numpy())
+    assert np.array_equal(out, g["gs_out"])
+
+
+def test_a12_third_unfold():
+    from conftest import gathers_inputs
+
+    g, _, feat0, feat1 = gathers_inputs()
+    kenc = g["un_kenc"].reshape(128, 64)
+    o0 = oracle.third_unfold(feat0.numpy(), g["un_mk0"], g["un_b"], kenc, g["un_rubbish"], g["un_mk0"], False)
+    o1 = oracle.third_unfold(feat1.numpy(), g["un_mk1"], g["un_b"], kenc, g["un_rubbish"], g["un_mk0"], True)
+    assert np.array_equal(o0, g["un_out0"]) and np.array_equal(o1, g["un_out1"])
+    with pytest.raises(IndexError):  # a window whose flat index leaves the tensor: the reference's gather raises
+        oracle.third_unfold(feat1.numpy(), np.array([[0.0, 0.0]], np.float32), np.array([0.0], np.float32), kenc, g["un_rubbish"],
+                            g["un_mk0"][:1], True)
