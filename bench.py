@@ -53,6 +53,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torch warnings) also write to fd 1, so the
+# real stdout is saved here and fd 1 is pointed at stderr for the rest of the run; emit() writes the line to the saved fd.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 # ------------------------------------------------------------------------------------------------------------
 # synthetic inputs of one step (seeded; host tensors)
 # ------------------------------------------------------------------------------------------------------------
@@ -407,7 +417,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -417,6 +427,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--pairs-per-step", type=int, default=1)
+    ap.add_argument("--streams", type=int, default=1,
+                    help="CUDA streams the device-resident steps alternate over (independent pairs overlap; 1 = strictly serial)")
+    ap.add_argument("--no-overlap", action="store_true", help="skip the informational two-stream pass")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -439,48 +452,76 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = args.pairs_per_step
 
-    step = DeviceStep(torch, dev, B, SEED + rank)
-    stream = torch.cuda.current_stream(dev)
-    sp = stream.cuda_stream
-    # inputs + outputs of one step far exceed the 126 MB L2 (level-3 plans alone: 2 x 81 MB per pair) -> no L2 flush needed
-    for _ in range(args.warmup):
-        step.run(sp)
-    torch.cuda.synchronize(dev)
-    nbad = int(step.o["ci_meta"][1].item())
-    assert nbad == 0, f"synthetic Compute_imgs inputs produced {nbad} invalid crops"
-    kf = int(step.o["gr_total"].item())
-
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize(dev)
 
-    l3_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.perf_counter()
-    e0.record()
-    launches = 0
-    for s in range(args.steps):
-        launches += step.run(sp, l3_events[s])
-    if world > 1:  # the path's one exchange: gather of the match lists, once, after the pair loop
-        from pats_b200.dist import gather_match_lists
-
-        gather_match_lists([torch.cat([step.o["ml"][:kf], step.o["mr"][:kf]], 1)])
-    e1.record()
-    barrier()
-    t_wall1 = time.perf_counter()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    gather = None
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+        from pats_b200.dist import gather_match_lists as gather
+
+    steps_all = [DeviceStep(torch, dev, B, SEED + rank)]
+    step = steps_all[0]
+
+    def timed_pass(S, n_steps, want_clocks):
+        """Times exactly n_steps steps alternating over S CUDA streams (S = 1: strictly serial on the current stream).
+        Pairs are independent (evaluate.py:25-35); with S > 1 one pair's single-problem level-1 kernels overlap another
+        pair's level-3 work.  Every step is one full pass of the hot path over `pairs_per_step` pairs."""
+        while len(steps_all) < S:
+            steps_all.append(DeviceStep(torch, dev, B, SEED + rank + 1000 * len(steps_all)))
+        main_stream = torch.cuda.current_stream(dev)
+        streams = [torch.cuda.Stream(dev) for _ in range(S)] if S > 1 else [main_stream]
+        # inputs + outputs of one step far exceed the 126 MB L2 (level-3 plans alone: 2 x 81 MB per pair) -> no L2 flush needed
+        for w in range(max(args.warmup, S)):
+            with torch.cuda.stream(streams[w % S]):
+                steps_all[w % S].run(streams[w % S].cuda_stream)
+        torch.cuda.synchronize(dev)
+        nbad = int(step.o["ci_meta"][1].item())
+        assert nbad == 0, f"synthetic Compute_imgs inputs produced {nbad} invalid crops"
+        kf = int(step.o["gr_total"].item())
+        if gather is not None:  # warm-up of the exchange too (NCCL builds its communicator lazily on the first collective)
+            gather([torch.cat([step.o["ml"][:kf], step.o["mr"][:kf]], 1)])
+        l3_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and want_clocks:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        done = [torch.cuda.Event() for _ in range(S)]
+        barrier()
+        t_wall0 = time.perf_counter()
+        e0.record(main_stream)
+        if S > 1:
+            for st in streams:
+                st.wait_event(e0)
+        launches = 0
+        for i in range(n_steps):
+            with torch.cuda.stream(streams[i % S]):
+                launches += steps_all[i % S].run(streams[i % S].cuda_stream, l3_events[i])
+        if S > 1:
+            for i, st in enumerate(streams):
+                done[i].record(st)
+                main_stream.wait_event(done[i])
+        if gather is not None:  # the path's one exchange: gather of the match lists (SURVEY.md 8e), once, after the pair loop
+            gather([torch.cat([step.o["ml"][:kf], step.o["mr"][:kf]], 1)])
+        e1.record(main_stream)
+        barrier()
+        t_wall1 = time.perf_counter()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        clocks = sampler.stop(t_wall0, t_wall1) if (rank == 0 and want_clocks) else None
+        l3 = sorted(a.elapsed_time(b) for a, b in l3_events)
+        return float(ms.item()), launches, sum(l3) / len(l3), clocks, kf
+
+    S = max(1, args.streams)
+    total_ms, launches, l3_avg, clocks, kf = timed_pass(S, args.steps, True)
     value = world * B * args.steps / (total_ms * 1e-3)
-    l3_ms = sorted(a.elapsed_time(b) for a, b in l3_events)
-    l3_avg = sum(l3_ms) / len(l3_ms)
+    overlap = None
+    if S == 1 and not args.no_overlap:
+        o_ms, _, _, _, _ = timed_pass(2, args.steps, False)
+        overlap = {"streams": 2, "value": world * B * args.steps / (o_ms * 1e-3), "unit": "pairs/s", "ms_per_step": o_ms / args.steps,
+                   "note": "same steps alternating over two CUDA streams (independent pairs overlap); informational"}
 
     # ---- e2e: public API, host buffers ------------------------------------------------------------------
     e2e = None
@@ -508,7 +549,7 @@ def main():
         fma_lane_peak = 148 * 128 * sm_mhz * 1e6                # FP32 FMA lanes/s
         fma_done = b3 * 65 * 65 * 2 * (ITERS - 1)               # two FMA passes over the plan per iteration
         roofline = {
-            "kernel": "sinkhorn_w65_kernel (level-3 OT, one warp per 65x65 problem, %d problems)" % b3,
+            "kernel": "sinkhorn_w65x2_kernel (level-3 OT, two warps per 65x65 problem, %d problems per launch)" % b3,
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
             "peak_source": peak_src, "ms_per_launch": l3_avg, "algorithmic_bytes": alg_bytes,
             "note": "plan is register-resident: HBM moves only the compulsory read+write, so the streaming-model fraction exceeds 1; "
@@ -530,12 +571,12 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "pats_hot_path_pair640x480", "pairs_per_step": B, "P2": P2, "K3": K3, "sinkhorn_iters": ITERS,
+            "config": {"workload": "pats_hot_path_pair640x480", "pairs_per_step": B, "streams": S, "P2": P2, "K3": K3, "sinkhorn_iters": ITERS,
                        "l2_flush": "not needed: one step streams > 300 MB of distinct plans per pair (L2 = 126 MB)",
                        "matches_per_pair": kf // B, "exchange": "all_gather of match lists once after the pair loop (N>1)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "overlap": overlap,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
