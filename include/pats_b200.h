@@ -65,7 +65,7 @@ int pats_sinkhorn_kernel_kind(int M, int N);
 /* Force the generic log-domain kernel for every shape (tests: exercises the fallback path). */
 void pats_sinkhorn_force_generic(int on);
 /* Routing of 65 x 65 problems (tests / A-B timing): 0 = two warps per problem (default), 1 = padded 72 x 68 warp
- * kernel, 2 = one-warp 65 x 65 kernel. */
+ * kernel, 2 / 3 = one-warp 65 x 65 kernel compiled for 2 / 3 CTAs per SM. */
 void pats_sinkhorn_disable_w65(int mode);
 /* Route 145 x 145 problems through the padded 160 x 160 CTA kernel instead of the dedicated 9-warp kernel (tests). */
 void pats_sinkhorn_disable_c145(int on);

@@ -643,7 +643,8 @@ __device__ __forceinline__ void ag_cols(float (&v)[16]) {  // all-gather over pr
 }
 __device__ __forceinline__ float finite_or_zero(float m) { return (fabsf(m) == INFINITY) ? 0.f : m; }
 
-__global__ void __launch_bounds__(W65_WARPS * 32) sinkhorn_w65_kernel(SinkArgs a) {
+template <int MIN_CTAS>  // 2: 255 registers, no spills in the loop; 3: 170 registers (3 warps per scheduler), ~19 spill ops per iteration
+__global__ void __launch_bounds__(W65_WARPS * 32, MIN_CTAS) sinkhorn_w65_kernel(SinkArgs a) {
     constexpr int D = 64;  // dustbin index; M = N = 65
     __shared__ float s_fb[W65_WARPS][65 + 65 + 64];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1441,7 +1442,7 @@ static int g_force_generic = 0;
 static int g_cluster_variant = 0;  // <= 320 x 320 plans: 0 = 8 CTAs x 256 threads, 1 = 4 CTAs x 512 threads
 static int g_disable_c145 = 0;  // 145 x 145 routing: 0 = dedicated 9-warp kernel (default), 1 = padded 160 x 160 CTA kernel
 static int g_disable_w65 = 0;  // 65 x 65 routing: 0 = two warps per problem (default), 1 = padded 72 x 68 warp kernel,
-                               //                  2 = one-warp 65 x 65 kernel (tests / A-B timing)
+                               //                  2 / 3 = one-warp 65 x 65 kernel at 2 / 3 CTAs per SM (tests / A-B timing)
 static int *g_fb_total = nullptr;  // device counter
 static std::mutex g_mu;
 
@@ -1525,8 +1526,9 @@ static int run_sinkhorn(SinkArgs a, void *stream) {
                 PATS_LAUNCH_CHECK("sinkhorn_w65x2_kernel");
                 return PATS_OK;
             }
-            if (a.M == 65 && a.N == 65 && g_disable_w65 == 2) {
-                sinkhorn_w65_kernel<<<(a.b + W65_WARPS - 1) / W65_WARPS, W65_WARPS * 32, 0, st>>>(a);
+            if (a.M == 65 && a.N == 65 && (g_disable_w65 == 2 || g_disable_w65 == 3)) {
+                if (g_disable_w65 == 2) sinkhorn_w65_kernel<2><<<(a.b + W65_WARPS - 1) / W65_WARPS, W65_WARPS * 32, 0, st>>>(a);
+                else sinkhorn_w65_kernel<3><<<(a.b + W65_WARPS - 1) / W65_WARPS, W65_WARPS * 32, 0, st>>>(a);
                 PATS_LAUNCH_CHECK("sinkhorn_w65_kernel");
                 return PATS_OK;
             }
@@ -1577,7 +1579,7 @@ PATS_API int pats_sinkhorn_kernel_kind(int M, int N) { return kernel_kind(M, N);
 PATS_API void pats_sinkhorn_force_generic(int on) { g_force_generic = on ? 1 : 0; }
 PATS_API void pats_sinkhorn_cluster_variant(int v) { g_cluster_variant = v == 1 ? 1 : 0; }
 PATS_API void pats_sinkhorn_disable_c145(int on) { g_disable_c145 = on ? 1 : 0; }
-PATS_API void pats_sinkhorn_disable_w65(int mode) { g_disable_w65 = (mode >= 0 && mode <= 2) ? mode : 0; }
+PATS_API void pats_sinkhorn_disable_w65(int mode) { g_disable_w65 = (mode >= 0 && mode <= 3) ? mode : 0; }
 
 PATS_API int pats_sinkhorn_fallback_count(int reset) {
     if (ensure_counter() != PATS_OK) return -1;

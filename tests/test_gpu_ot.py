@@ -195,7 +195,7 @@ def test_all_three_65x65_kernels_agree(M, lib, dev):
     ns = areas(g, b, 64, 16.0)
     for iters in (100, 0, 1, 2, 9):
         ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), iters)
-        for mode in (0, 1, 2):
+        for mode in (0, 1, 2, 3):
             lib.pats_sinkhorn_disable_w65(mode)
             try:
                 out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), iters).cpu().numpy()

@@ -58,7 +58,7 @@ for name, (b, m, n) in {"L3_4800x65": (4800, 65, 65), "L3_30000x65": (30000, 65,
         assert rc == 0
 
     if m == 65:
-        for mode in (1, 2):
+        for mode in (1, 2, 3):
             lib.pats_sinkhorn_disable_w65(mode)
             tv = timeit(run)
             res[f"{name}_w65mode{mode}"] = tv
