@@ -67,8 +67,9 @@ void pats_sinkhorn_force_generic(int on);
 /* Routing of 65 x 65 problems (tests / A-B timing): 0 = two warps per problem (default), 1 = padded 72 x 68 warp
  * kernel, 2 / 3 = one-warp 65 x 65 kernel compiled for 2 / 3 CTAs per SM. */
 void pats_sinkhorn_disable_w65(int mode);
-/* Route 145 x 145 problems through the padded 160 x 160 CTA kernel instead of the dedicated 9-warp kernel (tests). */
-void pats_sinkhorn_disable_c145(int on);
+/* Routing of 145 x 145 problems (tests / A-B timing): 0 = 8-warp kernel, two CTAs per SM (default), 1 = padded
+ * 160 x 160 CTA kernel, 2 = 9-warp kernel. */
+void pats_sinkhorn_disable_c145(int mode);
 /* Cluster shape for plans up to 320 x 320 (A-B timing): 0 = 8 CTAs x 256 threads (default), 1 = 4 CTAs x 512 threads. */
 void pats_sinkhorn_cluster_variant(int v);
 /* Problems the register-resident kernels handed to the log-domain fallback since the last reset

@@ -1430,6 +1430,302 @@ __global__ void __launch_bounds__(C145_T) sinkhorn_c145_kernel(SinkArgs a) {  //
 #undef LCOL
 }
 
+// ---------------------------------------------------------------------------------------------
+// Level-2 kernel, 8-warp tiling (default for 145 x 145): warp w keeps the 18-column slab [18w, 18w+18) of the core,
+// a 9 x 9 tile per lane (rows pr + 16k; columns 18w + qc + 2*(c ^ cmask(pr)) for slots c < 8 and 18w + qc + 16 for
+// slot 8).  256 threads at <= 128 registers: TWO CTAs per SM (16 warps), so one CTA's barrier phases overlap the
+// other's FFMA2 stream -- the 9-warp kernel above is limited to one CTA per SM by the per-scheduler register file.
+// Slots 0..7 reduce with the select-free tree (twins pr, pr^8 own slot 0), slot 8 with a plain 4-step all-reduce.
+// ---------------------------------------------------------------------------------------------
+constexpr int C145B_W = 8, C145B_T = 256;
+
+template <class Op>
+__device__ __forceinline__ float allreduce_pr16(float v, Op op) {  // over pr (lane bits 1..4)
+    v = op(v, __shfl_xor_sync(0xffffffffu, v, 2));
+    v = op(v, __shfl_xor_sync(0xffffffffu, v, 4));
+    v = op(v, __shfl_xor_sync(0xffffffffu, v, 8));
+    return op(v, __shfl_xor_sync(0xffffffffu, v, 16));
+}
+
+__global__ void __launch_bounds__(C145B_T, 2) sinkhorn_c145b_kernel(SinkArgs a) {
+    constexpr int D = 144;
+    __shared__ float s_part[C145B_W][144];
+    __shared__ float s_row[144];
+    __shared__ float s_red[2][8];
+    __shared__ float s_keep[144];
+    __shared__ float s_fb[145 + 145 + 2 * C145B_T];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int p = blockIdx.x;
+    if (p >= a.b) return;
+    const int pr = lane >> 1, qc = lane & 1;
+    const int cmask = ((pr & 1) << 2) | (((pr >> 1) & 1) << 1) | ((pr >> 2) & 1);
+    const bool col_owner = (pr & 8) == 0;   // counts the owned slot-0 column once per twin pair
+    const bool col8_owner = pr == 0;        // counts the slot-8 column once per 16 lanes
+    // rows are finished by the qc==0 lanes (row 16w + pr) and, for rows 128..143, the qc==1 lanes of warp 0
+    const int myrow = qc == 0 ? 16 * w + pr : (w == 0 ? 128 + pr : -1);
+    const bool row_thread = myrow >= 0;
+    const Marg g = problem_marginals(a, p, lane);
+#define LROW(k) (pr + 16 * (k))
+#define LCOL(c) (18 * w + qc + 2 * ((c) ^ cmask))
+#define LCOL8 (18 * w + qc + 16)
+    auto red8 = [&](int which) {
+        float t = s_red[which][0];
+#pragma unroll
+        for (int i = 1; i < C145B_W; ++i) t += s_red[which][i];
+        return t;
+    };
+    auto max8 = [&](int which) {
+        float t = s_red[which][0];
+#pragma unroll
+        for (int i = 1; i < C145B_W; ++i) t = fmaxf(t, s_red[which][i]);
+        return t;
+    };
+    auto row_sum8 = [&](int row) {
+        float t = s_part[0][row];
+#pragma unroll
+        for (int i = 1; i < C145B_W; ++i) t += s_part[i][row];
+        return t;
+    };
+
+    // ---- load ------------------------------------------------------------------------------------------------------
+    float z[9][9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) z[k][c] = z_at(a, g, p, LROW(k), LCOL(c));
+        z[k][8] = z_at(a, g, p, LROW(k), LCOL8);
+    }
+    const float zr = z_at(a, g, p, D, LCOL(0)), zr8 = z_at(a, g, p, D, LCOL8);
+    const float zc = row_thread ? z_at(a, g, p, myrow, D) : 0.f;
+    const float zcorner = z_at(a, g, p, D, D);
+    const float mu_t = row_thread ? expf(lmu_at(a, g, p, myrow)) : 0.f;
+    const float nu_o = expf(lnu_at(a, g, p, LCOL(0))), nu8 = expf(lnu_at(a, g, p, LCOL8));
+    const float mud = expf(lmu_at(a, g, p, D)), nud = expf(lnu_at(a, g, p, D));
+    float v1_o = 0.f, v1_8 = 0.f, u1d = 0.f, v1d = 0.f, Dc = 0.f, Dr = 0.f, Dr8 = 0.f, corner = 0.f;
+
+    // ---- iteration 1, exact in the log domain ---------------------------------------------------------------------
+    if (a.iters >= 1) {
+        float u1[9], v1[8], u1_t = 0.f;
+        {
+            float mx[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                float m = z[k][0];
+#pragma unroll
+                for (int c = 1; c < 9; ++c) m = fmaxf(m, z[k][c]);
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                if (qc == 0) s_part[w][LROW(k)] = m;
+            }
+            const float drm_w = warp_max(fmaxf(zr, zr8));
+            if (lane == 0) s_red[0][w] = drm_w;
+            __syncthreads();
+            float rm = 0.f;
+            if (row_thread) {
+                rm = s_part[0][myrow];
+#pragma unroll
+                for (int i = 1; i < C145B_W; ++i) rm = fmaxf(rm, s_part[i][myrow]);
+                rm = finite_or_zero(fmaxf(rm, zc));
+                s_row[myrow] = rm;
+            }
+            const float drm = finite_or_zero(fmaxf(max8(0), zcorner));
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 9; ++k) mx[k] = s_row[LROW(k)];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) sacc += fast_exp(z[k][c] - mx[k]);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                u1[k] = sacc;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                if (qc == 0) s_part[w][LROW(k)] = u1[k];
+            const float drs_w = warp_sum((col_owner ? fast_exp(zr - drm) : 0.f) + (col8_owner ? fast_exp(zr8 - drm) : 0.f));
+            if (lane == 0) s_red[0][w] = drs_w;
+            __syncthreads();
+            if (row_thread) {
+                const float sacc = row_sum8(myrow) + fast_exp(zc - rm);
+                u1_t = lmu_at(a, g, p, myrow) - (fast_log(sacc) + rm);
+                s_row[myrow] = u1_t;
+                s_keep[myrow] = u1_t;
+            }
+            u1d = lmu_at(a, g, p, D) - (fast_log(red8(0) + fast_exp(zcorner - drm)) + drm);
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 9; ++k) u1[k] = s_row[LROW(k)];
+        }
+        {
+            float mx[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float m = z[0][c] + u1[0];
+#pragma unroll
+                for (int k = 1; k < 9; ++k) m = fmaxf(m, z[k][c] + u1[k]);
+                mx[c] = m;
+            }
+            float m8 = z[0][8] + u1[0];
+#pragma unroll
+            for (int k = 1; k < 9; ++k) m8 = fmaxf(m8, z[k][8] + u1[k]);
+            rs_c145(mx, OpMax());
+            mx[0] = finite_or_zero(fmaxf(mx[0], zr + u1d));
+            ag_c145(mx);
+            m8 = finite_or_zero(fmaxf(allreduce_pr16(m8, OpMax()), zr8 + u1d));
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) sacc += fast_exp((z[k][c] + u1[k]) - mx[c]);
+                v1[c] = sacc;
+            }
+            float s8 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) s8 += fast_exp((z[k][8] + u1[k]) - m8);
+            rs_c145(v1, OpSum());
+            v1[0] = lnu_at(a, g, p, LCOL(0)) - (fast_log(v1[0] + fast_exp((zr + u1d) - mx[0])) + mx[0]);
+            ag_c145(v1);
+            s8 = allreduce_pr16(s8, OpSum());
+            v1_8 = lnu_at(a, g, p, LCOL8) - (fast_log(s8 + fast_exp((zr8 + u1d) - m8)) + m8);
+            const float dcm_w = warp_max(row_thread ? zc + u1_t : -INFINITY);
+            if (lane == 0) s_red[1][w] = dcm_w;
+            __syncthreads();
+            const float dcm = finite_or_zero(fmaxf(max8(1), zcorner + u1d));
+            __syncthreads();
+            const float dcs_w = warp_sum(row_thread ? fast_exp((zc + u1_t) - dcm) : 0.f);
+            if (lane == 0) s_red[1][w] = dcs_w;
+            __syncthreads();
+            v1d = lnu_at(a, g, p, D) - (fast_log(red8(1) + fast_exp((zcorner + u1d) - dcm)) + dcm);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) z[k][c] = fast_exp((z[k][c] + u1[k]) + v1[c]);
+            z[k][8] = fast_exp((z[k][8] + u1[k]) + v1_8);
+        }
+        Dc = row_thread ? fast_exp((zc + u1_t) + v1d) : 0.f;
+        Dr = fast_exp((zr + u1d) + v1[0]);
+        Dr8 = fast_exp((zr8 + u1d) + v1_8);
+        v1_o = v1[0];
+        corner = fast_exp((zcorner + u1d) + v1d);
+    }
+    __syncthreads();
+
+    // ---- iterations 2..iters (same barrier structure as sinkhorn_c145_kernel) -----------------------------------------
+    float2 Kp[9][4];
+    float K8[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) Kp[k][h] = make_float2(z[k][2 * h], z[k][2 * h + 1]);
+        K8[k] = z[k][8];
+    }
+    float be[8], be8 = 1.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) be[c] = 1.f;
+    float al_t = 1.f, ald = 1.f, bed = 1.f;
+    {
+        const float srp = warp_sum((col_owner ? Dr : 0.f) + (col8_owner ? Dr8 : 0.f));
+        if (lane == 0) s_red[0][w] = srp;
+    }
+    float lo = INFINITY, hi = 0.f;
+
+    for (int it = 1; it < a.iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) acc = ffma2(Kp[k][h], make_float2(be[2 * h], be[2 * h + 1]), acc);
+            float r = fmaf(K8[k], be8, acc.x + acc.y);
+            r += __shfl_xor_sync(0xffffffffu, r, 1);
+            if (qc == 0) s_part[w][LROW(k)] = r;
+        }
+        __syncthreads();  // B1
+        if (it > 1) bed = nud * fast_rcp(fmaf(corner, ald, red8(1)));
+        ald = mud * fast_rcp(fmaf(corner, bed, red8(0)));
+        if (row_thread) {
+            al_t = mu_t * fast_rcp(fmaf(Dc, bed, row_sum8(myrow)));
+            s_row[myrow] = al_t;
+        }
+        __syncthreads();  // B2
+        {
+            const float scp = warp_sum(row_thread ? Dc * al_t : 0.f);
+            if (lane == 0) s_red[1][w] = scp;  // read after the next B1
+        }
+        float2 s2[4];
+        float s8 = 0.f;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) s2[h] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float ak = s_row[LROW(k)];
+            const float2 ak2 = make_float2(ak, ak);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) s2[h] = ffma2(Kp[k][h], ak2, s2[h]);
+            s8 = fmaf(K8[k], ak, s8);
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) be[2 * h] = s2[h].x, be[2 * h + 1] = s2[h].y;
+        rs_c145(be, OpSum());
+        s8 = allreduce_pr16(s8, OpSum());
+        be[0] = nu_o * fast_rcp(fmaf(Dr, ald, be[0]));
+        be8 = nu8 * fast_rcp(fmaf(Dr8, ald, s8));
+        {
+            const float srp = warp_sum((col_owner ? Dr * be[0] : 0.f) + (col8_owner ? Dr8 * be8 : 0.f));
+            if (lane == 0) s_red[0][w] = srp;  // read after the next B1
+        }
+        if ((it & 7) == 0 || it == a.iters - 1) {
+            const float at = row_thread ? al_t : ald;
+            lo = fminf(fminf(lo, at), fminf(fminf(ald, be[0]), fminf(be8, bed)));
+            hi = fmaxf(fmaxf(hi, at), fmaxf(fmaxf(ald, be[0]), fmaxf(be8, bed)));
+        }
+        ag_c145(be);
+    }
+    __syncthreads();
+    if (a.iters >= 2) bed = nud * fast_rcp(fmaf(corner, ald, red8(1)));
+
+    // ---- potentials, health check, output ------------------------------------------------------------------------------
+    const float shift = (a.mode == MODE_RAW) ? 0.f : g.norm;
+    bool bad = !(lo >= 1e-13f && hi <= 1e13f) || (a.iters >= 2 && !(bed >= 1e-13f && bed <= 1e13f));
+    float U_t = 0.f, Ud = 0.f, Vd = -shift, V[8], V8;
+    if (a.iters >= 1) U_t = row_thread ? s_keep[myrow] : 0.f, Ud = u1d, Vd = v1d - shift;
+    if (a.iters >= 2) U_t += fast_log(al_t), Ud += fast_log(ald), Vd += fast_log(bed);
+    if (row_thread && !(fabsf(U_t) < INFINITY)) bad = true;
+    if (!(fabsf(Ud) < INFINITY) || !(fabsf(Vd) < INFINITY)) bad = true;
+    {
+        float tv = 0.f, t8 = 0.f;
+        if (a.iters >= 1) tv = v1_o, t8 = v1_8;
+        if (a.iters >= 2) tv += fast_log(be[0]), t8 += fast_log(be8);
+        if (!(fabsf(tv) < INFINITY) || !(fabsf(t8) < INFINITY)) bad = true;
+        V[0] = tv - shift;
+        V8 = t8 - shift;
+    }
+    if (row_thread) s_row[myrow] = U_t;
+    if (__syncthreads_or(bad ? 1 : 0)) {
+        if (tid == 0 && a.fb_total) atomicAdd(a.fb_total, 1);
+        log_domain_solve<C145B_T>(a, g, p, s_fb, s_fb + 145, s_fb + 290, tid, BlockSync());
+        return;
+    }
+    ag_c145(V);
+    float *o = a.out + (size_t)p * 145 * 145;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int row = LROW(k);
+        const float Uk = s_row[row];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[row * 145 + LCOL(c)] = (z_at(a, g, p, row, LCOL(c)) + Uk) + V[c];
+        o[row * 145 + LCOL8] = (z_at(a, g, p, row, LCOL8) + Uk) + V8;
+    }
+    if (row_thread) o[myrow * 145 + D] = (z_at(a, g, p, myrow, D) + U_t) + Vd;
+    if (col_owner) o[D * 145 + LCOL(0)] = (z_at(a, g, p, D, LCOL(0)) + Ud) + V[0];
+    if (col8_owner) o[D * 145 + LCOL8] = (z_at(a, g, p, D, LCOL8) + Ud) + V8;
+    if (tid == 0) o[D * 145 + D] = (z_at(a, g, p, D, D) + Ud) + Vd;
+#undef LROW
+#undef LCOL
+#undef LCOL8
+}
+
 // ---- host dispatch ------------------------------------------------------------------------------
 using CfgTiny = RegCfg<1, 2, 4, 8, 4>;         // <= 32 x 32, one warp per problem, 4 problems per CTA
 using CfgWarp = RegCfg<1, 2, 9, 17, 4>;        // <= 72 x 68  (level 3: 65 x 65)
@@ -1440,7 +1736,8 @@ using CfgCl512 = RegCfg<16, 5, 4, 16, 1, 8>;   // <= 512 x 512, cluster of 8 CTA
 
 static int g_force_generic = 0;
 static int g_cluster_variant = 0;  // <= 320 x 320 plans: 0 = 8 CTAs x 256 threads, 1 = 4 CTAs x 512 threads
-static int g_disable_c145 = 0;  // 145 x 145 routing: 0 = dedicated 9-warp kernel (default), 1 = padded 160 x 160 CTA kernel
+static int g_disable_c145 = 0;  // 145 x 145 routing: 0 = 8-warp kernel, two CTAs per SM (default), 1 = padded 160 x 160 CTA kernel,
+                                //                    2 = 9-warp kernel
 static int g_disable_w65 = 0;  // 65 x 65 routing: 0 = two warps per problem (default), 1 = padded 72 x 68 warp kernel,
                                //                  2 / 3 = one-warp 65 x 65 kernel at 2 / 3 CTAs per SM (tests / A-B timing)
 static int *g_fb_total = nullptr;  // device counter
@@ -1535,7 +1832,12 @@ static int run_sinkhorn(SinkArgs a, void *stream) {
             if (a.M <= CfgTiny::MAXM && a.N <= CfgTiny::MAXN) return launch_reg<CfgTiny>(a, st);
             return launch_reg<CfgWarp>(a, st);
         case 1:
-            if (a.M == 145 && a.N == 145 && !g_disable_c145) {
+            if (a.M == 145 && a.N == 145 && g_disable_c145 == 0) {
+                sinkhorn_c145b_kernel<<<a.b, C145B_T, 0, st>>>(a);
+                PATS_LAUNCH_CHECK("sinkhorn_c145b_kernel");
+                return PATS_OK;
+            }
+            if (a.M == 145 && a.N == 145 && g_disable_c145 == 2) {
                 sinkhorn_c145_kernel<<<a.b, C145_T, 0, st>>>(a);
                 PATS_LAUNCH_CHECK("sinkhorn_c145_kernel");
                 return PATS_OK;
@@ -1578,7 +1880,7 @@ PATS_API int pats_log_optimal_transport2_f32(const float *scores, const float *o
 PATS_API int pats_sinkhorn_kernel_kind(int M, int N) { return kernel_kind(M, N); }
 PATS_API void pats_sinkhorn_force_generic(int on) { g_force_generic = on ? 1 : 0; }
 PATS_API void pats_sinkhorn_cluster_variant(int v) { g_cluster_variant = v == 1 ? 1 : 0; }
-PATS_API void pats_sinkhorn_disable_c145(int on) { g_disable_c145 = on ? 1 : 0; }
+PATS_API void pats_sinkhorn_disable_c145(int mode) { g_disable_c145 = (mode >= 0 && mode <= 2) ? mode : 0; }
 PATS_API void pats_sinkhorn_disable_w65(int mode) { g_disable_w65 = (mode >= 0 && mode <= 3) ? mode : 0; }
 
 PATS_API int pats_sinkhorn_fallback_count(int reset) {

@@ -227,7 +227,7 @@ def test_kernel_variants_145_and_cluster(M, lib, dev):
     ns = areas(g, 7, 144, 256.0)
     for iters in (100, 0, 1, 2, 10):
         ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), iters)
-        for off in (0, 1):
+        for off in (0, 1, 2):
             lib.pats_sinkhorn_disable_c145(off)
             try:
                 out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), iters).cpu().numpy()

@@ -65,10 +65,11 @@ for name, (b, m, n) in {"L3_4800x65": (4800, 65, 65), "L3_30000x65": (30000, 65,
             print(name, "w65 mode", mode, tv["median_ms"], flush=True)
         lib.pats_sinkhorn_disable_w65(0)
     if m == 145:
-        lib.pats_sinkhorn_disable_c145(1)
-        tv = timeit(run)
-        res[f"{name}_paddedcta"] = tv
-        print(name, "padded cta", tv["median_ms"], flush=True)
+        for mode in (1, 2):
+            lib.pats_sinkhorn_disable_c145(mode)
+            tv = timeit(run)
+            res[f"{name}_c145mode{mode}"] = tv
+            print(name, "c145 mode", mode, tv["median_ms"], flush=True)
         lib.pats_sinkhorn_disable_c145(0)
     t = timeit(run)
     t["us_per_problem"] = 1e3 * t["median_ms"] / b
