@@ -60,8 +60,12 @@ int pats_log_optimal_transport2_f32(const float *scores, const float *one, const
                                     int iters, float *out, void *stream);
 
 /* Which kernel family the dispatcher picks for a shape (0 = register-resident warp kernel, 1 = register-resident
- * CTA kernel, 3 = register-resident 8-CTA cluster kernel, 2 = generic log-domain kernel); for tests and the bench. */
+ * CTA kernel, 3 = register-resident 8-CTA cluster kernel, 4 = grid-cooperative streaming kernel for plans beyond
+ * 512 x 512 (up to 4097 columns), 2 = generic log-domain kernel); for tests and the bench. */
 int pats_sinkhorn_kernel_kind(int M, int N);
+/* CTAs per problem of the grid-cooperative kernel (0 = automatic: floor(SMs / b), at least one row per warp);
+ * tests / A-B timing. */
+void pats_sinkhorn_grid_ctas_per_problem(int g);
 /* Force the generic log-domain kernel for every shape (tests: exercises the fallback path). */
 void pats_sinkhorn_force_generic(int on);
 /* Routing of 65 x 65 problems (tests / A-B timing): 0 = two warps per problem (default), 1 = padded 72 x 68 warp
@@ -70,7 +74,8 @@ void pats_sinkhorn_disable_w65(int mode);
 /* Routing of 145 x 145 problems (tests / A-B timing): 0 = 8-warp kernel, two CTAs per SM (default), 1 = padded
  * 160 x 160 CTA kernel, 2 = 9-warp kernel. */
 void pats_sinkhorn_disable_c145(int mode);
-/* Cluster shape for plans up to 320 x 320 (A-B timing): 0 = 8 CTAs x 256 threads (default), 1 = 4 CTAs x 512 threads. */
+/* Cluster shape for plans up to 320 x 320 (A-B timing): 0 = 8 CTAs x 256 threads (default), 1 = 4 CTAs x 512 threads,
+ * 2 = 8 x 256 with a one-hop all-to-all exchange of the column partials. */
 void pats_sinkhorn_cluster_variant(int v);
 /* Problems the register-resident kernels handed to the log-domain fallback since the last reset
  * (device counter, read with a synchronising copy; tests / diagnostics only). */

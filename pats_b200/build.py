@@ -18,7 +18,7 @@ SO = os.path.join(HERE, "libpats_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 # source -> extra flags.  regroup.cu is compiled without FMA contraction: its f32 expressions must round
 # exactly like the C oracle's (integer results hang off them).
-SOURCES = {"api.cu": [], "sinkhorn.cu": [], "subdivide.cu": [], "regroup.cu": ["-fmad=false"], "gather.cu": []}
+SOURCES = {"api.cu": [], "sinkhorn.cu": [], "sinkhorn_grid.cu": [], "subdivide.cu": [], "regroup.cu": ["-fmad=false"], "gather.cu": []}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -41,7 +41,7 @@ def needs_build() -> bool:
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "pats_b200.h")]
+    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "sinkhorn_common.cuh"), os.path.join(INCLUDE, "pats_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for cmd, pr in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, cmd)
-    link = [_nvcc(), "-shared", "-o", SO, *objs]
+    link = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, *objs]
     if verbose:
         print(" ".join(link))
     subprocess.run(link, check=True, env=env)

@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
     bd0 = bd1 = max0 / a.grid_w;
     bd2 = bd3 = max0 % a.grid_w;
     const int width = a.width, height = a.height;
-    const float fwidth = (float)width;
     float last_sum = E[max0], last_nom = O[max0];
 
     // ---- box growth (utils.py:1213-1243): lanes 0..11 of the half = (direction, quantity); the strip is summed

@@ -25,157 +25,11 @@
 
 #include <mutex>
 
-#include "common.cuh"
+#include "sinkhorn_common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace pats {
-
-enum { MODE_RAW = 0, MODE_OT = 1, MODE_OT2 = 2 };
-
-struct SinkArgs {
-    const float *Z;       // raw/OT2: [b,M,N]; OT: un-augmented scores [b,M-1,N-1]
-    const float *log_mu;  // raw only [b,M]
-    const float *log_nu;  // raw only [b,N]
-    const float *alpha;   // OT: dustbin score (device scalar); OT2: `one` (device scalar)
-    const float *ns;      // OT/OT2: [b,N-1] target areas
-    float *out;           // [b,M,N]
-    int b, M, N, iters, mode;
-    int *fb_total;        // device counter: problems sent to the log-domain fallback
-};
-
-struct Marg {
-    float norm, lms, lnsum, fill;
-};
-
-__device__ __forceinline__ float z_at(const SinkArgs &a, const Marg &g, int p, int row, int col) {
-    if (a.mode == MODE_OT) {
-        const int zm = a.M - 1, zn = a.N - 1;  // couplings = [[scores, alpha],[alpha, alpha]]  (modules.py:152-156)
-        return (row < zm && col < zn) ? __ldg(a.Z + ((size_t)p * zm + row) * zn + col) : g.fill;
-    }
-    return __ldg(a.Z + ((size_t)p * a.M + row) * a.N + col);
-}
-
-__device__ __forceinline__ float lmu_at(const SinkArgs &a, const Marg &g, int p, int row) {
-    if (a.mode == MODE_RAW) return __ldg(a.log_mu + (size_t)p * a.M + row);
-    return row < a.M - 1 ? g.norm : g.lnsum + g.norm;  // modules.py:159 / :178
-}
-
-__device__ __forceinline__ float lnu_at(const SinkArgs &a, const Marg &g, int p, int col) {
-    if (a.mode == MODE_RAW) return __ldg(a.log_nu + (size_t)p * a.N + col);
-    return col < a.N - 1 ? logf(__ldg(a.ns + (size_t)p * (a.N - 1) + col)) + g.norm : g.lms + g.norm;  // :158 / :177
-}
-
-// Per-problem scalars of the marginals (modules.py:157 / :175).  Every warp computes them
-// redundantly in the same order, so all warps of a CTA hold bit-identical values.
-__device__ __forceinline__ Marg problem_marginals(const SinkArgs &a, int p, int lane) {
-    Marg g;
-    g.norm = 0.f, g.lms = 0.f, g.lnsum = 0.f, g.fill = 0.f;
-    if (a.mode != MODE_RAW) {
-        const int nr = a.N - 1;
-        float s = 0.f;
-        for (int j = lane; j < nr; j += 32) s += __ldg(a.ns + (size_t)p * nr + j);
-        s = warp_sum(s);
-        const float sc = __ldg(a.alpha);
-        const float ms = (a.mode == MODE_OT2) ? (float)(a.M - 1) * sc : (float)(a.M - 1);
-        g.norm = -logf(ms + s);
-        g.lms = logf(ms);
-        g.lnsum = logf(s);
-        g.fill = (a.mode == MODE_OT) ? sc : 0.f;
-    }
-    return g;
-}
-
-struct BlockSync {
-    __device__ __forceinline__ void operator()() const { __syncthreads(); }
-};
-struct WarpSync {
-    __device__ __forceinline__ void operator()() const { __syncwarp(); }
-};
-
-// ---------------------------------------------------------------------------------------------
-// Exact log-domain Sinkhorn by a group of GT threads (modules.py:137-143 as written: max-shifted
-// log-sum-exp for rows, then columns).  u[M], v[N] live in shared memory; `red` holds 2*GT floats.
-// Used (a) as the in-kernel fallback of the register kernels and (b) as the kernel for shapes
-// that do not fit in registers.
-// ---------------------------------------------------------------------------------------------
-template <int GT, class Sync>
-__device__ void log_domain_solve(const SinkArgs &a, const Marg &g, int p, float *u, float *v, float *red, int gtid,
-                                 Sync gsync) {
-    const int M = a.M, N = a.N;
-    const int lane = gtid & 31, warp = gtid >> 5;
-    constexpr int NW = GT / 32;
-    for (int j = gtid; j < N; j += GT) v[j] = 0.f;
-    for (int i = gtid; i < M; i += GT) u[i] = 0.f;
-    // column pass geometry: NP columns (padded to a warp multiple) x G row groups
-    const int NP = (N + 31) & ~31;
-    const int G = (NP <= GT) ? GT / NP : 1;
-    gsync();
-    for (int it = 0; it < a.iters; ++it) {
-        for (int i = warp; i < M; i += NW) {
-            float mx = -INFINITY;
-            for (int j = lane; j < N; j += 32) mx = fmaxf(mx, z_at(a, g, p, i, j) + v[j]);
-            mx = warp_max(mx);
-            const float mxs = (fabsf(mx) == INFINITY) ? 0.f : mx;
-            float s = 0.f;
-            for (int j = lane; j < N; j += 32) s += expf((z_at(a, g, p, i, j) + v[j]) - mxs);
-            s = warp_sum(s);
-            if (lane == 0) u[i] = lmu_at(a, g, p, i) - (logf(s) + mxs);
-        }
-        gsync();
-        if (G > 1) {
-            const int jj = gtid % NP, gi = gtid / NP;
-            float mx = -INFINITY, s = 0.f;
-            if (gi < G && jj < N) {
-                for (int i = gi; i < M; i += G) mx = fmaxf(mx, z_at(a, g, p, i, jj) + u[i]);
-                const float mxs = (fabsf(mx) == INFINITY) ? 0.f : mx;
-                for (int i = gi; i < M; i += G) s += expf((z_at(a, g, p, i, jj) + u[i]) - mxs);
-                red[2 * (gi * NP + jj)] = mx;
-                red[2 * (gi * NP + jj) + 1] = s;
-            }
-            gsync();
-            if (gi == 0 && jj < N) {
-                float m2 = -INFINITY;
-                for (int q = 0; q < G; ++q) m2 = fmaxf(m2, red[2 * (q * NP + jj)]);
-                const float m2s = (fabsf(m2) == INFINITY) ? 0.f : m2;
-                float s2 = 0.f;
-                for (int q = 0; q < G; ++q) {
-                    const float mq = red[2 * (q * NP + jj)];
-                    const float mqs = (fabsf(mq) == INFINITY) ? 0.f : mq;
-                    s2 += red[2 * (q * NP + jj) + 1] * expf(mqs - m2s);
-                }
-                v[jj] = lnu_at(a, g, p, jj) - (logf(s2) + m2s);
-            }
-        } else {
-            for (int j = gtid; j < N; j += GT) {
-                float mx = -INFINITY;
-                for (int i = 0; i < M; ++i) mx = fmaxf(mx, z_at(a, g, p, i, j) + u[i]);
-                const float mxs = (fabsf(mx) == INFINITY) ? 0.f : mx;
-                float s = 0.f;
-                for (int i = 0; i < M; ++i) s += expf((z_at(a, g, p, i, j) + u[i]) - mxs);
-                v[j] = lnu_at(a, g, p, j) - (logf(s) + mxs);
-            }
-        }
-        gsync();
-    }
-    const float shift = (a.mode == MODE_RAW) ? 0.f : g.norm;  // modules.py:161 / :181
-    float *o = a.out + (size_t)p * M * N;
-    for (int e = gtid; e < M * N; e += GT) {
-        const int i = e / N, j = e - i * N;
-        o[e] = ((z_at(a, g, p, i, j) + u[i]) + v[j]) - shift;
-    }
-}
-
-template <int GT>
-__global__ void __launch_bounds__(GT) sinkhorn_generic_kernel(SinkArgs a) {
-    extern __shared__ float sm[];
-    float *u = sm, *v = sm + a.M, *red = sm + a.M + a.N;
-    for (int p = blockIdx.x; p < a.b; p += gridDim.x) {
-        const Marg g = problem_marginals(a, p, threadIdx.x & 31);
-        log_domain_solve<GT>(a, g, p, u, v, red, threadIdx.x, BlockSync());
-        __syncthreads();
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Register-resident kernel.
@@ -189,9 +43,10 @@ __global__ void __launch_bounds__(GT) sinkhorn_generic_kernel(SinkArgs a) {
 //   rank*PR*RT + pr + PR*k.  Row sums stay inside a CTA; column sums are pushed into every CTA's shared
 //   memory (DSMEM) as a reduce-scatter + broadcast over the cluster: st.async stores that complete bytes on the
 //   receiver's mbarrier (no cluster barrier, no MEMBAR in the iteration loop).
-template <int WARPS_, int QC_LOG2_, int RT_, int CT_, int GROUPS_, int CL_ = 1>
+template <int WARPS_, int QC_LOG2_, int RT_, int CT_, int GROUPS_, int CL_ = 1, int HOP1_ = 0>
 struct RegCfg {
     static constexpr int W = WARPS_, QCL = QC_LOG2_, RT = RT_, CT = CT_, GROUPS = GROUPS_, CL = CL_;
+    static constexpr bool HOP1 = HOP1_ != 0;  // cluster exchange: all-to-all broadcast of partials (one DSMEM hop, CL x the traffic)
     static constexpr int GT = W * 32;       // threads per CTA working on the problem
     static constexpr int QC = 1 << QCL;     // lanes along a row
     static constexpr int PRW = 32 / QC;     // row groups per warp
@@ -215,7 +70,8 @@ struct Smem {
     static constexpr int PART = V1 + C::GROUPS * C::MAXN;          // [W][MAXN]       per-warp column partials
     static constexpr int TOT = PART + (C::BLOCK ? C::W * C::MAXN : 0);   // [MAXN]
     static constexpr int XBUF = TOT + (C::BLOCK ? C::MAXN : 0);          // [2][CL][MAXN/CL] cluster exchange: slice partials
-    static constexpr int TOTB = XBUF + (C::CL > 1 ? 2 * C::MAXN : 0);    // [2][MAXN]        cluster exchange: finished values
+    static constexpr int TOTB = XBUF + (C::CL > 1 ? 2 * C::MAXN * (C::HOP1 ? C::CL : 1) : 0);  // HOP1: XBUF is [2][CL][MAXN]
+                                                                         // [2][MAXN]        cluster exchange: finished values
     static constexpr int MBAR = (TOTB + (C::CL > 1 ? 2 * C::MAXN : 0) + 3) & ~3;  // 4 mbarriers (8 B each), 16-B aligned
     static constexpr int XFLAG = MBAR + (C::CL > 1 ? 8 : 0);       // [CL]
     static constexpr int FB = XFLAG + (C::CL > 1 ? C::CL : 0);     // fallback scratch: u[MAXM], v[MAXN], red[2*GT] per group
@@ -321,6 +177,35 @@ __device__ __forceinline__ void col_reduce(float (&v)[C::CT], Op op, float *sm, 
         static_assert(SL * C::CL == C::MAXN, "column slices must tile the padded width");
         const int q = parity & 1;
         const unsigned phase = (unsigned)(parity >> 1) & 1u;
+        if (C::HOP1) {
+            // One-hop variant: every CTA st.async's its CTA-level partials of ALL columns to every CTA (itself included),
+            // each CTA then adds the CL partial rows in rank order itself.  CL x the DSMEM traffic, one hop instead of two.
+            // Buffer reuse is ordered as above: a sender reaches call n+2 only after receiving every peer's call n+1
+            // partials, which each peer sent after its own reads of call n.
+            float *ab = sm + Smem<C>::XBUF + q * C::CL * C::MAXN;  // [CL][MAXN], one row per sender
+            const unsigned mb_a = smem_u32(sm + Smem<C>::MBAR) + 16u * q;
+            if (gtid == 0) mbar_expect_tx(mb_a, (unsigned)(C::CL * C::MAXN * sizeof(float)));
+            for (int j = gtid; j < C::MAXN; j += C::GT) {
+                float t = s_part[j];
+#pragma unroll
+                for (int w = 1; w < C::W; ++w) t = op(t, s_part[w * C::MAXN + j]);
+                const unsigned a_loc = smem_u32(ab + rank * C::MAXN + j);
+#pragma unroll
+                for (unsigned r = 0; r < (unsigned)C::CL; ++r) st_async_f32(mapa_u32(a_loc, r), t, mapa_u32(mb_a, r));
+            }
+            mbar_wait(mb_a, phase);
+            for (int j = gtid; j < C::MAXN; j += C::GT) {
+                float t = ab[j];
+#pragma unroll
+                for (int r = 1; r < C::CL; ++r) t = op(t, ab[r * C::MAXN + j]);
+                s_tot[j] = SCALE ? s_nu[j] * fast_rcp(t) : t;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < C::CT; ++c) v[c] = s_tot[qc + C::QC * c];
+            parity += 1;
+            return;
+        }
         float *xb = sm + Smem<C>::XBUF + q * C::MAXN;     // [CL][SL] partials of my slice, one row per sender
         float *tb = sm + Smem<C>::TOTB + q * C::MAXN;     // [MAXN] finished values
         const unsigned mb_x = smem_u32(sm + Smem<C>::MBAR) + 16u * q, mb_t = mb_x + 8u;
@@ -641,7 +526,6 @@ __device__ __forceinline__ void ag_cols(float (&v)[16]) {  // all-gather over pr
 #pragma unroll
     for (int t = 0; t < 8; ++t) v[t + 8] = __shfl_xor_sync(0xffffffffu, v[t], 4);
 }
-__device__ __forceinline__ float finite_or_zero(float m) { return (fabsf(m) == INFINITY) ? 0.f : m; }
 
 template <int MIN_CTAS>  // 2: 255 registers, no spills in the loop; 3: 170 registers (3 warps per scheduler), ~19 spill ops per iteration
 __global__ void __launch_bounds__(W65_WARPS * 32, MIN_CTAS) sinkhorn_w65_kernel(SinkArgs a) {
@@ -1731,11 +1615,12 @@ using CfgTiny = RegCfg<1, 2, 4, 8, 4>;         // <= 32 x 32, one warp per probl
 using CfgWarp = RegCfg<1, 2, 9, 17, 4>;        // <= 72 x 68  (level 3: 65 x 65)
 using CfgCta = RegCfg<8, 4, 10, 10, 1>;        // <= 160 x 160 (level 2: 145 x 145), 16 x 16 threads
 using CfgCl320 = RegCfg<8, 5, 5, 10, 1, 8>;    // <= 320 x 320 (level 1: 301 x 301), cluster of 8 CTAs x 256 threads
+using CfgCl320h = RegCfg<8, 5, 5, 10, 1, 8, 1>;  // same tiling, one-hop all-to-all exchange (A/B variant 2)
 using CfgCl320b = RegCfg<16, 5, 5, 10, 1, 4>;  // <= 320 x 320, cluster of 4 CTAs x 512 threads (A/B variant)
 using CfgCl512 = RegCfg<16, 5, 4, 16, 1, 8>;   // <= 512 x 512, cluster of 8 CTAs x 512 threads
 
 static int g_force_generic = 0;
-static int g_cluster_variant = 0;  // <= 320 x 320 plans: 0 = 8 CTAs x 256 threads, 1 = 4 CTAs x 512 threads
+static int g_cluster_variant = 0;  // <= 320 x 320 plans: 0 = 8 CTAs x 256 threads, 1 = 4 CTAs x 512 threads, 2 = 8 x 256 one-hop exchange
 static int g_disable_c145 = 0;  // 145 x 145 routing: 0 = 8-warp kernel, two CTAs per SM (default), 1 = padded 160 x 160 CTA kernel,
                                 //                    2 = 9-warp kernel
 static int g_disable_w65 = 0;  // 65 x 65 routing: 0 = two warps per problem (default), 1 = padded 72 x 68 warp kernel,
@@ -1757,6 +1642,7 @@ static int kernel_kind(int M, int N) {
     if (M <= CfgWarp::MAXM && N <= CfgWarp::MAXN) return 0;
     if (M <= CfgCta::MAXM && N <= CfgCta::MAXN) return 1;
     if (M <= CfgCl512::MAXM && N <= CfgCl512::MAXN) return 3;
+    if (grid_plan_supported(M, N)) return 4;
     return 2;
 }
 
@@ -1791,7 +1677,7 @@ static int launch_reg(const SinkArgs &a, cudaStream_t st) {
     return PATS_OK;
 }
 
-static int launch_generic(const SinkArgs &a, cudaStream_t st) {
+int launch_generic(const SinkArgs &a, cudaStream_t st) {
     constexpr int GT = 1024;
     const size_t smem = sizeof(float) * ((size_t)a.M + a.N + 2 * GT);
     if (smem > 200 * 1024) return invalid("sinkhorn: M+N = %d exceeds the shared-memory budget of the generic kernel", a.M + a.N);
@@ -1845,8 +1731,12 @@ static int run_sinkhorn(SinkArgs a, void *stream) {
             return launch_reg<CfgCta>(a, st);
         case 3:
             if (a.M <= CfgCl320::MAXM && a.N <= CfgCl320::MAXN)
-                return g_cluster_variant == 1 ? launch_reg<CfgCl320b>(a, st) : launch_reg<CfgCl320>(a, st);
+                return g_cluster_variant == 1   ? launch_reg<CfgCl320b>(a, st)
+                       : g_cluster_variant == 2 ? launch_reg<CfgCl320h>(a, st)
+                                                : launch_reg<CfgCl320>(a, st);
             return launch_reg<CfgCl512>(a, st);
+        case 4:
+            return launch_grid(a, st);
         default:
             return launch_generic(a, st);
     }
@@ -1879,7 +1769,7 @@ PATS_API int pats_log_optimal_transport2_f32(const float *scores, const float *o
 
 PATS_API int pats_sinkhorn_kernel_kind(int M, int N) { return kernel_kind(M, N); }
 PATS_API void pats_sinkhorn_force_generic(int on) { g_force_generic = on ? 1 : 0; }
-PATS_API void pats_sinkhorn_cluster_variant(int v) { g_cluster_variant = v == 1 ? 1 : 0; }
+PATS_API void pats_sinkhorn_cluster_variant(int v) { g_cluster_variant = (v >= 0 && v <= 2) ? v : 0; }
 PATS_API void pats_sinkhorn_disable_c145(int mode) { g_disable_c145 = (mode >= 0 && mode <= 2) ? mode : 0; }
 PATS_API void pats_sinkhorn_disable_w65(int mode) { g_disable_w65 = (mode >= 0 && mode <= 3) ? mode : 0; }
 

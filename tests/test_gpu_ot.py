@@ -240,7 +240,7 @@ def test_kernel_variants_145_and_cluster(M, lib, dev):
     s = 0.1 * torch.randn(2, 300, 300, generator=g)
     ns = areas(g, 2, 300, 16.0)
     ref = oracle.log_optimal_transport(s.numpy(), 1.0, ns.numpy(), 100)
-    for v in (0, 1):
+    for v in (0, 1, 2):
         lib.pats_sinkhorn_cluster_variant(v)
         try:
             out = M.log_optimal_transport(s.to(dev), 1.0, ns.to(dev), 100).cpu().numpy()
@@ -308,15 +308,15 @@ def test_full_size_marginals_and_subset_parity(M, dev, b, m, n, span):
 
 
 @pytest.mark.parametrize("N,iters", [(1536, 100), (1024, 100)])
-def test_large_plan_generic_kernel(M, lib, dev, N, iters):
+def test_large_plan_grid_kernel_vs_torch(M, lib, dev, N, iters):
     """BASELINE.json's synthetic kernel sizes (N=1536) and the 1024x1024-pair coarse plan (1024 -> 1025):
-    generic log-domain kernel against a torch fp32 logsumexp restatement on the same device."""
+    grid-cooperative streaming kernel against a torch fp32 logsumexp restatement on the same device."""
     g = torch.Generator().manual_seed(8000 + N)
     b = 2
     s = (0.1 * torch.randn(b, N, N, generator=g)).to(dev)
     ns = areas(g, b, N, 16.0).to(dev)
     alpha = torch.tensor(1.0, device=dev)
-    assert lib.pats_sinkhorn_kernel_kind(N + 1, N + 1) == 2
+    assert lib.pats_sinkhorn_kernel_kind(N + 1, N + 1) == 4
     out = M.log_optimal_transport(s, alpha, ns, iters)
     Z = torch.cat([torch.cat([s, alpha.expand(b, N, 1)], 2), alpha.expand(b, 1, N + 1)], 1)
     nsum = ns.sum(2).reshape(b)
@@ -326,3 +326,72 @@ def test_large_plan_generic_kernel(M, lib, dev, N, iters):
     ref = _torch_lse_sinkhorn(Z, lmu, lnu, iters) - norm[:, None, None]
     assert (out - ref).abs().max().item() <= TOL
     assert torch.equal(out.argmax(2), ref.argmax(2))
+
+
+# ---- grid-cooperative streaming kernel (plans beyond 512 x 512) ---------------------------------------------
+@pytest.mark.parametrize("mode,b,m,n,iters", [
+    ("ot", 1, 1024, 1024, 100),    # level-1 plan of a 1024 x 1024 pair (1025 x 1025), all SMs on one problem
+    ("ot", 3, 600, 513, 30),       # core width 513 -> 32 columns per lane, ragged
+    ("ot2", 2, 1537, 1537, 30),    # BASELINE.json's N = 1536 (48 columns per lane)
+    ("ot2", 2, 530, 513, 40),      # core width 512 -> 16 columns per lane
+    ("ot2", 1, 700, 2049, 12),     # core width 2048 -> 64 columns per lane, 8 warps
+    ("ot2", 1, 520, 2300, 8),      # > 2048 columns: exponentials recomputed instead of kept
+    ("raw", 2, 513, 40, 25),       # tall and narrow: M alone exceeds the cluster kernel
+    ("raw", 150, 520, 30, 10),     # more problems than SMs: one CTA per problem, problems looped
+])
+def test_grid_kernel_vs_oracle(M, lib, dev, mode, b, m, n, iters):
+    g = torch.Generator().manual_seed(9000 + m + n)
+    if mode == "ot":
+        s = 0.1 * torch.randn(b, m, n, generator=g)
+        ns = areas(g, b, n, 16.0)
+        assert lib.pats_sinkhorn_kernel_kind(m + 1, n + 1) == 4
+        out = M.log_optimal_transport(s.to(dev), 1.0, ns.to(dev), iters).cpu().numpy()
+        ref = oracle.log_optimal_transport(s.numpy(), 1.0, ns.numpy(), iters)
+    elif mode == "ot2":
+        s = 0.1 * torch.randn(b, m, n, generator=g)
+        ns = areas(g, b, n - 1, 16.0)
+        assert lib.pats_sinkhorn_kernel_kind(m, n) == 4
+        out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), iters).cpu().numpy()
+        ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), iters)
+    else:
+        s = 0.5 * torch.randn(b, m, n, generator=g)
+        lmu = torch.log_softmax(torch.randn(b, m, generator=g), 1)
+        lnu = torch.log_softmax(torch.randn(b, n, generator=g), 1)
+        assert lib.pats_sinkhorn_kernel_kind(m, n) == 4
+        out = M.log_sinkhorn_iterations(s.to(dev), lmu.to(dev), lnu.to(dev), iters).cpu().numpy()
+        ref = oracle.log_sinkhorn_iterations(s.numpy(), lmu.numpy(), lnu.numpy(), iters)
+    assert_plan_equal(out, ref)
+
+
+def test_grid_kernel_cta_split_and_iteration_counts(M, lib, dev):
+    """Any split of the rows over CTAs gives the same plan (to rounding), for every iteration-count branch."""
+    g = torch.Generator().manual_seed(9500)
+    b, m, n = 2, 640, 600
+    s = 0.1 * torch.randn(b, m, n, generator=g)
+    ns = areas(g, b, n - 1, 16.0)
+    sd, nsd = s.to(dev), ns.to(dev)
+    for iters in (0, 1, 2, 9):
+        ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), iters)
+        for G in (0, 1, 3, 40, 74):
+            lib.pats_sinkhorn_grid_ctas_per_problem(G)
+            try:
+                out = M.log_optimal_transport2(sd, 1.0, nsd, iters).cpu().numpy()
+            finally:
+                lib.pats_sinkhorn_grid_ctas_per_problem(0)
+            np.testing.assert_allclose(out, ref, atol=TOL, rtol=0, err_msg=f"iters={iters} G={G}")
+
+
+def test_grid_kernel_flags_extreme_problems_for_the_log_domain_kernel(M, lib, dev):
+    g = torch.Generator().manual_seed(9600)
+    b, m, n = 3, 560, 530
+    s = 0.1 * torch.randn(b, m, n, generator=g)
+    s[1] *= 300.0
+    ns = areas(g, b, n - 1, 16.0)
+    lib.pats_sinkhorn_fallback_count(1)
+    out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), 20).cpu().numpy()
+    n_fb = lib.pats_sinkhorn_fallback_count(1)
+    ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), 20)
+    assert np.isfinite(out).all()
+    np.testing.assert_allclose(out[[0, 2]], ref[[0, 2]], atol=TOL, rtol=0)
+    np.testing.assert_allclose(out[1], ref[1], atol=TOL, rtol=2e-5)
+    assert n_fb == 1

@@ -45,7 +45,10 @@ def test_kernel_dispatch_table():
     assert lib.pats_sinkhorn_kernel_kind(145, 145) == 1    # level 2: one CTA per problem
     assert lib.pats_sinkhorn_kernel_kind(301, 301) == 3    # level 1: one 8-CTA cluster per problem
     assert lib.pats_sinkhorn_kernel_kind(512, 512) == 3
-    assert lib.pats_sinkhorn_kernel_kind(1537, 1537) == 2  # generic log-domain kernel
+    assert lib.pats_sinkhorn_kernel_kind(1537, 1537) == 4  # rows split over co-resident CTAs, plan streamed
+    assert lib.pats_sinkhorn_kernel_kind(1025, 1025) == 4
+    assert lib.pats_sinkhorn_kernel_kind(4097, 4097) == 4
+    assert lib.pats_sinkhorn_kernel_kind(5000, 5000) == 2  # generic log-domain kernel
 
 
 def test_argument_validation_needs_no_gpu():

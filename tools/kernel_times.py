@@ -87,12 +87,39 @@ for name, (b, m, n) in {"L3_4800x65": (4800, 65, 65), "L3_30000x65": (30000, 65,
 for name, (b, m) in {"L1_1x300": (1, 300), "L1_32x300": (32, 300)}.items():
     s = (0.1 * torch.randn(b, m, m, generator=g)).to(dev)
     ns = torch.exp((torch.rand(b, 1, m, generator=g) * 2 - 1) * 2.77).to(dev)
-    for v in (0, 1):
+    for v in (0, 1, 2):
         lib.pats_sinkhorn_cluster_variant(v)
         t = timeit(lambda: modules.log_optimal_transport(s, one, ns, 100), reps=10)
         res[f"{name}_cluster_variant{v}"] = t
         print(name, "cluster variant", v, t, flush=True)
     lib.pats_sinkhorn_cluster_variant(0)
+
+# plans beyond 512 x 512: grid-cooperative streaming kernel against the HBM roofline (SURVEY section 8d:
+# B_alg = b * 4 * (M+1)(N+1) * (iters + 2)) and against the one-CTA-per-problem log-domain kernel
+try:
+    PEAK = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6462.1)
+except Exception:
+    PEAK = 6462.1
+for name, (b, n, iters) in {"BIG_32x1536": (32, 1536, 100), "BIG_1x1024": (1, 1024, 100), "BIG_8x1024": (8, 1024, 100),
+                            "BIG_1x4096_it200": (1, 4096, 200)}.items():
+    if os.environ.get("KT_ONLY") and not name.startswith(os.environ["KT_ONLY"]):
+        continue
+    s = (0.1 * torch.randn(b, n, n, generator=g)).to(dev)
+    ns = torch.exp((torch.rand(b, 1, n, generator=g) * 2 - 1) * 2.77).to(dev)
+    t = timeit(lambda: modules.log_optimal_transport(s, one, ns, iters), reps=5, warm=2)
+    balg = b * 4 * (n + 1) * (n + 1) * (iters + 2)
+    t["gbs_alg"] = balg / (t["median_ms"] * 1e-3) / 1e9
+    t["frac_hbm"] = t["gbs_alg"] / PEAK
+    res[name] = t
+    print(name, t, flush=True)
+    if b * n <= 8192 * 4:
+        lib.pats_sinkhorn_force_generic(1)
+        tg = timeit(lambda: modules.log_optimal_transport(s, one, ns, iters), reps=2, warm=1)
+        lib.pats_sinkhorn_force_generic(0)
+        res[name + "_generic"] = tg
+        print(name, "generic", tg, flush=True)
+    del s, ns
+    torch.cuda.empty_cache()
 
 src = torch.floor(torch.rand(1, 3, 736, 896, generator=g) * 256).to(dev)
 rows = []
