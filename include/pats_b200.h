@@ -66,6 +66,9 @@ int pats_sinkhorn_kernel_kind(int M, int N);
 /* CTAs per problem of the grid-cooperative kernel (0 = automatic: floor(SMs / b), at least one row per warp);
  * tests / A-B timing. */
 void pats_sinkhorn_grid_ctas_per_problem(int g);
+/* A-B hook of the grid-cooperative kernel: 1 = 16 warps x 1 CTA per SM instead of 8 warps x 2 CTAs per SM (plans up
+ * to 1537 columns). */
+void pats_sinkhorn_grid_variant(int v);
 /* Force the generic log-domain kernel for every shape (tests: exercises the fallback path). */
 void pats_sinkhorn_force_generic(int on);
 /* Routing of 65 x 65 problems (tests / A-B timing): 0 = two warps per problem (default), 1 = padded 72 x 68 warp

@@ -2,8 +2,8 @@
 // 1024 x 1024 image pair, the synthetic N = 1536 / 4096 cases of BASELINE.json) -- models/modules.py:137-182.
 //
 // The plan is STREAMED: this is the HBM-roofline kernel of the family (B_alg = b * 4 * M * N * (iters + 2) bytes).
-//   * A problem is split by rows over G co-resident CTAs (cooperative launch, G = floor(CTAs / b)); a warp owns whole
-//     rows, lane l the columns l + 32c.  One pass over a row does BOTH half-iterations: it loads Z_i (coalesced 128-B
+//   * A problem is split by rows over G co-resident CTAs (cooperative launch; 8 warps x 2 CTAs per SM up to 1537
+//     columns, G = floor(296 / b) but at least one row per warp); a warp owns whole rows, lane l the columns l + 32c.  One pass over a row does BOTH half-iterations: it loads Z_i (coalesced 128-B
 //     warp loads, all of a row's loads in flight at once), forms K_ij = exp(Z_ij + u1_i + v1_j) in registers, reduces
 //     r_i = sum_j K_ij beta_j with one warp butterfly, alpha_i = mu_i / r_i, and accumulates K_ij * alpha_i into the
 //     lane's per-column registers.  The plan is read ONCE per iteration; nothing but two N-vectors is written.
@@ -13,6 +13,10 @@
 //   * Iteration 1 is exact in the log domain (row log-sum-exp, then column max and column sum passes), as in the
 //     register-resident kernels; scalings are monitored and a problem that leaves [1e-13, 1e13] is flagged and
 //     re-solved by the log-domain kernel after this one.  No CPU path.
+//   Measured on B200 (tools/kernel_times.py): b = 32, 1537 x 1537, 100 iterations: 7.2 ms = 4.3 TB/s algorithmic =
+//   66 % of the measured HBM peak (the one-CTA-per-problem log-domain kernel needs > 1 s); 1025 x 1025, b = 1: 0.65 ms.
+//   Variants that lost the A/B and were removed: register prefetch of the next row across the exchange (register
+//   pressure), a one-barrier exchange where every CTA sums all partials, 16 warps x 1 CTA per SM (kept as a hook).
 #include <map>
 #include <mutex>
 
@@ -59,7 +63,7 @@ __device__ __forceinline__ void group_barrier(unsigned *ctr, unsigned &epoch, un
     __syncthreads();
 }
 
-template <int CPL, int W, bool KEEP>
+template <int CPL, int W>
 struct GridSmem {
     static constexpr int NC = 32 * CPL;  // padded core width
     // floats: v1[NC+1] beta[NC+1] colbuf[W][NC] last[W] + 3 * rpc (u1, mu, alpha)
@@ -109,9 +113,9 @@ __device__ __forceinline__ RowRef row_ref(const SinkArgs &a, const Marg &g, int 
     return r;
 }
 
-template <int CPL, int W, bool KEEP>
-__global__ void __launch_bounds__(W * 32, 1) sinkhorn_grid_kernel(GridArgs ga) {
-    using S = GridSmem<CPL, W, KEEP>;
+template <int CPL, int W, int OCC, bool KEEP>
+__global__ void __launch_bounds__(W * 32, OCC) sinkhorn_grid_kernel(GridArgs ga) {
+    using S = GridSmem<CPL, W>;
     constexpr int NCP = S::NC, T = W * 32;
     constexpr int CH = KEEP ? CPL : 32;  // column slots loaded per batch; !KEEP: rows are re-swept instead of kept
     static_assert(CPL % CH == 0, "chunking");
@@ -148,6 +152,32 @@ __global__ void __launch_bounds__(W * 32, 1) sinkhorn_grid_kernel(GridArgs ga) {
 #pragma unroll
             for (int q = 1; q < W; ++q) t = is_max ? fmaxf(t, lastbuf[q]) : t + lastbuf[q];
             __stcg(dst + NC, t);
+        }
+    };
+
+    // my column slice of the G per-CTA partials: fin(j, total).  Few CTAs: a thread per column (coalesced over j);
+    // many CTAs: a warp per column, lanes over the partials (fixed butterfly order, so the sum is deterministic).
+    auto combine = [&](const float *partg, bool is_max, auto &&fin) {
+        if (G >= 16u) {
+            for (int j = c0 + w; j < c1; j += W) {
+                float t = is_max ? -INFINITY : 0.f;
+                for (unsigned q = lane; q < G; q += 32) {
+                    const float x = __ldcg(partg + (size_t)q * ga.npad + j);
+                    t = is_max ? fmaxf(t, x) : t + x;
+                }
+                t = is_max ? warp_max(t) : warp_sum(t);
+                if (lane == 0) fin(j, t);
+            }
+        } else {
+            for (int j = c0 + tid; j < c1; j += T) {
+                float t = __ldcg(partg + j);
+#pragma unroll 8
+                for (unsigned q = 1; q < G; ++q) {  // unrolled: the partial loads of a column are issued together
+                    const float x = __ldcg(partg + (size_t)q * ga.npad + j);
+                    t = is_max ? fmaxf(t, x) : t + x;
+                }
+                fin(j, t);
+            }
         }
     };
 
@@ -201,11 +231,7 @@ __global__ void __launch_bounds__(W * 32, 1) sinkhorn_grid_kernel(GridArgs ga) {
             }
             publish(cm, cml, mypart, true);
             group_barrier(ctr, epoch, G);
-            for (int j = c0 + tid; j < c1; j += T) {
-                float t = __ldcg(partg + j);
-                for (unsigned q = 1; q < G; ++q) t = fmaxf(t, __ldcg(partg + (size_t)q * ga.npad + j));
-                __stcg(crg + j, finite_or_zero(t));
-            }
+            combine(partg, true, [&](int j, float t) { __stcg(crg + j, finite_or_zero(t)); });
             group_barrier(ctr, epoch, G);
             for (int j = tid; j < NC; j += T) bes[j] = __ldcg(crg + j);  // bes holds the column reference for this pass
             if (tid == 0) bes[NCP] = __ldcg(crg + NC);
@@ -224,12 +250,10 @@ __global__ void __launch_bounds__(W * 32, 1) sinkhorn_grid_kernel(GridArgs ga) {
             __syncthreads();
             publish(cs, csl, mypart, false);
             group_barrier(ctr, epoch, G);
-            for (int j = c0 + tid; j < c1; j += T) {
-                float t = __ldcg(partg + j);
-                for (unsigned q = 1; q < G; ++q) t += __ldcg(partg + (size_t)q * ga.npad + j);
+            combine(partg, false, [&](int j, float t) {
                 __stcg(v1g + j, lnu_at(a, g, p, j) - (fast_log(t) + __ldcg(crg + j)));
                 __stcg(beg + j, 1.f);
-            }
+            });
             group_barrier(ctr, epoch, G);
             for (int j = tid; j < NC; j += T) v1s[j] = __ldcg(v1g + j), bes[j] = 1.f;
             if (tid == 0) v1s[NCP] = __ldcg(v1g + NC), bes[NCP] = 1.f;
@@ -238,23 +262,31 @@ __global__ void __launch_bounds__(W * 32, 1) sinkhorn_grid_kernel(GridArgs ga) {
 
         // ---- iterations 2..iters: one pass over the plan per iteration -------------------------------------------------
         float lo = INFINITY, hi = 0.f;
+        float k[KEEP ? CPL : 1];  // KEEP: one row of exp(Z + u1 + v1), kept between the row sum and the column accumulation
+        const int ifirst = r0 + w;
         for (int it = 1; it < a.iters; ++it) {
             float cacc[CPL], cl = 0.f;
 #pragma unroll
             for (int c = 0; c < CPL; ++c) cacc[c] = 0.f;
             const float v1l = v1s[NCP], bel = bes[NCP];
             const bool check = (it & 7) == 0 || it == a.iters - 1;
-            for (int i = r0 + w; i < r1; i += W) {
+            for (int i = ifirst; i < r1; i += W) {
                 const RowRef rr = row_ref(a, g, p, i);
                 const float u = u1s[i - r0];
                 float rsum = 0.f;
-                float k[KEEP ? CPL : 1];
-                for_row<CPL, CH>(rr, lane, NC, [&](int c, float zz) {
-                    const int j = lane + 32 * c;
-                    const float kk = fast_exp((zz + u) + v1s[j]);
-                    if (KEEP) k[c] = kk;
-                    rsum = fmaf(kk, bes[j], rsum);
-                });
+                if constexpr (KEEP) {
+                    for_row<CPL, CH>(rr, lane, NC, [&](int c, float zz) {
+                        const int j = lane + 32 * c;
+                        const float kk = fast_exp((zz + u) + v1s[j]);
+                        k[c] = kk;
+                        rsum = fmaf(kk, bes[j], rsum);
+                    });
+                } else {
+                    for_row<CPL, CH>(rr, lane, NC, [&](int c, float zz) {
+                        const int j = lane + 32 * c;
+                        rsum = fmaf(fast_exp((zz + u) + v1s[j]), bes[j], rsum);
+                    });
+                }
                 const float kl = fast_exp((rr.last + u) + v1l);
                 rsum = fmaf(kl, bel, warp_sum(rsum));
                 const float al = mus[i - r0] * fast_rcp(rsum);
@@ -273,13 +305,11 @@ __global__ void __launch_bounds__(W * 32, 1) sinkhorn_grid_kernel(GridArgs ga) {
             __syncthreads();  // colbuf of the previous iteration has been read by every thread (barrier inside publish)
             publish(cacc, cl, mypart, false);
             group_barrier(ctr, epoch, G);
-            for (int j = c0 + tid; j < c1; j += T) {
-                float t = __ldcg(partg + j);
-                for (unsigned q = 1; q < G; ++q) t += __ldcg(partg + (size_t)q * ga.npad + j);
+            combine(partg, false, [&](int j, float t) {
                 const float be = expf(lnu_at(a, g, p, j)) * fast_rcp(t);
                 if (check) lo = fminf(lo, be), hi = fmaxf(hi, be);
                 __stcg(beg + j, be);
-            }
+            });
             group_barrier(ctr, epoch, G);
             for (int j = tid; j < NC; j += T) bes[j] = __ldcg(beg + j);
             if (tid == 0) bes[NCP] = __ldcg(beg + NC);
@@ -358,30 +388,40 @@ void *grid_workspace(cudaStream_t st, size_t bytes) {
 }
 
 int g_grid_ctas_per_problem = 0;  // test hook: 0 = automatic
+int g_grid_variant = 0;            // A/B hook: 1 = 16 warps x 1 CTA per SM instead of 8 warps x 2 CTAs per SM
 
-template <int CPL, int W, bool KEEP>
+template <int CPL, int W, int OCC, bool KEEP>
 int launch_grid_cfg(const SinkArgs &a, cudaStream_t st) {
-    auto kern = sinkhorn_grid_kernel<CPL, W, KEEP>;
+    auto kern = sinkhorn_grid_kernel<CPL, W, OCC, KEEP>;
     const int sms = sm_count() > 0 ? sm_count() : 148;
     GridArgs ga;
     ga.s = a;
-    // CTAs per problem: as many as are co-resident, but at least one row per warp
-    int G = sms / a.b;
-    if (G < 1) G = 1;
+    // CTAs per problem: as many as are co-resident (OCC per SM), but at least one row per warp.  The row block and
+    // with it the shared-memory size depend on G, so settle G against the occupancy the smaller block really gets.
     const int gmax = (a.M + W - 1) / W;
-    if (G > gmax) G = gmax;
-    if (g_grid_ctas_per_problem > 0 && g_grid_ctas_per_problem <= sms) G = g_grid_ctas_per_problem < gmax ? g_grid_ctas_per_problem : gmax;
+    int G = 1, slots = sms;
+    size_t smem = 0;
+    for (int occ_try = OCC; occ_try >= 1; --occ_try) {
+        slots = sms * occ_try;
+        G = slots / a.b;
+        if (G < 1) G = 1;
+        if (G > gmax) G = gmax;
+        if (g_grid_ctas_per_problem > 0 && g_grid_ctas_per_problem <= slots)
+            G = g_grid_ctas_per_problem < gmax ? g_grid_ctas_per_problem : gmax;
+        smem = GridSmem<CPL, W>::bytes((a.M + G - 1) / G);
+        if (smem > 227 * 1024) continue;
+        PATS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        PATS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem));
+        if (occ >= occ_try) break;
+        if (occ_try == 1) return invalid("sinkhorn (grid kernel): %d x %d does not fit an SM (%zu B of shared memory)", a.M, a.N, smem);
+    }
+    if (smem > 227 * 1024) return invalid("sinkhorn (grid kernel): %d x %d needs %zu B of shared memory", a.M, a.N, smem);
     ga.G = G;
-    ga.groups = a.b < sms / G ? a.b : sms / G;
+    ga.groups = a.b < slots / G ? a.b : slots / G;
     ga.rpc = (a.M + G - 1) / G;
     ga.slice = (a.N + G - 1) / G;
     ga.npad = (a.N + 3) & ~3;
-    const size_t smem = GridSmem<CPL, W, KEEP>::bytes(ga.rpc);
-    if (smem > 227 * 1024) return invalid("sinkhorn (grid kernel): %d x %d needs %zu B of shared memory", a.M, a.N, smem);
-    PATS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    PATS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem));
-    if (occ < 1) return invalid("sinkhorn (grid kernel): configuration does not fit an SM");
     const size_t vec = (size_t)a.b * ga.npad;
     const size_t floats = vec * (3 + (size_t)G);
     const size_t bytes = floats * sizeof(float) + 2 * (size_t)a.b * sizeof(unsigned);
@@ -412,13 +452,19 @@ bool grid_plan_supported(int M, int N) { return M >= 2 && N >= 2 && N - 1 <= 409
 
 int launch_grid(const SinkArgs &a, cudaStream_t st) {
     const int nc = a.N - 1;
-    if (nc <= 512) return launch_grid_cfg<16, 16, true>(a, st);
-    if (nc <= 1024) return launch_grid_cfg<32, 16, true>(a, st);
-    if (nc <= 1536) return launch_grid_cfg<48, 16, true>(a, st);
-    if (nc <= 2048) return launch_grid_cfg<64, 8, true>(a, st);
-    return launch_grid_cfg<128, 8, false>(a, st);
+    if (g_grid_variant & 1) {
+        if (nc <= 512) return launch_grid_cfg<16, 16, 1, true>(a, st);
+        if (nc <= 1024) return launch_grid_cfg<32, 16, 1, true>(a, st);
+        if (nc <= 1536) return launch_grid_cfg<48, 16, 1, true>(a, st);
+    }
+    if (nc <= 512) return launch_grid_cfg<16, 8, 2, true>(a, st);
+    if (nc <= 1024) return launch_grid_cfg<32, 8, 2, true>(a, st);
+    if (nc <= 1536) return launch_grid_cfg<48, 8, 2, true>(a, st);
+    if (nc <= 2048) return launch_grid_cfg<64, 8, 1, true>(a, st);
+    return launch_grid_cfg<128, 8, 1, false>(a, st);
 }
 
 }  // namespace pats
 
 PATS_API void pats_sinkhorn_grid_ctas_per_problem(int g) { pats::g_grid_ctas_per_problem = g > 0 ? g : 0; }
+PATS_API void pats_sinkhorn_grid_variant(int v) { pats::g_grid_variant = v & 1; }

@@ -112,7 +112,13 @@ for name, (b, n, iters) in {"BIG_32x1536": (32, 1536, 100), "BIG_1x1024": (1, 10
     t["frac_hbm"] = t["gbs_alg"] / PEAK
     res[name] = t
     print(name, t, flush=True)
-    if b * n <= 8192 * 4:
+    for v in (1,):
+        lib.pats_sinkhorn_grid_variant(v)
+        tv = timeit(lambda: modules.log_optimal_transport(s, one, ns, iters), reps=5, warm=2)
+        lib.pats_sinkhorn_grid_variant(0)
+        res[f"{name}_variant{v}"] = tv
+        print(name, "variant", v, tv["median_ms"], flush=True)
+    if os.environ.get("KT_GENERIC") and b * n <= 8192 * 4:
         lib.pats_sinkhorn_force_generic(1)
         tg = timeit(lambda: modules.log_optimal_transport(s, one, ns, iters), reps=2, warm=1)
         lib.pats_sinkhorn_force_generic(0)
