@@ -41,9 +41,26 @@ static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStre
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-// exp / log on the SFU (MUFU.EX2 / MUFU.LG2): 2 ulp class, ample for the 1e-4 log-domain tolerance.
+// exp / log on the SFU (MUFU.EX2 / MUFU.LG2): 2 ulp class, ample for the 1e-4 log-domain tolerance.  The .ftz forms
+// are spelled out: exp2f() / __log2f() without them wrap the MUFU in a denormal range test (FSETP + two predicated
+// FMULs per call), which tripled the cost of the first (log-domain) iteration.  Results below 2^-126 flush to zero.
+__device__ __forceinline__ float fast_exp2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_log2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#ifdef PATS_AB_LEGACY_EXP
 __device__ __forceinline__ float fast_exp(float x) { return exp2f(x * kLog2e); }
 __device__ __forceinline__ float fast_log(float x) { return __log2f(x) * kLn2; }
+#else
+__device__ __forceinline__ float fast_exp(float x) { return fast_exp2(x * kLog2e); }
+__device__ __forceinline__ float fast_log(float x) { return fast_log2(x) * kLn2; }
+#endif
 __device__ __forceinline__ float fast_rcp(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

@@ -817,15 +817,23 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
     } while (0)
 
     // ---- load ------------------------------------------------------------------------------------------------------
-    float z[8][8], zc[2];
+    float z[8][8], zc[2], zr, zcorner;
+    {
+        const PlanRef pl = plan_ref(a, g, p);
+        int coff[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
+        for (int c = 0; c < 8; ++c) coff[c] = LCOL(c);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) z[k][c] = z_at(a, g, p, LROW(k), LCOL(c));
+        for (int k = 0; k < 8; ++k) {
+            const int roff = LROW(k) * pl.stride;
 #pragma unroll
-    for (int t = 0; t < 2; ++t) zc[t] = z_at(a, g, p, LROW(t), D);
-    const float zr = z_at(a, g, p, D, LCOL(0));  // dustbin-row entry of the one column this lane owns
-    const float zcorner = z_at(a, g, p, D, D);
+            for (int c = 0; c < 8; ++c) z[k][c] = pl.core(roff, coff[c]);
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) zc[t] = pl.edge(LROW(t), D);
+        zr = pl.edge(D, LCOL(0));  // dustbin-row entry of the one column this lane owns
+        zcorner = pl.edge(D, D);
+    }
     float mu2[2];
 #pragma unroll
     for (int t = 0; t < 2; ++t) mu2[t] = expf(lmu_at(a, g, p, LROW(t)));
@@ -1007,18 +1015,28 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
     ag_rows(U);
     ag_cols8(V);
     float *o = a.out + (size_t)p * 65 * 65;
+    const PlanRef pl = plan_ref(a, g, opaque(p));  // recomputed: keeping the load-time copy alive costs registers in the loop
+    {
+        int coff[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int row = LROW(k);
+        for (int c = 0; c < 8; ++c) coff[c] = LCOL(c);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) o[row * 65 + LCOL(c)] = (z_at(a, g, p, row, LCOL(c)) + U[k]) + V[c];
-        if (w == 0 && qc == 0) o[row * 65 + D] = (z_at(a, g, p, row, D) + U[k]) + Vd;
+        for (int k = 0; k < 8; ++k) {
+            const int row = LROW(k);
+            const int roff = row * pl.stride;
+            float zz[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) zz[c] = pl.core(roff, coff[c]);  // all eight loads of the row in flight (L2 hits)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[row * 65 + coff[c]] = (zz[c] + U[k]) + V[c];
+            if (w == 0 && qc == 0) o[row * 65 + D] = (pl.edge(row, D) + U[k]) + Vd;
+        }
+        if (pr == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[D * 65 + coff[c]] = (pl.edge(D, coff[c]) + Ud) + V[c];
+        }
     }
-    if (pr == 0) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) o[D * 65 + LCOL(c)] = (z_at(a, g, p, D, LCOL(c)) + Ud) + V[c];
-    }
-    if (w == 0 && lane == 0) o[D * 65 + D] = (z_at(a, g, p, D, D) + Ud) + Vd;
+    if (w == 0 && lane == 0) o[D * 65 + D] = (pl.edge(D, D) + Ud) + Vd;
 #undef PAIR_XCHG
 #undef LROW
 #undef LCOL
@@ -1372,16 +1390,28 @@ __global__ void __launch_bounds__(C145B_T, 2) sinkhorn_c145b_kernel(SinkArgs a) 
     };
 
     // ---- load ------------------------------------------------------------------------------------------------------
-    float z[9][9];
+    float z[9][9], zr, zr8, zc, zcorner;
+    {
+        const PlanRef pl = plan_ref(a, g, p);
+        int coff[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
+        for (int c = 0; c < 8; ++c) coff[c] = LCOL(c);
+        coff[8] = LCOL8;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) z[k][c] = z_at(a, g, p, LROW(k), LCOL(c));
-        z[k][8] = z_at(a, g, p, LROW(k), LCOL8);
+        for (int k = 0; k < 9; ++k) {
+            const int roff = LROW(k) * pl.stride;
+#ifdef PATS_AB_C145_ZAT_LOAD
+#pragma unroll
+            for (int c = 0; c < 9; ++c) z[k][c] = z_at(a, g, p, LROW(k), coff[c]);
+#else
+#pragma unroll
+            for (int c = 0; c < 9; ++c) z[k][c] = pl.core(roff, coff[c]);
+#endif
+        }
+        zr = pl.edge(D, LCOL(0)), zr8 = pl.edge(D, LCOL8);
+        zc = row_thread ? pl.edge(myrow, D) : 0.f;
+        zcorner = pl.edge(D, D);
     }
-    const float zr = z_at(a, g, p, D, LCOL(0)), zr8 = z_at(a, g, p, D, LCOL8);
-    const float zc = row_thread ? z_at(a, g, p, myrow, D) : 0.f;
-    const float zcorner = z_at(a, g, p, D, D);
     const float mu_t = row_thread ? expf(lmu_at(a, g, p, myrow)) : 0.f;
     const float nu_o = expf(lnu_at(a, g, p, LCOL(0))), nu8 = expf(lnu_at(a, g, p, LCOL8));
     const float mud = expf(lmu_at(a, g, p, D)), nud = expf(lnu_at(a, g, p, D));
@@ -1593,18 +1623,35 @@ __global__ void __launch_bounds__(C145B_T, 2) sinkhorn_c145b_kernel(SinkArgs a) 
     }
     ag_c145(V);
     float *o = a.out + (size_t)p * 145 * 145;
+    const PlanRef pl = plan_ref(a, g, opaque(p));  // recomputed: keeping the load-time copy alive costs registers in the loop
+    {
+        int coff[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const int row = LROW(k);
-        const float Uk = s_row[row];
+        for (int c = 0; c < 8; ++c) coff[c] = LCOL(c);
+        coff[8] = LCOL8;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) o[row * 145 + LCOL(c)] = (z_at(a, g, p, row, LCOL(c)) + Uk) + V[c];
-        o[row * 145 + LCOL8] = (z_at(a, g, p, row, LCOL8) + Uk) + V8;
+        for (int k = 0; k < 9; ++k) {
+            const int row = LROW(k);
+            const int roff = row * pl.stride;
+            const float Uk = s_row[row];
+#ifdef PATS_AB_OUT_INTERLEAVE
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[row * 145 + coff[c]] = (pl.core(roff, coff[c]) + Uk) + V[c];
+            o[row * 145 + coff[8]] = (pl.core(roff, coff[8]) + Uk) + V8;
+#else
+            float zz[9];
+#pragma unroll
+            for (int c = 0; c < 9; ++c) zz[c] = pl.core(roff, coff[c]);  // the nine loads of the row in flight together (L2 hits)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) o[row * 145 + coff[c]] = (zz[c] + Uk) + V[c];
+            o[row * 145 + coff[8]] = (zz[8] + Uk) + V8;
+#endif
+        }
     }
-    if (row_thread) o[myrow * 145 + D] = (z_at(a, g, p, myrow, D) + U_t) + Vd;
-    if (col_owner) o[D * 145 + LCOL(0)] = (z_at(a, g, p, D, LCOL(0)) + Ud) + V[0];
-    if (col8_owner) o[D * 145 + LCOL8] = (z_at(a, g, p, D, LCOL8) + Ud) + V8;
-    if (tid == 0) o[D * 145 + D] = (z_at(a, g, p, D, D) + Ud) + Vd;
+    if (row_thread) o[myrow * 145 + D] = (pl.edge(myrow, D) + U_t) + Vd;
+    if (col_owner) o[D * 145 + LCOL(0)] = (pl.edge(D, LCOL(0)) + Ud) + V[0];
+    if (col8_owner) o[D * 145 + LCOL8] = (pl.edge(D, LCOL8) + Ud) + V8;
+    if (tid == 0) o[D * 145 + D] = (pl.edge(D, D) + Ud) + Vd;
 #undef LROW
 #undef LCOL
 #undef LCOL8

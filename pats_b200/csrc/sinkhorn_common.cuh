@@ -61,6 +61,33 @@ __device__ __forceinline__ Marg problem_marginals(const SinkArgs &a, int p, int 
     return g;
 }
 
+// Branch-free view of one problem's plan for the fixed-shape kernels: the core (rows < M-1, columns < N-1) is always
+// in memory (row stride N-1 for log_optimal_transport's un-augmented scores, N otherwise); only the dustbin row /
+// column entries depend on the mode (virtual `fill` for MODE_OT).  z_at() tests the mode per element, which put every
+// load of the 64-element tiles into its own basic block (~8 instructions each).
+struct PlanRef {
+    const float *base;
+    int stride;
+    bool aug;
+    float fill;
+    __device__ __forceinline__ float core(int row_off, int col) const { return __ldg(base + (row_off + col)); }  // row_off = row * stride
+    __device__ __forceinline__ float edge(int row, int col) const { return aug ? fill : __ldg(base + (row * stride + col)); }
+};
+__device__ __forceinline__ PlanRef plan_ref(const SinkArgs &a, const Marg &g, int p) {
+    PlanRef r;
+    r.aug = a.mode == MODE_OT;
+    r.stride = r.aug ? a.N - 1 : a.N;
+    r.base = a.Z + (size_t)p * (size_t)(r.aug ? (a.M - 1) * (a.N - 1) : a.M * a.N);
+    r.fill = g.fill;
+    return r;
+}
+
+// identity the compiler cannot see through: stops common-subexpression reuse across the iteration loop
+__device__ __forceinline__ int opaque(int v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+
 struct BlockSync {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
