@@ -71,6 +71,11 @@ void pats_sinkhorn_grid_ctas_per_problem(int g);
 void pats_sinkhorn_grid_variant(int v);
 /* Force the generic log-domain kernel for every shape (tests: exercises the fallback path). */
 void pats_sinkhorn_force_generic(int on);
+/* Plan hand-over inside the composite calls pats_second_layer_match_f32 / pats_third_layer_match_f32 (default on): the
+ * 145 x 145 / 65 x 65 Sinkhorn kernel publishes a per-problem "plan complete" flag and the kernel that consumes the
+ * plans is launched with programmatic stream serialization, so it works on finished problems while the solve's last
+ * wave is still running.  0 = plain stream order between the two kernels (tests / A-B timing). */
+void pats_plan_handover(int on);
 /* Routing of 65 x 65 problems (tests / A-B timing): 0 = two warps per problem (default), 1 = padded 72 x 68 warp
  * kernel, 2 / 3 = one-warp 65 x 65 kernel compiled for 2 / 3 CTAs per SM. */
 void pats_sinkhorn_disable_w65(int mode);
@@ -167,6 +172,17 @@ int pats_est_position_f32(const float *Z, const float *scalex, const float *scal
                           float *y_scale, uint8_t *if_nomatching1, uint8_t *if_nomatching2, float *core_cost,
                           int64_t *bound, void *stream);
 
+/* SecondLayer.forward, the matching block                    models/second_layer.py:103-116
+ *   scores = log_optimal_transport2(scores, one, ns, iters); scores[:, :, -1] += edge_add; scores[:, -1, :] += edge_add
+ *   (edge_add = log 2 outdoor / log 3 indoor, :108-112; the corner gets it twice); est_position(scores, ...).
+ *   scores [b,n+1,n+1] (n = grid_h*grid_w; already x0.1), one: DEVICE scalar, ns [b,1,n], scalex,scaley [b,n]
+ *   -> Z_out [b,n+1,n+1] (the plan the reference keeps as 'scores') + every output of pats_est_position_f32.
+ *   One call so that the two kernels can be handed over problem by problem (see pats_plan_handover). */
+int pats_second_layer_match_f32(const float *scores, const float *one, const float *ns, const float *scalex, const float *scaley,
+                                int b, int grid_h, int grid_w, int iters, float edge_add, float lower_bound, int iter_num,
+                                float *Z_out, float *trust_score, float *average_point, float *x_scale, float *y_scale,
+                                uint8_t *if_nomatching1, uint8_t *if_nomatching2, float *core_cost, int64_t *bound, void *stream);
+
 /* SecondLayer.merge_patches_new / merge_patches_old         models/second_layer.py:189-238 / :137-186
  *   trust_score [P,144] f32 and nm_L2 [P,144] u8 are MUTATED in place exactly as the reference mutates its
  *   arguments; nm_L1 [B,hw] u8; scores_back [B,hw,16,9] f64 in/out (carried across chunks for `new`, zeroed on
@@ -195,6 +211,14 @@ int pats_third_compute_result_f32(const float *scores, const float *scale_x, con
 int pats_third_result_from_log_f32(const float *Z, const float *scale_x, const float *scale_y, const int64_t *p_s,
                                    const int64_t *p_t, int K, float *mkpts0_f, float *mkpts1_f, uint8_t *if_matching1,
                                    void *stream);
+
+/* ThirdLayer.forward, the matching block                     models/third_layer.py:158-167
+ *   scores_origin = log_optimal_transport2(scores, one, ns, iters); Compute_result(exp(scores_origin), ...) + label test.
+ *   scores [K,65,65] (already x0.1), ns [K,1,64] -> Z_out [K,65,65], mkpts0_f, mkpts1_f [K,16,2], if_matching1 [K,16] u8.
+ *   One call for the same reason as pats_second_layer_match_f32. */
+int pats_third_layer_match_f32(const float *scores, const float *one, const float *ns, const float *scale_x, const float *scale_y,
+                               const int64_t *p_s, const int64_t *p_t, int K, int iters, float *Z_out, float *mkpts0_f,
+                               float *mkpts1_f, uint8_t *if_matching1, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Feature gathers next to the path                  (models/second_layer.py:71-80, models/third_layer.py:119-146)

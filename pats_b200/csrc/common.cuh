@@ -88,6 +88,26 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// ---- plan hand-over between the Sinkhorn kernels and the kernels that consume their plans (see sinkhorn_common.cuh) ----
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// consumer side: one thread spins, then the caller synchronises its group.  A producer that died leaves the flag unset:
+// trap after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void await_problem(const unsigned *done, unsigned epoch, int p) {
+    const long long t0 = clock64();
+    unsigned v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(done + p) : "memory");
+        if (v != epoch && clock64() - t0 > (4ll << 30)) __trap();
+    } while (v != epoch);
+}
+
 #endif  // __CUDACC__
+
+// host side (sinkhorn.cu): log_optimal_transport2 with per-problem "plan complete" flags for a consumer launched right
+// behind it (the composite entry points of regroup.cu).  *done == nullptr on return: the kernel for this shape does not
+// publish -- launch the consumer in plain stream order.  edge_add: see SinkArgs::edge_add.
+int sinkhorn_ot2_publish(const float *scores, const float *one, const float *ns, int b, int m, int n, int iters, float edge_add,
+                         float *out, cudaStream_t st, const unsigned **done, unsigned *epoch);
+extern int g_handover;  // pats_plan_handover(): 0 = never publish (plain stream order everywhere)
 
 }  // namespace pats

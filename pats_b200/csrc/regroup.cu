@@ -17,9 +17,9 @@
 
 namespace pats {
 
-// Per-stream scratch (grown on demand, never shrunk).  Calls on one stream are ordered, so a stream's buffer is
-// never used by two launches at once.
-static void *stream_workspace(cudaStream_t st, size_t bytes) {
+// Per-stream scratch that is all-zero whenever no kernel is using it: zeroed at allocation, and every user restores
+// the zeros before it finishes (est_position's column maxima / arrival counters).
+static void *zeroed_workspace(cudaStream_t st, size_t bytes) {
     static std::mutex mu;
     static std::map<cudaStream_t, std::pair<void *, size_t>> pool;
     std::lock_guard<std::mutex> lk(mu);
@@ -29,9 +29,15 @@ static void *stream_workspace(cudaStream_t st, size_t bytes) {
             cudaStreamSynchronize(st);
             cudaFree(e.first);
         }
-        size_t cap = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
+        const size_t cap = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
+        e.first = nullptr, e.second = 0;
         if (cudaMalloc(&e.first, cap) != cudaSuccess) {
-            e.first = nullptr, e.second = 0;
+            e.first = nullptr;
+            return nullptr;
+        }
+        if (cudaMemsetAsync(e.first, 0, cap, st) != cudaSuccess) {
+            cudaFree(e.first);
+            e.first = nullptr;
             return nullptr;
         }
         e.second = cap;
@@ -55,8 +61,11 @@ struct ExpandArgs {
     uint8_t *nomatch;
     // fused column-argmax mask of est_position (log_input only): nm2[j] = (argmax_i Z[i][j] == dustbin row)
     uint8_t *nm2;
-    unsigned *colmax;   // [b, n] order-preserving encoding of max_i<m Z[i][j], zero-initialised
-    unsigned *counter;  // [b] CTAs finished, zero-initialised
+    unsigned *colmax;   // [b, n] order-preserving encoding of max_i<m Z[i][j]; zero on entry, zeroed again by the last CTA
+    unsigned *counter;  // [b] CTAs finished; zero on entry, zeroed again by the last CTA
+    // plan hand-over (sinkhorn_common.cuh): when set, problem bb's plan is ready once done[bb] == epoch
+    const unsigned *done;
+    unsigned epoch;
 };
 
 // monotone map float -> unsigned (atomicMax on floats of either sign); every key is > 0
@@ -82,8 +91,13 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
     const int hbase = threadIdx.x & 16;                            // first lane of this half inside its warp
     float *E = sm + (4 + half) * stride;                           // this row (+ dustbin col, + zero slot)
     const float *opp = a.scores + ((size_t)bb * (m + 1) + m) * (n + 1);
+    if (a.done) {  // launched early (programmatic dependent launch): wait until the Sinkhorn kernel has published this problem
+        if (threadIdx.x == 0) await_problem(a.done, a.epoch, bb);
+        __syncthreads();
+    }
+    // the plan is read with ld.global.cg: it may have been written by a still-running producer grid
     for (int j = threadIdx.x; j < stride; j += blockDim.x) {
-        O[j] = j < n ? (a.log_input ? expf(opp[j]) : opp[j]) : kZero;
+        O[j] = j < n ? (a.log_input ? expf(__ldcg(opp + j)) : __ldcg(opp + j)) : kZero;
         SX[j] = j < n ? a.sx[(size_t)bb * n + j] : kZero;  // slots n, n+1: SX*SY == 1e-14 exactly (the `zero` padding of
         SY[j] = j < n ? a.sy[(size_t)bb * n + j] : 1.0f;   // expand_scale, utils.py:1208-1209)
         CM[j] = 0u;
@@ -96,7 +110,7 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
     for (int j = hl; j < stride; j += 16) {
         float v = kZero;
         if (j <= n) {
-            v = row[j];
+            v = __ldcg(row + j);
             if (a.nm2 && j < n && row_ok) atomicMax(&CM[j], enc_f32(v));
             if (a.log_input) v = expf(v);
         }
@@ -113,8 +127,10 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
             __threadfence();
             for (int j = threadIdx.x; j < n; j += blockDim.x) {
                 const unsigned best = *reinterpret_cast<volatile unsigned *>(&a.colmax[(size_t)bb * n + j]);
-                a.nm2[(size_t)bb * n + j] = enc_f32(opp[j]) > best;  // strictly larger: ties go to the first (real) row
-            }
+                a.nm2[(size_t)bb * n + j] = enc_f32(__ldcg(opp + j)) > best;  // strictly larger: ties go to the first (real) row
+                a.colmax[(size_t)bb * n + j] = 0u;  // leave the scratch zeroed for the next call (no memset between the
+            }                                       // Sinkhorn kernel and this one: it would serialise the early launch)
+            if (threadIdx.x == 0) a.counter[bb] = 0u;
         }
     }
     auto Sval = [&](int idx) -> float { return SX[idx] * SY[idx]; };
@@ -539,16 +555,20 @@ __global__ void __launch_bounds__(TH_K * 16) third_result_kernel(const float *__
                                                                  const float *__restrict__ scale_y, const int64_t *__restrict__ p_s,
                                                                  const int64_t *__restrict__ p_t, int K, int log_input,
                                                                  float *__restrict__ mk0, float *__restrict__ mk1,
-                                                                 uint8_t *__restrict__ if_matching1) {
+                                                                 uint8_t *__restrict__ if_matching1, const unsigned *done, unsigned epoch) {
     constexpr int W = 8, T = 5, NN = 65;
     __shared__ float rows[TH_K * 16][NN];
     __shared__ float gx[TH_K][64], gy[TH_K][64];
     const int k0 = blockIdx.x * TH_K;
+    if (done) {  // launched early (plan hand-over, sinkhorn_common.cuh): wait for this CTA's problems
+        if (threadIdx.x < TH_K && k0 + threadIdx.x < K) await_problem(done, epoch, k0 + threadIdx.x);
+        __syncthreads();
+    }
     for (int e = threadIdx.x; e < TH_K * 16 * NN; e += blockDim.x) {
         const int rr = e / NN, j = e - rr * NN;
         const int k = k0 + rr / 16, c16 = rr % 16;
         const int srow = (2 + c16 / 4) * W + 2 + c16 % 4;  // inner 4x4 of the 8x8 source window (:186)
-        const float v = k < K ? __ldg(scores + ((size_t)k * NN + srow) * NN + j) : 0.f;
+        const float v = k < K ? __ldcg(scores + ((size_t)k * NN + srow) * NN + j) : 0.f;  // .cg: the producer grid may still run
         rows[rr][j] = (log_input && k < K) ? expf(v) : v;  // third_layer.py:159 scores = exp(scores_origin)
     }
     for (int e = threadIdx.x; e < TH_K * 64; e += blockDim.x) {
@@ -612,6 +632,7 @@ PATS_API int pats_iterative_expand_matrix_f32(const float *scores_in, const floa
     a.whole = whole_cost, a.core = core_cost, a.avg = average_point, a.xs = x_scale, a.ys = y_scale;
     a.bound = bound, a.nomatch = if_nomatching;
     a.nm2 = nullptr, a.colmax = nullptr, a.counter = nullptr;
+    a.done = nullptr, a.epoch = 0u;
     const size_t smem = sizeof(float) * (size_t)(4 + EX_ROWS) * (n + 2);
     if (smem > 200 * 1024) return invalid("iterative_expand_matrix: grid of %lld cells exceeds the shared-memory budget", n);
     if (smem > 48 * 1024)
@@ -692,8 +713,27 @@ PATS_API int pats_third_compute_result_f32(const float *scores, const float *sca
     if (!scores || !scale_x || !scale_y || !p_s || !p_t || !mkpts0_f || !mkpts1_f || !if_matching1)
         return invalid("third_compute_result: null pointer");
     third_result_kernel<<<(K + TH_K - 1) / TH_K, TH_K * 16, 0, as_stream(stream)>>>(scores, scale_x, scale_y, p_s, p_t, K, 0, mkpts0_f,
-                                                                                  mkpts1_f, if_matching1);
+                                                                                  mkpts1_f, if_matching1, nullptr, 0u);
     PATS_LAUNCH_CHECK("third_result_kernel");
+    return PATS_OK;
+}
+
+// third-layer result from the log-domain plans; `done` != nullptr: launched early behind the Sinkhorn kernel that is still
+// producing them (plan hand-over, sinkhorn_common.cuh)
+static int third_result_from_log_launch(const float *Z, const float *scale_x, const float *scale_y, const int64_t *p_s, const int64_t *p_t,
+                                        int K, float *mkpts0_f, float *mkpts1_f, uint8_t *if_matching1, cudaStream_t st,
+                                        const unsigned *done, unsigned epoch) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((K + TH_K - 1) / TH_K);
+    cfg.blockDim = dim3(TH_K * 16);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = done ? 1 : 0;
+    PATS_CUDA_TRY(cudaLaunchKernelEx(&cfg, third_result_kernel, Z, scale_x, scale_y, p_s, p_t, K, 1, mkpts0_f, mkpts1_f, if_matching1, done,
+                                     epoch));
     return PATS_OK;
 }
 
@@ -704,16 +744,30 @@ PATS_API int pats_third_result_from_log_f32(const float *Z, const float *scale_x
     if (K == 0) return PATS_OK;
     if (!Z || !scale_x || !scale_y || !p_s || !p_t || !mkpts0_f || !mkpts1_f || !if_matching1)
         return invalid("third_result_from_log: null pointer");
-    third_result_kernel<<<(K + TH_K - 1) / TH_K, TH_K * 16, 0, as_stream(stream)>>>(Z, scale_x, scale_y, p_s, p_t, K, 1, mkpts0_f,
-                                                                                  mkpts1_f, if_matching1);
-    PATS_LAUNCH_CHECK("third_result_kernel");
-    return PATS_OK;
+    return third_result_from_log_launch(Z, scale_x, scale_y, p_s, p_t, K, mkpts0_f, mkpts1_f, if_matching1, as_stream(stream), nullptr, 0u);
 }
 
-PATS_API int pats_est_position_f32(const float *Z, const float *scalex, const float *scaley, int b, int grid_h, int grid_w,
-                                   float lower_bound, int iter_num, float *trust_score, float *average_point, float *x_scale,
-                                   float *y_scale, uint8_t *if_nomatching1, uint8_t *if_nomatching2, float *core_cost,
-                                   int64_t *bound, void *stream) {
+// third_layer.py:158-167 in one call: log_optimal_transport2 (65 x 65, 100 it) -> exp -> Compute_result + label test.
+// The result kernel starts on finished problems while the solve's last wave is still running.
+PATS_API int pats_third_layer_match_f32(const float *scores, const float *one, const float *ns, const float *scale_x, const float *scale_y,
+                                        const int64_t *p_s, const int64_t *p_t, int K, int iters, float *Z_out, float *mkpts0_f,
+                                        float *mkpts1_f, uint8_t *if_matching1, void *stream) {
+    if (K < 0 || iters < 0) return invalid("third_layer_match: bad sizes");
+    if (K == 0) return PATS_OK;
+    if (!scores || !one || !ns || !scale_x || !scale_y || !p_s || !p_t || !Z_out || !mkpts0_f || !mkpts1_f || !if_matching1)
+        return invalid("third_layer_match: null pointer");
+    cudaStream_t st = as_stream(stream);
+    const unsigned *done = nullptr;
+    unsigned epoch = 0u;
+    const int rc = sinkhorn_ot2_publish(scores, one, ns, K, 65, 65, iters, 0.f, Z_out, st, &done, &epoch);
+    if (rc) return rc;
+    return third_result_from_log_launch(Z_out, scale_x, scale_y, p_s, p_t, K, mkpts0_f, mkpts1_f, if_matching1, st, done, epoch);
+}
+
+static int est_position_launch(const float *Z, const float *scalex, const float *scaley, int b, int grid_h, int grid_w, float lower_bound,
+                               int iter_num, float *trust_score, float *average_point, float *x_scale, float *y_scale,
+                               uint8_t *if_nomatching1, uint8_t *if_nomatching2, float *core_cost, int64_t *bound, cudaStream_t st,
+                               const unsigned *done, unsigned epoch) {
     const long long n = (long long)grid_h * grid_w;
     if (b < 0 || grid_h <= 0 || grid_w <= 0 || iter_num < 1) return invalid("est_position: bad sizes");
     if (b == 0) return PATS_OK;
@@ -734,15 +788,52 @@ PATS_API int pats_est_position_f32(const float *Z, const float *scalex, const fl
     if (smem > 48 * 1024)
         PATS_CUDA_TRY(cudaFuncSetAttribute(area_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (b > 65535) return invalid("est_position: batch %d exceeds gridDim.y", b);
-    cudaStream_t st = as_stream(stream);
-    // column-argmax mask fused into the expansion kernel: encoded column maxima + per-problem arrival counters
+    // column-argmax mask fused into the expansion kernel: encoded column maxima + per-problem arrival counters, in a
+    // scratch buffer that is zero between calls (zeroed when allocated, re-zeroed by the kernel's last CTA per problem;
+    // a memset here would sit between the Sinkhorn kernel and this one and serialise the early launch)
     const size_t ws_bytes = sizeof(unsigned) * ((size_t)b * n + b);
-    unsigned *ws = static_cast<unsigned *>(stream_workspace(st, ws_bytes));
+    unsigned *ws = static_cast<unsigned *>(zeroed_workspace(st, ws_bytes));
     if (!ws) return cuda_fail(cudaGetLastError(), "est_position workspace");
-    PATS_CUDA_TRY(cudaMemsetAsync(ws, 0, ws_bytes, st));
     a.nm2 = if_nomatching2, a.colmax = ws, a.counter = ws + (size_t)b * n;
-    dim3 grid(((int)n + EX_ROWS - 1) / EX_ROWS, b);
-    area_expand_kernel<<<grid, EX_ROWS * 16, smem, st>>>(a);
-    PATS_LAUNCH_CHECK("area_expand_kernel");
+    a.done = done, a.epoch = epoch;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(((int)n + EX_ROWS - 1) / EX_ROWS, b);
+    cfg.blockDim = dim3(EX_ROWS * 16);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = done ? 1 : 0;
+    PATS_CUDA_TRY(cudaLaunchKernelEx(&cfg, area_expand_kernel, a));
     return PATS_OK;
+}
+
+PATS_API int pats_est_position_f32(const float *Z, const float *scalex, const float *scaley, int b, int grid_h, int grid_w,
+                                   float lower_bound, int iter_num, float *trust_score, float *average_point, float *x_scale,
+                                   float *y_scale, uint8_t *if_nomatching1, uint8_t *if_nomatching2, float *core_cost,
+                                   int64_t *bound, void *stream) {
+    return est_position_launch(Z, scalex, scaley, b, grid_h, grid_w, lower_bound, iter_num, trust_score, average_point, x_scale, y_scale,
+                               if_nomatching1, if_nomatching2, core_cost, bound, as_stream(stream), nullptr, 0u);
+}
+
+// second_layer.py:103-116 in one call: log_optimal_transport2 on the [b, n+1, n+1] scores -> dustbin column / row +=
+// edge_add (log 2 outdoor, log 3 indoor; :108-112) -> est_position.  Z_out is the plan the reference returns as 'scores'.
+// The expansion starts on finished problems while the solve's last wave is still running (plan hand-over).
+PATS_API int pats_second_layer_match_f32(const float *scores, const float *one, const float *ns, const float *scalex, const float *scaley,
+                                         int b, int grid_h, int grid_w, int iters, float edge_add, float lower_bound, int iter_num,
+                                         float *Z_out, float *trust_score, float *average_point, float *x_scale, float *y_scale,
+                                         uint8_t *if_nomatching1, uint8_t *if_nomatching2, float *core_cost, int64_t *bound, void *stream) {
+    const long long n = (long long)grid_h * grid_w;
+    if (b < 0 || grid_h <= 0 || grid_w <= 0 || iters < 0 || n > 4096) return invalid("second_layer_match: bad sizes");
+    if (b == 0) return PATS_OK;
+    if (!scores || !one || !ns || !Z_out) return invalid("second_layer_match: null pointer");
+    cudaStream_t st = as_stream(stream);
+    const unsigned *done = nullptr;
+    unsigned epoch = 0u;
+    const int rc = sinkhorn_ot2_publish(scores, one, ns, b, (int)n + 1, (int)n + 1, iters, edge_add, Z_out, st, &done, &epoch);
+    if (rc) return rc;
+    return est_position_launch(Z_out, scalex, scaley, b, grid_h, grid_w, lower_bound, iter_num, trust_score, average_point, x_scale, y_scale,
+                               if_nomatching1, if_nomatching2, core_cost, bound, st, done, epoch);
 }

@@ -23,6 +23,7 @@
 //     No CPU path exists.
 #include <cooperative_groups.h>
 
+#include <map>
 #include <mutex>
 
 #include "sinkhorn_common.cuh"
@@ -792,6 +793,7 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int pair = wib >> 1, w = wib & 1;
     const int p = blockIdx.x * X2_PAIRS + pair;
+    pdl_launch_dependents();
     if (p >= a.b) return;  // uniform over the pair; the named barrier below involves this pair only
     const PairSync psync{1 + pair};
     const int pr = lane >> 2, qc = lane & 3;
@@ -1010,6 +1012,8 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
         if (w == 0 && lane == 0 && a.fb_total) atomicAdd(a.fb_total, 1);
         psync();  // everybody is done with s_x before the scratch is reused
         log_domain_solve<64>(a, g, p, s_fb[pair], s_fb[pair] + 65, s_fb[pair] + 130, w * 32 + lane, psync);
+        psync();
+        if (w == 0 && lane == 0) publish_problem(a, p);
         return;
     }
     ag_rows(U);
@@ -1037,6 +1041,10 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
         }
     }
     if (w == 0 && lane == 0) o[D * 65 + D] = (pl.edge(D, D) + Ud) + Vd;
+    if (a.done) {  // both warps of the pair have stored their halves
+        psync();
+        if (w == 0 && lane == 0) publish_problem(a, p);
+    }
 #undef PAIR_XCHG
 #undef LROW
 #undef LCOL
@@ -1358,6 +1366,7 @@ __global__ void __launch_bounds__(C145B_T, 2) sinkhorn_c145b_kernel(SinkArgs a) 
     __shared__ float s_fb[145 + 145 + 2 * C145B_T];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int p = blockIdx.x;
+    pdl_launch_dependents();
     if (p >= a.b) return;
     const int pr = lane >> 1, qc = lane & 1;
     const int cmask = ((pr & 1) << 2) | (((pr >> 1) & 1) << 1) | ((pr >> 2) & 1);
@@ -1619,6 +1628,8 @@ __global__ void __launch_bounds__(C145B_T, 2) sinkhorn_c145b_kernel(SinkArgs a) 
     if (__syncthreads_or(bad ? 1 : 0)) {
         if (tid == 0 && a.fb_total) atomicAdd(a.fb_total, 1);
         log_domain_solve<C145B_T>(a, g, p, s_fb, s_fb + 145, s_fb + 290, tid, BlockSync());
+        __syncthreads();
+        if (tid == 0) publish_problem(a, p);
         return;
     }
     ag_c145(V);
@@ -1648,10 +1659,15 @@ __global__ void __launch_bounds__(C145B_T, 2) sinkhorn_c145b_kernel(SinkArgs a) 
 #endif
         }
     }
-    if (row_thread) o[myrow * 145 + D] = (pl.edge(myrow, D) + U_t) + Vd;
-    if (col_owner) o[D * 145 + LCOL(0)] = (pl.edge(D, LCOL(0)) + Ud) + V[0];
-    if (col8_owner) o[D * 145 + LCOL8] = (pl.edge(D, LCOL8) + Ud) + V8;
-    if (tid == 0) o[D * 145 + D] = (pl.edge(D, D) + Ud) + Vd;
+    const float ea = a.edge_add;  // second_layer.py:108-112: dustbin column += c, then dustbin row += c (x + 0.f == x bit for bit)
+    if (row_thread) o[myrow * 145 + D] = ((pl.edge(myrow, D) + U_t) + Vd) + ea;
+    if (col_owner) o[D * 145 + LCOL(0)] = ((pl.edge(D, LCOL(0)) + Ud) + V[0]) + ea;
+    if (col8_owner) o[D * 145 + LCOL8] = ((pl.edge(D, LCOL8) + Ud) + V8) + ea;
+    if (tid == 0) o[D * 145 + D] = (((pl.edge(D, D) + Ud) + Vd) + ea) + ea;
+    if (a.done) {
+        __syncthreads();
+        if (tid == 0) publish_problem(a, p);
+    }
 #undef LROW
 #undef LCOL
 #undef LCOL8
@@ -1682,6 +1698,53 @@ static int ensure_counter() {
         PATS_CUDA_TRY(cudaMemset(g_fb_total, 0, sizeof(int)));
     }
     return PATS_OK;
+}
+
+// ---- plan hand-over: per-stream flag pool (see sinkhorn_common.cuh) -----------------------------------------------------
+namespace {
+struct HandOver {
+    unsigned *flags = nullptr;  // [cap] per stream, zero-initialised; epochs start at 1 and only grow
+    size_t cap = 0;
+    unsigned epoch = 0;
+};
+std::mutex g_ho_mu;
+std::map<cudaStream_t, HandOver> g_ho;
+
+// flags for a launch of b problems on `st`; nullptr (hand-over off) if the pool cannot be grown
+unsigned *handover_begin(cudaStream_t st, int b, unsigned *epoch) {
+    std::lock_guard<std::mutex> lk(g_ho_mu);
+    HandOver &h = g_ho[st];
+    if (h.cap < (size_t)b) {
+        if (h.flags) {
+            cudaStreamSynchronize(st);
+            cudaFree(h.flags);
+        }
+        const size_t cap = (size_t)b * 2 < 4096 ? 4096 : (size_t)b * 2;
+        h.flags = nullptr, h.cap = 0;
+        if (cudaMalloc(&h.flags, cap * sizeof(unsigned)) != cudaSuccess || cudaMemset(h.flags, 0, cap * sizeof(unsigned)) != cudaSuccess) {
+            h.flags = nullptr;
+            cudaGetLastError();
+            return nullptr;
+        }
+        h.cap = cap;
+    }
+    h.epoch += 1;
+    if (h.epoch == 0) h.epoch = 1;  // 0 is the "never written" value
+    *epoch = h.epoch;
+    return h.flags;
+}
+}  // namespace
+
+// dustbin column += add, then dustbin row += add (the corner gets both, in that order)
+__global__ void edge_add_kernel(float *out, int b, int M, int N, float add) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = M + N;
+    if (e >= (long long)b * per) return;
+    const int p = (int)(e / per), t = (int)(e - (long long)p * per);
+    float *o = out + (size_t)p * M * N;
+    if (t < M - 1) o[(size_t)t * N + (N - 1)] += add;                        // dustbin column, rows 0..M-2
+    else if (t == M - 1) o[(size_t)t * N + (N - 1)] = (o[(size_t)t * N + (N - 1)] + add) + add;  // corner
+    else if (t - M < N - 1) o[(size_t)(M - 1) * N + (t - M)] += add;         // dustbin row, columns 0..N-2
 }
 
 static int kernel_kind(int M, int N) {
@@ -1739,7 +1802,17 @@ int launch_generic(const SinkArgs &a, cudaStream_t st) {
     return PATS_OK;
 }
 
-static int run_sinkhorn(SinkArgs a, void *stream) {
+// publish: ask the kernel to raise per-problem "plan complete" flags (plan hand-over); *done stays nullptr when the kernel
+// chosen for the shape does not publish.
+static int run_sinkhorn(SinkArgs a, void *stream, bool publish = false, const unsigned **done = nullptr, unsigned *epoch = nullptr) {
+    struct Report {  // hands the flags of the launch (if any) back on every return path
+        SinkArgs &a;
+        const unsigned **done;
+        unsigned *epoch;
+        ~Report() {
+            if (done) *done = a.done, *epoch = a.epoch;
+        }
+    } report{a, done, epoch};
     if (a.b < 0 || a.M <= 0 || a.N <= 0 || a.iters < 0) return invalid("sinkhorn: bad sizes b=%d M=%d N=%d iters=%d", a.b, a.M, a.N, a.iters);
     if (a.mode != MODE_RAW && (a.M < 2 || a.N < 2)) return invalid("optimal transport needs at least one real row and column");
     if (a.b == 0) return PATS_OK;
@@ -1749,9 +1822,21 @@ static int run_sinkhorn(SinkArgs a, void *stream) {
     if (rc) return rc;
     a.fb_total = g_fb_total;
     cudaStream_t st = as_stream(stream);
+    const bool c145b = kernel_kind(a.M, a.N) == 1 && a.M == 145 && a.N == 145 && g_disable_c145 == 0;
+    if (a.edge_add != 0.f && !c145b && kernel_kind(a.M, a.N) != 2) {  // kernels without the edge epilogue: solve, then one more pass
+        const float add = a.edge_add;
+        a.edge_add = 0.f;
+        rc = run_sinkhorn(a, stream);
+        if (rc) return rc;
+        const long long cells = (long long)a.b * (a.M + a.N);
+        edge_add_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(a.out, a.b, a.M, a.N, add);
+        PATS_LAUNCH_CHECK("edge_add_kernel");
+        return PATS_OK;
+    }
     switch (kernel_kind(a.M, a.N)) {
         case 0:
             if (a.M == 65 && a.N == 65 && g_disable_w65 == 0) {
+                if (publish) a.done = handover_begin(st, a.b, &a.epoch);
                 sinkhorn_w65x2_kernel<<<(a.b + X2_PAIRS - 1) / X2_PAIRS, X2_PAIRS * 64, 0, st>>>(a);
                 PATS_LAUNCH_CHECK("sinkhorn_w65x2_kernel");
                 return PATS_OK;
@@ -1766,6 +1851,7 @@ static int run_sinkhorn(SinkArgs a, void *stream) {
             return launch_reg<CfgWarp>(a, st);
         case 1:
             if (a.M == 145 && a.N == 145 && g_disable_c145 == 0) {
+                if (publish) a.done = handover_begin(st, a.b, &a.epoch);
                 sinkhorn_c145b_kernel<<<a.b, C145B_T, 0, st>>>(a);
                 PATS_LAUNCH_CHECK("sinkhorn_c145b_kernel");
                 return PATS_OK;
@@ -1796,26 +1882,38 @@ using namespace pats;
 PATS_API int pats_log_sinkhorn_iterations_f32(const float *Z, const float *log_mu, const float *log_nu, int b, int M, int N,
                                               int iters, float *out, void *stream) {
     if (b > 0 && (!log_mu || !log_nu)) return invalid("log_sinkhorn_iterations: null marginals");
-    SinkArgs a{Z, log_mu, log_nu, nullptr, nullptr, out, b, M, N, iters, MODE_RAW, nullptr};
+    SinkArgs a{Z, log_mu, log_nu, nullptr, nullptr, out, b, M, N, iters, MODE_RAW, nullptr, nullptr, 0u, 0.f};
     return run_sinkhorn(a, stream);
 }
 
 PATS_API int pats_log_optimal_transport_f32(const float *scores, const float *alpha, const float *ns, int b, int m, int n,
                                             int iters, float *out, void *stream) {
     if (b > 0 && (!alpha || !ns)) return invalid("log_optimal_transport: null alpha / ns");
-    SinkArgs a{scores, nullptr, nullptr, alpha, ns, out, b, m + 1, n + 1, iters, MODE_OT, nullptr};
+    SinkArgs a{scores, nullptr, nullptr, alpha, ns, out, b, m + 1, n + 1, iters, MODE_OT, nullptr, nullptr, 0u, 0.f};
     return run_sinkhorn(a, stream);
 }
 
 PATS_API int pats_log_optimal_transport2_f32(const float *scores, const float *one, const float *ns, int b, int m, int n,
                                              int iters, float *out, void *stream) {
     if (b > 0 && (!one || !ns)) return invalid("log_optimal_transport2: null one / ns");
-    SinkArgs a{scores, nullptr, nullptr, one, ns, out, b, m, n, iters, MODE_OT2, nullptr};
+    SinkArgs a{scores, nullptr, nullptr, one, ns, out, b, m, n, iters, MODE_OT2, nullptr, nullptr, 0u, 0.f};
     return run_sinkhorn(a, stream);
 }
 
 PATS_API int pats_sinkhorn_kernel_kind(int M, int N) { return kernel_kind(M, N); }
 PATS_API void pats_sinkhorn_force_generic(int on) { g_force_generic = on ? 1 : 0; }
+PATS_API void pats_plan_handover(int on) { g_handover = on ? 1 : 0; }
+
+namespace pats {
+int g_handover = 1;
+int sinkhorn_ot2_publish(const float *scores, const float *one, const float *ns, int b, int m, int n, int iters, float edge_add,
+                         float *out, cudaStream_t st, const unsigned **done, unsigned *epoch) {
+    if (b > 0 && (!one || !ns)) return invalid("log_optimal_transport2: null one / ns");
+    SinkArgs a{scores, nullptr, nullptr, one, ns, out, b, m, n, iters, MODE_OT2, nullptr, nullptr, 0u, edge_add};
+    *done = nullptr, *epoch = 0u;
+    return run_sinkhorn(a, st, g_handover != 0, done, epoch);
+}
+}  // namespace pats
 PATS_API void pats_sinkhorn_cluster_variant(int v) { g_cluster_variant = (v >= 0 && v <= 2) ? v : 0; }
 PATS_API void pats_sinkhorn_disable_c145(int mode) { g_disable_c145 = (mode >= 0 && mode <= 2) ? mode : 0; }
 PATS_API void pats_sinkhorn_disable_w65(int mode) { g_disable_w65 = (mode >= 0 && mode <= 3) ? mode : 0; }

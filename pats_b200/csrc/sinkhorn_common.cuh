@@ -17,6 +17,14 @@ struct SinkArgs {
     float *out;           // [b,M,N]
     int b, M, N, iters, mode;
     int *fb_total;        // device counter: problems sent to the log-domain fallback
+    // Producer side of the early-start hand-over to the kernel that consumes the plans (est_position / Compute_result):
+    // done[p] = epoch once problem p's plan is complete in memory (nullptr: off).  See "plan hand-over" below.
+    unsigned *done;
+    unsigned epoch;
+    // added to the dustbin column, then to the dustbin row, of the finished plan (second_layer.py:108-112 does this in
+    // place right after the solve; the corner gets it twice).  Only the 145 x 145 kernel and the log-domain solver apply
+    // it in their epilogue; run_sinkhorn() covers the other kernels with a separate pass.
+    float edge_add;
 };
 
 struct Marg {
@@ -88,6 +96,19 @@ __device__ __forceinline__ int opaque(int v) {
     return v;
 }
 
+// ---- plan hand-over (programmatic dependent launch) ------------------------------------------------------------------
+// The level-2 / level-3 solves end in a tail: 300 problems on 296 CTA slots, 4800 on 1184.  The consumer of the plans
+// (area expansion, third-layer result) works per problem, so it is launched with programmatic stream serialization:
+// its CTAs start as soon as every producer CTA has STARTED (griddepcontrol.launch_dependents at the top of the
+// producer), wait for "their" problem's flag and overlap the producer's tail.  One thread of the producer publishes a
+// problem after a barrier that follows all of its stores (fence + release store); the consumer acquires the flag and
+// reads the plan with ld.global.cg.  Without a consumer the flags cost one store per problem.
+__device__ __forceinline__ void publish_problem(const SinkArgs &a, int p) {  // one thread, after the problem's last store + barrier
+    if (a.done) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.done + p), "r"(a.epoch) : "memory");
+    }
+}
 struct BlockSync {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
@@ -164,7 +185,12 @@ __device__ void log_domain_solve(const SinkArgs &a, const Marg &g, int p, float 
     float *o = a.out + (size_t)p * M * N;
     for (int e = gtid; e < M * N; e += GT) {
         const int i = e / N, j = e - i * N;
-        o[e] = ((z_at(a, g, p, i, j) + u[i]) + v[j]) - shift;
+        float r = ((z_at(a, g, p, i, j) + u[i]) + v[j]) - shift;
+        if (a.edge_add != 0.f) {
+            if (j == N - 1) r += a.edge_add;
+            if (i == M - 1) r += a.edge_add;
+        }
+        o[e] = r;
     }
 }
 

@@ -141,7 +141,96 @@ def third_result_from_log(Z, scale_x, scale_y, p_s, p_t):
     return m0, m1, im
 
 
-__all__ += ["est_position", "first_layer_est_position", "second_layer_est_position", "third_result_from_log"]
+_EDGE_CACHE: dict = {}
+
+
+def second_layer_match(scores, one, scale, scale_x, scale_y, iters: int = 100, outdoor: bool = True, grid: int = 12, *, return_extra=False):
+    """The matching block of SecondLayer.forward (second_layer.py:103-116) in one call:
+
+        scores = log_optimal_transport2(scores, one, scale, iters)
+        scores[:, :, -1] += log(2 or 3); scores[:, -1, :] += log(2 or 3)          # outdoor / indoor, :108-112
+        trust_score, pts, x_scale, y_scale, if_nomatching1, if_nomatching2 = est_position(scores, scale_x, scale_y, ...)
+
+    `scores` is the already scaled input (0.1 * einsum / sqrt(d)), [P, grid^2+1, grid^2+1].  Returns (scores_out, trust_score,
+    pts, x_scale, y_scale, if_nomatching1, if_nomatching2); scores_out is what the reference keeps as 'scores'.  The area
+    expansion starts on finished problems while the Sinkhorn kernel's last wave is still running."""
+    import math
+
+    scores = cuda_f32(scores, "scores")
+    b, M, N = scores.shape
+    n = grid * grid
+    if M != n + 1 or N != n + 1:
+        raise ValueError(f"second_layer_match: scores {tuple(scores.shape)} is not [b,{n + 1},{n + 1}]")
+    dev = scores.device
+    ns = cuda_f32(scale, "scale")
+    if ns.numel() != b * n:
+        raise ValueError(f"scale must hold b*{n} values, got {tuple(ns.shape)}")
+    sx = cuda_f32(scale_x, "scale_x").reshape(b, n)
+    sy = cuda_f32(scale_y, "scale_y").reshape(b, n)
+    from ._torchutil import scalar_on
+
+    one_t = scalar_on(dev, one, "one")
+    # f32(log(f32(one) * k)) as torch.log(self.one * 2) computes it.  A number costs nothing; a CUDA tensor (the reference's
+    # nn.Parameter `one`) is read back once per distinct (storage, version) and cached -- no device sync in steady state.
+    k = 2.0 if outdoor else 3.0
+    if isinstance(one, torch.Tensor):
+        key = (one.data_ptr(), one._version, k)
+        edge = _EDGE_CACHE.get(key)
+        if edge is None:
+            edge = float(torch.log(one.detach().float().cpu() * k))
+            _EDGE_CACHE.clear()
+            _EDGE_CACHE[key] = edge
+    else:
+        edge = float(torch.log(torch.tensor(float(one), dtype=torch.float32) * k))
+    Z = torch.empty_like(scores)
+    trust = torch.empty((b, n), dtype=torch.float32, device=dev)
+    avg = torch.empty((b, n, 2), dtype=torch.float32, device=dev)
+    xs, ys, core = torch.empty_like(trust), torch.empty_like(trust), torch.empty_like(trust)
+    nm1 = torch.empty((b, n), dtype=torch.bool, device=dev)
+    nm2 = torch.empty_like(nm1)
+    bound = torch.empty((b, n, 4), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pats_second_layer_match_f32(scores.data_ptr(), one_t.data_ptr(), ns.data_ptr(), sx.data_ptr(), sy.data_ptr(), b, grid, grid,
+                                                     int(iters), edge, 1e-3, 8, Z.data_ptr(), trust.data_ptr(), avg.data_ptr(), xs.data_ptr(),
+                                                     ys.data_ptr(), nm1.data_ptr(), nm2.data_ptr(), core.data_ptr(), bound.data_ptr(), stream_ptr(dev))
+    _lib.check(rc, "second_layer_match")
+    out = (Z, trust, avg, xs, ys, nm1, nm2)
+    return out + (core, bound) if return_extra else out
+
+
+def third_layer_match(scores, one, scale, scale_x, scale_y, p_s, p_t, iters: int = 100):
+    """The matching block of ThirdLayer.forward (third_layer.py:158-167) in one call: log_optimal_transport2 on the [K,65,65]
+    scores (already 0.1 * einsum / sqrt(128)), exp, Compute_result and the label test.
+    Returns (scores_origin [K,65,65], mkpts0_f, mkpts1_f [K,16,2], if_matching1 [K,16])."""
+    scores = cuda_f32(scores, "scores")
+    K = scores.shape[0]
+    if scores.shape[1:] != (65, 65):
+        raise ValueError(f"third layer scores are [K,65,65] (W=8), got {tuple(scores.shape)}")
+    dev = scores.device
+    ns = cuda_f32(scale, "scale")
+    if ns.numel() != K * 64:
+        raise ValueError(f"scale must hold K*64 values, got {tuple(ns.shape)}")
+    sx = cuda_f32(scale_x, "scale_x").reshape(K, 64)
+    sy = cuda_f32(scale_y, "scale_y").reshape(K, 64)
+    ps = p_s.to(device=dev, dtype=torch.int64).contiguous()
+    pt = p_t.to(device=dev, dtype=torch.int64).contiguous()
+    from ._torchutil import scalar_on
+
+    one_t = scalar_on(dev, one, "one")
+    Z = torch.empty_like(scores)
+    m0 = torch.empty((K, 16, 2), dtype=torch.float32, device=dev)
+    m1 = torch.empty_like(m0)
+    im = torch.empty((K, 16), dtype=torch.bool, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.load().pats_third_layer_match_f32(scores.data_ptr(), one_t.data_ptr(), ns.data_ptr(), sx.data_ptr(), sy.data_ptr(), ps.data_ptr(),
+                                                    pt.data_ptr(), K, int(iters), Z.data_ptr(), m0.data_ptr(), m1.data_ptr(), im.data_ptr(),
+                                                    stream_ptr(dev))
+    _lib.check(rc, "third_layer_match")
+    return Z, m0, m1, im
+
+
+__all__ += ["est_position", "first_layer_est_position", "second_layer_est_position", "third_result_from_log", "second_layer_match",
+            "third_layer_match"]
 
 
 def grid_sample12(maps, row_num: int = 12):

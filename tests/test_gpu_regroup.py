@@ -261,3 +261,82 @@ def test_grid_sample12_and_third_unfold_golden(dev):
     idx = torch.randperm(K, generator=gen)[:64]
     r = oracle.third_unfold(feat.numpy(), mk1[idx].numpy(), b[idx].numpy(), kk.numpy(), rub.numpy(), mk0[idx].numpy(), True)
     assert np.array_equal(o[idx.numpy()], r)
+
+
+# ---- composite calls (second_layer.py:103-116, third_layer.py:158-167) with the plan hand-over ----------------------------
+def _l2_inputs(b, n, seed, dev, scale=0.1):
+    g = torch.Generator().manual_seed(seed)
+    s = (scale * torch.randn(b, n + 1, n + 1, generator=g)).to(dev)
+    sx = torch.exp((torch.rand(b, n, generator=g) * 2 - 1) * math.log(16.0)).to(dev)
+    sy = torch.exp((torch.rand(b, n, generator=g) * 2 - 1) * math.log(16.0)).to(dev)
+    return s, sx, sy
+
+
+@pytest.mark.parametrize("b,grid,outdoor,handover", [(7, 12, True, 1), (301, 12, True, 1), (301, 12, False, 0), (5, 4, True, 1), (3, 15, False, 1)])
+def test_second_layer_match_equals_separate_calls(dev, b, grid, outdoor, handover):
+    """One call == log_optimal_transport2, the in-place dustbin offsets of second_layer.py:108-112, est_position --
+    bit for bit, with and without the early launch, on the 145 x 145 kernel and on shapes that take other kernels."""
+    from pats_b200 import _lib, layers as Ly, modules as M
+
+    n = grid * grid
+    s, sx, sy = _l2_inputs(b, n, 100 + b + grid, dev)
+    ns = (sx * sy).reshape(b, 1, n)
+    one = torch.tensor(1.0, device=dev)
+    Z = M.log_optimal_transport2(s, one, ns, 100)
+    c = torch.log(one * (2 if outdoor else 3))
+    Z[:, :, -1] += c
+    Z[:, -1, :] += c
+    ref = Ly.est_position(Z, sx, sy, grid, grid, 8, 1e-3, return_extra=True)
+    lib = _lib.load()
+    lib.pats_plan_handover(handover)
+    try:
+        for _ in range(3):  # repeated calls reuse the flag pool (epochs) and the self-cleaning scratch of est_position
+            out = Ly.second_layer_match(s, one, ns, sx, sy, 100, outdoor, grid, return_extra=True)
+            assert torch.equal(out[0], Z)
+            for got, want in zip(out[1:], ref):
+                assert torch.equal(got, want)
+    finally:
+        lib.pats_plan_handover(1)
+
+
+def test_second_layer_match_vs_oracle(dev):
+    from pats_b200 import layers as Ly
+
+    b, n = 6, 144
+    s, sx, sy = _l2_inputs(b, n, 77, dev)
+    ns = (sx * sy).reshape(b, 1, n)
+    Z, trust, avg, xs, ys, nm1, nm2, core, bound = Ly.second_layer_match(s, 1.0, ns, sx, sy, 100, True, 12, return_extra=True)
+    Zo = oracle.log_optimal_transport2(s.cpu().numpy(), 1.0, ns.cpu().numpy(), 100)
+    c = np.float32(np.log(np.float32(2.0)))
+    Zo[:, :, -1] += c
+    Zo[:, -1, :] += c
+    np.testing.assert_allclose(Z.cpu().numpy(), Zo, atol=1e-4, rtol=0)
+    # the integer results hang off the plan: compare them on the kernel's own plan (the oracle's plan differs by ~1e-6)
+    w = oracle.iterative_expand_matrix(Z.exp().cpu().numpy(), sx.cpu().numpy(), sy.cpu().numpy(), 12, 12, 1e-3, 8)
+    assert np.array_equal(bound.cpu().numpy(), w[5])
+    o1, o2 = oracle.est_nomatching(Z.cpu().numpy(), n)
+    assert np.array_equal(nm1.cpu().numpy(), o1) and np.array_equal(nm2.cpu().numpy(), o2)
+
+
+@pytest.mark.parametrize("K,handover", [(5, 1), (4801, 1), (4801, 0)])
+def test_third_layer_match_equals_separate_calls(dev, K, handover):
+    from pats_b200 import _lib, layers as Ly, modules as M
+
+    g = torch.Generator().manual_seed(K)
+    s = (0.1 * torch.randn(K, 65, 65, generator=g)).to(dev)
+    ns = torch.exp((torch.rand(K, 1, 64, generator=g) * 2 - 1) * math.log(16.0)).to(dev)
+    sxy = (ns.reshape(K, 64) + 1e-8).sqrt()
+    p_s = (torch.randint(0, 24, (K, 2), generator=g) * 4).to(dev)
+    p_t = (torch.randint(0, 25, (K, 2), generator=g) * 4).to(dev)
+    Z = M.log_optimal_transport2(s, 1.0, ns, 100)
+    ref = Ly.third_result_from_log(Z, sxy, sxy, p_s, p_t)
+    lib = _lib.load()
+    lib.pats_plan_handover(handover)
+    try:
+        for _ in range(3):
+            out = Ly.third_layer_match(s, 1.0, ns, sxy, sxy, p_s, p_t, 100)
+            assert torch.equal(out[0], Z)
+            for got, want in zip(out[1:], ref):
+                assert torch.equal(got, want)
+    finally:
+        lib.pats_plan_handover(1)

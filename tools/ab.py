@@ -38,7 +38,7 @@ def build(specs):
             for rel in ["include/pats_b200.h"] + ["pats_b200/csrc/" + f for f in ("api.cu", "sinkhorn.cu", "sinkhorn_grid.cu", "common.cuh", "sinkhorn_common.cuh")]:
                 open(os.path.join(root, rel), "w").write(subprocess.run(["git", "-C", REPO, "show", f"{rev}:{rel}"], capture_output=True, text=True, check=True).stdout)
         so = os.path.join(OUT, f"lib_{name}.so")
-        cmd = ["/usr/local/cuda/bin/nvcc", *FLAGS, *flags.split(), "-o", so] + [os.path.join(csrc, s) for s in ("api.cu", "sinkhorn.cu", "sinkhorn_grid.cu")]
+        cmd = ["/usr/local/cuda/bin/nvcc", *FLAGS, *flags.split(), "-o", so] + [os.path.join(csrc, s) for s in ("api.cu", "sinkhorn.cu", "sinkhorn_grid.cu", "sinkhorn_c145.cu") if os.path.exists(os.path.join(csrc, s))]
         procs.append((name, subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for name, p in procs:
         out, _ = p.communicate()
