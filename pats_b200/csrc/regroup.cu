@@ -49,6 +49,7 @@ static void *zeroed_workspace(cudaStream_t st, size_t bytes) {
 // a8/a9  area expansion: one half-warp (16 lanes) per (problem, source row), 16 rows per CTA
 // =================================================================================================
 constexpr int EX_ROWS = 16;      // rows (half-warps) per CTA
+constexpr int EX_SM = 5;         // shared per-CTA arrays in front of the rows: O, SX, SY, CM, SV
 constexpr float kZero = 1e-14f;  // `zero` of utils/utils.py:1203
 
 struct ExpandArgs {
@@ -80,6 +81,10 @@ __device__ __forceinline__ double half_sum_f64(double v) {
     return v;
 }
 
+// WIDTH > 0: the strip length (= a.width) at compile time, so the strip loops unroll completely -- the shared-memory
+// loads of a strip are then in flight together and only the additions stay sequential (the order is the oracle's).
+// WIDTH == 0: any grid.
+template <int WIDTH>
 __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a) {
     extern __shared__ float sm[];
     __shared__ bool s_last;
@@ -87,9 +92,10 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
     const int stride = n + 2;
     float *O = sm, *SX = sm + stride, *SY = sm + 2 * stride;  // dustbin row, target scales (shared by the CTA)
     unsigned *CM = reinterpret_cast<unsigned *>(sm + 3 * stride);  // per-CTA column maxima (encoded)
+    float *SV = sm + 4 * stride;                                   // SX * SY, the product every strip sum reads
     const int hl = threadIdx.x & 15, half = threadIdx.x >> 4;      // lane within the half-warp, row slot
     const int hbase = threadIdx.x & 16;                            // first lane of this half inside its warp
-    float *E = sm + (4 + half) * stride;                           // this row (+ dustbin col, + zero slot)
+    float *E = sm + (EX_SM + half) * stride;                          // this row (+ dustbin col, + zero slot)
     const float *opp = a.scores + ((size_t)bb * (m + 1) + m) * (n + 1);
     if (a.done) {  // launched early (programmatic dependent launch): wait until the Sinkhorn kernel has published this problem
         if (threadIdx.x == 0) await_problem(a.done, a.epoch, bb);
@@ -98,8 +104,9 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
     // the plan is read with ld.global.cg: it may have been written by a still-running producer grid
     for (int j = threadIdx.x; j < stride; j += blockDim.x) {
         O[j] = j < n ? (a.log_input ? expf(__ldcg(opp + j)) : __ldcg(opp + j)) : kZero;
-        SX[j] = j < n ? a.sx[(size_t)bb * n + j] : kZero;  // slots n, n+1: SX*SY == 1e-14 exactly (the `zero` padding of
-        SY[j] = j < n ? a.sy[(size_t)bb * n + j] : 1.0f;   // expand_scale, utils.py:1208-1209)
+        const float sxv = j < n ? a.sx[(size_t)bb * n + j] : kZero;  // slots n, n+1: SX*SY == 1e-14 exactly (the `zero` padding of
+        const float syv = j < n ? a.sy[(size_t)bb * n + j] : 1.0f;   // expand_scale, utils.py:1208-1209)
+        SX[j] = sxv, SY[j] = syv, SV[j] = sxv * syv;
         CM[j] = 0u;
     }
     __syncthreads();
@@ -107,14 +114,21 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
     const bool row_ok = i_raw < m;
     const int i = row_ok ? i_raw : m - 1;  // surplus half-warps recompute the last row and discard it (keeps shuffles full)
     const float *row = a.scores + ((size_t)bb * (m + 1) + i) * (n + 1);
-    for (int j = hl; j < stride; j += 16) {
-        float v = kZero;
-        if (j <= n) {
-            v = __ldcg(row + j);
-            if (a.nm2 && j < n && row_ok) atomicMax(&CM[j], enc_f32(v));
-            if (a.log_input) v = expf(v);
+    for (int j = hl; j < stride; j += 16) E[j] = j <= n ? __ldcg(row + j) : kZero;  // raw values (Z when log_input)
+    __syncthreads();
+    if (a.nm2) {
+        // this CTA's column maxima of the raw Z: a thread per column over the staged rows (no shared-memory atomics --
+        // sixteen half-warps hammering the same 144 words cost a quarter of the kernel), then one global atomic each
+        const int rows_here = min(EX_ROWS, m - (int)blockIdx.x * EX_ROWS);
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            unsigned best = 0u;
+            for (int r = 0; r < rows_here; ++r) best = max(best, enc_f32(sm[(EX_SM + r) * stride + j]));
+            CM[j] = best;
         }
-        E[j] = v;
+        __syncthreads();
+    }
+    if (a.log_input) {
+        for (int j = hl; j <= n; j += 16) E[j] = expf(E[j]);  // each half-warp its own row
     }
     __syncthreads();
     if (a.nm2) {  // publish this CTA's column maxima; the last CTA of the problem writes the mask
@@ -133,7 +147,7 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
             if (threadIdx.x == 0) a.counter[bb] = 0u;
         }
     }
-    auto Sval = [&](int idx) -> float { return SX[idx] * SY[idx]; };
+    auto Sval = [&](int idx) -> float { return SV[idx]; };
     const float lbv = a.lb;
 
     // ---- argmax over real targets (first maximum), dustbin test (utils.py:1182,1194) ------------------------
@@ -156,7 +170,7 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
     int bd0, bd1, bd2, bd3, dy = 0, dx = 0, sdy = 0, sdx = 0;
     bd0 = bd1 = max0 / a.grid_w;
     bd2 = bd3 = max0 % a.grid_w;
-    const int width = a.width, height = a.height;
+    const int width = WIDTH > 0 ? WIDTH : a.width, height = a.height;
     float last_sum = E[max0], last_nom = O[max0];
 
     // ---- box growth (utils.py:1213-1243): lanes 0..11 of the half = (direction, quantity); the strip is summed
@@ -175,15 +189,27 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
             else if (d12 == 2) off = bd2 + bd0 * width - 1, lim = dy;
             else off = bd3 + bd0 * width + 1, lim = dy;
             const int stepi = (d12 < 2) ? 1 : width;
-            const int tmax = min(max(dx, dy) + 1, width);  // uniform over the half-warp
-            for (int t = 0; t < tmax; ++t) {
-                int sidx = off + t * stepi;
-                if (sidx < 0 || sidx > n - 1 || t > lim) sidx = n + 1;
-                const float e = E[sidx], o = O[sidx], sv = SX[sidx] * SY[sidx];
-                const float t1 = (e > lbv) ? o : kZero;
-                acc += (q12 == 0) ? e : ((q12 == 1) ? t1 : sv);
+            const float *const A12 = (q12 == 2) ? SV : E;
+            if (WIDTH > 0) {
+                // beyond the extent every quantity adds `zero` (slot n+1 holds it for E, O and SX*SY), so one loop of WIDTH
+                // steps is the same sequence of additions as the extent loop followed by the padding loop below
+#pragma unroll
+                for (int t = 0; t < WIDTH; ++t) {
+                    int sidx = off + t * stepi;
+                    if (sidx < 0 || sidx > n - 1 || t > lim) sidx = n + 1;
+                    const float x = A12[sidx], o = O[sidx];  // x: E for the plain / thresholded sums, SX*SY for the scale sum
+                    acc += (q12 == 1) ? ((x > lbv) ? o : kZero) : x;
+                }
+            } else {
+                const int tmax = min(max(dx, dy) + 1, width);  // uniform over the half-warp
+                for (int t = 0; t < tmax; ++t) {
+                    int sidx = off + t * stepi;
+                    if (sidx < 0 || sidx > n - 1 || t > lim) sidx = n + 1;
+                    const float x = A12[sidx], o = O[sidx];  // x: E for the plain / thresholded sums, SX*SY for the scale sum
+                    acc += (q12 == 1) ? ((x > lbv) ? o : kZero) : x;
+                }
+                for (int t = tmax; t < width; ++t) acc += kZero;
             }
-            for (int t = tmax; t < width; ++t) acc += kZero;
         }
         float es0 = __shfl_sync(0xffffffffu, acc, hbase + 0), es1 = __shfl_sync(0xffffffffu, acc, hbase + 3);
         float es2 = __shfl_sync(0xffffffffu, acc, hbase + 6), es3 = __shfl_sync(0xffffffffu, acc, hbase + 9);
@@ -221,14 +247,23 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
         else if (d == 2) off = bd2 + bd0 * width, lim = sdy;
         else off = bd3 + bd0 * width, lim = sdy;
         const int stepi = (d < 2) ? 1 : width;
-        const int tmax = min(max(sdx, sdy) + 1, width);
-        for (int t = 0; t < tmax; ++t) {
-            int sidx = off + t * stepi;
-            if (sidx < 0 || sidx > n - 1 || t > lim) sidx = n + 1;
-            const float e = E[sidx], sv = SX[sidx] * SY[sidx];
-            acc += (q == 0) ? e : sv;
+        const float *const Aq = (q == 0) ? E : SV;
+        if (WIDTH > 0) {
+#pragma unroll
+            for (int t = 0; t < WIDTH; ++t) {
+                int sidx = off + t * stepi;
+                if (sidx < 0 || sidx > n - 1 || t > lim) sidx = n + 1;
+                acc += Aq[sidx];
+            }
+        } else {
+            const int tmax = min(max(sdx, sdy) + 1, width);
+            for (int t = 0; t < tmax; ++t) {
+                int sidx = off + t * stepi;
+                if (sidx < 0 || sidx > n - 1 || t > lim) sidx = n + 1;
+                acc += Aq[sidx];
+            }
+            for (int t = tmax; t < width; ++t) acc += kZero;
         }
-        for (int t = tmax; t < width; ++t) acc += kZero;
     }
     const float e0 = __shfl_sync(0xffffffffu, acc, hbase + 0), e1 = __shfl_sync(0xffffffffu, acc, hbase + 2);
     const float e2 = __shfl_sync(0xffffffffu, acc, hbase + 4), e3 = __shfl_sync(0xffffffffu, acc, hbase + 6);
@@ -253,7 +288,7 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
         sxs += (double)ox;
         sys += (double)oy;
         const float o = ox * oy;
-        wsc += (double)(o * (SX[p] * SY[p]));
+        wsc += (double)(o * SV[p]);
         psum += (double)o;
     }
     for (int j = hl; j <= n; j += 16) ts += (double)E[j];
@@ -610,6 +645,29 @@ __global__ void __launch_bounds__(TH_K * 16) third_result_kernel(const float *__
     o0[1] = ((float)p_s[(size_t)k * 2 + 1] + (float)(c16 / 4) * 2.0f) - 3.0f;
 }
 
+template <int WIDTH>
+static int launch_area_expand_w(const ExpandArgs &a, dim3 grid, size_t smem, cudaStream_t st, bool early) {
+    if (smem > 48 * 1024)
+        PATS_CUDA_TRY(cudaFuncSetAttribute(area_expand_kernel<WIDTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(EX_ROWS * 16);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // plan hand-over: start behind a still-running producer
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = early ? 1 : 0;
+    PATS_CUDA_TRY(cudaLaunchKernelEx(&cfg, area_expand_kernel<WIDTH>, a));
+    return PATS_OK;
+}
+// strip length 20 (level 1: 15 x 20 coarse grid, one problem) is compiled in; anything else takes the loops
+static int launch_area_expand(const ExpandArgs &a, dim3 grid, size_t smem, cudaStream_t st, bool early) {
+    if (a.width == 20 && a.b * a.m <= 4096) return launch_area_expand_w<20>(a, grid, smem, st, early);  // few rows: latency-bound
+    return launch_area_expand_w<0>(a, grid, smem, st, early);  // many rows: issue-bound, the short extent loops win
+}
+
 }  // namespace pats
 
 using namespace pats;
@@ -633,15 +691,10 @@ PATS_API int pats_iterative_expand_matrix_f32(const float *scores_in, const floa
     a.bound = bound, a.nomatch = if_nomatching;
     a.nm2 = nullptr, a.colmax = nullptr, a.counter = nullptr;
     a.done = nullptr, a.epoch = 0u;
-    const size_t smem = sizeof(float) * (size_t)(4 + EX_ROWS) * (n + 2);
+    const size_t smem = sizeof(float) * (size_t)(EX_SM + EX_ROWS) * (n + 2);
     if (smem > 200 * 1024) return invalid("iterative_expand_matrix: grid of %lld cells exceeds the shared-memory budget", n);
-    if (smem > 48 * 1024)
-        PATS_CUDA_TRY(cudaFuncSetAttribute(area_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (b > 65535) return invalid("iterative_expand_matrix: batch %d exceeds gridDim.y", b);
-    dim3 grid((m + EX_ROWS - 1) / EX_ROWS, b);
-    area_expand_kernel<<<grid, EX_ROWS * 16, smem, as_stream(stream)>>>(a);
-    PATS_LAUNCH_CHECK("area_expand_kernel");
-    return PATS_OK;
+    return launch_area_expand(a, dim3((m + EX_ROWS - 1) / EX_ROWS, b), smem, as_stream(stream), false);
 }
 
 PATS_API int pats_est_nomatching_f32(const float *Z, int b, int M, int N, int dust, uint8_t *nm1, uint8_t *nm2, void *stream) {
@@ -783,10 +836,8 @@ static int est_position_launch(const float *Z, const float *scalex, const float 
     a.iters = iter_num, a.lb = lower_bound, a.log_input = 1;
     a.whole = trust_score, a.core = core_cost, a.avg = average_point, a.xs = x_scale, a.ys = y_scale;
     a.bound = bound, a.nomatch = if_nomatching1;
-    const size_t smem = sizeof(float) * (size_t)(4 + EX_ROWS) * (n + 2);
+    const size_t smem = sizeof(float) * (size_t)(EX_SM + EX_ROWS) * (n + 2);
     if (smem > 200 * 1024) return invalid("est_position: grid of %lld cells exceeds the shared-memory budget", n);
-    if (smem > 48 * 1024)
-        PATS_CUDA_TRY(cudaFuncSetAttribute(area_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (b > 65535) return invalid("est_position: batch %d exceeds gridDim.y", b);
     // column-argmax mask fused into the expansion kernel: encoded column maxima + per-problem arrival counters, in a
     // scratch buffer that is zero between calls (zeroed when allocated, re-zeroed by the kernel's last CTA per problem;
@@ -796,18 +847,7 @@ static int est_position_launch(const float *Z, const float *scalex, const float 
     if (!ws) return cuda_fail(cudaGetLastError(), "est_position workspace");
     a.nm2 = if_nomatching2, a.colmax = ws, a.counter = ws + (size_t)b * n;
     a.done = done, a.epoch = epoch;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(((int)n + EX_ROWS - 1) / EX_ROWS, b);
-    cfg.blockDim = dim3(EX_ROWS * 16);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = done ? 1 : 0;
-    PATS_CUDA_TRY(cudaLaunchKernelEx(&cfg, area_expand_kernel, a));
-    return PATS_OK;
+    return launch_area_expand(a, dim3(((int)n + EX_ROWS - 1) / EX_ROWS, b), smem, st, done != nullptr);
 }
 
 PATS_API int pats_est_position_f32(const float *Z, const float *scalex, const float *scaley, int b, int grid_h, int grid_w,
