@@ -464,6 +464,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-streaming", action="store_true", help="skip the b=32 N=1536 streaming-kernel roofline sample")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the torch-CUDA restatement of the reference's OT")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -601,6 +603,61 @@ def main():
             "frac_fp32_fma": fma_done / (l3_avg * 1e-3) / fma_lane_peak,
             "share_of_step": l3_avg * args.steps / total_ms,
         }
+        # ---- the streaming member of the kernel family against the HBM roofline it is really bound by ------------------
+        # BASELINE.json configs[2]: b = 32, N = 1536 (-> 1537 x 1537 plans, 302 MB in + 302 MB out: nothing fits on chip,
+        # the plan is read from HBM once per iteration).  Algorithmic bytes per SURVEY.md 8(d): b*4*(N+1)^2*(iters+2).
+        streaming = None
+        if world == 1 and not args.no_streaming:
+            from pats_b200 import modules as M
+
+            g2 = torch.Generator().manual_seed(SEED)
+            bs, Ns = 32, 1536
+            sc = (0.1 * torch.randn(bs, Ns, Ns, generator=g2)).to(dev)
+            nss = torch.exp((torch.rand(bs, 1, Ns, generator=g2) * 2 - 1) * math.log(16.0)).to(dev)
+            one_d = torch.tensor(1.0, device=dev)
+            for _ in range(3):
+                M.log_optimal_transport(sc, one_d, nss, ITERS)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+            for e0_, e1_ in evs:
+                e0_.record()
+                M.log_optimal_transport(sc, one_d, nss, ITERS)
+                e1_.record()
+            torch.cuda.synchronize(dev)
+            ms_s = sum(a_.elapsed_time(b_) for a_, b_ in evs) / len(evs)
+            bytes_s = bs * 4 * (Ns + 1) * (Ns + 1) * (ITERS + 2)
+            streaming = {"kernel": "sinkhorn_grid_kernel (plans beyond 512 x 512: rows split over co-resident CTAs, one HBM pass per iteration)",
+                         "workload": "BASELINE.json configs[2]: b=32, N=1536, 100 it", "bound": "hbm", "achieved": bytes_s / (ms_s * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": bytes_s / (ms_s * 1e-3) / 1e9 / peak, "ms_per_launch": ms_s,
+                         "algorithmic_bytes": bytes_s, "traffic": None}
+            del sc, nss
+            torch.cuda.empty_cache()
+        # ---- the reference's own formulation (log-domain, ~6 ATen ops per iteration: modules.py:137-182) on this GPU -------
+        torch_cuda = None
+        if world == 1 and not args.no_torch_baseline:
+            def torch_ot2(sx_, ns_, iters):
+                b_, m_, n_ = sx_.shape
+                nsum = ns_.sum(2).reshape(b_)
+                norm = -(float(m_ - 1) + nsum).log()
+                lnu = torch.cat([ns_.reshape(b_, -1).log() + norm[:, None], (math.log(float(m_ - 1)) + norm)[:, None]], 1)
+                lmu = torch.cat([norm[:, None].expand(b_, m_ - 1), (nsum.log() + norm)[:, None]], 1)
+                u, v = torch.zeros_like(lmu), torch.zeros_like(lnu)
+                for _ in range(iters):
+                    u = lmu - torch.logsumexp(sx_ + v[:, None, :], 2)
+                    v = lnu - torch.logsumexp(sx_ + u[:, :, None], 1)
+                return sx_ + u[:, :, None] + v[:, None, :] - norm[:, None, None]
+
+            tc = {}
+            for name, sk, nk in (("ot2_300x145", "l2_scores", "l2_ns"), ("ot3_4800x65", "l3_scores", "l3_ns")):
+                torch_ot2(step.i[sk], step.i[nk], 3)
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ea.record()
+                torch_ot2(step.i[sk], step.i[nk], ITERS)
+                eb.record()
+                torch.cuda.synchronize(dev)
+                tc[name + "_ms"] = ea.elapsed_time(eb)
+            torch_cuda = {"what": "log_optimal_transport2 restated with the reference's ATen ops (logsumexp per half-iteration), same GPU, same inputs, "
+                                  "CUDA events; informational -- the contract's baseline is the CPU arm", **tc,
+                          "ours_ot3_ms": l3_avg, "speedup_ot3": tc["ot3_4800x65_ms"] / l3_avg}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             import oracle
@@ -617,7 +674,8 @@ def main():
             "config": {"workload": "pats_hot_path_pair640x480", "pairs_per_step": B, "streams": S, "P2": P2, "K3": K3, "sinkhorn_iters": ITERS,
                        "l2_flush": "not needed: one step streams > 300 MB of distinct plans per pair (L2 = 126 MB)",
                        "matches_per_pair": kf // B, "exchange": "all_gather of match lists once after the pair loop (N>1)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "overlap": overlap,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_streaming": streaming, "cpu_baseline": cpu, "torch_cuda": torch_cuda,
+            "overlap": overlap,
         }
         emit(line)
     if world > 1:

@@ -39,6 +39,7 @@ struct GridArgs {
     float *part;      // [b][G][npad] per-CTA column partials
     unsigned *bar;    // [b] arrival counters (zeroed before launch)
     unsigned *flag;   // [b] 1 = scalings left the safe range -> log-domain re-solve
+    int l2_prefetch;  // 1: the batch of plans does not stay in L2 between iterations -> prefetch each warp's next row into L2
 };
 
 __device__ __forceinline__ void red_release_add(unsigned *p, unsigned v) {
@@ -97,6 +98,20 @@ __device__ __forceinline__ void for_row(const RowRef &rr, int lane, int NC, F &&
     }
 }
 
+// Pull a row this warp will sweep a little later from HBM into L2 with ONE instruction and no registers
+// (cp.async.bulk.prefetch.L2): the sweep's own loads then see L2 latency instead of DRAM latency, which is what limits a
+// warp that can only keep one row's loads in flight (a second row of loads in registers did not fit).  Needs a 16-byte
+// aligned row; other shapes simply skip it.
+__device__ __forceinline__ void prefetch_row_l2(const RowRef &rr, int NC, int lane) {
+#ifndef PATS_AB_NO_L2PF
+    if (lane == 0 && !rr.is_fill) {
+        const unsigned bytes = (unsigned)(NC * sizeof(float)) & ~15u;
+        if (bytes && (reinterpret_cast<uintptr_t>(rr.base) & 15) == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rr.base), "r"(bytes) : "memory");
+    }
+#endif
+}
+
 __device__ __forceinline__ RowRef row_ref(const SinkArgs &a, const Marg &g, int p, int row) {
     RowRef r;
     r.fill = g.fill;
@@ -109,6 +124,20 @@ __device__ __forceinline__ RowRef row_ref(const SinkArgs &a, const Marg &g, int 
         r.is_fill = false;
         r.base = a.Z + ((size_t)p * a.M + row) * a.N;
         r.last = __ldg(r.base + a.N - 1);
+    }
+    return r;
+}
+
+__device__ __forceinline__ RowRef row_ref_base_only(const SinkArgs &a, int p, int row) {  // base / is_fill only (for the prefetch)
+    RowRef r;
+    r.fill = 0.f, r.last = 0.f;
+    if (a.mode == MODE_OT) {
+        const int zm = a.M - 1, zn = a.N - 1;
+        r.is_fill = row >= zm;
+        r.base = a.Z + ((size_t)p * zm + (r.is_fill ? 0 : row)) * zn;
+    } else {
+        r.is_fill = false;
+        r.base = a.Z + ((size_t)p * a.M + row) * a.N;
     }
     return r;
 }
@@ -272,6 +301,7 @@ __global__ void __launch_bounds__(W * 32, OCC) sinkhorn_grid_kernel(GridArgs ga)
             const bool check = (it & 7) == 0 || it == a.iters - 1;
             for (int i = ifirst; i < r1; i += W) {
                 const RowRef rr = row_ref(a, g, p, i);
+                if (ga.l2_prefetch && i + W < r1) prefetch_row_l2(row_ref_base_only(a, p, i + W), NC, lane);
                 const float u = u1s[i - r0];
                 float rsum = 0.f;
                 if constexpr (KEEP) {
@@ -422,6 +452,7 @@ int launch_grid_cfg(const SinkArgs &a, cudaStream_t st) {
     ga.rpc = (a.M + G - 1) / G;
     ga.slice = (a.N + G - 1) / G;
     ga.npad = (a.N + 3) & ~3;
+    ga.l2_prefetch = (size_t)a.b * a.M * a.N * sizeof(float) > ((size_t)64 << 20);  // measured: +3 % at 302 MB, -2.5 % at 4 MB
     const size_t vec = (size_t)a.b * ga.npad;
     const size_t floats = vec * (3 + (size_t)G);
     const size_t bytes = floats * sizeof(float) + 2 * (size_t)a.b * sizeof(unsigned);
