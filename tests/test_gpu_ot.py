@@ -115,6 +115,24 @@ def test_transport2_vs_oracle(M, lib, dev, b, m, n, scale, span):
     assert_plan_equal(out, ref)
 
 
+@pytest.mark.parametrize("iters", [0, 1, 2, 100])
+def test_level3_direct_start_and_log_start_agree_with_the_oracle(M, dev, iters):
+    """The 65 x 65 kernel starts directly on exp(Z) when every |z| <= 12 and takes the log-domain first iteration otherwise
+    (decided per problem).  Mix both kinds in one batch, at the threshold, for the iteration counts that take different
+    code paths (0, 1: no / one scaling pass; 2; 100)."""
+    g = torch.Generator().manual_seed(4242 + iters)
+    b = 96
+    s = 0.5 * torch.randn(b, 65, 65, generator=g)
+    s[0::4, 3, 7] = 12.0          # exactly at the bound: direct
+    s[1::4, 11, 60] = 12.5        # just beyond: log-domain start
+    s[2::4, 64, 5] = -13.0        # dustbin row entry beyond the bound
+    s[3::4] = s[3::4].clamp(-11.9, 11.9)
+    ns = areas(g, b, 64, 16.0)
+    out = M.log_optimal_transport2(s.to(dev), 1.0, ns.to(dev), iters).cpu().numpy()
+    ref = oracle.log_optimal_transport2(s.numpy(), 1.0, ns.numpy(), iters)
+    assert_plan_equal(out, ref)
+
+
 @pytest.mark.parametrize("b,m,n,alpha", [(1, 300, 300, 1.0), (3, 64, 64, 0.7), (2, 20, 33, 0.0), (2, 144, 144, 2.0), (1, 160, 100, 1.0)])
 def test_transport_vs_oracle(M, dev, b, m, n, alpha):
     g = torch.Generator().manual_seed(2000 + m)
