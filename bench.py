@@ -464,6 +464,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-chain", action="store_true", help="A/B: plain kernel launches instead of launch chaining (pats_launch_chaining(0))")
+    ap.add_argument("--no-handover", action="store_true", help="A/B: no plan hand-over inside the composite calls (pats_plan_handover(0))")
     ap.add_argument("--no-streaming", action="store_true", help="skip the b=32 N=1536 streaming-kernel roofline sample")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the torch-CUDA restatement of the reference's OT")
     args = ap.parse_args()
@@ -494,6 +496,13 @@ def main():
     if world > 1:
         from pats_b200.dist import gather_match_lists as gather
 
+    if args.no_chain or args.no_handover:
+        from pats_b200 import _lib as _l
+
+        if args.no_chain:
+            _l.load().pats_launch_chaining(0)
+        if args.no_handover:
+            _l.load().pats_plan_handover(0)
     steps_all = [DeviceStep(torch, dev, B, SEED + rank)]
     step = steps_all[0]
 

@@ -76,6 +76,10 @@ void pats_sinkhorn_force_generic(int on);
  * plans is launched with programmatic stream serialization, so it works on finished problems while the solve's last
  * wave is still running.  0 = plain stream order between the two kernels (tests / A-B timing). */
 void pats_plan_handover(int on);
+/* Launch chaining (default on): the kernels of the path are launched with programmatic stream serialization and begin
+ * with griddepcontrol.wait, so the next kernel is resident when its predecessor finishes (ordering unchanged; only the
+ * launch gap between small dependent kernels disappears).  0 = plain launches (tests / A-B timing). */
+void pats_launch_chaining(int on);
 /* Routing of 65 x 65 problems (tests / A-B timing): 0 = two warps per problem (default), 1 = padded 72 x 68 warp
  * kernel, 2 / 3 = one-warp 65 x 65 kernel compiled for 2 / 3 CTAs per SM. */
 void pats_sinkhorn_disable_w65(int mode);

@@ -30,6 +30,7 @@ SIGNATURES = {
     "pats_sinkhorn_grid_variant": [_I],
     "pats_sinkhorn_force_generic": [_I],
     "pats_plan_handover": [_I],
+    "pats_launch_chaining": [_I],
     "pats_sinkhorn_disable_w65": [_I],
     "pats_sinkhorn_disable_c145": [_I],
     "pats_sinkhorn_cluster_variant": [_I],
@@ -54,7 +55,7 @@ SIGNATURES = {
     "pats_second_layer_match_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "pats_third_layer_match_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
 }
-_RESTYPE = {"pats_last_error": C.c_char_p, "pats_sinkhorn_force_generic": None, "pats_plan_handover": None, "pats_sinkhorn_disable_w65": None, "pats_sinkhorn_disable_c145": None, "pats_sinkhorn_cluster_variant": None, "pats_sinkhorn_grid_ctas_per_problem": None, "pats_sinkhorn_grid_variant": None}
+_RESTYPE = {"pats_last_error": C.c_char_p, "pats_sinkhorn_force_generic": None, "pats_plan_handover": None, "pats_launch_chaining": None, "pats_sinkhorn_disable_w65": None, "pats_sinkhorn_disable_c145": None, "pats_sinkhorn_cluster_variant": None, "pats_sinkhorn_grid_ctas_per_problem": None, "pats_sinkhorn_grid_variant": None}
 
 
 def library_path() -> str:

@@ -90,6 +90,16 @@ __device__ __forceinline__ float warp_max(float v) {
 
 // ---- plan hand-over between the Sinkhorn kernels and the kernels that consume their plans (see sinkhorn_common.cuh) ----
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ---- launch chaining: every kernel of the path is launched with programmatic stream serialization (launch_chained()
+// below) and begins with pdl_prologue(): wait until the grids it depends on have completed and flushed -- exactly the
+// ordering a plain launch gives -- THEN allow the next kernel in the stream to become resident.  Nothing runs early;
+// what disappears is the drain -> launch -> ramp-up gap between the 16 small dependent kernels of a step (~2 us each).
+// Wait-before-trigger keeps the dependency transitive: a grid is resident only after everything before it has finished.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+    pdl_wait();
+    pdl_launch_dependents();
+}
 // consumer side: one thread spins, then the caller synchronises its group.  A producer that died leaves the flag unset:
 // trap after ~2 s instead of hanging the GPU.
 __device__ __forceinline__ void await_problem(const unsigned *done, unsigned epoch, int p) {
@@ -109,5 +119,23 @@ __device__ __forceinline__ void await_problem(const unsigned *done, unsigned epo
 int sinkhorn_ot2_publish(const float *scores, const float *one, const float *ns, int b, int m, int n, int iters, float edge_add,
                          float *out, cudaStream_t st, const unsigned **done, unsigned *epoch);
 extern int g_handover;  // pats_plan_handover(): 0 = never publish (plain stream order everywhere)
+extern int g_chain;     // pats_launch_chaining(): 0 = plain launches
+
+// launch with programmatic stream serialization (see pdl_prologue); the kernel MUST start with pdl_prologue() (or, for
+// the hand-over consumers, wait on the per-problem flags instead)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_chain ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace pats

@@ -97,9 +97,12 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
     const int hbase = threadIdx.x & 16;                            // first lane of this half inside its warp
     float *E = sm + (EX_SM + half) * stride;                          // this row (+ dustbin col, + zero slot)
     const float *opp = a.scores + ((size_t)bb * (m + 1) + m) * (n + 1);
-    if (a.done) {  // launched early (programmatic dependent launch): wait until the Sinkhorn kernel has published this problem
+    if (a.done) {  // launched early (plan hand-over): wait until the Sinkhorn kernel has published this problem
+        pdl_launch_dependents();
         if (threadIdx.x == 0) await_problem(a.done, a.epoch, bb);
         __syncthreads();
+    } else {
+        pdl_prologue();
     }
     // the plan is read with ld.global.cg: it may have been written by a still-running producer grid
     for (int j = threadIdx.x; j < stride; j += blockDim.x) {
@@ -375,6 +378,7 @@ __global__ void __launch_bounds__(256) est_nomatching_kernel(const float *__rest
 // Ordered index maps between matched level-1 patches q (row-major over [B,hw]) and window numbers p.
 __global__ void __launch_bounds__(1024) window_maps_kernel(const uint8_t *__restrict__ nm_L1, int total, int *__restrict__ qmap,
                                                            int *__restrict__ pmap, int capacity, int *count) {
+    pdl_prologue();
     __shared__ int warp_tot[32];
     __shared__ int base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -406,6 +410,7 @@ __global__ void __launch_bounds__(1024) window_maps_kernel(const uint8_t *__rest
 // scores_back (:210 / :157).
 __global__ void merge_rings_kernel(float *__restrict__ trust, uint8_t *__restrict__ nm_L2, double *__restrict__ scores_back,
                                    const int *__restrict__ qmap, int P, int merge_new) {
+    pdl_prologue();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= P * 144) return;
     const int p = e / 144, cell = e - p * 144;
@@ -429,6 +434,7 @@ __global__ void merge_rings_kernel(float *__restrict__ trust, uint8_t *__restric
 __global__ void merge_select_kernel(const uint8_t *__restrict__ nm_L2, const double *__restrict__ scores_back,
                                     const int *__restrict__ qmap, const int *__restrict__ pmap, int P, int height, int width,
                                     int merge_new, uint8_t *__restrict__ out) {
+    pdl_prologue();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= P * 144) return;
     const int p = e / 144, cell = e - p * 144;
@@ -477,6 +483,7 @@ __global__ void merge_select_kernel(const uint8_t *__restrict__ nm_L2, const dou
 // a14  get_result: two-level ordered compaction + affine composition
 // =================================================================================================
 __global__ void __launch_bounds__(256) count_rows_kernel(const uint8_t *__restrict__ nm1, int n1, int *__restrict__ cnt) {
+    pdl_prologue();
     __shared__ int part[8];
     const int p = blockIdx.x;
     int c = 0;
@@ -493,6 +500,7 @@ __global__ void __launch_bounds__(256) count_rows_kernel(const uint8_t *__restri
 
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int *__restrict__ cnt, int P, long long *__restrict__ off,
                                                               long long *total) {
+    pdl_prologue();
     __shared__ long long warp_tot[32];
     __shared__ long long base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -534,6 +542,7 @@ struct ResultArgs {
 };
 
 __global__ void __launch_bounds__(256) assemble_matches_kernel(ResultArgs a) {
+    pdl_prologue();
     __shared__ int warp_tot[8];
     __shared__ long long base;
     const int p = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -596,8 +605,11 @@ __global__ void __launch_bounds__(TH_K * 16) third_result_kernel(const float *__
     __shared__ float gx[TH_K][64], gy[TH_K][64];
     const int k0 = blockIdx.x * TH_K;
     if (done) {  // launched early (plan hand-over, sinkhorn_common.cuh): wait for this CTA's problems
+        pdl_launch_dependents();
         if (threadIdx.x < TH_K && k0 + threadIdx.x < K) await_problem(done, epoch, k0 + threadIdx.x);
         __syncthreads();
+    } else {
+        pdl_prologue();
     }
     for (int e = threadIdx.x; e < TH_K * 16 * NN; e += blockDim.x) {
         const int rr = e / NN, j = e - rr * NN;
@@ -658,7 +670,7 @@ static int launch_area_expand_w(const ExpandArgs &a, dim3 grid, size_t smem, cud
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // plan hand-over: start behind a still-running producer
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = early ? 1 : 0;
+    cfg.numAttrs = (early || g_chain) ? 1 : 0;  // hand-over consumer, or plain launch chaining (the kernel then starts with pdl_prologue)
     PATS_CUDA_TRY(cudaLaunchKernelEx(&cfg, area_expand_kernel<WIDTH>, a));
     return PATS_OK;
 }
@@ -718,13 +730,13 @@ PATS_API int pats_merge_patches(int merge_new, float *trust_score, const uint8_t
     cudaStream_t st = as_stream(stream);
     const int total = B * height * width;
     int *qmap = workspace, *pmap = workspace + total, *count = workspace + 2 * total;  // workspace: 2*B*hw+1 ints
-    window_maps_kernel<<<1, 1024, 0, st>>>(nm_L1, total, qmap, pmap, P, count);
+    PATS_CUDA_TRY(launch_chained(window_maps_kernel, dim3(1), dim3(1024), 0, st, nm_L1, total, qmap, pmap, P, count));
     PATS_LAUNCH_CHECK("window_maps_kernel");
     if (P == 0) return PATS_OK;
     const int cells = P * 144;
-    merge_rings_kernel<<<(cells + 255) / 256, 256, 0, st>>>(trust_score, nm_L2, scores_back, qmap, P, merge_new ? 1 : 0);
+    PATS_CUDA_TRY(launch_chained(merge_rings_kernel, dim3((cells + 255) / 256), dim3(256), 0, st, trust_score, nm_L2, scores_back, qmap, P, merge_new ? 1 : 0));
     PATS_LAUNCH_CHECK("merge_rings_kernel");
-    merge_select_kernel<<<(cells + 255) / 256, 256, 0, st>>>(nm_L2, scores_back, qmap, pmap, P, height, width, merge_new ? 1 : 0, out);
+    PATS_CUDA_TRY(launch_chained(merge_select_kernel, dim3((cells + 255) / 256), dim3(256), 0, st, nm_L2, scores_back, qmap, pmap, P, height, width, merge_new ? 1 : 0, out));
     PATS_LAUNCH_CHECK("merge_select_kernel");
     if (!merge_new) PATS_CUDA_TRY(cudaMemsetAsync(scores_back, 0, sizeof(double) * (size_t)total * 144, st));  // second_layer.py:186
     return PATS_OK;
@@ -741,19 +753,19 @@ PATS_API int pats_get_result_f32(const uint8_t *nm0, const float *pt0, const flo
     // workspace layout: off[P+1] (i64) | qmap[tot0] | pmap[tot0] | count | cnt[P]
     long long *off = (long long *)workspace;
     int *qmap = (int *)(off + P + 1), *pmap = qmap + tot0, *count = pmap + tot0, *cnt = count + 1;
-    window_maps_kernel<<<1, 1024, 0, st>>>(nm0, tot0, qmap, pmap, P, count);
+    PATS_CUDA_TRY(launch_chained(window_maps_kernel, dim3(1), dim3(1024), 0, st, nm0, tot0, qmap, pmap, P, count));
     PATS_LAUNCH_CHECK("window_maps_kernel");
     if (P == 0) {
         PATS_CUDA_TRY(cudaMemsetAsync(total, 0, sizeof(long long), st));
         return PATS_OK;
     }
     if (!nm1 || !pt1 || !sc1 || !matches_l || !matches_r) return invalid("get_result: null pointer");
-    count_rows_kernel<<<P, 256, 0, st>>>(nm1, n1, cnt);
+    PATS_CUDA_TRY(launch_chained(count_rows_kernel, dim3(P), dim3(256), 0, st, nm1, n1, cnt));
     PATS_LAUNCH_CHECK("count_rows_kernel");
-    exclusive_scan_kernel<<<1, 1024, 0, st>>>(cnt, P, off, total);
+    PATS_CUDA_TRY(launch_chained(exclusive_scan_kernel, dim3(1), dim3(1024), 0, st, cnt, P, off, total));
     PATS_LAUNCH_CHECK("exclusive_scan_kernel");
     ResultArgs a{nm1, pt0, sc0, pt1, sc1, qmap, off, P, n0, w0, ps0, n1, w1, ps1, capacity, matches_l, matches_r};
-    assemble_matches_kernel<<<P, 256, 0, st>>>(a);
+    PATS_CUDA_TRY(launch_chained(assemble_matches_kernel, dim3(P), dim3(256), 0, st, a));
     PATS_LAUNCH_CHECK("assemble_matches_kernel");
     return PATS_OK;
 }
@@ -784,7 +796,7 @@ static int third_result_from_log_launch(const float *Z, const float *scale_x, co
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = done ? 1 : 0;
+    cfg.numAttrs = (done || g_chain) ? 1 : 0;
     PATS_CUDA_TRY(cudaLaunchKernelEx(&cfg, third_result_kernel, Z, scale_x, scale_y, p_s, p_t, K, 1, mkpts0_f, mkpts1_f, if_matching1, done,
                                      epoch));
     return PATS_OK;

@@ -247,6 +247,7 @@ __device__ __forceinline__ void col_reduce(float (&v)[C::CT], Op op, float *sm, 
 
 template <class C>
 __global__ void __launch_bounds__(C::THREADS) sinkhorn_reg_kernel(SinkArgs a) {
+    pdl_prologue();
     constexpr int RT = C::RT, CT = C::CT, CT2 = C::CT2, QC = C::QC, PR = C::PR;
     constexpr bool ODD = C::ODD;
     extern __shared__ __align__(16) float sm[];
@@ -794,7 +795,7 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int pair = wib >> 1, w = wib & 1;
     const int p = blockIdx.x * X2_PAIRS + pair;
-    pdl_launch_dependents();
+    pdl_prologue();
     if (p >= a.b) return;  // uniform over the pair; the named barrier below involves this pair only
     const PairSync psync{1 + pair};
     const int pr = lane >> 2, qc = lane & 3;
@@ -1396,7 +1397,7 @@ __global__ void __launch_bounds__(C145B_T, 2) sinkhorn_c145b_kernel(SinkArgs a) 
     __shared__ float s_fb[145 + 145 + 2 * C145B_T];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int p = blockIdx.x;
-    pdl_launch_dependents();
+    pdl_prologue();
     if (p >= a.b) return;
     const int pr = lane >> 1, qc = lane & 1;
     const int cmask = ((pr & 1) << 2) | (((pr >> 1) & 1) << 1) | ((pr >> 2) & 1);
@@ -1803,18 +1804,25 @@ static int launch_reg(const SinkArgs &a, cudaStream_t st) {
     cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (g_chain) {  // launch chaining (common.cuh): the kernel starts with pdl_prologue()
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     if (C::CL > 1) {
         cfg.gridDim = dim3((unsigned)a.b * C::CL);
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = C::CL;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = C::CL;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
     } else {
         cfg.gridDim = dim3((unsigned)((a.b + C::GROUPS - 1) / C::GROUPS));
     }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
     PATS_CUDA_TRY(cudaLaunchKernelEx(&cfg, sinkhorn_reg_kernel<C>, a));
     return PATS_OK;
 }
@@ -1869,8 +1877,7 @@ static int run_sinkhorn(SinkArgs a, void *stream, bool publish = false, const un
         case 0:
             if (a.M == 65 && a.N == 65 && g_disable_w65 == 0) {
                 if (publish) a.done = handover_begin(st, a.b, &a.epoch);
-                sinkhorn_w65x2_kernel<<<(a.b + X2_PAIRS - 1) / X2_PAIRS, X2_PAIRS * 64, 0, st>>>(a);
-                PATS_LAUNCH_CHECK("sinkhorn_w65x2_kernel");
+                PATS_CUDA_TRY(launch_chained(sinkhorn_w65x2_kernel, dim3((a.b + X2_PAIRS - 1) / X2_PAIRS), dim3(X2_PAIRS * 64), 0, st, a));
                 return PATS_OK;
             }
             if (a.M == 65 && a.N == 65 && (g_disable_w65 == 2 || g_disable_w65 == 3)) {
@@ -1884,8 +1891,7 @@ static int run_sinkhorn(SinkArgs a, void *stream, bool publish = false, const un
         case 1:
             if (a.M == 145 && a.N == 145 && g_disable_c145 == 0) {
                 if (publish) a.done = handover_begin(st, a.b, &a.epoch);
-                sinkhorn_c145b_kernel<<<a.b, C145B_T, 0, st>>>(a);
-                PATS_LAUNCH_CHECK("sinkhorn_c145b_kernel");
+                PATS_CUDA_TRY(launch_chained(sinkhorn_c145b_kernel, dim3(a.b), dim3(C145B_T), 0, st, a));
                 return PATS_OK;
             }
             if (a.M == 145 && a.N == 145 && g_disable_c145 == 2) {
@@ -1935,9 +1941,11 @@ PATS_API int pats_log_optimal_transport2_f32(const float *scores, const float *o
 PATS_API int pats_sinkhorn_kernel_kind(int M, int N) { return kernel_kind(M, N); }
 PATS_API void pats_sinkhorn_force_generic(int on) { g_force_generic = on ? 1 : 0; }
 PATS_API void pats_plan_handover(int on) { g_handover = on ? 1 : 0; }
+PATS_API void pats_launch_chaining(int on) { g_chain = on ? 1 : 0; }
 
 namespace pats {
 int g_handover = 1;
+int g_chain = 1;
 int sinkhorn_ot2_publish(const float *scores, const float *one, const float *ns, int b, int m, int n, int iters, float edge_add,
                          float *out, cudaStream_t st, const unsigned **done, unsigned *epoch) {
     if (b > 0 && (!one || !ns)) return invalid("log_optimal_transport2: null one / ns");

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(1024) compute_imgs_plan_kernel(const float *__
                                                                  int64_t *__restrict__ bound5, float *__restrict__ xs_new,
                                                                  float *__restrict__ ys_new, float *__restrict__ avg_new,
                                                                  int capacity, int *count) {
+    pdl_prologue();
     __shared__ int warp_tot[32];
     __shared__ int base;
     const int total = B * n;
@@ -216,6 +217,7 @@ template <class V>
 __global__ void __launch_bounds__(256) left_windows_kernel(const V *__restrict__ left, V *__restrict__ out,
                                                            const int64_t *__restrict__ bound5, const int *__restrict__ count,
                                                            int H, int W, int ps, int width, int seg_v /* V per ps pixels */) {
+    pdl_prologue();
     const int p = blockIdx.x;
     if (p >= *count) return;
     const long long seq = bound5[(size_t)p * 5 + 4];
@@ -242,6 +244,7 @@ template <class T>
 __global__ void __launch_bounds__(256) right_patches_kernel(const T *__restrict__ right, float *__restrict__ out,
                                                             const int64_t *__restrict__ bound5, const int *__restrict__ count,
                                                             int B, int H, int W, int margin, int oh, int ow, int *bad_rows) {
+    pdl_prologue();
     // grid (P, bands): each CTA produces a band of output rows of one patch (P alone would leave most SMs idle)
     const int p = blockIdx.x;
     if (p >= *count) return;
@@ -404,21 +407,19 @@ PATS_API int pats_compute_imgs(const float *x_scale, const float *y_scale, const
         return invalid("compute_imgs: patch rows must be 16-byte multiples and images 16-byte aligned");
     cudaStream_t st = as_stream(stream);
     const int n = height * width, H = ps * height, W = ps * width;
-    compute_imgs_plan_kernel<<<1, 1024, 0, st>>>(x_scale, y_scale, average_point, if_nomatching, B, n, height, width, ps, margin,
-                                                 bound5, x_scale_new, y_scale_new, average_new, capacity, count);
-    PATS_LAUNCH_CHECK("compute_imgs_plan_kernel");
+    PATS_CUDA_TRY(launch_chained(compute_imgs_plan_kernel, dim3(1), dim3(1024), 0, st, x_scale, y_scale, average_point, if_nomatching, B, n, height,
+                                 width, ps, margin, bound5, x_scale_new, y_scale_new, average_new, capacity, count));
     const int grid = capacity < B * n ? capacity : B * n;
     if (grid == 0) return PATS_OK;
     const int seg_v = (int)((size_t)ps * 3 * elem / 16);
-    left_windows_kernel<uint4><<<grid, 256, 0, st>>>((const uint4 *)left, (uint4 *)new_left, bound5, count, H, W, ps, width, seg_v);
-    PATS_LAUNCH_CHECK("left_windows_kernel");
+    PATS_CUDA_TRY(launch_chained(left_windows_kernel<uint4>, dim3(grid), dim3(256), 0, st, (const uint4 *)left, (uint4 *)new_left, bound5, count, H, W,
+                                 ps, width, seg_v));
     const dim3 rgrid(grid, 8);
     if (elem == 1)
-        right_patches_kernel<uint8_t><<<rgrid, 256, 0, st>>>((const uint8_t *)right, new_right, bound5, count, B, H, W, margin, 3 * ps,
-                                                           3 * ps, bad_rows);
+        PATS_CUDA_TRY(launch_chained(right_patches_kernel<uint8_t>, rgrid, dim3(256), 0, st, (const uint8_t *)right, new_right, bound5, count, B, H, W,
+                                     margin, 3 * ps, 3 * ps, bad_rows));
     else
-        right_patches_kernel<float><<<rgrid, 256, 0, st>>>((const float *)right, new_right, bound5, count, B, H, W, margin, 3 * ps, 3 * ps,
-                                                         bad_rows);
-    PATS_LAUNCH_CHECK("right_patches_kernel");
+        PATS_CUDA_TRY(launch_chained(right_patches_kernel<float>, rgrid, dim3(256), 0, st, (const float *)right, new_right, bound5, count, B, H, W,
+                                     margin, 3 * ps, 3 * ps, bad_rows));
     return PATS_OK;
 }

@@ -340,3 +340,37 @@ def test_third_layer_match_equals_separate_calls(dev, K, handover):
                 assert torch.equal(got, want)
     finally:
         lib.pats_plan_handover(1)
+
+
+def test_launch_chaining_on_and_off_give_identical_results(dev):
+    """Programmatic-stream-serialization launches (griddepcontrol.wait at the top of every kernel) must not change anything:
+    run a chain of dependent calls with chaining on and off and compare bit for bit."""
+    from pats_b200 import _lib, layers as Ly, modules as M, utils as U
+
+    g = torch.Generator().manual_seed(99)
+    b, n = 40, 144
+    s, sx, sy = _l2_inputs(b, n, 5, dev)
+    ns = (sx * sy).reshape(b, 1, n)
+    s1 = (0.1 * torch.randn(1, 300, 300, generator=g)).to(dev)
+    ns1 = torch.exp((torch.rand(1, 1, 300, generator=g) * 2 - 1) * math.log(16.0)).to(dev)
+    lib = _lib.load()
+
+    def run():
+        Z1 = M.log_optimal_transport(s1, 1.0, ns1, 100)
+        e1 = Ly.est_position(Z1, ns1, ns1, 15, 20, 15, 1e-5, return_extra=True)
+        out = Ly.second_layer_match(s, 1.0, ns, sx, sy, 100, True, 12, return_extra=True)
+        nm_L1 = torch.zeros(1, 300, dtype=torch.bool, device=dev)
+        nm_L1[0, b:] = True
+        keep, sb = Ly.merge_patches_new(None, b, out[1].clone(), [480, 640], nm_L1, out[5].clone(), torch.zeros(1, 300, 16, 9, dtype=torch.float64, device=dev))
+        torch.cuda.synchronize()
+        return [Z1, *e1, *out, keep, sb]
+
+    lib.pats_launch_chaining(0)
+    try:
+        ref = run()
+    finally:
+        lib.pats_launch_chaining(1)
+    for _ in range(3):
+        got = run()
+        for a_, b_ in zip(got, ref):
+            assert torch.equal(a_, b_)
