@@ -482,8 +482,11 @@ __global__ void merge_select_kernel(const uint8_t *__restrict__ nm_L2, const dou
 // =================================================================================================
 // a14  get_result: two-level ordered compaction + affine composition
 // =================================================================================================
+// Launched behind window_maps_kernel, which it does not depend on: it is resident only after every window_maps CTA has
+// passed its own wait (so everything older is complete), runs concurrently with it, and waits for it at the END so that
+// "this grid complete" still implies "everything before it complete" for the kernels chained behind.
 __global__ void __launch_bounds__(256) count_rows_kernel(const uint8_t *__restrict__ nm1, int n1, int *__restrict__ cnt) {
-    pdl_prologue();
+    pdl_launch_dependents();
     __shared__ int part[8];
     const int p = blockIdx.x;
     int c = 0;
@@ -496,6 +499,7 @@ __global__ void __launch_bounds__(256) count_rows_kernel(const uint8_t *__restri
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
         cnt[p] = t;
     }
+    pdl_wait();
 }
 
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int *__restrict__ cnt, int P, long long *__restrict__ off,
@@ -535,7 +539,9 @@ struct ResultArgs {
     const uint8_t *nm1;
     const float *pt0, *sc0, *pt1, *sc1;
     const int *qmap;
-    const long long *off;
+    const long long *off;   // exclusive scan of cnt (exclusive_scan_kernel), or nullptr: every CTA sums cnt[0..p) itself
+    const int *cnt;         // matches per window
+    long long *total;       // written by the last CTA when off == nullptr
     int P, n0, w0, ps0, n1, w1, ps1;
     long long capacity;
     float *ml, *mr;
@@ -557,7 +563,23 @@ __global__ void __launch_bounds__(256) assemble_matches_kernel(ResultArgs a) {
         l0[d] = 0.f + dl;
         r0[d] = 0.f + dr;
     }
-    if (threadIdx.x == 0) base = a.off[p];
+    if (a.off) {
+        if (threadIdx.x == 0) base = a.off[p];
+    } else {  // few windows: the prefix over the preceding windows' counts costs less than one more kernel in the chain
+        long long t = 0;
+        for (int i = threadIdx.x; i < p; i += blockDim.x) t += a.cnt[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        __shared__ long long wsum[8];
+        if (lane == 0) wsum[warp] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long b0 = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) b0 += wsum[w];
+            base = b0;
+            if (p == a.P - 1) *a.total = b0 + a.cnt[p];
+        }
+    }
     __syncthreads();
     for (int start = 0; start < a.n1; start += blockDim.x) {
         const int c1 = start + threadIdx.x;
@@ -762,9 +784,12 @@ PATS_API int pats_get_result_f32(const uint8_t *nm0, const float *pt0, const flo
     if (!nm1 || !pt1 || !sc1 || !matches_l || !matches_r) return invalid("get_result: null pointer");
     PATS_CUDA_TRY(launch_chained(count_rows_kernel, dim3(P), dim3(256), 0, st, nm1, n1, cnt));
     PATS_LAUNCH_CHECK("count_rows_kernel");
-    PATS_CUDA_TRY(launch_chained(exclusive_scan_kernel, dim3(1), dim3(1024), 0, st, cnt, P, off, total));
-    PATS_LAUNCH_CHECK("exclusive_scan_kernel");
-    ResultArgs a{nm1, pt0, sc0, pt1, sc1, qmap, off, P, n0, w0, ps0, n1, w1, ps1, capacity, matches_l, matches_r};
+    const bool own_prefix = P <= 2048;
+    if (!own_prefix) {
+        PATS_CUDA_TRY(launch_chained(exclusive_scan_kernel, dim3(1), dim3(1024), 0, st, cnt, P, off, total));
+        PATS_LAUNCH_CHECK("exclusive_scan_kernel");
+    }
+    ResultArgs a{nm1, pt0, sc0, pt1, sc1, qmap, own_prefix ? nullptr : off, cnt, total, P, n0, w0, ps0, n1, w1, ps1, capacity, matches_l, matches_r};
     PATS_CUDA_TRY(launch_chained(assemble_matches_kernel, dim3(P), dim3(256), 0, st, a));
     PATS_LAUNCH_CHECK("assemble_matches_kernel");
     return PATS_OK;

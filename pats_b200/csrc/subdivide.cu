@@ -244,10 +244,15 @@ template <class T>
 __global__ void __launch_bounds__(256) right_patches_kernel(const T *__restrict__ right, float *__restrict__ out,
                                                             const int64_t *__restrict__ bound5, const int *__restrict__ count,
                                                             int B, int H, int W, int margin, int oh, int ow, int *bad_rows) {
-    pdl_prologue();
+    // launched behind left_windows_kernel, which it does not depend on (both read the plan kernel's bounds): runs
+    // concurrently with it and waits for it at the END, see count_rows_kernel in regroup.cu
+    pdl_launch_dependents();
     // grid (P, bands): each CTA produces a band of output rows of one patch (P alone would leave most SMs idle)
     const int p = blockIdx.x;
-    if (p >= *count) return;
+    if (p >= *count) {
+        pdl_wait();
+        return;
+    }
     const int Hp = H + 2 * margin, Wp = W + 2 * margin;
     const Crop c = read_crop(bound5, p, B, Hp, Wp);
     float *dst = out + (size_t)p * 3 * oh * ow;
@@ -258,6 +263,7 @@ __global__ void __launch_bounds__(256) right_patches_kernel(const T *__restrict_
         for (int ch = 0; ch < 3; ++ch)
             for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) dst[(size_t)ch * total + e] = 0.f;
         if (blockIdx.y == 0 && threadIdx.x == 0 && bad_rows) atomicAdd(bad_rows, 1);
+        pdl_wait();
         return;
     }
     const T *img = right + (size_t)c.img * H * W * 3;
@@ -277,6 +283,7 @@ __global__ void __launch_bounds__(256) right_patches_kernel(const T *__restrict_
             dst[(size_t)ch * total + e] = lerp2<kShipVariant>(ay.l0, ay.l1, ax.l0, ax.l1, a, b, cc, d);
         }
     }
+    pdl_wait();
 }
 
 template <int V>
