@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) right_patches_kernel(const T *__restrict_
     float *dst = out + (size_t)p * 3 * oh * ow;
     const int total = oh * ow;
     const int rows_per = (oh + gridDim.y - 1) / gridDim.y;
-    const int e0 = blockIdx.y * rows_per * ow, e1 = min(total, e0 + rows_per * ow);
+    const int e0 = blockIdx.y * rows_per * ow, e1 = min(total, e0 + rows_per * ow);  // the band as a flat range (zero fill below)
     if (!c.ok) {
         for (int ch = 0; ch < 3; ++ch)
             for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) dst[(size_t)ch * total + e] = 0.f;
@@ -268,19 +268,32 @@ __global__ void __launch_bounds__(256) right_patches_kernel(const T *__restrict_
     }
     const T *img = right + (size_t)c.img * H * W * 3;
     const float sh = axis_scale(c.h, oh), sw = axis_scale(c.w, ow);
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-        const int oy = e / ow, ox = e - oy * ow;
-        const Axis ay = axis_coord(sh, oy, c.h), ax = axis_coord(sw, ox, c.w);
-        const int ya = (int)c.y0 + ay.i0 - margin, yb = (int)c.y0 + ay.i1 - margin;
-        const int xa = (int)c.x0 + ax.i0 - margin, xb = (int)c.x0 + ax.i1 - margin;
-        const bool vya = ya >= 0 && ya < H, vyb = yb >= 0 && yb < H, vxa = xa >= 0 && xa < W, vxb = xb >= 0 && xb < W;
+    // A thread owns output columns (its x coordinates, weights and validity are computed once) and walks down the band's
+    // rows: no division per element, two row pointers per row, 32-bit offsets.
+    const int row0 = blockIdx.y * rows_per, row1 = min(oh, row0 + rows_per);
+    const int lanes_x = min(ow, (int)blockDim.x);          // threads along x
+    const int ty = threadIdx.x / lanes_x, ny = max(1, (int)blockDim.x / lanes_x);
+    if (ty < ny) {
+        for (int ox = threadIdx.x - ty * lanes_x; ox < ow; ox += lanes_x) {
+            const Axis ax = axis_coord(sw, ox, c.w);
+            const int xa = (int)c.x0 + ax.i0 - margin, xb = (int)c.x0 + ax.i1 - margin;
+            const bool vxa = xa >= 0 && xa < W, vxb = xb >= 0 && xb < W;
+            const int xa3 = vxa ? xa * 3 : 0, xb3 = vxb ? xb * 3 : 0;
+            for (int oy = row0 + ty; oy < row1; oy += ny) {
+                const Axis ay = axis_coord(sh, oy, c.h);
+                const int ya = (int)c.y0 + ay.i0 - margin, yb = (int)c.y0 + ay.i1 - margin;
+                const bool vya = ya >= 0 && ya < H, vyb = yb >= 0 && yb < H;
+                const T *ra = img + (size_t)(vya ? ya : 0) * W * 3, *rb = img + (size_t)(vyb ? yb : 0) * W * 3;
+                float *o = dst + oy * ow + ox;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float a = (vya && vxa) ? (float)__ldg(img + ((size_t)ya * W + xa) * 3 + ch) : 0.f;
-            const float b = (vya && vxb) ? (float)__ldg(img + ((size_t)ya * W + xb) * 3 + ch) : 0.f;
-            const float cc = (vyb && vxa) ? (float)__ldg(img + ((size_t)yb * W + xa) * 3 + ch) : 0.f;
-            const float d = (vyb && vxb) ? (float)__ldg(img + ((size_t)yb * W + xb) * 3 + ch) : 0.f;
-            dst[(size_t)ch * total + e] = lerp2<kShipVariant>(ay.l0, ay.l1, ax.l0, ax.l1, a, b, cc, d);
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float a = (vya && vxa) ? (float)__ldg(ra + xa3 + ch) : 0.f;
+                    const float b = (vya && vxb) ? (float)__ldg(ra + xb3 + ch) : 0.f;
+                    const float cc = (vyb && vxa) ? (float)__ldg(rb + xa3 + ch) : 0.f;
+                    const float d = (vyb && vxb) ? (float)__ldg(rb + xb3 + ch) : 0.f;
+                    o[(size_t)ch * total] = lerp2<kShipVariant>(ay.l0, ay.l1, ax.l0, ax.l1, a, b, cc, d);
+                }
+            }
         }
     }
     pdl_wait();
@@ -422,11 +435,12 @@ PATS_API int pats_compute_imgs(const float *x_scale, const float *y_scale, const
     PATS_CUDA_TRY(launch_chained(left_windows_kernel<uint4>, dim3(grid), dim3(256), 0, st, (const uint4 *)left, (uint4 *)new_left, bound5, count, H, W,
                                  ps, width, seg_v));
     const dim3 rgrid(grid, 8);
+    const int ow_ = 3 * ps, rthreads = ow_ >= 256 ? 256 : (256 / ow_) * ow_;  // whole output rows per CTA pass (96 -> 192 threads)
     if (elem == 1)
-        PATS_CUDA_TRY(launch_chained(right_patches_kernel<uint8_t>, rgrid, dim3(256), 0, st, (const uint8_t *)right, new_right, bound5, count, B, H, W,
+        PATS_CUDA_TRY(launch_chained(right_patches_kernel<uint8_t>, rgrid, dim3(rthreads), 0, st, (const uint8_t *)right, new_right, bound5, count, B, H, W,
                                      margin, 3 * ps, 3 * ps, bad_rows));
     else
-        PATS_CUDA_TRY(launch_chained(right_patches_kernel<float>, rgrid, dim3(256), 0, st, (const float *)right, new_right, bound5, count, B, H, W,
+        PATS_CUDA_TRY(launch_chained(right_patches_kernel<float>, rgrid, dim3(rthreads), 0, st, (const float *)right, new_right, bound5, count, B, H, W,
                                      margin, 3 * ps, 3 * ps, bad_rows));
     return PATS_OK;
 }
