@@ -633,12 +633,27 @@ __global__ void __launch_bounds__(TH_K * 16) third_result_kernel(const float *__
     } else {
         pdl_prologue();
     }
-    for (int e = threadIdx.x; e < TH_K * 16 * NN; e += blockDim.x) {
-        const int rr = e / NN, j = e - rr * NN;
-        const int k = k0 + rr / 16, c16 = rr % 16;
-        const int srow = (2 + c16 / 4) * W + 2 + c16 % 4;  // inner 4x4 of the 8x8 source window (:186)
-        const float v = k < K ? __ldcg(scores + ((size_t)k * NN + srow) * NN + j) : 0.f;  // .cg: the producer grid may still run
-        rows[rr][j] = (log_input && k < K) ? expf(v) : v;  // third_layer.py:159 scores = exp(scores_origin)
+    // 8320 plan entries per CTA = 65 per thread: loaded 13 at a time so that the loads of a batch are in flight together
+    // (one load per loop trip left the kernel waiting on L2 latency for half of its time)
+    constexpr int PER = TH_K * 16 * NN / (TH_K * 16), BATCH = 13;
+    static_assert(PER == NN && NN % BATCH == 0, "65 entries per thread in 5 batches of 13");
+    float *rows_flat = &rows[0][0];
+#pragma unroll 1
+    for (int b0 = 0; b0 < PER; b0 += BATCH) {
+        float v[BATCH];
+        bool ok[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) {
+            const int e = (b0 + u) * (TH_K * 16) + threadIdx.x;
+            const int rr = e / NN, j = e - rr * NN;
+            const int k = k0 + rr / 16, c16 = rr % 16;
+            const int srow = (2 + c16 / 4) * W + 2 + c16 % 4;  // inner 4x4 of the 8x8 source window (:186)
+            ok[u] = k < K;
+            v[u] = ok[u] ? __ldcg(scores + ((size_t)k * NN + srow) * NN + j) : 0.f;  // .cg: the producer grid may still run
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u)  // third_layer.py:159 scores = exp(scores_origin)
+            rows_flat[(b0 + u) * (TH_K * 16) + threadIdx.x] = (log_input && ok[u]) ? expf(v[u]) : v[u];
     }
     for (int e = threadIdx.x; e < TH_K * 64; e += blockDim.x) {
         const int k = k0 + e / 64;
