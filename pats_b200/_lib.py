@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libpats_b200.so")
+_SO = os.environ.get("PATS_B200_LIB") or os.path.join(_HERE, "libpats_b200.so")  # override: A/B of two builds of the library
 _lib = None
 
 _P = C.c_void_p
