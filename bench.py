@@ -185,7 +185,8 @@ class DeviceStep:
                                            B * K3, ITERS, p(o["l3_Z"]), p(o["mk0"]), p(o["mk1"]), p(o["im1"]), stream_ptr), "third_layer_match")
         n += 2
         c(L.pats_get_result_f32(p(i["gr_nm0"]), p(i["gr_pt0"]), p(i["gr_sc0"]), B, 32, GH, GW, p(self.gr_nm1_u8), p(i["gr_pt1"]), p(i["gr_sc1"]),
-                                B * P2, 2, 48, 48, p(o["ml"]), p(o["mr"]), B * P2 * 2304, p(o["gr_total"]), p(o["gr_ws"]), stream_ptr), "result"); n += 4
+                                B * P2, 2, 48, 48, p(o["ml"]), p(o["mr"]), B * P2 * 2304, p(o["gr_total"]), p(o["gr_ws"]), stream_ptr), "result")
+        n += 3 if B * P2 <= 2048 else 4  # window_maps, count_rows, (exclusive_scan for many windows), assemble_matches
         DeviceStep.LAUNCHES = n
         return n
 
