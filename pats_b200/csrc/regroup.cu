@@ -48,7 +48,10 @@ static void *zeroed_workspace(cudaStream_t st, size_t bytes) {
 // =================================================================================================
 // a8/a9  area expansion: one half-warp (16 lanes) per (problem, source row), 16 rows per CTA
 // =================================================================================================
-constexpr int EX_ROWS = 16;      // rows (half-warps) per CTA
+#ifndef EX_ROWS_N
+#define EX_ROWS_N 16
+#endif
+constexpr int EX_ROWS = EX_ROWS_N;  // rows (half-warps) per CTA
 constexpr int EX_SM = 5;         // shared per-CTA arrays in front of the rows: O, SX, SY, CM, SV
 constexpr float kZero = 1e-14f;  // `zero` of utils/utils.py:1203
 
@@ -615,7 +618,10 @@ __global__ void __launch_bounds__(256) assemble_matches_kernel(ResultArgs a) {
 // =================================================================================================
 // a13  ThirdLayer.Compute_result: one thread per (problem, inner source cell), rows staged in smem
 // =================================================================================================
-constexpr int TH_K = 8;  // problems per CTA
+#ifndef TH_K_N
+#define TH_K_N 8
+#endif
+constexpr int TH_K = TH_K_N;  // problems per CTA
 
 __global__ void __launch_bounds__(TH_K * 16) third_result_kernel(const float *__restrict__ scores, const float *__restrict__ scale_x,
                                                                  const float *__restrict__ scale_y, const int64_t *__restrict__ p_s,

@@ -434,7 +434,10 @@ PATS_API int pats_compute_imgs(const float *x_scale, const float *y_scale, const
     const int seg_v = (int)((size_t)ps * 3 * elem / 16);
     PATS_CUDA_TRY(launch_chained(left_windows_kernel<uint4>, dim3(grid), dim3(256), 0, st, (const uint4 *)left, (uint4 *)new_left, bound5, count, H, W,
                                  ps, width, seg_v));
-    const dim3 rgrid(grid, 8);
+#ifndef RP_BANDS
+#define RP_BANDS 8
+#endif
+    const dim3 rgrid(grid, RP_BANDS);
     const int ow_ = 3 * ps, rthreads = ow_ >= 256 ? 256 : (256 / ow_) * ow_;  // whole output rows per CTA pass (96 -> 192 threads)
     if (elem == 1)
         PATS_CUDA_TRY(launch_chained(right_patches_kernel<uint8_t>, rgrid, dim3(rthreads), 0, st, (const uint8_t *)right, new_right, bound5, count, B, H, W,
