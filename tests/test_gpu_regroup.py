@@ -374,3 +374,35 @@ def test_launch_chaining_on_and_off_give_identical_results(dev):
         got = run()
         for a_, b_ in zip(got, ref):
             assert torch.equal(a_, b_)
+
+
+def test_plan_handover_stress_sizes_streams_and_epochs(dev):
+    """The per-stream flag pools (epochs, growth) and the self-cleaning est_position scratch under changing batch sizes on two
+    streams: every composite result must equal the separately launched pair of calls, bit for bit."""
+    from pats_b200 import layers as Ly, modules as M
+
+    n = 144
+    sizes = [300, 7, 301, 149, 2, 600, 296]
+    data = {}
+    for b in sizes:
+        s, sx, sy = _l2_inputs(b, n, 900 + b, dev)
+        ns = (sx * sy).reshape(b, 1, n)
+        Z = M.log_optimal_transport2(s, 1.0, ns, 30)
+        c = torch.log(torch.tensor(2.0, device=dev))
+        Z[:, :, -1] += c
+        Z[:, -1, :] += c
+        data[b] = (s, sx, sy, ns, Z, Ly.est_position(Z, sx, sy, 12, 12, 8, 1e-3, return_extra=True))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    results = []
+    for rep in range(4):
+        for i, b in enumerate(sizes):
+            s, sx, sy, ns, Z, ref = data[b]
+            with torch.cuda.stream(streams[(i + rep) % 2]):
+                results.append((b, Ly.second_layer_match(s, 1.0, ns, sx, sy, 30, True, 12, return_extra=True)))
+    torch.cuda.synchronize()
+    for b, out in results:
+        _, _, _, _, Z, ref = data[b]
+        assert torch.equal(out[0], Z), b
+        for got, want in zip(out[1:], ref):
+            assert torch.equal(got, want), b
