@@ -405,11 +405,11 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
+def ncu_traffic(key="sinkhorn_warp_dram_bytes_per_launch"):
     path = os.path.join(REPO, "profiles", "roofline_traffic.json")
     if os.path.exists(path):
         try:
-            return json.load(open(path)).get("sinkhorn_warp_dram_bytes_per_launch")
+            return json.load(open(path)).get(key)
         except Exception:
             return None
     return None
@@ -638,7 +638,7 @@ def main():
             streaming = {"kernel": "sinkhorn_grid_kernel (plans beyond 512 x 512: rows split over co-resident CTAs, one HBM pass per iteration)",
                          "workload": "BASELINE.json configs[2]: b=32, N=1536, 100 it", "bound": "hbm", "achieved": bytes_s / (ms_s * 1e-3) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": bytes_s / (ms_s * 1e-3) / 1e9 / peak, "ms_per_launch": ms_s,
-                         "algorithmic_bytes": bytes_s, "traffic": None}
+                         "algorithmic_bytes": bytes_s, "traffic": ncu_traffic("grid_dram_bytes_per_launch")}
             del sc, nss
             torch.cuda.empty_cache()
         # ---- the reference's own formulation (log-domain, ~6 ATen ops per iteration: modules.py:137-182) on this GPU -------
