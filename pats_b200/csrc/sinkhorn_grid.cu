@@ -13,8 +13,8 @@
 //   * Iteration 1 is exact in the log domain (row log-sum-exp, then column max and column sum passes), as in the
 //     register-resident kernels; scalings are monitored and a problem that leaves [1e-13, 1e13] is flagged and
 //     re-solved by the log-domain kernel after this one.  No CPU path.
-//   Measured on B200 (tools/kernel_times.py): b = 32, 1537 x 1537, 100 iterations: 7.2 ms = 4.3 TB/s algorithmic =
-//   66 % of the measured HBM peak (the one-CTA-per-problem log-domain kernel needs > 1 s); 1025 x 1025, b = 1: 0.65 ms.
+//   Measured on B200 (tools/kernel_times.py): b = 32, 1537 x 1537, 100 iterations: 5.5 ms = 5.6 TB/s algorithmic =
+//   86 % of the measured HBM peak (the one-CTA-per-problem log-domain kernel needs > 1 s); 1025 x 1025, b = 1: 0.65 ms.
 //   Variants that lost the A/B and were removed: register prefetch of the next row across the exchange (register
 //   pressure), a one-barrier exchange where every CTA sums all partials, 16 warps x 1 CTA per SM (kept as a hook).
 #include <map>
