@@ -325,7 +325,7 @@ def test_full_size_marginals_and_subset_parity(M, dev, b, m, n, span):
     assert_plan_equal(out[idx].cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("N,iters", [(1536, 100), (1024, 100)])
+@pytest.mark.parametrize("N,iters", [(1536, 100), (1024, 100), (4096, 40)])  # 4096: BASELINE.json's stress size (clamp-free recompute sweep)
 def test_large_plan_grid_kernel_vs_torch(M, lib, dev, N, iters):
     """BASELINE.json's synthetic kernel sizes (N=1536) and the 1024x1024-pair coarse plan (1024 -> 1025):
     grid-cooperative streaming kernel against a torch fp32 logsumexp restatement on the same device."""
