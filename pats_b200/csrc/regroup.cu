@@ -240,6 +240,13 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
         dy = bd1 - bd0, dx = bd3 - bd2;
         last_sum += add_sum;
         last_nom += add_nom;
+        // A box that did not grow is a fixed point: every later iteration sees the same strips, grows nothing and adds
+        // `zero` to both sums.  Once neither row of this warp grows, only those additions are left (peaked plans -- what
+        // the trained network produces -- stop after two or three of the 8 / 15 iterations).
+        if (__all_sync(0xffffffffu, !(mx > a.lb))) {
+            for (int rest = it + 1; rest < a.iters; ++rest) last_sum += kZero, last_nom += kZero;
+            break;
+        }
     }
     const bool core_exist = (dy > 1) && (dx > 1);
 
