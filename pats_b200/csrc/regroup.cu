@@ -243,10 +243,12 @@ __global__ void __launch_bounds__(EX_ROWS * 16) area_expand_kernel(ExpandArgs a)
         // A box that did not grow is a fixed point: every later iteration sees the same strips, grows nothing and adds
         // `zero` to both sums.  Once neither row of this warp grows, only those additions are left (peaked plans -- what
         // the trained network produces -- stop after two or three of the 8 / 15 iterations).
+#ifndef PATS_AB_NO_EARLY_EXIT
         if (__all_sync(0xffffffffu, !(mx > a.lb))) {
             for (int rest = it + 1; rest < a.iters; ++rest) last_sum += kZero, last_nom += kZero;
             break;
         }
+#endif
     }
     const bool core_exist = (dy > 1) && (dx > 1);
 
@@ -500,7 +502,17 @@ __global__ void __launch_bounds__(256) count_rows_kernel(const uint8_t *__restri
     __shared__ int part[8];
     const int p = blockIdx.x;
     int c = 0;
-    for (int e = threadIdx.x; e < n1; e += blockDim.x) c += nm1[(size_t)p * n1 + e] == 0;
+    const uint8_t *row = nm1 + (size_t)p * n1;
+    if ((n1 & 15) == 0 && (reinterpret_cast<uintptr_t>(nm1) & 15) == 0) {
+        // 16 flags per load (a 48 x 48 window row is 144 loads: one per thread, all in flight together)
+        const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+        for (int e = threadIdx.x; e < (n1 >> 4); e += blockDim.x) {
+            const uint4 v = __ldg(row4 + e);
+            c += (__popc(__vcmpeq4(v.x, 0u)) + __popc(__vcmpeq4(v.y, 0u)) + __popc(__vcmpeq4(v.z, 0u)) + __popc(__vcmpeq4(v.w, 0u))) >> 3;
+        }
+    } else {
+        for (int e = threadIdx.x; e < n1; e += blockDim.x) c += row[e] == 0;
+    }
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -591,6 +603,64 @@ __global__ void __launch_bounds__(256) assemble_matches_kernel(ResultArgs a) {
         }
     }
     __syncthreads();
+    constexpr int kMaxChunks = 32;  // fast path: windows of up to 32 * 256 cells
+    const int nch = (a.n1 + (int)blockDim.x - 1) / (int)blockDim.x;
+    const bool aligned8 = ((reinterpret_cast<uintptr_t>(a.sc1) | reinterpret_cast<uintptr_t>(a.pt1) | reinterpret_cast<uintptr_t>(a.ml) |
+                            reinterpret_cast<uintptr_t>(a.mr)) & 7) == 0;  // (y, x) pairs move as one 8-byte access
+    if (nch <= kMaxChunks && blockDim.x == 256 && aligned8) {
+        // Every chunk's ballots first (one pass over the flags, all loads in flight), one scan over the (chunk, warp)
+        // counts in output order, then the writes: two CTA barriers per window instead of three per chunk.  Lane-consecutive
+        // cells still go to consecutive output rows, so the gathers of pt1 / sc1 and the stores stay coalesced.
+        __shared__ unsigned ball[kMaxChunks * 8];
+        __shared__ int pre[kMaxChunks * 8];
+        for (int c = 0; c < nch; ++c) {
+            const int c1 = c * 256 + threadIdx.x;
+            const bool matched = c1 < a.n1 && a.nm1[(size_t)p * a.n1 + c1] == 0;
+            const unsigned mm = __ballot_sync(0xffffffffu, matched);
+            if (lane == 0) ball[c * 8 + warp] = mm;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int carry = 0;
+            for (int s0 = 0; s0 < nch * 8; s0 += 32) {
+                const int idx = s0 + lane;
+                const int v = idx < nch * 8 ? __popc(ball[idx]) : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (idx < nch * 8) pre[idx] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+        __syncthreads();
+        const long long base0 = base;
+        for (int c = 0; c < nch; ++c) {
+            const int c1 = c * 256 + threadIdx.x;
+            const unsigned mm = ball[c * 8 + warp];
+            if (!((mm >> lane) & 1u)) continue;
+            const long long pos = base0 + pre[c * 8 + warp] + __popc(mm & ((1u << lane) - 1u));
+            if (pos >= a.capacity) continue;
+            const size_t e = (size_t)p * a.n1 + c1;
+            const float pos1[2] = {(float)((c1 / a.w1) * a.ps1), (float)((c1 % a.w1) * a.ps1)};
+            const float2 sc = __ldg(reinterpret_cast<const float2 *>(a.sc1) + e), pt = __ldg(reinterpret_cast<const float2 *>(a.pt1) + e);
+            const float ptv[2] = {pt.x, pt.y};
+            float lv[2], rv[2];
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                // last level (utils.py:209-210)
+                const float dl = (pos1[d] + 0.5f * (float)a.ps1) * sc.y;
+                const float dr = (ptv[d] * (float)a.ps1) * sc.x;
+                lv[d] = l0[d] + dl;
+                rv[d] = r0[d] + dr;
+            }
+            reinterpret_cast<float2 *>(a.ml)[pos] = make_float2(lv[0], lv[1]);
+            reinterpret_cast<float2 *>(a.mr)[pos] = make_float2(rv[0], rv[1]);
+        }
+        return;
+    }
     for (int start = 0; start < a.n1; start += blockDim.x) {
         const int c1 = start + threadIdx.x;
         const size_t e = (size_t)p * a.n1 + c1;
