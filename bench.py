@@ -472,6 +472,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="A/B: do not bind the process to the GPU's NUMA node before allocating pinned memory")
     ap.add_argument("--no-chain", action="store_true", help="A/B: plain kernel launches instead of launch chaining (pats_launch_chaining(0))")
     ap.add_argument("--no-handover", action="store_true", help="A/B: no plan hand-over inside the composite calls (pats_plan_handover(0))")
     ap.add_argument("--no-streaming", action="store_true", help="skip the b=32 N=1536 streaming-kernel roofline sample")
@@ -491,6 +492,15 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the hot path is CUDA-only (there is no CPU fallback to time)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU: run on the CPUs of the GPU's NUMA node, so that the pinned staging buffers of the e2e leg are local
+    # to the GPU's PCIe root (the CPU-baseline leg below gets the full CPU set back)
+    cpus_before = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa = {"bound": False, "why": "--no-numa"}
+    if not args.no_numa:
+        from pats_b200.dist import bind_host_to_gpu
+
+        numa = bind_host_to_gpu(local_rank)
+        log(f"[bench] rank {rank}: NUMA binding {numa}")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.pairs_per_step
@@ -680,6 +690,9 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             import oracle
 
+            if cpus_before is not None:
+                os.sched_setaffinity(0, cpus_before)  # the CPU arm uses every host core
+
             cores = os.cpu_count() or 1
             oracle.set_num_threads(cores)
             torch.set_num_threads(cores)
@@ -698,6 +711,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "pats_hot_path_pair640x480", "pairs_per_step": B, "streams": S, "P2": P2, "K3": K3, "sinkhorn_iters": ITERS,
+                       "host_numa": numa,
                        "l2_flush": "not needed: one step streams > 300 MB of distinct plans per pair (L2 = 126 MB)",
                        "matches_per_pair": kf // B, "exchange": "all_gather of match lists once after the pair loop (N>1)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_streaming": streaming, "cpu_baseline": cpu, "torch_cuda": torch_cuda,

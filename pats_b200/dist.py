@@ -55,3 +55,53 @@ def gather_match_lists(matches: Sequence[torch.Tensor], group=None) -> List[List
             off += c
         out.append(rows)
     return out
+
+
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device_index: int) -> dict:
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs `local_cpulist` of its PCI function).
+
+    One process per GPU stages its inputs in pinned host memory; pinned pages are placed on the node of the allocating
+    thread, so a rank that runs on the far socket pulls every host->device byte over the socket interconnect and all ranks
+    together exhaust one socket's memory channels.  Call this BEFORE allocating pinned buffers.  Returns what was done
+    ({"bound": False, "why": ...} when the topology cannot be read); never raises.
+    """
+    import os
+
+    info = {"bound": False}
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(base + "/local_cpulist") as f:
+            local = _parse_cpulist(f.read())
+        node = -1
+        try:
+            with open(base + "/numa_node") as f:
+                node = int(f.read().strip())
+        except OSError:
+            pass
+        allowed = os.sched_getaffinity(0)
+        target = local & allowed
+        info.update({"pci": bdf, "numa_node": node, "cpus_local": len(local), "cpus_allowed": len(allowed)})
+        if not target:
+            info["why"] = "no allowed CPU on the GPU's node"
+            return info
+        if target == allowed:
+            info["why"] = "already local (single node or pre-bound)"
+            return info
+        os.sched_setaffinity(0, target)
+        info["bound"] = True
+        info["cpus"] = len(target)
+    except Exception as e:  # no sysfs entry, no permission, not Linux ...
+        info["why"] = f"{type(e).__name__}: {e}"
+    return info
