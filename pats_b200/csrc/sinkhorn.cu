@@ -969,7 +969,16 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
 #pragma unroll
     for (int k = 0; k < 8; ++k) al[k] = 1.f;
     float ald = 1.f, bed = 1.f;
+#ifndef PATS_AB_NO_PIPE_SRP
+    // this warp's half of sum_j K[D][j] beta_j: the 5-level butterfly is split over the loop's back-edge -- two levels behind
+    // the beta update, three between the FFMA2 groups of the next row pass (ptxas does not move code across the back-edge,
+    // and an in-order warp otherwise sits on every SHFL -> FADD pair of the chain with nothing else to issue: -1.6 %)
+    float Srp = Dr;
+    Srp += __shfl_xor_sync(0xffffffffu, Srp, 16);
+    Srp += __shfl_xor_sync(0xffffffffu, Srp, 8);
+#else
     float Srp = warp_sum(Dr);  // this warp's half of sum_j K[D][j] beta_j
+#endif
     float lo = INFINITY, hi = 0.f;
 
     for (int it = it0; it < a.iters; ++it) {
@@ -981,6 +990,9 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
             const float2 bp = make_float2(be[2 * h], be[2 * h + 1]);
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[k] = ffma2(Kp[k][h], bp, acc[k]);
+#ifndef PATS_AB_NO_PIPE_SRP
+            if (h < 3) Srp += __shfl_xor_sync(0xffffffffu, Srp, 4 >> h);
+#endif
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) al[k] = acc[k].x + acc[k].y;
@@ -990,6 +1002,8 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
         al[0] = mu2[0] * fast_rcp(fmaf(Dc[0], bed, al[0] + o0));
         al[1] = mu2[1] * fast_rcp(fmaf(Dc[1], bed, al[1] + o1));
         ald = mud * fast_rcp(fmaf(corner, bed, Srp + oS));
+        // (deferring this butterfly and the beta_D update into the next row pass as well was measured 2.7 % SLOWER: beta_D's
+        // reciprocal then sits in front of the alpha update)
         const float Sc = warp_sum(fmaf(Dc[0], al[0], Dc[1] * al[1]));
         ag_rows(al);
         float2 s2[4];
@@ -1006,7 +1020,13 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
         rs_cols8_op(be, OpSum());
         be[0] = nu1 * fast_rcp(fmaf(Dr, ald, be[0]));
         bed = nud * fast_rcp(fmaf(corner, ald, Sc));
+#ifndef PATS_AB_NO_PIPE_SRP
+        Srp = Dr * be[0];
+        Srp += __shfl_xor_sync(0xffffffffu, Srp, 16);
+        Srp += __shfl_xor_sync(0xffffffffu, Srp, 8);
+#else
         Srp = warp_sum(Dr * be[0]);
+#endif
         if ((it & 7) == 0 || it == a.iters - 1) {
             lo = fminf(fminf(fminf(lo, al[0]), fminf(al[1], ald)), fminf(be[0], bed));
             hi = fmaxf(fmaxf(fmaxf(hi, al[0]), fmaxf(al[1], ald)), fmaxf(be[0], bed));
@@ -1019,6 +1039,7 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
     const bool ran = a.iters > it0;  // the scaling loop ran at least once
     float U[8], V[8], Ud = 0.f, Vd = -shift;
     bool bad = !(lo >= 1e-13f && hi <= 1e13f);
+
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
         float tu = 0.f;
@@ -1572,7 +1593,9 @@ __global__ void __launch_bounds__(C145B_T, 2) sinkhorn_c145b_kernel(SinkArgs a) 
     }
     __syncthreads();
 
-    // ---- iterations 2..iters (same barrier structure as sinkhorn_c145_kernel) -----------------------------------------
+    // ---- iterations 2..iters (same barrier structure as sinkhorn_c145_kernel).  Splitting the two dustbin butterflies over the
+    //      back-edge as in sinkhorn_w65x2_kernel was measured 3-7 % SLOWER here (the carried partials cost registers in a loop
+    //      that sits at the 128-register limit) --------------------------------------------------------------------------
     float2 Kp[9][4];
     float K8[9];
 #pragma unroll
