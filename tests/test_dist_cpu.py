@@ -58,3 +58,13 @@ def test_gather_match_lists_gloo_world2():
 
 def test_gather_match_lists_uneven_and_empty_rank():
     mp.spawn(_worker, args=(2, _free_port(), 1), nprocs=2, join=True)
+
+
+def test_parse_cpulist_and_numa_binding_never_raises():
+    """bind_host_to_gpu reads the GPU's sysfs `local_cpulist`; without a GPU (here) it must report, not raise."""
+    from pats_b200.dist import _parse_cpulist, bind_host_to_gpu
+
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    info = bind_host_to_gpu(0)
+    assert info["bound"] is False and "why" in info
