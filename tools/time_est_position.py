@@ -18,7 +18,7 @@ sx = ns.reshape(b, n).sqrt().contiguous()
 ys, xs = torch.meshgrid(torch.arange(12.0), torch.arange(12.0), indexing="ij")
 src = torch.stack([ys.reshape(-1), xs.reshape(-1)], 1)
 out = {}
-for tag, sharp in (("diffuse", 0.0), ("peaked", 6.0)):
+for tag, sharp in (("diffuse", 0.0), ("peaked", 6.0), ("sharp", 80.0)):
     sc = 0.1 * torch.randn(b, n + 1, n + 1, generator=g)
     if sharp:
         t = torch.randn(b, 1, 2, generator=g) * 1.5
