@@ -86,8 +86,9 @@ void pats_sinkhorn_disable_w65(int mode);
 /* Routing of 145 x 145 problems (tests / A-B timing): 0 = 8-warp kernel, two CTAs per SM (default), 1 = padded
  * 160 x 160 CTA kernel, 2 = 9-warp kernel. */
 void pats_sinkhorn_disable_c145(int mode);
-/* Cluster shape for plans up to 320 x 320 (A-B timing): 0 = 8 CTAs x 256 threads (default), 1 = 4 CTAs x 512 threads,
- * 2 = 8 x 256 with a one-hop all-to-all exchange of the column partials. */
+/* Cluster shape for plans up to 320 x 320 (A-B timing): 0 = auto (10 CTAs x 256 threads for batches up to 8 problems, a
+ * non-portable cluster size of which a GPC hosts one at a time; 8 CTAs x 256 beyond), 1 = 4 CTAs x 512 threads,
+ * 2 = 8 x 256 with a one-hop all-to-all exchange of the column partials, 3 = 8 x 256, 4 = 10 x 256. */
 void pats_sinkhorn_cluster_variant(int v);
 /* Problems the register-resident kernels handed to the log-domain fallback since the last reset
  * (device counter, read with a synchronising copy; tests / diagnostics only). */

@@ -1741,10 +1741,16 @@ using CfgCta = RegCfg<8, 4, 10, 10, 1>;        // <= 160 x 160 (level 2: 145 x 1
 using CfgCl320 = RegCfg<8, 5, 5, 10, 1, 8>;    // <= 320 x 320 (level 1: 301 x 301), cluster of 8 CTAs x 256 threads
 using CfgCl320h = RegCfg<8, 5, 5, 10, 1, 8, 1>;  // same tiling, one-hop all-to-all exchange (A/B variant 2)
 using CfgCl320b = RegCfg<16, 5, 5, 10, 1, 4>;  // <= 320 x 320, cluster of 4 CTAs x 512 threads (A/B variant)
+// <= 320 x 320, cluster of 10 CTAs x 256 threads, 4 x 10 tiles: 32 rows per CTA cover 301 rows without the 8-CTA tiling's idle
+// row groups, and a column slice is exactly one warp wide.  Non-portable cluster size (one cluster per GPC at a time), so it is
+// the default only for small batches.  Measured for one 301 x 301 problem through the wrapper: 121.8 us (8 x 256) -> 111.4 us;
+// 16 CTAs x 256 (3 x 10 tiles) 118.8 us, 16 CTAs x 128 (6 x 10) 127.6 us.
+using CfgCl320z = RegCfg<8, 5, 4, 10, 1, 10>;
 using CfgCl512 = RegCfg<16, 5, 4, 16, 1, 8>;   // <= 512 x 512, cluster of 8 CTAs x 512 threads
 
 static int g_force_generic = 0;
-static int g_cluster_variant = 0;  // <= 320 x 320 plans: 0 = 8 CTAs x 256 threads, 1 = 4 CTAs x 512 threads, 2 = 8 x 256 one-hop exchange
+static int g_cluster_variant = 0;  // <= 320 x 320 plans: 0 = auto (10 x 256 for b <= 8, else 8 x 256), 1 = 4 CTAs x 512 threads, 2 = 8 x 256 one-hop exchange,
+                                   // 3 = 8 x 256, 4 = 10 x 256
 static int g_disable_c145 = 0;  // 145 x 145 routing: 0 = 8-warp kernel, two CTAs per SM (default), 1 = padded 160 x 160 CTA kernel,
                                 //                    2 = 9-warp kernel
 static int g_disable_w65 = 0;  // 65 x 65 routing: 0 = two warps per problem (default), 1 = padded 72 x 68 warp kernel,
@@ -1826,6 +1832,13 @@ static int launch_reg(const SinkArgs &a, cudaStream_t st) {
         if (!configured) {
             PATS_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_reg_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = true;
+        }
+    }
+    if (C::CL > 8) {  // beyond the portable cluster size
+        static bool allowed = false;
+        if (!allowed) {
+            PATS_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_reg_kernel<C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            allowed = true;
         }
     }
     cudaLaunchConfig_t cfg = {};
@@ -1932,6 +1945,9 @@ static int run_sinkhorn(SinkArgs a, void *stream, bool publish = false, const un
             if (a.M <= CfgCl320::MAXM && a.N <= CfgCl320::MAXN)
                 return g_cluster_variant == 1   ? launch_reg<CfgCl320b>(a, st)
                        : g_cluster_variant == 2 ? launch_reg<CfgCl320h>(a, st)
+                       : g_cluster_variant == 3 ? launch_reg<CfgCl320>(a, st)
+                       : g_cluster_variant == 4 ? launch_reg<CfgCl320z>(a, st)
+                       : (a.b <= 8)             ? launch_reg<CfgCl320z>(a, st)   // auto: 10-CTA clusters while every GPC can host one
                                                 : launch_reg<CfgCl320>(a, st);
             return launch_reg<CfgCl512>(a, st);
         case 4:
@@ -1982,7 +1998,7 @@ int sinkhorn_ot2_publish(const float *scores, const float *one, const float *ns,
     return run_sinkhorn(a, st, g_handover != 0, done, epoch);
 }
 }  // namespace pats
-PATS_API void pats_sinkhorn_cluster_variant(int v) { g_cluster_variant = (v >= 0 && v <= 2) ? v : 0; }
+PATS_API void pats_sinkhorn_cluster_variant(int v) { g_cluster_variant = (v >= 0 && v <= 4) ? v : 0; }
 PATS_API void pats_sinkhorn_disable_c145(int mode) { g_disable_c145 = (mode >= 0 && mode <= 2) ? mode : 0; }
 PATS_API void pats_sinkhorn_disable_w65(int mode) { g_disable_w65 = (mode >= 0 && mode <= 3) ? mode : 0; }
 

@@ -238,7 +238,8 @@ def test_all_three_65x65_kernels_agree(M, lib, dev):
 
 
 def test_kernel_variants_145_and_cluster(M, lib, dev):
-    """145 x 145: dedicated 9-warp kernel vs the padded 160 x 160 CTA kernel; 301 x 301: both cluster shapes."""
+    """145 x 145: dedicated 9-warp kernel vs the padded 160 x 160 CTA kernel; 301 x 301: every cluster shape (auto = 10 CTAs x 256
+    for small batches, 4 x 512, 8 x 256 one-hop, 8 x 256, 10 x 256) and the auto rule's large-batch side."""
     g = torch.Generator().manual_seed(6300)
     s = 0.3 * torch.randn(7, 145, 145, generator=g)
     s[2] *= 250.0  # one problem that needs the log-domain fallback
@@ -258,13 +259,18 @@ def test_kernel_variants_145_and_cluster(M, lib, dev):
     s = 0.1 * torch.randn(2, 300, 300, generator=g)
     ns = areas(g, 2, 300, 16.0)
     ref = oracle.log_optimal_transport(s.numpy(), 1.0, ns.numpy(), 100)
-    for v in (0, 1, 2):
+    for v in (0, 1, 2, 3, 4):
         lib.pats_sinkhorn_cluster_variant(v)
         try:
             out = M.log_optimal_transport(s.to(dev), 1.0, ns.to(dev), 100).cpu().numpy()
         finally:
             lib.pats_sinkhorn_cluster_variant(0)
         assert_plan_equal(out, ref)
+    # b > 8 takes the portable 8-CTA clusters under the auto rule; all problems must still be solved (repeat the two plans)
+    s9, ns9 = s.repeat(5, 1, 1)[:9].contiguous(), ns.repeat(5, 1, 1)[:9].contiguous()
+    out9 = M.log_optimal_transport(s9.to(dev), 1.0, ns9.to(dev), 100).cpu().numpy()
+    for i in range(9):
+        assert_plan_equal(out9[i:i + 1], ref[i % 2:i % 2 + 1])
 
 
 def test_cluster_kernel_fallback(M, lib, dev):
