@@ -865,7 +865,8 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
 #pragma unroll
             for (int c = 0; c < 8; ++c) ok = ok && (fabsf(z[k][c]) <= kDirectZ);  // NaN fails the comparison
         const float mine = __all_sync(0xffffffffu, ok) ? 1.f : 0.f;
-        float d0, d1, other;
+        [[maybe_unused]] float d0, d1;
+        float other;
         PAIR_XCHG(0.f, 0.f, mine, d0, d1, other);
         (void)d0, (void)d1;
         if (mine != 0.f && other != 0.f) it0 = 0;
@@ -1060,7 +1061,8 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
     if (!(fabsf(Ud) < INFINITY) || !(fabsf(Vd) < INFINITY)) bad = true;
     {
         const float mine = __any_sync(0xffffffffu, bad) ? 1.f : 0.f;
-        float d0, d1, other;
+        [[maybe_unused]] float d0, d1;
+        float other;
         PAIR_XCHG(0.f, 0.f, mine, d0, d1, other);
         (void)d0, (void)d1;
         bad = (mine != 0.f) || (other != 0.f);
