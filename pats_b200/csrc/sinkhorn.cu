@@ -1887,6 +1887,35 @@ int launch_generic(const SinkArgs &a, cudaStream_t st) {
 
 // publish: ask the kernel to raise per-problem "plan complete" flags (plan hand-over); *done stays nullptr when the kernel
 // chosen for the shape does not publish.
+// Can this device schedule the 10-CTA cluster shape (a non-portable cluster size)?  Asked once; any error or "zero clusters"
+// keeps the portable 8-CTA shape.
+static bool cluster10_ok() {
+    static int ok = -1;
+    if (ok < 0) {
+        using C = CfgCl320z;
+        int n = 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(C::CL);
+        cfg.blockDim = dim3(C::THREADS);
+        cfg.dynamicSmemBytes = Smem<C>::BYTES;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = C::CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaSuccess;
+        if (Smem<C>::BYTES > 48 * 1024)
+            e = cudaFuncSetAttribute(sinkhorn_reg_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<C>::BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(sinkhorn_reg_kernel<C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, sinkhorn_reg_kernel<C>, &cfg);
+        if (e != cudaSuccess) (void)cudaGetLastError();  // not sticky: clear it, the 8-CTA shape runs instead
+        ok = (e == cudaSuccess && n >= 1) ? 1 : 0;
+    }
+    return ok == 1;
+}
+
 static int run_sinkhorn(SinkArgs a, void *stream, bool publish = false, const unsigned **done = nullptr, unsigned *epoch = nullptr) {
     struct Report {  // hands the flags of the launch (if any) back on every return path
         SinkArgs &a;
@@ -1949,8 +1978,8 @@ static int run_sinkhorn(SinkArgs a, void *stream, bool publish = false, const un
                        : g_cluster_variant == 2 ? launch_reg<CfgCl320h>(a, st)
                        : g_cluster_variant == 3 ? launch_reg<CfgCl320>(a, st)
                        : g_cluster_variant == 4 ? launch_reg<CfgCl320z>(a, st)
-                       : (a.b <= 8)             ? launch_reg<CfgCl320z>(a, st)   // auto: 10-CTA clusters while every GPC can host one
-                                                : launch_reg<CfgCl320>(a, st);
+                       : (a.b <= 8 && cluster10_ok()) ? launch_reg<CfgCl320z>(a, st)   // auto: 10-CTA clusters while every GPC can host one
+                                                      : launch_reg<CfgCl320>(a, st);
             return launch_reg<CfgCl512>(a, st);
         case 4:
             return launch_grid(a, st);
