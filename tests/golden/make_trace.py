@@ -224,11 +224,12 @@ REDUCERS = {
 # recorder
 # ---------------------------------------------------------------------------------------------------------------
 class Recorder:
-    def __init__(self, caps, per_name_limit):
+    def __init__(self, caps, per_name_limit, default_limit=3):
         self.store = Store()
         self.calls = []
         self.caps = caps
         self.limit = per_name_limit
+        self.default_limit = default_limit
         self.count = {}
         self.replaying = False
 
@@ -240,7 +241,7 @@ class Recorder:
                 return fn(*args, **kw)
             n = rec.count.get(name, 0)
             rec.count[name] = n + 1
-            keep = n < rec.limit.get(name, 3)
+            keep = n < rec.limit.get(name, rec.default_limit)
             if keep:
                 red = REDUCERS.get(name)
                 r_args, r_kw = red(args, kw, rec.caps) if red else (args, kw)
@@ -302,15 +303,15 @@ def install_recorders(ref, rec):
     return restore
 
 
-def run(tag, if_local, caps, limit):
+def run(tag, if_local, caps, limit, merge_new=True, default_limit=3):
     ref = load_reference()
     torch.manual_seed(SEED)
-    cfg = types.SimpleNamespace(if_local=if_local, if_outdoor=True, merge_new=True)
+    cfg = types.SimpleNamespace(if_local=if_local, if_outdoor=True, merge_new=merge_new)
     model = ref.pats.PATS(cfg).eval()
     g = torch.Generator().manual_seed(SEED)
     image0 = torch.randint(0, 256, (1, 480, 640, 3), generator=g, dtype=torch.uint8)
     image1 = torch.roll(image0, (16, 24), dims=(1, 2)).contiguous()
-    rec = Recorder(caps, limit)
+    rec = Recorder(caps, limit, default_limit)
     restore = install_recorders(ref, rec)
     t0 = time.time()
     try:
@@ -320,7 +321,7 @@ def run(tag, if_local, caps, limit):
         for owner, name, orig in restore:
             setattr(owner, name, orig)
     print(f"[{tag}] forward {time.time() - t0:.1f} s; matches {tuple(out['matches_l'].shape)}; calls seen {rec.count}")
-    meta = {"tag": tag, "cfg": {"if_local": if_local, "if_outdoor": True, "merge_new": True}, "seed": SEED, "image": [480, 640],
+    meta = {"tag": tag, "cfg": {"if_local": if_local, "if_outdoor": True, "merge_new": merge_new}, "seed": SEED, "image": [480, 640],
             "calls_seen": rec.count, "matches": int(out["matches_l"].shape[0]), "calls": rec.calls}
     path = os.path.join(HERE, f"trace_{tag}.npz")
     np.savez_compressed(path, __schema__=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **rec.store.arrays)
@@ -330,7 +331,7 @@ def run(tag, if_local, caps, limit):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["global", "local"]
+    which = sys.argv[1:] or ["global", "local", "mergeold"]
     if "global" in which:
         run("global", False, caps={301: 1, 145: 5, 65: 32},
             limit={"log_sinkhorn_iterations": 3, "log_optimal_transport2": 2, "tensor_resize": 1, "origin_extract": 1})
@@ -340,3 +341,6 @@ if __name__ == "__main__":
             limit={"log_sinkhorn_iterations": 0, "log_optimal_transport": 0, "FirstLayer.est_position": 0, "Iterative_expand_matrix": 3,
                    "log_optimal_transport2": 4, "tensor_resize": 0, "origin_extract": 0, "Compute_imgs": 1, "SecondLayer.est_position": 2,
                    "SecondLayer.merge_patches_new": 4, "ThirdLayer.Compute_result": 2, "get_result": 3, "split_patches": 1})
+    if "mergeold" in which:
+        # merge_new=False (the branch configs/*.yaml never select): merge_patches_old over two chunks, scores_back reset per call
+        run("mergeold", True, caps={301: 1, 145: 3, 65: 12}, limit={"SecondLayer.merge_patches_old": 3}, merge_new=False, default_limit=0)

@@ -21,7 +21,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-TAGS = ("global", "local")
+TAGS = ("global", "local")          # replayed on the GPU (tests/test_gpu_trace.py) and on the oracle
+ORACLE_ONLY_TAGS = ("mergeold",)     # merge_new=False forward pass, recorded after the round's last GPU run: oracle only for now
 
 EXACT = "exact"
 OT = ("ot", 1e-4, 2e-6)
@@ -55,9 +56,9 @@ def load(tag):
     return z, meta
 
 
-def records():
+def records(tags=TAGS):
     out = []
-    for tag in TAGS:
+    for tag in tags:
         if os.path.exists(path_of(tag)):
             _, meta = load(tag)
             out += [(tag, c["seq"], c["name"]) for c in meta["calls"]]
