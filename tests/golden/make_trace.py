@@ -303,13 +303,13 @@ def install_recorders(ref, rec):
     return restore
 
 
-def run(tag, if_local, caps, limit, merge_new=True, default_limit=3):
+def run(tag, if_local, caps, limit, merge_new=True, default_limit=3, hw=(480, 640)):
     ref = load_reference()
     torch.manual_seed(SEED)
     cfg = types.SimpleNamespace(if_local=if_local, if_outdoor=True, merge_new=merge_new)
     model = ref.pats.PATS(cfg).eval()
     g = torch.Generator().manual_seed(SEED)
-    image0 = torch.randint(0, 256, (1, 480, 640, 3), generator=g, dtype=torch.uint8)
+    image0 = torch.randint(0, 256, (1, hw[0], hw[1], 3), generator=g, dtype=torch.uint8)
     image1 = torch.roll(image0, (16, 24), dims=(1, 2)).contiguous()
     rec = Recorder(caps, limit, default_limit)
     restore = install_recorders(ref, rec)
@@ -321,7 +321,7 @@ def run(tag, if_local, caps, limit, merge_new=True, default_limit=3):
         for owner, name, orig in restore:
             setattr(owner, name, orig)
     print(f"[{tag}] forward {time.time() - t0:.1f} s; matches {tuple(out['matches_l'].shape)}; calls seen {rec.count}")
-    meta = {"tag": tag, "cfg": {"if_local": if_local, "if_outdoor": True, "merge_new": merge_new}, "seed": SEED, "image": [480, 640],
+    meta = {"tag": tag, "cfg": {"if_local": if_local, "if_outdoor": True, "merge_new": merge_new}, "seed": SEED, "image": list(hw),
             "calls_seen": rec.count, "matches": int(out["matches_l"].shape[0]), "calls": rec.calls}
     path = os.path.join(HERE, f"trace_{tag}.npz")
     np.savez_compressed(path, __schema__=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **rec.store.arrays)
@@ -331,7 +331,7 @@ def run(tag, if_local, caps, limit, merge_new=True, default_limit=3):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["global", "local", "mergeold"]
+    which = sys.argv[1:] or ["global", "local", "mergeold", "portrait"]
     if "global" in which:
         run("global", False, caps={301: 1, 145: 5, 65: 32},
             limit={"log_sinkhorn_iterations": 3, "log_optimal_transport2": 2, "tensor_resize": 1, "origin_extract": 1})
@@ -344,3 +344,11 @@ if __name__ == "__main__":
     if "mergeold" in which:
         # merge_new=False (the branch configs/*.yaml never select): merge_patches_old over two chunks, scores_back reset per call
         run("mergeold", True, caps={301: 1, 145: 3, 65: 12}, limit={"SecondLayer.merge_patches_old": 3}, merge_new=False, default_limit=0)
+    if "portrait" in which:
+        # 640 rows x 480 columns: a 20 x 15 coarse grid (height > width), the case in which the reference's strip geometry
+        # (max(h, w)) and its width / height argument order matter
+        run("portrait", False, caps={301: 1, 145: 3, 65: 12},
+            limit={"log_sinkhorn_iterations": 0, "log_optimal_transport": 1, "FirstLayer.est_position": 1, "Iterative_expand_matrix": 2,
+                   "split_patches": 1, "Compute_imgs": 1, "origin_extract": 1, "tensor_resize": 0, "log_optimal_transport2": 2,
+                   "SecondLayer.est_position": 1, "SecondLayer.merge_patches_new": 1, "ThirdLayer.Compute_result": 1, "get_result": 1},
+            hw=(640, 480))

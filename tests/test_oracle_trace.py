@@ -20,8 +20,11 @@ def _kw(kwargs, args, pos, name, default):
 
 def _expand(args, kwargs):
     scores_in, sx, sy, limitation, ranges, positions = args[:6]
-    gw = ranges.shape[0]
-    gh = positions.shape[0] // gw
+    # the TRUE grid: limitation = [0, height, 0, width] (first_layer.py:165, second_layer.py:246).  The reference itself
+    # rebuilds (height, width) from ranges / positions (utils.py:1181), which swaps them for portrait grids -- a quirk the
+    # oracle reproduces internally from the true grid.
+    gh, gw = int(limitation[1]), int(limitation[3])
+    assert gh * gw == positions.shape[0] and ranges.shape[0] == max(gh, gw)
     lb = _kw(kwargs, args, 6, "lower_bound", 1e-3)
     it = _kw(kwargs, args, 8, "iter_num", 15)
     whole, core, avg, xs, ys, bound, _ = oracle.iterative_expand_matrix(scores_in, sx, sy, gh, gw, lower_bound=lb, iter_num=it)
