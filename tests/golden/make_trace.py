@@ -331,7 +331,7 @@ def run(tag, if_local, caps, limit, merge_new=True, default_limit=3, hw=(480, 64
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["global", "local", "mergeold", "portrait"]
+    which = sys.argv[1:] or ["global", "local", "mergeold", "portrait", "big"]
     if "global" in which:
         run("global", False, caps={301: 1, 145: 5, 65: 32},
             limit={"log_sinkhorn_iterations": 3, "log_optimal_transport2": 2, "tensor_resize": 1, "origin_extract": 1})
@@ -352,3 +352,10 @@ if __name__ == "__main__":
                    "split_patches": 1, "Compute_imgs": 1, "origin_extract": 1, "tensor_resize": 0, "log_optimal_transport2": 2,
                    "SecondLayer.est_position": 1, "SecondLayer.merge_patches_new": 1, "ThirdLayer.Compute_result": 1, "get_result": 1},
             hw=(640, 480))
+    if "big" in which:
+        # BASELINE.json configs[4]: a 1024 x 1024 pair = 32 x 32 coarse grid (1024 patches, level-1 plan 1025 x 1025); only the
+        # records that stay small are kept (the level-1 plan and the images alone are 4 - 8 MB each)
+        run("big", False, caps={145: 2, 65: 8},
+            limit={"Iterative_expand_matrix": 2, "split_patches": 1, "SecondLayer.merge_patches_new": 1, "get_result": 1,
+                   "SecondLayer.est_position": 1, "ThirdLayer.Compute_result": 1},
+            default_limit=0, hw=(1024, 1024))

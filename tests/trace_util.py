@@ -22,7 +22,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 TAGS = ("global", "local")          # replayed on the GPU (tests/test_gpu_trace.py) and on the oracle
-ORACLE_ONLY_TAGS = ("mergeold", "portrait")     # merge_new=False forward pass, recorded after the round's last GPU run: oracle only for now
+ORACLE_ONLY_TAGS = ("mergeold", "portrait", "big")     # merge_new=False forward pass, recorded after the round's last GPU run: oracle only for now
 
 EXACT = "exact"
 OT = ("ot", 1e-4, 2e-6)
