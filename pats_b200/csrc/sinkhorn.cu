@@ -827,6 +827,9 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
 
     // ---- load ------------------------------------------------------------------------------------------------------
     float z[8][8], zc[2], zr, zcorner;
+#ifdef PATS_AB_RS2
+    float zr2;
+#endif
     {
         const PlanRef pl = plan_ref(a, g, p);
         int coff[8];
@@ -842,11 +845,18 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
         for (int t = 0; t < 2; ++t) zc[t] = pl.edge(LROW(t), D);
         zr = pl.edge(D, LCOL(0));  // dustbin-row entry of the one column this lane owns
         zcorner = pl.edge(D, D);
+#ifdef PATS_AB_RS2
+        zr2 = pl.edge(D, LCOL(1));  // ... and of its twin's (lane ^ 16) column, finished redundantly by both (see the loop)
+#endif
     }
     float mu2[2];
 #pragma unroll
     for (int t = 0; t < 2; ++t) mu2[t] = expf(lmu_at(a, g, p, LROW(t)));
     const float nu1 = expf(lnu_at(a, g, p, LCOL(0)));
+#ifdef PATS_AB_RS2
+    const float nu1b = expf(lnu_at(a, g, p, LCOL(1)));
+    float Drb = 0.f;
+#endif
     const float mud = expf(lmu_at(a, g, p, D)), nud = expf(lnu_at(a, g, p, D));
     float u1o[2] = {0.f, 0.f}, v1o = 0.f, u1d = 0.f, v1d = 0.f;
     float Dc[2] = {0.f, 0.f}, Dr = 0.f, corner = 0.f;
@@ -878,6 +888,9 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
             for (int c = 0; c < 8; ++c) z[k][c] = fast_exp(z[k][c]);
         Dc[0] = fast_exp(zc[0]), Dc[1] = fast_exp(zc[1]);
         Dr = fast_exp(zr);
+#ifdef PATS_AB_RS2
+        Drb = fast_exp(zr2);
+#endif
         corner = fast_exp(zcorner);
     } else
 #endif
@@ -954,6 +967,9 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
             u1o[t] = u1[t];
         }
         Dr = fast_exp((zr + u1d) + v1[0]);
+#ifdef PATS_AB_RS2
+        Drb = fast_exp((zr2 + u1d) + v1[1]);
+#endif
         v1o = v1[0];
         corner = fast_exp((zcorner + u1d) + v1d);
     }
@@ -1018,8 +1034,24 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) be[2 * h] = s2[h].x, be[2 * h + 1] = s2[h].y;
+#ifdef PATS_AB_RS2
+        // reduce-scatter 8 -> 2 over lane bits 2, 3, then ONE all-reduce level over bit 4: the twins (lane, lane ^ 16) finish the
+        // same two columns redundantly (one more reciprocal), and the gather below starts from two slots -- a SHFL level less
+        // in each direction.  Operands are the base version's (a + b == b + a), so the betas are bit-identical.
+#pragma unroll
+        for (int t = 0; t < 4; ++t) be[t] += __shfl_xor_sync(0xffffffffu, be[t + 4], 4);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) be[t] += __shfl_xor_sync(0xffffffffu, be[t + 2], 8);
+        {
+            const float x0 = be[0] + __shfl_xor_sync(0xffffffffu, be[1], 16);
+            const float x1 = be[1] + __shfl_xor_sync(0xffffffffu, be[0], 16);
+            be[0] = nu1 * fast_rcp(fmaf(Dr, ald, x0));
+            be[1] = nu1b * fast_rcp(fmaf(Drb, ald, x1));
+        }
+#else
         rs_cols8_op(be, OpSum());
         be[0] = nu1 * fast_rcp(fmaf(Dr, ald, be[0]));
+#endif
         bed = nud * fast_rcp(fmaf(corner, ald, Sc));
 #ifndef PATS_AB_NO_PIPE_SRP
         Srp = Dr * be[0];
@@ -1032,7 +1064,14 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
             lo = fminf(fminf(fminf(lo, al[0]), fminf(al[1], ald)), fminf(be[0], bed));
             hi = fmaxf(fmaxf(fmaxf(hi, al[0]), fmaxf(al[1], ald)), fmaxf(be[0], bed));
         }
+#ifdef PATS_AB_RS2
+#pragma unroll
+        for (int t = 0; t < 2; ++t) be[t + 2] = __shfl_xor_sync(0xffffffffu, be[t], 8);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) be[t + 4] = __shfl_xor_sync(0xffffffffu, be[t], 4);
+#else
         ag_cols8(be);
+#endif
     }
 
     // ---- potentials, health check (agreed over the pair), output -----------------------------------------------------------
