@@ -1,6 +1,7 @@
 """Record the hot-path CALL TRACE of the unmodified reference `PATS.forward` (this container only).
 
-    python tests/golden/make_trace.py            # writes tests/golden/trace_global.npz, trace_local.npz
+    python tests/golden/make_trace.py [tag ...]  # writes tests/golden/trace_<tag>.npz; tags: global, local (if_local=True),
+                                                 # mergeold (merge_new=False), portrait (640 x 480 rows x cols), big (1024 x 1024)
 
 The reference model (models/pats.py, random-init weights, seed 18027) is run on the synthetic
 640x480 pair; every hot-path name that `pats_b200.install` rebinds is wrapped AT THE SAME BINDING SITE (module globals of
