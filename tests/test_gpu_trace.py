@@ -70,6 +70,8 @@ def test_replay_reference_call(tag, seq, name):
     # arguments the reference mutates in place (second_layer.py:194-207: trust_score, if_nomatching1_L2, scores_back)
     for m in c["mutated"]:
         path = m["path"]
+        if name.endswith("merge_patches_old") and path[:2] == [0, 6]:
+            continue  # the reference's final content of this argument is unobservable (pats.py:37 keeps the return value); INTEGRATION.md section 5
         root = args if path[0] == 0 else kwargs
         T.compare(name, T.get_path(root, path[1:]), T.decode(m["value"], z, None), T.EXACT, f"{name}<arg {path[1:]} after the call>")
     if name in ("log_optimal_transport", "log_optimal_transport2"):
