@@ -690,8 +690,11 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             import oracle
 
-            if cpus_before is not None:
-                os.sched_setaffinity(0, cpus_before)  # the CPU arm uses every host core
+            if cpus_before is not None and numa.get("bound"):
+                try:
+                    os.sched_setaffinity(0, cpus_before)  # the CPU arm uses every host core
+                except OSError:
+                    pass
 
             cores = os.cpu_count() or 1
             oracle.set_num_threads(cores)
