@@ -65,6 +65,31 @@ def build_ref(force: bool = False, verbose: bool = False) -> str | None:
     return out
 
 
+PY_DIR = os.path.join(OUT_DIR, "py")
+
+
+def stage_reference_python(force: bool = False) -> str | None:
+    """Stage the reference's Python hot-path callers for the GPU box: models/*.py and utils/*.py are copied VERBATIM from
+    /root/reference into oracle/_ref/py/ (a git-ignored build output, like the compiled op above: it never enters the
+    history, and gpurun ships it).  The live-forward tests and bench.py's `forward` leg import the UNMODIFIED
+    models/pats.py from there when /root/reference does not exist.  Returns the directory, or None if neither exists."""
+    import shutil
+
+    src_ok = os.path.exists(os.path.join(REF_ROOT, "models", "pats.py"))
+    if not src_ok:
+        return PY_DIR if os.path.exists(os.path.join(PY_DIR, "models", "pats.py")) else None
+    for pkg in ("models", "utils"):
+        dst = os.path.join(PY_DIR, pkg)
+        os.makedirs(dst, exist_ok=True)
+        for f in sorted(os.listdir(os.path.join(REF_ROOT, pkg))):
+            if not f.endswith(".py"):
+                continue
+            a, b = os.path.join(REF_ROOT, pkg, f), os.path.join(dst, f)
+            if force or not os.path.exists(b) or os.path.getmtime(b) < os.path.getmtime(a):
+                shutil.copyfile(a, b)
+    return PY_DIR
+
+
 def load_ref():
     """Import the compiled reference module (needs torch imported first)."""
     import importlib.util
@@ -83,3 +108,4 @@ def load_ref():
 if __name__ == "__main__":
     p = build_ref(force="--force" in sys.argv, verbose=True)
     print("built:" if p else "unavailable:", p)
+    print("staged python:", stage_reference_python(force="--force" in sys.argv))

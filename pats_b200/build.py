@@ -37,12 +37,18 @@ def sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
+def headers():
+    """Every header a translation unit may include: an edit to any of them rebuilds every object (the TUs share struct layouts)."""
+    import glob
+
+    return sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(INCLUDE, "*.h")))
+
+
 def needs_build() -> bool:
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "sinkhorn_common.cuh"), os.path.join(INCLUDE, "pats_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in sources() + headers())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -51,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     env = dict(os.environ)
     env.pop("CC", None)  # the image exports a CC that nvcc's host pass must not pick up
     os.makedirs(OBJ_DIR, exist_ok=True)
-    deps_t = max(os.path.getmtime(d) for d in (os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "pats_b200.h")))
+    deps_t = max(os.path.getmtime(d) for d in headers())
     objs, procs = [], []
     for src in sources():
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")

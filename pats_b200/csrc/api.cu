@@ -28,13 +28,27 @@ int cuda_fail(cudaError_t e, const char *what) {
     return PATS_E_CUDA;
 }
 
+int current_device() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        set_error("cudaGetDevice failed");
+        return -1;
+    }
+    if (dev < 0 || dev >= kMaxDevices) {
+        set_error("device ordinal %d beyond the %d devices the library keeps state for", dev, kMaxDevices);
+        return -1;
+    }
+    return dev;
+}
+
 int sm_count() {
-    static int cached = -1;
-    if (cached >= 0) return cached;
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    static int cached[kMaxDevices];  // 0 = not asked yet
+    const int dev = current_device();
+    if (dev < 0) return 0;
+    int n = __atomic_load_n(&cached[dev], __ATOMIC_RELAXED);
+    if (n > 0) return n;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    cached = n;
+    __atomic_store_n(&cached[dev], n, __ATOMIC_RELAXED);
     return n;
 }
 

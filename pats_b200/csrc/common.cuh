@@ -19,7 +19,20 @@ namespace pats {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 int invalid(const char *fmt, ...);
-int sm_count();
+int sm_count();                 // of the CURRENT device (cached per device ordinal)
+// Every piece of cached state in the library is per DEVICE: kernel attributes (cudaFuncSetAttribute applies to the current
+// device only), scratch buffers, flag pools and counters live in memory of the device they were made on.  The ordinal of the
+// current device, or -1 (error set) beyond kMaxDevices.
+constexpr int kMaxDevices = 64;
+int current_device();
+// "has this (kernel, attribute) been configured on the current device?"  One 64-bit mask per call site: bit = device ordinal.
+struct PerDeviceOnce {
+    unsigned long long mask = 0ull;
+    bool done(int dev) const { return dev >= 0 && ((__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> dev) & 1ull); }
+    void mark(int dev) {
+        if (dev >= 0) __atomic_fetch_or(&mask, 1ull << dev, __ATOMIC_RELEASE);
+    }
+};
 
 #define PATS_CUDA_TRY(expr)                                            \
     do {                                                               \
@@ -100,14 +113,19 @@ __device__ __forceinline__ void pdl_prologue() {
     pdl_wait();
     pdl_launch_dependents();
 }
-// consumer side: one thread spins, then the caller synchronises its group.  A producer that died leaves the flag unset:
-// trap after ~2 s instead of hanging the GPU.
+// consumer side: one thread spins, then the caller synchronises its group.  The spin is bounded: after ~2 s (a producer slowed
+// down by a debugger / sanitizer / time-slicing, or a huge batch in the log-domain fallback) the thread stops polling and
+// executes griddepcontrol.wait, which returns when the producer GRID has completed and flushed -- always correct, merely
+// without the overlap.  Nothing traps: a slow producer must never cost the CUDA context.
 __device__ __forceinline__ void await_problem(const unsigned *done, unsigned epoch, int p) {
     const long long t0 = clock64();
     unsigned v;
     do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(done + p) : "memory");
-        if (v != epoch && clock64() - t0 > (4ll << 30)) __trap();
+        if (v != epoch && clock64() - t0 > (4ll << 30)) {
+            pdl_wait();
+            return;
+        }
     } while (v != epoch);
 }
 

@@ -21,9 +21,11 @@ namespace pats {
 // the zeros before it finishes (est_position's column maxima / arrival counters).
 static void *zeroed_workspace(cudaStream_t st, size_t bytes) {
     static std::mutex mu;
-    static std::map<cudaStream_t, std::pair<void *, size_t>> pool;
+    static std::map<std::pair<int, cudaStream_t>, std::pair<void *, size_t>> pool;  // (device, stream): stream 0 exists on every device
+    const int dev = current_device();
+    if (dev < 0) return nullptr;
     std::lock_guard<std::mutex> lk(mu);
-    auto &e = pool[st];
+    auto &e = pool[std::make_pair(dev, st)];
     if (e.second < bytes) {
         if (e.first) {
             cudaStreamSynchronize(st);

@@ -1796,15 +1796,18 @@ static int g_disable_c145 = 0;  // 145 x 145 routing: 0 = 8-warp kernel, two CTA
                                 //                    2 = 9-warp kernel
 static int g_disable_w65 = 0;  // 65 x 65 routing: 0 = two warps per problem (default), 1 = padded 72 x 68 warp kernel,
                                //                  2 / 3 = one-warp 65 x 65 kernel at 2 / 3 CTAs per SM (tests / A-B timing)
-static int *g_fb_total = nullptr;  // device counter
+static int *g_fb_total[kMaxDevices];  // per device: counter of problems that took the log-domain fallback
 static std::mutex g_mu;
 
-static int ensure_counter() {
+static int ensure_counter(int **counter) {
+    const int dev = current_device();
+    if (dev < 0) return PATS_E_CUDA;
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!g_fb_total) {
-        PATS_CUDA_TRY(cudaMalloc(&g_fb_total, sizeof(int)));
-        PATS_CUDA_TRY(cudaMemset(g_fb_total, 0, sizeof(int)));
+    if (!g_fb_total[dev]) {
+        PATS_CUDA_TRY(cudaMalloc(&g_fb_total[dev], sizeof(int)));
+        PATS_CUDA_TRY(cudaMemset(g_fb_total[dev], 0, sizeof(int)));
     }
+    *counter = g_fb_total[dev];
     return PATS_OK;
 }
 
@@ -1816,12 +1819,19 @@ struct HandOver {
     unsigned epoch = 0;
 };
 std::mutex g_ho_mu;
-std::map<cudaStream_t, HandOver> g_ho;
+std::map<std::pair<int, cudaStream_t>, HandOver> g_ho;  // keyed by (device, stream): the default stream is 0 on every device
 
 // flags for a launch of b problems on `st`; nullptr (hand-over off) if the pool cannot be grown
 unsigned *handover_begin(cudaStream_t st, int b, unsigned *epoch) {
+    const int dev = current_device();
+    if (dev < 0) return nullptr;
+    cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap_st) != cudaSuccess || cap_st != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return nullptr;  // under stream capture: no pool growth (it synchronises), no spinning consumers -- plain stream order
+    }
     std::lock_guard<std::mutex> lk(g_ho_mu);
-    HandOver &h = g_ho[st];
+    HandOver &h = g_ho[std::make_pair(dev, st)];
     if (h.cap < (size_t)b) {
         if (h.flags) {
             cudaStreamSynchronize(st);
@@ -1868,18 +1878,20 @@ template <class C>
 static int launch_reg(const SinkArgs &a, cudaStream_t st) {
     constexpr size_t smem = Smem<C>::BYTES;
     static_assert(smem <= 200 * 1024, "shared-memory layout too large");
+    const int dev = current_device();
+    if (dev < 0) return PATS_E_CUDA;
     if (smem > 48 * 1024) {
-        static bool configured = false;  // per kernel instantiation
-        if (!configured) {
+        static PerDeviceOnce configured;  // per kernel instantiation and device
+        if (!configured.done(dev)) {
             PATS_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_reg_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = true;
+            configured.mark(dev);
         }
     }
     if (C::CL > 8) {  // beyond the portable cluster size
-        static bool allowed = false;
-        if (!allowed) {
+        static PerDeviceOnce allowed;
+        if (!allowed.done(dev)) {
             PATS_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_reg_kernel<C>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            allowed = true;
+            allowed.mark(dev);
         }
     }
     cudaLaunchConfig_t cfg = {};
@@ -1929,7 +1941,10 @@ int launch_generic(const SinkArgs &a, cudaStream_t st) {
 // Can this device schedule the 10-CTA cluster shape (a non-portable cluster size)?  Asked once; any error or "zero clusters"
 // keeps the portable 8-CTA shape.
 static bool cluster10_ok() {
-    static int ok = -1;
+    static int ok_dev[kMaxDevices];  // per device: 0 = not asked, 1 = yes, 2 = no
+    const int dev = current_device();
+    if (dev < 0) return false;
+    int ok = ok_dev[dev] == 0 ? -1 : (ok_dev[dev] == 1 ? 1 : 0);
     if (ok < 0) {
         using C = CfgCl320z;
         int n = 0;
@@ -1951,6 +1966,7 @@ static bool cluster10_ok() {
         if (e == cudaSuccess) e = cudaOccupancyMaxActiveClusters(&n, sinkhorn_reg_kernel<C>, &cfg);
         if (e != cudaSuccess) (void)cudaGetLastError();  // not sticky: clear it, the 8-CTA shape runs instead
         ok = (e == cudaSuccess && n >= 1) ? 1 : 0;
+        ok_dev[dev] = ok ? 1 : 2;
     }
     return ok == 1;
 }
@@ -1969,9 +1985,8 @@ static int run_sinkhorn(SinkArgs a, void *stream, bool publish = false, const un
     if (a.b == 0) return PATS_OK;
     if (!a.Z || !a.out) return invalid("sinkhorn: null pointer");
     if ((long long)a.M * a.N > 0x7fffffffLL / 2) return invalid("sinkhorn: problem too large");
-    int rc = ensure_counter();
+    int rc = ensure_counter(&a.fb_total);
     if (rc) return rc;
-    a.fb_total = g_fb_total;
     cudaStream_t st = as_stream(stream);
     const bool c145b = kernel_kind(a.M, a.N) == 1 && a.M == 145 && a.N == 145 && g_disable_c145 == 0;
     if (a.edge_add != 0.f && !c145b && kernel_kind(a.M, a.N) != 2) {  // kernels without the edge epilogue: solve, then one more pass
@@ -2073,10 +2088,11 @@ PATS_API void pats_sinkhorn_disable_c145(int mode) { g_disable_c145 = (mode >= 0
 PATS_API void pats_sinkhorn_disable_w65(int mode) { g_disable_w65 = (mode >= 0 && mode <= 3) ? mode : 0; }
 
 PATS_API int pats_sinkhorn_fallback_count(int reset) {
-    if (ensure_counter() != PATS_OK) return -1;
+    int *counter = nullptr;  // of the current device
+    if (ensure_counter(&counter) != PATS_OK) return -1;
     int v = 0;
-    if (cudaMemcpy(&v, g_fb_total, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    if (reset) cudaMemset(g_fb_total, 0, sizeof(int));
+    if (cudaMemcpy(&v, counter, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (reset) cudaMemset(counter, 0, sizeof(int));
     return v;
 }
 

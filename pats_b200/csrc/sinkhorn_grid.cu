@@ -447,9 +447,11 @@ __global__ void __launch_bounds__(1024) sinkhorn_grid_fallback_kernel(SinkArgs a
 
 void *grid_workspace(cudaStream_t st, size_t bytes) {
     static std::mutex mu;
-    static std::map<cudaStream_t, std::pair<void *, size_t>> pool;
+    static std::map<std::pair<int, cudaStream_t>, std::pair<void *, size_t>> pool;  // (device, stream)
+    const int dev = current_device();
+    if (dev < 0) return nullptr;
     std::lock_guard<std::mutex> lk(mu);
-    auto &e = pool[st];
+    auto &e = pool[std::make_pair(dev, st)];
     if (e.second < bytes) {
         if (e.first) {
             cudaStreamSynchronize(st);
@@ -515,10 +517,12 @@ int launch_grid_cfg(const SinkArgs &a, cudaStream_t st) {
     // flagged problems: exact log-domain iteration (device-side test of the flag, no host sync)
     const size_t fsmem = sizeof(float) * ((size_t)a.M + a.N + 2 * 1024);
     if (fsmem > 200 * 1024) return PATS_OK;  // shapes beyond the log-domain kernel's budget keep the scaling result
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    const int dev = current_device();
+    if (dev < 0) return PATS_E_CUDA;
+    if (!configured.done(dev)) {
         PATS_CUDA_TRY(cudaFuncSetAttribute(sinkhorn_grid_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
+        configured.mark(dev);
     }
     sinkhorn_grid_fallback_kernel<<<a.b < sms ? a.b : sms, 1024, fsmem, st>>>(a, ga.flag);
     PATS_LAUNCH_CHECK("sinkhorn_grid_fallback_kernel");

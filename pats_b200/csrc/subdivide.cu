@@ -139,8 +139,13 @@ __device__ __forceinline__ BoundOut bounds_one(float x_scale, float y_scale, flo
     b1 = (b1 < (float)(ps * height + 2 * margin)) ? b1 : (float)(ps * height - 1);  // :1362, board[1] :1351
     b3 = (b3 < (float)(ps * width + 2 * margin)) ? b3 : (float)(ps * width);        // :1363, board[3]
     BoundOut o;
-    o.xs = __fdiv_rn(__fadd_rn(__fsub_rn(b1, b0), 1.0f), (float)(3 * ps));  // :1364 ("x" from the y extent)
-    o.ys = __fdiv_rn(__fadd_rn(__fsub_rn(b3, b2), 1.0f), (float)(3 * ps));  // :1365
+    // `tensor / float(3 * patch_scale)`: on CUDA tensors ATen divides by a python scalar as a MULTIPLICATION by its reciprocal
+    // (BinaryDivTrueKernel.cu: inv_b = 1.0 / b in double, rounded to f32), which differs from the true quotient in the last
+    // bit for about a third of the values when the divisor is 96.  The reference runs on CUDA tensors (evaluate.py:26-28), so
+    // that is the arithmetic to reproduce (seen live: tests/test_gpu_live_forward.py); the CPU oracle keeps the true division.
+    const float inv = (float)(1.0 / (double)(3 * ps));
+    o.xs = __fmul_rn(__fadd_rn(__fsub_rn(b1, b0), 1.0f), inv);  // :1364 ("x" from the y extent)
+    o.ys = __fmul_rn(__fadd_rn(__fsub_rn(b3, b2), 1.0f), inv);  // :1365
     o.b0 = (long long)b0, o.b1 = (long long)b1, o.b2 = (long long)b2, o.b3 = (long long)b3;  // :1366 trunc
     o.av1 = __fadd_rn(__fsub_rn(__fdiv_rn((float)(o.b1 + o.b0), 2.0f), fm), 0.5f);  // :1368
     o.av0 = __fadd_rn(__fsub_rn(__fdiv_rn((float)(o.b2 + o.b3), 2.0f), fm), 0.5f);  // :1369

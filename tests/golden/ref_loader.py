@@ -1,8 +1,8 @@
-"""Import the UNMODIFIED Python reference from /root/reference (this container only).
+"""Import the UNMODIFIED Python reference: /root/reference in the build container, else the staged copy
+oracle/_ref/py/ (oracle/build_ref.py; git-ignored build artefact that gpurun ships to the GPU box).
 
-Used solely by tests/golden/make_golden.py to produce the committed fixtures; nothing in
-the -m gpu tests, smoke() or bench.py touches it (there is no /root/reference on the GPU
-box).  The shims are the ones SURVEY.md Appendix A verified: empty stand-ins for optional
+Used by tests/golden/make_golden.py / make_trace.py to produce the committed fixtures, by the live-forward GPU tests
+(tests/test_gpu_live_forward.py) and by bench.py's `forward` leg; nothing under pats_b200/ touches it.  The shims are the ones SURVEY.md Appendix A verified: empty stand-ins for optional
 top-level imports the hot path never touches, a kornia-0.5.5 `create_meshgrid`, resnet34
 without a download, and `Tensor.cuda` as identity on CPU.  No reference file is edited.
 """
@@ -13,8 +13,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("PATS_REFERENCE_ROOT", "/root/reference")
 REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+STAGED = os.path.join(REPO, "oracle", "_ref", "py")  # oracle/build_ref.py: copy of the reference's models/ + utils/ for the GPU box
+
+
+def _pick_root() -> str:
+    env = os.environ.get("PATS_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.exists("/root/reference/models/modules.py"):
+        return "/root/reference"
+    return STAGED
+
+
+REF_ROOT = _pick_root()
 
 
 def reference_available() -> bool:

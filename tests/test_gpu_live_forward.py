@@ -1,0 +1,174 @@
+"""The UNMODIFIED reference `PATS.forward` (models/pats.py:18-85, called as evaluate.py:20-39 does) run LIVE on the GPU, twice:
+
+(i)  the reference itself on CUDA tensors (ATen ops + its compiled setup/library.cpp) -- the oracle of record, SURVEY.md
+     section 8c -- with pats_b200's replacement executed next to EVERY hot-path call on clones of the same arguments
+     (tests/live_util.Shadow): transport plans within 1e-4 (absolute; the network is conditioned to realistic score
+     magnitudes, live_util.condition) with identical row / column argmax, every integer / boolean / byte result -- masks,
+     bounds, chunking, window copies, merge decisions, match lists -- bit-exact;
+(ii) `pats_b200.install.install()` and the same models/pats.py, free-running: the final match lists are compared with
+     (i)'s bit for bit.
+
+The reference's Python comes from oracle/_ref/py (staged by oracle/build_ref.py; /root/reference in the build container).
+Evidence of each run (call counts, max deviations, match counts, timings) goes to gpurun_out/live_forward_<case>.json.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import pytest
+
+import live_util as L
+import trace_util as T
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # configs/test_megadepth.yaml: if_local True, merge_new True, if_outdoor True
+    "local": dict(cfg=dict(if_local=True, merge_new=True), hw=(480, 640)),
+    "global": dict(cfg=dict(if_local=False, merge_new=True), hw=(480, 640)),
+    "mergeold": dict(cfg=dict(if_local=True, merge_new=False), hw=(480, 640)),
+    "portrait": dict(cfg=dict(if_local=False, merge_new=True), hw=(640, 480)),
+    "indoor": dict(cfg=dict(if_local=False, merge_new=True, if_outdoor=False), hw=(480, 640)),
+    "big": dict(cfg=dict(if_local=False, merge_new=True), hw=(1024, 1024)),
+}
+OT_LIVE = ("ot", 1e-4, 0.0)  # north_star: 1e-4 absolute
+RULES = dict(T.RULES)
+for _k in ("log_sinkhorn_iterations", "log_optimal_transport", "log_optimal_transport2"):
+    RULES[_k] = OT_LIVE
+RULES["tensor_resize"] = T.EXACT  # same device, same ATen kernel arithmetic: bit-identical (tests/test_gpu_subdivide.py)
+RULES["Compute_imgs"] = [T.EXACT, T.EXACT, T.EXACT, T.EXACT, T.EXACT]
+MUTATORS = ("SecondLayer.merge_patches_new", "SecondLayer.merge_patches_old")
+
+
+def _norm_split(r):
+    return [int(r[0]), [[int(v) for v in row] for row in r[1]], [[int(v) for v in row] for row in r[2]]]
+
+
+def _tensors(x, path=()):
+    import torch
+
+    if torch.is_tensor(x):
+        yield path, x
+    elif isinstance(x, (list, tuple)):
+        for i, v in enumerate(x):
+            yield from _tensors(v, path + (i,))
+    elif isinstance(x, dict):
+        for k, v in x.items():
+            yield from _tensors(v, path + (k,))
+
+
+def run_case(name, dev="cuda:0"):
+    import torch
+
+    ref = L.load_reference()
+    case = CASES[name]
+    cfg = L.config(**case["cfg"])
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model = L.build_model(ref, cfg, device=dev)
+    image0, image1 = L.synthetic_pair(case["hw"], device=dev)
+    data = {"image0": image0, "image1": image1}
+    log = {"case": name, "cfg": case["cfg"], "hw": list(case["hw"]), "calls": {}, "failures": []}
+
+    def on_call(fname, want, got, ref_after, got_after):
+        ent = log["calls"].setdefault(fname, {"n": 0, "max_abs_diff": 0.0, "ot_max_abs_diff": 0.0, "problems": 0})
+        ent["n"] += 1
+        try:
+            if fname == "split_patches":
+                assert _norm_split(got) == _norm_split(want), "chunking differs"
+                return
+            if fname == "ThirdLayer.Compute_result":
+                want, got = tuple(want[:2]), tuple(got[:2])
+            if fname in ("log_optimal_transport", "log_optimal_transport2", "log_sinkhorn_iterations"):
+                d = float((got - want).abs().max()) if want.numel() else 0.0
+                ent["ot_max_abs_diff"] = max(ent["ot_max_abs_diff"], d)
+                ent["problems"] += int(want.shape[0])
+                ent["max_abs_score"] = max(ent.get("max_abs_score", 0.0), float(ref_after[0][0].abs().max()))
+            T.compare(fname, got, want, RULES[fname])
+            if fname in ("log_optimal_transport", "log_optimal_transport2"):
+                T.check_argmax_parity(fname, got, want)
+            if fname in MUTATORS:  # trust_score, if_nomatching1_L2, scores_back are mutated in place (second_layer.py:194-207)
+                mine = dict(_tensors(got_after))
+                for path, t in _tensors(ref_after):
+                    if fname.endswith("merge_patches_old") and path[:2] == (0, 6):
+                        continue  # unobservable: pats.py:37 keeps the return value
+                    T.compare(fname, mine[path], t, T.EXACT, f"{fname}<arg {path} after the call>")
+        except AssertionError as e:
+            log["failures"].append(f"{fname} call {ent['n']}: {e}")
+            if len(log["failures"]) <= 4:  # keep the evidence: arguments before / after, both results (torch.load-able on any box)
+                cpu = lambda tree: [(list(p), t.detach().cpu()) for p, t in _tensors(tree)]  # noqa: E731
+                torch.save({"name": fname, "nth": ent["n"], "error": str(e), "want": cpu(want), "got": cpu(got), "ref_args_after": cpu(ref_after),
+                            "got_args_after": cpu(got_after)}, os.path.join(L.REPO, "gpurun_out", f"live_fail_{name}_{fname.replace('.', '_')}_{ent['n']}.pt"))
+
+    with torch.no_grad():
+        model(data)  # warm-up (cuDNN plans, lazy modules)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ref_out = model(data)
+        torch.cuda.synchronize()
+        log["reference_cuda_s"] = time.perf_counter() - t0
+        with L.Shadow(on_call) as sh:
+            shadow_out = model(data)
+        torch.cuda.synchronize()
+        log["calls_seen"] = dict(sh.count)
+        assert torch.equal(shadow_out["matches_l"], ref_out["matches_l"]) and torch.equal(shadow_out["matches_r"], ref_out["matches_r"]), \
+            "the reference forward is not reproducible run to run"
+
+        import pats_b200.install as inst
+
+        done = inst.install()
+        try:
+            model(data)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            our_out = model(data)
+            torch.cuda.synchronize()
+            log["installed_s"] = time.perf_counter() - t0
+        finally:
+            inst.uninstall()
+    log["installed_names"] = len(done)
+    log["matches_reference"] = int(ref_out["matches_l"].shape[0])
+    log["matches_installed"] = int(our_out["matches_l"].shape[0])
+    same_l = ref_out["matches_l"].shape == our_out["matches_l"].shape and bool(torch.equal(ref_out["matches_l"], our_out["matches_l"]))
+    same_r = ref_out["matches_r"].shape == our_out["matches_r"].shape and bool(torch.equal(ref_out["matches_r"], our_out["matches_r"]))
+    log["matches_l_bit_exact"], log["matches_r_bit_exact"] = same_l, same_r
+    if not (same_l and same_r) and ref_out["matches_l"].shape == our_out["matches_l"].shape and ref_out["matches_l"].numel():
+        log["matches_r_max_abs_diff"] = float((ref_out["matches_r"] - our_out["matches_r"]).abs().max())
+        log["matches_rows_differing"] = int(((ref_out["matches_r"] != our_out["matches_r"]).any(1) | (ref_out["matches_l"] != our_out["matches_l"]).any(1)).sum())
+    os.makedirs(os.path.join(L.REPO, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(L.REPO, "gpurun_out", f"live_forward_{name}.json"), "w") as f:
+        json.dump(log, f, indent=1)
+    return log
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_live_forward(name):
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    if L.reference_root() is None:
+        pytest.skip("reference Python not staged (oracle/_ref/py; run __graft_entry__.build() where /root/reference exists)")
+    log = run_case(name)
+    assert not log["failures"], "\n".join(log["failures"][:10])
+    seen = log["calls_seen"]
+    for must in ("log_optimal_transport", "log_optimal_transport2", "Compute_imgs", "FirstLayer.est_position", "SecondLayer.est_position",
+                 "ThirdLayer.Compute_result", "get_result", "split_patches"):
+        assert seen.get(must, 0) >= 1, f"{must} was never reached in the live forward"
+    assert log["matches_reference"] > 0, "the conditioned network produced no matches: the forward ended early"
+    assert log["matches_l_bit_exact"] and log["matches_r_bit_exact"], \
+        f"match lists differ: reference {log['matches_reference']} vs installed {log['matches_installed']} rows; {log.get('matches_rows_differing')} rows differ"
+
+
+if __name__ == "__main__":  # python tests/test_gpu_live_forward.py [case ...]: run without pytest, print the logs
+    import sys
+
+    for n in sys.argv[1:] or list(CASES):
+        lg = run_case(n)
+        print(json.dumps({k: v for k, v in lg.items() if k != "calls"}), flush=True)
+        for k, v in lg["calls"].items():
+            print("   ", k, v, flush=True)

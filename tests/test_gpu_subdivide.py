@@ -129,6 +129,27 @@ def test_origin_extract_golden_and_real_shape(dev):
     assert np.array_equal(out.cpu().numpy(), oracle.origin_extract(left.numpy(), 5, 5, 4))
 
 
+ULP1 = 1.2e-7
+
+
+def _scales_aten(x_scale, y_scale, average_point, height, width, margin=128, patch_scale=32):
+    """utils/utils.py:1346-1365 and :1375-1378 with the same ATen ops on the tensors' device (CUDA: `/ float(96)` is a multiply by
+    the rounded reciprocal, BinaryDivTrueKernel.cu) -- what the reference produces when it runs where it really runs."""
+    bound_new = torch.zeros([x_scale.shape[0], x_scale.shape[1], 4], device=x_scale.device)
+    board = torch.tensor([0.0, float(patch_scale * height - 1), 0.0, float(patch_scale * width)], device=x_scale.device)
+    bound_new[:, :, 0] = (average_point[:, :, 0] - y_scale * 3.0 / 2.0) * float(patch_scale) + margin
+    bound_new[:, :, 1] = (average_point[:, :, 0] + y_scale * 3.0 / 2.0) * float(patch_scale) + margin
+    bound_new[:, :, 2] = (average_point[:, :, 1] - x_scale * 3.0 / 2.0) * float(patch_scale) + margin
+    bound_new[:, :, 3] = (average_point[:, :, 1] + x_scale * 3.0 / 2.0) * float(patch_scale) + margin
+    bound_new = torch.where(bound_new >= 0, bound_new, board[0])
+    bound_new[:, :, 1] = torch.where(bound_new[:, :, 1] < patch_scale * height + 2 * margin, bound_new[:, :, 1], board[1])
+    bound_new[:, :, 3] = torch.where(bound_new[:, :, 3] < patch_scale * width + 2 * margin, bound_new[:, :, 3], board[3])
+    xs = (bound_new[:, :, 1] - bound_new[:, :, 0] + 1) / float(3 * patch_scale)
+    ys = (bound_new[:, :, 3] - bound_new[:, :, 2] + 1) / float(3 * patch_scale)
+    one = torch.ones_like(xs)
+    return torch.stack([xs, one], 2), torch.stack([ys, one], 2)
+
+
 def test_compute_imgs_golden(dev):
     from pats_b200 import utils as U
 
@@ -140,8 +161,10 @@ def test_compute_imgs_golden(dev):
     assert nr.shape == g["ci_new_right"].shape
     assert np.array_equal(nl.cpu().numpy(), g["ci_new_left"])
     np.testing.assert_allclose(nr.cpu().numpy(), g["ci_new_right"], atol=RESIZE_TOL, rtol=0)
-    assert np.array_equal(xs.cpu().numpy(), g["ci_x_scale_new"])
-    assert np.array_equal(ys.cpu().numpy(), g["ci_y_scale_new"])
+    # the golden is the reference on CPU tensors (true division by 96); on CUDA tensors ATen multiplies by the reciprocal:
+    # equal to one ulp here, bit-exact against the CUDA execution in test_compute_imgs_scales_match_aten_cuda below
+    np.testing.assert_allclose(xs.cpu().numpy(), g["ci_x_scale_new"], rtol=ULP1, atol=0)
+    np.testing.assert_allclose(ys.cpu().numpy(), g["ci_y_scale_new"], rtol=ULP1, atol=0)
     assert np.array_equal(avg.cpu().numpy(), g["ci_average_new"])
 
 
@@ -164,7 +187,11 @@ def test_compute_imgs_real_shape_vs_oracle(dev, dtype):
                                                height=h, return_bound=True)
     assert np.array_equal(b5.cpu().numpy(), ob5)
     assert np.array_equal(nl.cpu().numpy(), onl)
-    assert np.array_equal(xsn.cpu().numpy(), oxs) and np.array_equal(ysn.cpu().numpy(), oys) and np.array_equal(avn.cpu().numpy(), oavg)
+    np.testing.assert_allclose(xsn.cpu().numpy(), oxs, rtol=ULP1, atol=0)
+    np.testing.assert_allclose(ysn.cpu().numpy(), oys, rtol=ULP1, atol=0)
+    assert np.array_equal(avn.cpu().numpy(), oavg)
+    rxs, rys = _scales_aten(xs.to(dev), ys.to(dev), avg.to(dev), h, w)
+    assert torch.equal(xsn, rxs) and torch.equal(ysn, rys), "x/y_scale_new differ from utils.py:1355-1365 executed by ATen on this GPU"
     np.testing.assert_allclose(nr.cpu().numpy(), onr, atol=RESIZE_TOL, rtol=0)
     # fused path == padded-image path through tensor_resize (same kernel arithmetic)
     from pats_b200 import tensor_resize as tr

@@ -66,7 +66,12 @@ def test_replay_reference_call(tag, seq, name):
         return
     if name == "ThirdLayer.Compute_result":  # whole_loss (3rd value) is discarded by the only caller, third_layer.py:160
         want = tuple(want[:2])
-    T.compare(name, got, want)
+    if name in ("log_optimal_transport", "log_optimal_transport2"):
+        T.compare_plan_on_gpu(name, args, got, want)
+    elif name == "Compute_imgs":  # x / y_scale_new: the stored CPU run divides by 96, CUDA ATen multiplies by the reciprocal (1 ulp)
+        T.compare(name, got, want, [T.EXACT, (0.0, 6e-5), (1.2e-7, 0.0), (1.2e-7, 0.0), T.EXACT])
+    else:
+        T.compare(name, got, want)
     # arguments the reference mutates in place (second_layer.py:194-207: trust_score, if_nomatching1_L2, scores_back)
     for m in c["mutated"]:
         path = m["path"]

@@ -9,7 +9,7 @@ import pytest
 import oracle
 import trace_util as T
 
-ALL = T.records(T.TAGS + T.ORACLE_ONLY_TAGS)
+ALL = T.records(T.TAGS)
 
 
 def _kw(kwargs, args, pos, name, default):
