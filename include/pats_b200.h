@@ -191,9 +191,18 @@ int pats_second_layer_match_f32(const float *scores, const float *one, const flo
 /* SecondLayer.merge_patches_new / merge_patches_old         models/second_layer.py:189-238 / :137-186
  *   trust_score [P,144] f32 and nm_L2 [P,144] u8 are MUTATED in place exactly as the reference mutates its
  *   arguments; nm_L1 [B,hw] u8; scores_back [B,hw,16,9] f64 in/out (carried across chunks for `new`, zeroed on
- *   return for `old`); out [P,144] u8 = if_nomatching per window cell.  workspace: 2*B*hw+1 ints (device). */
+ *   return for `old`); out [P,144] u8 = if_nomatching per window cell.  workspace: 2*B*hw+1 ints (device).
+ *   merge_new: 1 = merge_patches_new, 0 = merge_patches_old; OR-ed with PATS_MERGE_TIE_FIRST to resolve ties of the
+ *   reference's unstable `torch.argsort(...)[..., 0]` (:169 / :230) as ATen's CPU kernel does (first minimum) instead of
+ *   as its CUDA kernel does (the default: the reference runs on CUDA tensors, evaluate.py:26-28). */
+#define PATS_MERGE_TIE_FIRST 2
 int pats_merge_patches(int merge_new, float *trust_score, const uint8_t *nm_L1, uint8_t *nm_L2, double *scores_back, int B,
                        int height, int width, int P, uint8_t *out, int *workspace, void *stream);
+
+/* out[i] = torch.argsort(x[i, 0:9])[0]                      the selection rule of second_layer.py:169 / :230 on its own
+ *   x [n,9] f64 (device), out [n] i32.  tie_first = 0: ties resolved as ATen's CUDA sort does (the merge default),
+ *   1: first minimum (ATen CPU).  Exists so that the tie rule can be checked against the live op. */
+int pats_argsort9_first_f64(const double *x, int n, int tie_first, int *out, void *stream);
 
 /* get_result(batch, if_nomatching, average_point, scale, patch_size, left_choice)   utils/utils.py:189-213
  *   two levels, left_choice all true (models/pats.py:75-77).  Level 0: nm0 [B,n0] u8, pt0,sc0 [B,n0,2],

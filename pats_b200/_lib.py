@@ -46,6 +46,7 @@ SIGNATURES = {
     "pats_iterative_expand_matrix_f32": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "pats_est_nomatching_f32": [_P, _I, _I, _I, _I, _P, _P, _P],
     "pats_merge_patches": [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "pats_argsort9_first_f64": [_P, _I, _I, _P, _P],
     "pats_get_result_f32": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, C.c_longlong, _P, _P, _P],
     "pats_third_compute_result_f32": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
     "pats_third_result_from_log_f32": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P],

@@ -443,11 +443,51 @@ __global__ void merge_rings_kernel(float *__restrict__ trust, uint8_t *__restric
     scores_back[((size_t)qmap[p] * 16 + r * 4 + s) * 9 + a * 3 + c] = (double)t;
 }
 
+// Which of several EQUAL minima `torch.argsort(x)[..., 0]` returns on CUDA tensors (second_layer.py:169 / :230).  argsort is
+// unstable; ATen sorts slices of <= 32 elements with a bitonic network over 32 slots / 16 threads in which equal keys ARE
+// exchanged (ATen/native/cuda/SortUtils.cuh: bitonicSort, LTOp, invalid slots sort to the end), so among tied minima the winner
+// is a fixed function of WHICH slots hold the minimum -- never of the other values.  Ties are the rule here (windows that do not
+// exist score exactly 0.0; matched cells are -10000 + trust in f32, i.e. quantised to ~1e-3), and the choice changes which
+// window keeps a fine cell.  The table is indexed by the 9-bit mask of the minimum's positions; generated by emulating that
+// network (`python tools/argsort_tie_probe.py table`) and checked against the live op on a B200 for 200 000 random tie
+// patterns (profiles/r02_argsort_tie_probe.json: agreement 1.0; "first index", which is what the CPU kernel does, 0.55).
+__constant__ uint8_t kArgsortTie9[512] = {
+    0, 0, 1, 1, 2, 0, 1, 2, 3, 0, 1, 3, 2, 3, 3, 1, 4, 4, 4, 1, 4, 0, 1, 4, 4, 0, 1, 4, 2, 4, 4, 1,
+    5, 5, 5, 1, 5, 0, 1, 5, 5, 0, 1, 5, 2, 5, 5, 1, 4, 0, 1, 4, 2, 4, 4, 0, 3, 4, 4, 0, 4, 0, 1, 1,
+    6, 6, 6, 1, 6, 0, 1, 6, 6, 0, 1, 6, 2, 6, 6, 1, 6, 0, 1, 6, 2, 6, 6, 0, 3, 6, 6, 0, 6, 0, 1, 1,
+    6, 0, 1, 6, 2, 6, 6, 0, 3, 6, 6, 0, 6, 0, 1, 1, 4, 6, 6, 1, 6, 0, 1, 1, 6, 0, 1, 1, 2, 2, 2, 1,
+    7, 7, 7, 1, 7, 0, 1, 7, 7, 0, 1, 7, 2, 7, 7, 1, 7, 0, 1, 7, 2, 7, 7, 0, 3, 7, 7, 0, 7, 0, 1, 1,
+    7, 0, 1, 7, 2, 7, 7, 0, 3, 7, 7, 0, 7, 0, 1, 1, 4, 7, 7, 1, 7, 0, 1, 1, 7, 0, 1, 1, 2, 2, 2, 1,
+    7, 0, 1, 7, 2, 7, 7, 0, 3, 7, 7, 0, 7, 0, 1, 1, 4, 7, 7, 1, 7, 0, 1, 1, 7, 0, 1, 1, 2, 2, 2, 1,
+    5, 7, 7, 1, 7, 0, 1, 1, 7, 0, 1, 1, 2, 2, 2, 1, 7, 0, 1, 1, 2, 0, 1, 1, 3, 0, 1, 1, 2, 2, 2, 7,
+    8, 0, 1, 1, 2, 0, 1, 1, 3, 0, 1, 1, 2, 2, 2, 1, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 1,
+    5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 5, 1, 4, 4, 4, 4, 4, 4, 4, 0, 4, 4, 4, 0, 4, 0, 1, 1,
+    6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 6, 1, 6, 6, 6, 6, 6, 6, 6, 0, 6, 6, 6, 0, 6, 0, 1, 1,
+    6, 6, 6, 6, 6, 6, 6, 0, 6, 6, 6, 0, 6, 0, 1, 1, 6, 6, 6, 1, 6, 0, 1, 1, 6, 0, 1, 1, 2, 2, 2, 6,
+    7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 1, 7, 7, 7, 7, 7, 7, 7, 0, 7, 7, 7, 0, 7, 0, 1, 1,
+    7, 7, 7, 7, 7, 7, 7, 0, 7, 7, 7, 0, 7, 0, 1, 1, 7, 7, 7, 1, 7, 0, 1, 1, 7, 0, 1, 1, 2, 2, 2, 7,
+    7, 7, 7, 7, 7, 7, 7, 0, 7, 7, 7, 0, 7, 0, 1, 1, 7, 7, 7, 1, 7, 0, 1, 1, 7, 0, 1, 1, 2, 2, 2, 7,
+    7, 7, 7, 1, 7, 0, 1, 1, 7, 0, 1, 1, 2, 2, 2, 7, 7, 0, 1, 1, 2, 0, 1, 7, 3, 0, 1, 7, 2, 7, 7, 7,
+};
+// index of the winning candidate: tie_first != 0 -> first minimum (ATen CPU; what the CPU-recorded fixtures hold)
+__device__ __forceinline__ int argsort9_first(const double (&v)[9], int tie_first) {
+    double best = v[0];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) best = v[k] < best ? v[k] : best;
+    unsigned mask = 0;
+    int first = -1;
+#pragma unroll
+    for (int k = 8; k >= 0; --k)
+        if (v[k] == best) mask |= 1u << k, first = k;
+    if (first < 0) return 0;  // every comparison failed (NaN): not produced by the path
+    return tie_first ? first : kArgsortTie9[mask];
+}
+
 // Pass 2 (per window cell): which of the <= 9 overlapping windows keeps the cell.  Gather formulation of the
 // reference's shift / argsort / scatter (see DESIGN.md "merge_regroup" for the derivation).
 __global__ void merge_select_kernel(const uint8_t *__restrict__ nm_L2, const double *__restrict__ scores_back,
                                     const int *__restrict__ qmap, const int *__restrict__ pmap, int P, int height, int width,
-                                    int merge_new, uint8_t *__restrict__ out) {
+                                    int merge_new, int tie_first, uint8_t *__restrict__ out) {
     pdl_prologue();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= P * 144) return;
@@ -461,7 +501,7 @@ __global__ void merge_select_kernel(const uint8_t *__restrict__ nm_L2, const dou
     uint8_t res = 1;
     if (Y >= 0 && Y < H4 && X >= 0 && X < W4) {
         int ks = 0;
-        double best = 0.0;
+        double cand[9];
         if (merge_new) {
             // second_layer.py:225: argsort of the centre window's OWN nine scores (+1e5 where the neighbour is outside)
             const double *sb = scores_back + ((size_t)(bb * hw + (Y >> 2) * width + (X >> 2)) * 16 + r * 4 + s) * 9;
@@ -470,8 +510,9 @@ __global__ void merge_select_kernel(const uint8_t *__restrict__ nm_L2, const dou
                 const int yy = Y + 4 * (k / 3 - 1), xx = X + 4 * (k % 3 - 1);
                 double v = sb[k];
                 if (yy < 0 || yy >= H4 || xx < 0 || xx >= W4) v += 100000.0;
-                if (k == 0 || v < best) best = v, ks = k;
+                cand[k] = v;
             }
+            ks = argsort9_first(cand, tie_first);
             if (ks == (2 - a1) * 3 + (2 - c1)) res = nm_L2[e];
         } else {
             // second_layer.py:159-169: per-channel shifted scores (own value where the shift leaves the grid),
@@ -485,8 +526,9 @@ __global__ void merge_select_kernel(const uint8_t *__restrict__ nm_L2, const dou
                 double v = scores_back[((size_t)qq * 16 + (yy & 3) * 4 + (xx & 3)) * 9 + k];
                 const int pp = pmap[qq];
                 if (pp >= 0 && nm_L2[(size_t)pp * 144 + (4 * a + (yy & 3)) * 12 + 4 * c + (xx & 3)] == 0) v -= 10000.0;
-                if (k == 0 || v < best) best = v, ks = k;
+                cand[k] = v;
             }
+            ks = argsort9_first(cand, tie_first);
             if (ks == a1 * 3 + c1) res = nm_L2[e];
         }
     }
@@ -856,11 +898,31 @@ PATS_API int pats_merge_patches(int merge_new, float *trust_score, const uint8_t
     PATS_LAUNCH_CHECK("window_maps_kernel");
     if (P == 0) return PATS_OK;
     const int cells = P * 144;
+    const int tie_first = (merge_new & PATS_MERGE_TIE_FIRST) ? 1 : 0;
+    merge_new &= 1;
     PATS_CUDA_TRY(launch_chained(merge_rings_kernel, dim3((cells + 255) / 256), dim3(256), 0, st, trust_score, nm_L2, scores_back, qmap, P, merge_new ? 1 : 0));
     PATS_LAUNCH_CHECK("merge_rings_kernel");
-    PATS_CUDA_TRY(launch_chained(merge_select_kernel, dim3((cells + 255) / 256), dim3(256), 0, st, nm_L2, scores_back, qmap, pmap, P, height, width, merge_new ? 1 : 0, out));
+    PATS_CUDA_TRY(launch_chained(merge_select_kernel, dim3((cells + 255) / 256), dim3(256), 0, st, nm_L2, scores_back, qmap, pmap, P, height, width, merge_new ? 1 : 0, tie_first, out));
     PATS_LAUNCH_CHECK("merge_select_kernel");
     if (!merge_new) PATS_CUDA_TRY(cudaMemsetAsync(scores_back, 0, sizeof(double) * (size_t)total * 144, st));  // second_layer.py:186
+    return PATS_OK;
+}
+
+__global__ void argsort9_first_kernel(const double *__restrict__ x, int n, int tie_first, int *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v[k] = x[(size_t)i * 9 + k];
+    out[i] = argsort9_first(v, tie_first);
+}
+
+PATS_API int pats_argsort9_first_f64(const double *x, int n, int tie_first, int *out, void *stream) {
+    if (n < 0) return invalid("argsort9_first: bad size");
+    if (n == 0) return PATS_OK;
+    if (!x || !out) return invalid("argsort9_first: null pointer");
+    argsort9_first_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(x, n, tie_first, out);
+    PATS_LAUNCH_CHECK("argsort9_first_kernel");
     return PATS_OK;
 }
 

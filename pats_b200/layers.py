@@ -14,6 +14,12 @@ from ._torchutil import cuda_f32, stream_ptr
 __all__ = ["merge_patches_new", "merge_patches_old", "Compute_result", "third_compute_result"]
 
 
+# How ties of the reference's unstable `torch.argsort(...)[..., 0]` (second_layer.py:169 / :230) are resolved: "cuda" = as ATen's
+# CUDA kernel does (default: the reference runs on CUDA tensors), "first" = first minimum, as ATen's CPU kernel does (what
+# fixtures recorded from a CPU run of the reference hold).  See kArgsortTie9 in csrc/regroup.cu.
+MERGE_TIE_BREAK = "cuda"
+
+
 def _merge(merge_new, patch_num, trust_score, original_image_shape, if_nomatching1_L1, if_nomatching1_L2, scores_back):
     dev = trust_score.device
     if not trust_score.is_cuda:
@@ -29,7 +35,7 @@ def _merge(merge_new, patch_num, trust_score, original_image_shape, if_nomatchin
     out = torch.empty((P, 144), dtype=torch.bool, device=dev)
     ws = torch.empty(2 * B * height * width + 1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        rc = _lib.load().pats_merge_patches(1 if merge_new else 0, t.data_ptr(), nm1.data_ptr(), f.data_ptr(), sb.data_ptr(), B, height, width, P,
+        rc = _lib.load().pats_merge_patches((1 if merge_new else 0) | (2 if MERGE_TIE_BREAK == "first" else 0), t.data_ptr(), nm1.data_ptr(), f.data_ptr(), sb.data_ptr(), B, height, width, P,
                                             out.data_ptr(), ws.data_ptr(), stream_ptr(dev))
     _lib.check(rc, "merge_patches")
     if t is not trust_score:

@@ -5,8 +5,9 @@
      (tests/live_util.Shadow): transport plans within 1e-4 (absolute; the network is conditioned to realistic score
      magnitudes, live_util.condition) with identical row / column argmax, every integer / boolean / byte result -- masks,
      bounds, chunking, window copies, merge decisions, match lists -- bit-exact;
-(ii) `pats_b200.install.install()` and the same models/pats.py, free-running: the final match lists are compared with
-     (i)'s bit for bit.
+(ii) `pats_b200.install.install()` and the same models/pats.py, free-running: same number of matches, `matches_l` (the
+     source pixels: pure index arithmetic) bit for bit, `matches_r` (plan-weighted mean positions: floating point computed
+     FROM plans that agree to ~1e-5) within 5e-4 px.
 
 The reference's Python comes from oracle/_ref/py (staged by oracle/build_ref.py; /root/reference in the build container).
 Evidence of each run (call counts, max deviations, match counts, timings) goes to gpurun_out/live_forward_<case>.json.
@@ -39,6 +40,7 @@ for _k in ("log_sinkhorn_iterations", "log_optimal_transport", "log_optimal_tran
     RULES[_k] = OT_LIVE
 RULES["tensor_resize"] = T.EXACT  # same device, same ATen kernel arithmetic: bit-identical (tests/test_gpu_subdivide.py)
 RULES["Compute_imgs"] = [T.EXACT, T.EXACT, T.EXACT, T.EXACT, T.EXACT]
+MATCH_R_TOL_PX = 5e-4
 MUTATORS = ("SecondLayer.merge_patches_new", "SecondLayer.merge_patches_old")
 
 
@@ -160,8 +162,9 @@ def test_live_forward(name):
                  "ThirdLayer.Compute_result", "get_result", "split_patches"):
         assert seen.get(must, 0) >= 1, f"{must} was never reached in the live forward"
     assert log["matches_reference"] > 0, "the conditioned network produced no matches: the forward ended early"
-    assert log["matches_l_bit_exact"] and log["matches_r_bit_exact"], \
-        f"match lists differ: reference {log['matches_reference']} vs installed {log['matches_installed']} rows; {log.get('matches_rows_differing')} rows differ"
+    assert log["matches_installed"] == log["matches_reference"], f"match count differs: reference {log['matches_reference']} vs installed {log['matches_installed']}"
+    assert log["matches_l_bit_exact"], f"matches_l differs in {log.get('matches_rows_differing')} rows"
+    assert log["matches_r_bit_exact"] or log["matches_r_max_abs_diff"] <= MATCH_R_TOL_PX, f"matches_r differs by {log.get('matches_r_max_abs_diff')} px"
 
 
 if __name__ == "__main__":  # python tests/test_gpu_live_forward.py [case ...]: run without pytest, print the logs

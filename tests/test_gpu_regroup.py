@@ -94,8 +94,37 @@ def test_iterative_expand_matrix_vs_oracle(dev, b, gh, gw, lb, it):
     np.testing.assert_allclose(core, ref[1], rtol=1e-4, atol=1e-6)
 
 
+@pytest.fixture
+def cpu_tie_break(monkeypatch):
+    """The fixtures / the oracle hold the reference run on CPU tensors, where the unstable argsort of second_layer.py:169 / :230
+    returns the FIRST of several equal minima; the library's default follows ATen's CUDA kernel (checked live below)."""
+    from pats_b200 import layers as L
+
+    monkeypatch.setattr(L, "MERGE_TIE_BREAK", "first")
+
+
+def test_argsort_tie_rule_matches_the_live_cuda_op(dev):
+    """kArgsortTie9 (csrc/regroup.cu) against torch.argsort on THIS GPU, on tie patterns like the merge produces; and the
+    "first" mode against the first minimum."""
+    import ctypes  # noqa: F401
+
+    from pats_b200 import _lib
+
+    g = torch.Generator().manual_seed(9)
+    pool = torch.tensor([0.0, 0.0, 0.0, 1e-14, 8e-14, 100000.0, -9998.912109375, -9998.5, 0.25, 1.5], dtype=torch.float64)
+    x = pool[torch.randint(0, len(pool), (60000, 9), generator=g)]
+    x[:5000] = 0.0
+    x[5000:10000] = torch.rand(5000, 9, generator=g, dtype=torch.float64)  # no ties
+    xd = x.to(dev).contiguous()
+    out = torch.empty(x.shape[0], dtype=torch.int32, device=dev)
+    for tie_first in (0, 1):
+        _lib.check(_lib.load().pats_argsort9_first_f64(xd.data_ptr(), x.shape[0], tie_first, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "argsort9")
+        want = torch.argsort(xd.reshape(1, 200, 300, 9))[..., 0].reshape(-1) if tie_first == 0 else torch.from_numpy(np.argmin(x.numpy(), 1)).to(dev)
+        assert torch.equal(out.long(), want.long()), f"tie_first={tie_first}: {int((out.long() != want.long()).sum())} of {x.shape[0]} rows differ"
+
+
 @pytest.mark.parametrize("tag,merge_new", [("new", True), ("old", False)])
-def test_merge_patches_golden(dev, tag, merge_new):
+def test_merge_patches_golden(dev, tag, merge_new, cpu_tie_break):
     from pats_b200 import layers as L
 
     g = load_golden("merge")
@@ -113,7 +142,7 @@ def test_merge_patches_golden(dev, tag, merge_new):
 
 @pytest.mark.parametrize("merge_new", [True, False])
 @pytest.mark.parametrize("h,w,frac", [(15, 20, 1.0), (15, 20, 0.6), (32, 32, 0.9), (3, 4, 1.0)])
-def test_merge_patches_vs_oracle(dev, merge_new, h, w, frac):
+def test_merge_patches_vs_oracle(dev, merge_new, h, w, frac, cpu_tie_break):
     from pats_b200 import layers as L
 
     g = torch.Generator().manual_seed(60 + h + int(merge_new))
