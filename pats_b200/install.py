@@ -47,8 +47,12 @@ _METHODS = {
 _saved: dict = {}
 
 
-def install(only=None) -> list:
-    """Rebind the hot-path names; returns the list of (module, name) pairs that were replaced."""
+def install(only=None, fused: bool = False) -> list:
+    """Rebind the hot-path names; returns the list of (module, name) pairs that were replaced.
+
+    fused=True additionally rebinds `SecondLayer.forward` and `ThirdLayer.forward` to pats_b200.forward's mirrors, which
+    reach the pieces of the path that are inline statements in the reference (12 x 12 grid sampling, 8 x 8 window unfold)
+    and the composite Sinkhorn -> consumer calls."""
     done = []
     sys.modules.setdefault("tensor_resize", _tensor_resize)
     for modname, table in _TABLE.items():
@@ -63,7 +67,12 @@ def install(only=None) -> list:
                 _saved.setdefault((modname, name), getattr(mod, name))
                 setattr(mod, name, repl)
                 done.append((modname, name))
-    for (modname, clsname, meth), repl in _METHODS.items():
+    methods = dict(_METHODS)
+    if fused:
+        from .forward import FORWARDS
+
+        methods.update(FORWARDS)
+    for (modname, clsname, meth), repl in methods.items():
         if only is not None and meth not in only:
             continue
         mod = sys.modules.get(modname)

@@ -111,8 +111,9 @@ class Shadow:
     result is what the forward pass continues with) and, on clones of the same arguments, pats_b200's replacement;
     `on_call(name, ref_out, got_out, ref_args_after, got_args_after)` receives both for comparison."""
 
-    def __init__(self, on_call):
+    def __init__(self, on_call, forwards=False):
         self.on_call = on_call
+        self.forwards = forwards  # also shadow SecondLayer.forward / ThirdLayer.forward with pats_b200.forward's mirrors
         self.restore = []
         self.count = {}
 
@@ -148,7 +149,12 @@ class Shadow:
                 else:
                     setattr(mod, name, self._wrap(name, orig, repl))
                 self.restore.append((mod, name, orig))
-        for (modname, clsname, meth), repl in inst._METHODS.items():
+        methods = dict(inst._METHODS)
+        if self.forwards:
+            from pats_b200.forward import FORWARDS
+
+            methods.update(FORWARDS)
+        for (modname, clsname, meth), repl in methods.items():
             cls = getattr(sys.modules.get(modname), clsname, None)
             if cls is None or not hasattr(cls, meth):
                 continue

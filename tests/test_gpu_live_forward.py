@@ -40,6 +40,12 @@ for _k in ("log_sinkhorn_iterations", "log_optimal_transport", "log_optimal_tran
     RULES[_k] = OT_LIVE
 RULES["tensor_resize"] = T.EXACT  # same device, same ATen kernel arithmetic: bit-identical (tests/test_gpu_subdivide.py)
 RULES["Compute_imgs"] = [T.EXACT, T.EXACT, T.EXACT, T.EXACT, T.EXACT]
+# layer-level mirrors (pats_b200.forward): the returned dictionaries, key by key
+_F = (2e-5, 2e-5)
+RULES["SecondLayer.forward"] = {"scales": T.EXACT, "scales_reproj": [(2e-5, 1e-6), (2e-5, 1e-6)], "scores": OT_LIVE, "features": T.EXACT,
+                                "features_before": T.EXACT, "pts": _F, "if_nomatching1": T.EXACT, "if_nomatching2": T.EXACT,
+                                "trust_score": (2e-4, 2e-6), "scores_back": (2e-4, 2e-6)}
+RULES["ThirdLayer.forward"] = {"mkpts0_f": T.EXACT, "mkpts1_f": (1e-5, 2e-5), "label": T.EXACT}
 MATCH_R_TOL_PX = 5e-4
 MUTATORS = ("SecondLayer.merge_patches_new", "SecondLayer.merge_patches_old")
 
@@ -90,6 +96,11 @@ def run_case(name, dev="cuda:0"):
                 ent["ot_max_abs_diff"] = max(ent["ot_max_abs_diff"], d)
                 ent["problems"] += int(want.shape[0])
                 ent["max_abs_score"] = max(ent.get("max_abs_score", 0.0), float(ref_after[0][0].abs().max()))
+            if isinstance(RULES[fname], dict):
+                assert set(got) == set(want), f"{fname}: keys differ"
+                for key, rule in RULES[fname].items():
+                    T.compare(fname, got[key], want[key], rule, f"{fname}[{key!r}]")
+                return
             T.compare(fname, got, want, RULES[fname])
             if fname in ("log_optimal_transport", "log_optimal_transport2"):
                 T.check_argmax_parity(fname, got, want)
@@ -113,7 +124,7 @@ def run_case(name, dev="cuda:0"):
         ref_out = model(data)
         torch.cuda.synchronize()
         log["reference_cuda_s"] = time.perf_counter() - t0
-        with L.Shadow(on_call) as sh:
+        with L.Shadow(on_call, forwards=True) as sh:
             shadow_out = model(data)
         torch.cuda.synchronize()
         log["calls_seen"] = dict(sh.count)
@@ -132,6 +143,22 @@ def run_case(name, dev="cuda:0"):
             log["installed_s"] = time.perf_counter() - t0
         finally:
             inst.uninstall()
+        # (iii) layer-level drop-ins too: SecondLayer.forward / ThirdLayer.forward on the fused entry points
+        done_f = inst.install(fused=True)
+        try:
+            model(data)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fused_out = model(data)
+            torch.cuda.synchronize()
+            log["installed_fused_s"] = time.perf_counter() - t0
+        finally:
+            inst.uninstall()
+    log["fused_names"] = len(done_f)
+    log["matches_fused"] = int(fused_out["matches_l"].shape[0])
+    log["fused_matches_l_bit_exact"] = fused_out["matches_l"].shape == ref_out["matches_l"].shape and bool(torch.equal(fused_out["matches_l"], ref_out["matches_l"]))
+    log["fused_matches_r_max_abs_diff"] = (float((fused_out["matches_r"] - ref_out["matches_r"]).abs().max())
+                                           if fused_out["matches_r"].shape == ref_out["matches_r"].shape and ref_out["matches_r"].numel() else None)
     log["installed_names"] = len(done)
     log["matches_reference"] = int(ref_out["matches_l"].shape[0])
     log["matches_installed"] = int(our_out["matches_l"].shape[0])
@@ -165,6 +192,11 @@ def test_live_forward(name):
     assert log["matches_installed"] == log["matches_reference"], f"match count differs: reference {log['matches_reference']} vs installed {log['matches_installed']}"
     assert log["matches_l_bit_exact"], f"matches_l differs in {log.get('matches_rows_differing')} rows"
     assert log["matches_r_bit_exact"] or log["matches_r_max_abs_diff"] <= MATCH_R_TOL_PX, f"matches_r differs by {log.get('matches_r_max_abs_diff')} px"
+    for must in ("SecondLayer.forward", "ThirdLayer.forward"):
+        assert seen.get(must, 0) >= 1, f"{must} was never reached in the live forward"
+    assert log["matches_fused"] == log["matches_reference"] and log["fused_matches_l_bit_exact"], \
+        f"install(fused=True): {log['matches_fused']} matches vs {log['matches_reference']}, matches_l equal: {log['fused_matches_l_bit_exact']}"
+    assert log["fused_matches_r_max_abs_diff"] is not None and log["fused_matches_r_max_abs_diff"] <= MATCH_R_TOL_PX
 
 
 if __name__ == "__main__":  # python tests/test_gpu_live_forward.py [case ...]: run without pytest, print the logs
