@@ -47,6 +47,7 @@ P2 = 300                               # matched windows of one pair (all coarse
 K3 = 4800                              # level-3 problems of one pair (60 x 80 fine cells)
 ITERS = 100
 SEED = 18027                           # configs/*.yaml `seed`
+DEFAULT_PAIRS_PER_STEP = 8             # pairs are independent (evaluate.py:25-35): a step batches 8 of them through every kernel
 LOG2_F32 = 0.6931471824645996          # f32(log(f32(2))): torch.log(self.one * 2), second_layer.py:109-110 (outdoor)
 L3_SAMPLE_EVERY = 8                    # every 8th timed step brackets the level-3 solve with events (roofline sample)
 
@@ -68,7 +69,41 @@ def emit(obj):
 # ------------------------------------------------------------------------------------------------------------
 # synthetic inputs of one step (seeded; host tensors)
 # ------------------------------------------------------------------------------------------------------------
-def make_inputs(torch, pairs: int, seed: int):
+WORKLOAD = "pats_hot_path_pair640x480"
+SURVIVE = 0.05                         # fraction of fine points that end up in the match list (the live conditioned forward keeps 0.1 - 2 %)
+
+
+def planted_scores(torch, g, b, gh, gw, sharp, noise, floor, dustbin=False, peak=5.0):
+    """Affinity of a smooth random warp between two gh x gw grids: peaked, spatially coherent plans, i.e. what a trained matcher
+    hands to the Sinkhorn (and what the conditioned live forward produces: |0.1 * scores| <= 12 .. 26, std 2.5).  With random
+    `0.1 * randn` scores -- the `diffuse` workload -- every plan is flat, boxes grow to the iteration limit and the log-domain
+    paths are never touched.  Returns (scores, area [b]): area = source cells per target cell of the warp, the consistent value of the
+    target areas `ns` (first_layer.py:106-107).  dustbin=True appends the dustbin row / column of log_optimal_transport2's [b, n+1, n+1] input."""
+    n = gh * gw
+    ys, xs = torch.meshgrid(torch.arange(gh).float(), torch.arange(gw).float(), indexing="ij")
+    src = torch.stack([ys.reshape(-1), xs.reshape(-1)], 1)
+    ctr = torch.tensor([gh / 2.0, gw / 2.0])
+    out = torch.empty(b, n + int(dustbin), n + int(dustbin))
+    area = torch.empty(b)
+    step = max(1, min(b, (1 << 24) // (n * n)))
+    for lo in range(0, b, step):
+        c = min(step, b - lo)
+        A = torch.eye(2)[None] * (0.6 + 0.8 * torch.rand(c, 1, 1, generator=g)) + 0.1 * torch.randn(c, 2, 2, generator=g)
+        t = torch.randn(c, 1, 2, generator=g) * (0.12 * max(gh, gw))  # part of the source cells land outside the target grid: they feed the dustbin
+        area[lo:lo + c] = (1.0 / torch.linalg.det(A).abs()).clamp(1.0 / 16, 16.0)  # source cells per target cell: the target "area" ns
+        warped = (src - ctr) @ A.transpose(1, 2) + ctr + t
+        d2 = ((warped[:, :, None, :] - src[None, None, :, :]) ** 2).sum(-1)
+        sc = (peak - d2 / sharp + noise * torch.randn(c, n, n, generator=g)).clamp_min(floor)  # a true match scores ~peak: it must beat the dustbin (score ~ -1 .. 1, mass = n) by ln(n) + a few nats to keep its row
+        if dustbin:
+            out[lo:lo + c, :n, :n] = sc
+            out[lo:lo + c, n, :] = -1.0 + 0.3 * torch.randn(c, n + 1, generator=g)
+            out[lo:lo + c, :, n] = -1.0 + 0.3 * torch.randn(c, n + 1, generator=g)
+        else:
+            out[lo:lo + c] = sc
+    return out, area
+
+
+def make_inputs(torch, pairs: int, seed: int, kind: str = "planted"):
     g = torch.Generator().manual_seed(seed)
 
     def areas(*shape, span):
@@ -76,26 +111,40 @@ def make_inputs(torch, pairs: int, seed: int):
 
     B = pairs
     d = {}
-    d["l1_scores"] = 0.1 * torch.randn(B, N1, N1, generator=g)            # first_layer.py:110-114 (already x0.1)
-    d["l1_ns"] = areas(B, 1, N1, span=16.0)                                # first_layer.py:106-107
+    if kind == "planted":
+        d["l1_scores"], a1 = planted_scores(torch, g, B, GH, GW, sharp=1.5, noise=0.3, floor=-20.0, peak=12.0)      # first_layer.py:110-114 (already x0.1)
+        d["l1_ns"] = (a1.reshape(B, 1, 1) * areas(B, 1, N1, span=1.2)).contiguous()                       # first_layer.py:106-107
+    else:
+        d["l1_scores"] = 0.1 * torch.randn(B, N1, N1, generator=g)
+        d["l1_ns"] = areas(B, 1, N1, span=16.0)
     d["alpha"] = torch.tensor([1.0])                                      # |bin_score| (init 0.0 would switch the dustbin off)
     d["left"] = torch.randint(0, 256, (B, H, W_IMG, 3), generator=g, dtype=torch.uint8)   # evaluate.py:26-27
     d["right"] = torch.roll(d["left"], (16, 24), dims=(1, 2)).contiguous()
-    # Compute_imgs inputs as est_position would hand them over (well inside the image so every crop is valid)
+    # Compute_imgs inputs for the `diffuse` workload, whose est_position output is meaningless (the planted workload feeds
+    # Compute_imgs from est_position on the device, as first_layer.py:121-140 does)
     d["ci_xs"] = areas(B, N1, span=1.6)
     d["ci_ys"] = areas(B, N1, span=1.6)
     cy = torch.arange(GH).float().reshape(1, GH, 1).expand(B, GH, GW) + 0.5 + 0.6 * torch.randn(B, GH, GW, generator=g)
     cx = torch.arange(GW).float().reshape(1, 1, GW).expand(B, GH, GW) + 0.5 + 0.6 * torch.randn(B, GH, GW, generator=g)
     d["ci_avg"] = torch.stack([cy, cx], -1).reshape(B, N1, 2).contiguous()
     d["ci_nm"] = torch.zeros(B, N1, dtype=torch.bool)
-    d["l2_scores"] = 0.1 * torch.randn(B * P2, 145, 145, generator=g)      # second_layer.py:100-104
-    d["l2_sx"] = areas(B * P2, 144, span=16.0)                             # second_layer.py:92-98
-    d["l2_sy"] = areas(B * P2, 144, span=16.0)
+    if kind == "planted":
+        d["l2_scores"], a2 = planted_scores(torch, g, B * P2, 12, 12, sharp=1.5, noise=0.3, floor=-20.0, dustbin=True, peak=9.0)   # second_layer.py:100-104
+        d["l2_sx"] = (a2.sqrt().reshape(-1, 1) * areas(B * P2, 144, span=1.1)).contiguous()                               # second_layer.py:92-98
+        d["l2_sy"] = (a2.sqrt().reshape(-1, 1) * areas(B * P2, 144, span=1.1)).contiguous()
+    else:
+        d["l2_scores"] = 0.1 * torch.randn(B * P2, 145, 145, generator=g)
+        d["l2_sx"] = areas(B * P2, 144, span=16.0)
+        d["l2_sy"] = areas(B * P2, 144, span=16.0)
     d["l2_ns"] = (d["l2_sx"] * d["l2_sy"]).reshape(B * P2, 1, 144).contiguous()
     d["one"] = torch.tensor([1.0])
     d["nm1_L1"] = torch.zeros(B, N1, dtype=torch.bool)
-    d["l3_scores"] = 0.1 * torch.randn(B * K3, 65, 65, generator=g)        # third_layer.py:156-158
-    d["l3_ns"] = areas(B * K3, 1, 64, span=16.0)                           # third_layer.py:151-152
+    if kind == "planted":
+        d["l3_scores"], a3 = planted_scores(torch, g, B * K3, 8, 8, sharp=1.5, noise=0.3, floor=-10.0, dustbin=True, peak=7.0)     # third_layer.py:156-158
+        d["l3_ns"] = (a3.reshape(-1, 1, 1) * areas(B * K3, 1, 64, span=1.2)).contiguous()                                 # third_layer.py:151-152
+    else:
+        d["l3_scores"] = 0.1 * torch.randn(B * K3, 65, 65, generator=g)
+        d["l3_ns"] = areas(B * K3, 1, 64, span=16.0)
     d["l3_sxy"] = (d["l3_ns"].reshape(B * K3, 64) + 1e-8).sqrt()           # third_layer.py:153-154
     d["p_s"] = torch.randint(0, 24, (B * K3, 2), generator=g) * 4
     d["p_t"] = torch.randint(0, 25, (B * K3, 2), generator=g) * 4
@@ -103,7 +152,7 @@ def make_inputs(torch, pairs: int, seed: int):
     d["gr_nm0"] = torch.zeros(B, N1, dtype=torch.bool)
     d["gr_pt0"] = (d["ci_avg"].flip(2) / 1.0).contiguous()
     d["gr_sc0"] = torch.cat([areas(B, N1, 1, span=1.6), torch.ones(B, N1, 1)], 2).contiguous()
-    d["gr_nm1"] = torch.rand(B * P2, 2304, generator=g) < 0.75             # ~25 % of the fine points survive
+    d["gr_nm1"] = torch.rand(B * P2, 2304, generator=g) >= (SURVIVE if kind == "planted" else 0.25)
     d["gr_pt1"] = torch.rand(B * P2, 2304, 2, generator=g) * 48
     d["gr_sc1"] = d["gr_sc0"].reshape(B * N1, 1, 2).repeat(1, 2304, 1).contiguous()
     return d
@@ -115,13 +164,14 @@ def make_inputs(torch, pairs: int, seed: int):
 class DeviceStep:
     LAUNCHES = 0  # kernels of ours enqueued per step (counted from the launch table below)
 
-    def __init__(self, torch, dev, pairs: int, seed: int):
+    def __init__(self, torch, dev, pairs: int, seed: int, kind: str = "planted"):
         from pats_b200 import _lib
 
         self.torch, self.dev, self.B = torch, dev, pairs
         self.lib = _lib.load()
         self.check = _lib.check
-        host = make_inputs(torch, pairs, seed)
+        self.kind = kind
+        host = make_inputs(torch, pairs, seed, kind)
         self.i = {k: v.to(dev) for k, v in host.items()}
         self.host_inputs = host
         B = pairs
@@ -162,7 +212,11 @@ class DeviceStep:
         c(L.pats_log_optimal_transport_f32(p(i["l1_scores"]), p(i["alpha"]), p(i["l1_ns"]), B, N1, N1, ITERS, p(o["l1_Z"]), stream_ptr), "ot1"); n += 1
         c(L.pats_est_position_f32(p(o["l1_Z"]), p(i["l1_ns"]), p(i["l1_ns"]), B, GH, GW, 1e-5, 15, p(o["l1_trust"]), p(o["l1_avg"]), p(o["l1_xs"]),
                                   p(o["l1_ys"]), p(o["l1_nm1"]), p(o["l1_nm2"]), p(o["l1_core"]), p(o["l1_bound"]), stream_ptr), "est1"); n += 1
-        c(L.pats_compute_imgs(p(i["ci_xs"]), p(i["ci_ys"]), p(i["ci_avg"]), p(i["ci_nm"]), p(i["left"]), p(i["right"]), 1, B, GH, GW, PS, 128,
+        # first_layer.py:121-140: est_position's areas, centres and mask ARE Compute_imgs' arguments (planted workload); the diffuse
+        # workload's est_position output is noise, so there Compute_imgs keeps its own seeded inputs
+        chain = self.kind == "planted"
+        c(L.pats_compute_imgs(p(o["l1_xs"] if chain else i["ci_xs"]), p(o["l1_ys"] if chain else i["ci_ys"]), p(o["l1_avg"] if chain else i["ci_avg"]),
+                              p(o["l1_nm1"] if chain else i["ci_nm"]), p(i["left"]), p(i["right"]), 1, B, GH, GW, PS, 128,
                               p(o["new_left"]), p(o["new_right"]), p(o["bound5"]), p(o["ci_xs_new"]), p(o["ci_ys_new"]), p(o["ci_avg_new"]), B * N1,
                               p(o["ci_meta"]), p(o["ci_meta"]) + 4, stream_ptr), "imgs"); n += 3
         # ---- level 2 (second_layer.py:103-116 in one call: OT -> dustbin offsets -> est_position, handed over per problem) ----
@@ -199,8 +253,8 @@ class E2EStep:
     Steps are software-pipelined over two device input buffers: the copies of step i+1 run on a copy stream while
     step i computes (every step still pays its own H2D and D2H inside the timed region)."""
 
-    def __init__(self, torch, dev, pairs: int, host_inputs):
-        self.torch, self.dev, self.B = torch, dev, pairs
+    def __init__(self, torch, dev, pairs: int, host_inputs, kind: str = "planted"):
+        self.torch, self.dev, self.B, self.kind = torch, dev, pairs, kind
         # every stage input lives in ONE pinned host arena and goes over in ONE cudaMemcpyAsync per step (a copy per
         # tensor costs ~17 DMA set-ups per step); the device-side tensors are views into the arena's device twin
         offs, total = {}, 0
@@ -242,7 +296,10 @@ class E2EStep:
         # level 1
         Z1 = M.log_optimal_transport(d["l1_scores"], d["alpha"], d["l1_ns"], ITERS)
         trust1, avg1, xs1, ys1, nm1a, nm1b = Ly.est_position(Z1, d["l1_ns"], d["l1_ns"], GH, GW, 15, 1e-5)
-        new_left, new_right, xsn, ysn, avn = U.Compute_imgs(d["ci_xs"], d["ci_ys"], d["ci_avg"], d["ci_nm"], d["left"], d["right"], width=GW, height=GH)
+        if self.kind == "planted":  # first_layer.py:121-140: est_position's outputs are Compute_imgs' arguments
+            new_left, new_right, xsn, ysn, avn = U.Compute_imgs(xs1, ys1, avg1, nm1a, d["left"], d["right"], width=GW, height=GH)
+        else:
+            new_left, new_right, xsn, ysn, avn = U.Compute_imgs(d["ci_xs"], d["ci_ys"], d["ci_avg"], d["ci_nm"], d["left"], d["right"], width=GW, height=GH)
         # level 2
         Z2, trust2, avg2, xs2, ys2, nm2a, nm2b = Ly.second_layer_match(d["l2_scores"], 1.0, d["l2_ns"], d["l2_sx"], d["l2_sy"], ITERS, True, 12)
         sb = torch.zeros(B, N1, 16, 9, dtype=torch.float64, device=dev)
@@ -419,6 +476,78 @@ def ncu_traffic(key="sinkhorn_warp_dram_bytes_per_launch"):
     return None
 
 
+def forward_leg(torch, dev, args):
+    """image-pairs/s through the UNMODIFIED reference `PATS.forward` (models/pats.py:18-85, driven like evaluate.py:25-33: uint8
+    images host -> device, forward, match lists device -> host), three ways on the same seeded random-init network
+    (tests/live_util: conditioned to realistic score magnitudes) and the same synthetic 640x480 pairs:
+        reference_cuda   the stock reference on CUDA tensors (ATen ops + its compiled setup/library.cpp) -- how it really runs
+        installed        + pats_b200.install.install(): every hot-path function on the CUDA library
+        installed_fused  + install(fused=True): the two layer forwards on the fused entry points as well
+        reference_cpu    the stock reference on CPU tensors, all host threads (one pair; --no-forward-cpu skips it)
+    The ResNet / attention networks are NOT part of the path (they stay the reference's own PyTorch modules in every arm), so
+    this leg bounds what the hot path is worth inside the whole forward pass; `value` / `e2e` above isolate the path itself."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import live_util as L
+
+    if L.reference_root() is None:
+        return {"unavailable": "reference Python not staged (oracle/_ref/py: run __graft_entry__.build() where /root/reference exists)"}
+    ref = L.load_reference()
+    import pats_b200.install as inst
+
+    cfg = L.config(if_local=True, merge_new=True, if_outdoor=True)  # configs/test_megadepth.yaml
+    n_pairs, n_warm = 6, 2
+    host = [tuple(t.pin_memory() for t in L.synthetic_pair((H, W_IMG), seed=SEED + i)) for i in range(n_pairs)]
+    out = {"config": "configs/test_megadepth.yaml flags (if_local, merge_new, if_outdoor), 640x480, seeded random-init weights conditioned by tests/live_util.py",
+           "pairs_timed": n_pairs - n_warm, "unit": "pairs/s"}
+
+    def run(model, device, pairs):
+        n_match = 0
+        for i0, i1 in pairs:
+            data = {"image0": i0.to(device, non_blocking=True), "image1": i1.to(device, non_blocking=True)}
+            r = model(data)
+            n_match += int(r["matches_l"].cpu().shape[0]) + 0 * int(r["matches_r"].cpu().shape[0])
+        return n_match
+
+    with torch.no_grad():
+        model = L.build_model(ref, cfg, device=dev)
+        for name, setup in (("reference_cuda", None), ("installed", dict(fused=False)), ("installed_fused", dict(fused=True))):
+            if setup is not None:
+                inst.install(**setup)
+            try:
+                run(model, dev, host[:n_warm])
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                m = run(model, dev, host[n_warm:])
+                torch.cuda.synchronize(dev)
+                dt = time.perf_counter() - t0
+            finally:
+                if setup is not None:
+                    inst.uninstall()
+            out[name] = {"value": (n_pairs - n_warm) / dt, "s_per_pair": dt / (n_pairs - n_warm), "matches": m}
+        if not args.no_forward_cpu:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            cpu_model = L.build_model(ref, cfg, device="cpu")
+            orig_cuda = torch.Tensor.cuda
+            torch.Tensor.cuda = lambda self, *a, **k: self  # models/pats.py:76 hard-codes .cuda(); this arm runs on CPU tensors
+            try:
+                t0 = time.perf_counter()
+                m = run(cpu_model, "cpu", host[n_warm:n_warm + 1])
+                dt = time.perf_counter() - t0
+            finally:
+                torch.Tensor.cuda = orig_cuda
+            out["reference_cpu"] = {"value": 1.0 / dt, "s_per_pair": dt, "matches": m, "cores": cores, "pairs_timed": 1}
+    out["speedup_installed_vs_reference_cuda"] = out["installed"]["value"] / out["reference_cuda"]["value"]
+    out["speedup_fused_vs_reference_cuda"] = out["installed_fused"]["value"] / out["reference_cuda"]["value"]
+    return out
+
+
+def workload_config(pairs_per_step: int) -> dict:
+    """The `config` of BOTH arms (key for key: the driver compares them)."""
+    return {"workload": WORKLOAD, "scores": "planted (peaked, area-consistent plans; make_inputs)", "pairs_per_step": pairs_per_step, "P2": P2, "K3": K3,
+            "sinkhorn_iters": ITERS}
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on the host cores (oracle port + oracle/_ref)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -431,7 +560,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     oracle.set_num_threads(cores)
     torch.set_num_threads(cores)
-    host = make_inputs(torch, 1, SEED)
+    host = make_inputs(torch, 1, SEED, "planted")  # every step = ONE pair of the step's `pairs_per_step` (they are independent and identical in cost)
     # a full pair costs ~1.3 s on 16 host threads: every step is the whole pair (no sampling, no scaling); a box with few
     # cores falls back to a quarter / an eighth of the level-2 / level-3 problems so that the run stays within minutes
     t0 = time.perf_counter()
@@ -448,11 +577,13 @@ def run_reference(args):
             break
     per_pair = sum(times) / len(times)
     value = 1.0 / per_pair
+    B = args.pairs_per_step
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1),
-        "ms_per_step": per_pair * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "pats_hot_path_pair640x480", "pairs_per_step": 1, "P2": P2, "K3": K3, "sinkhorn_iters": ITERS},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": oracle.num_threads(), "kind": "port", "sample": desc},
+        "ms_per_step": per_pair * B * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(B),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": oracle.num_threads(), "kind": "port",
+                         "sample": f"each timed step = 1 of the step's {B} pairs (independent, equal cost; ms_per_step = {B} x that): " + desc},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -465,7 +596,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--pairs-per-step", type=int, default=1)
+    ap.add_argument("--pairs-per-step", type=int, default=DEFAULT_PAIRS_PER_STEP)
+    ap.add_argument("--workload", default="planted", choices=["planted", "diffuse"], help="synthetic score model (make_inputs)")
+    ap.add_argument("--no-diffuse", action="store_true", help="skip the second, short pass on the diffuse (0.1 * randn) workload")
+    ap.add_argument("--no-forward", action="store_true", help="skip the PATS.forward leg (reference on CUDA vs install())")
+    ap.add_argument("--no-forward-cpu", action="store_true", help="forward leg: skip the reference PATS.forward on CPU tensors (one pair, ~20 s)")
     ap.add_argument("--streams", type=int, default=1,
                     help="CUDA streams the device-resident steps alternate over (independent pairs overlap; 1 = strictly serial)")
     ap.add_argument("--no-overlap", action="store_true", help="skip the informational two-stream pass")
@@ -521,15 +656,19 @@ def main():
             _l.load().pats_launch_chaining(0)
         if args.no_handover:
             _l.load().pats_plan_handover(0)
-    steps_all = [DeviceStep(torch, dev, B, SEED + rank)]
-    step = steps_all[0]
+    kind = args.workload
+    steps_by_kind = {}
 
-    def timed_pass(S, n_steps, want_clocks):
+    def timed_pass(S, n_steps, want_clocks, kind=kind):
         """Times exactly n_steps steps alternating over S CUDA streams (S = 1: strictly serial on the current stream).
-        Pairs are independent (evaluate.py:25-35); with S > 1 one pair's single-problem level-1 kernels overlap another
-        pair's level-3 work.  Every step is one full pass of the hot path over `pairs_per_step` pairs."""
+        Pairs are independent (evaluate.py:25-35); with S > 1 one batch's single-problem level-1 kernels overlap another
+        batch's level-3 work.  Every step is one full pass of the hot path over `pairs_per_step` pairs.  With more than one
+        rank the timed region ends with the path's one exchange: EVERY step's match list of every rank is gathered to
+        rank 0 (BASELINE config 4: contiguous shards of the pair list, evaluate.py:29-35 computes the metrics in one place)."""
+        steps_all = steps_by_kind.setdefault(kind, [])
         while len(steps_all) < S:
-            steps_all.append(DeviceStep(torch, dev, B, SEED + rank + 1000 * len(steps_all)))
+            steps_all.append(DeviceStep(torch, dev, B, SEED + rank + 1000 * len(steps_all), kind))
+        step = steps_all[0]
         main_stream = torch.cuda.current_stream(dev)
         streams = [torch.cuda.Stream(dev) for _ in range(S)] if S > 1 else [main_stream]
         # inputs + outputs of one step far exceed the 126 MB L2 (level-3 plans alone: 2 x 81 MB per pair) -> no L2 flush needed
@@ -539,15 +678,19 @@ def main():
         torch.cuda.synchronize(dev)
         nbad = int(step.o["ci_meta"][1].item())
         assert nbad == 0, f"synthetic Compute_imgs inputs produced {nbad} invalid crops"
-        kf = int(step.o["gr_total"].item())
+        kfs = [int(st_.o["gr_total"].item()) for st_ in steps_all[:S]]  # match rows per step (fixed inputs -> fixed count)
+        windows = int(step.o["ci_meta"][0].item())
+        # this rank's shard of the pair list: n_steps * B pairs; every step appends its match rows [yl, xl, yr, xr] to `acc`
+        acc = torch.empty((sum(kfs[i % S] for i in range(n_steps)), 4), dtype=torch.float32, device=dev) if gather is not None else None
+        gstats = {}
         if gather is not None:  # warm-up of the exchange too (NCCL builds its communicator lazily on the first collective)
-            gather([torch.cat([step.o["ml"][:kf], step.o["mr"][:kf]], 1)])
+            gather([acc[: kfs[0]]], max_pairs=1, dst=0)
         l3_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if (i % L3_SAMPLE_EVERY) == L3_SAMPLE_EVERY - 1 or
                      n_steps < L3_SAMPLE_EVERY else None for i in range(n_steps)]
         sampler = ClockSampler(local_rank)
         if rank == 0 and want_clocks:
             sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1, eg = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         done = [torch.cuda.Event() for _ in range(S)]
         barrier()
         t_wall0 = time.perf_counter()
@@ -555,39 +698,66 @@ def main():
         if S > 1:
             for st in streams:
                 st.wait_event(e0)
-        launches = 0
+        launches, off = 0, 0
         for i in range(n_steps):
             with torch.cuda.stream(streams[i % S]):
-                launches += steps_all[i % S].run(streams[i % S].cuda_stream, l3_events[i])
+                st_ = steps_all[i % S]
+                launches += st_.run(streams[i % S].cuda_stream, l3_events[i])
+                if acc is not None:  # keep this step's list (two device copies; no host sync, no allocation)
+                    k = kfs[i % S]
+                    acc[off:off + k, :2].copy_(st_.o["ml"][:k])
+                    acc[off:off + k, 2:].copy_(st_.o["mr"][:k])
+                    off += k
         if S > 1:
             for i, st in enumerate(streams):
                 done[i].record(st)
                 main_stream.wait_event(done[i])
-        if gather is not None:  # the path's one exchange: gather of the match lists, once, after the pair loop
-            gather([torch.cat([step.o["ml"][:kf], step.o["mr"][:kf]], 1)])
+        eg.record(main_stream)
+        if gather is not None:  # one list per step (= per batch of B pairs), all of them, to rank 0
+            lists, o2 = [], 0
+            for i in range(n_steps):
+                lists.append(acc[o2:o2 + kfs[i % S]])
+                o2 += kfs[i % S]
+            gather(lists, max_pairs=n_steps, dst=0, stats=gstats)
         e1.record(main_stream)
         barrier()
         t_wall1 = time.perf_counter()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([e0.elapsed_time(e1), eg.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         clocks = sampler.stop(t_wall0, t_wall1) if (rank == 0 and want_clocks) else None
         l3 = sorted(ev[0].elapsed_time(ev[1]) for ev in l3_events if ev is not None)
-        return float(ms.item()), launches, sum(l3) / len(l3), clocks, kf
+        info = {"kf": kfs[0], "windows": windows, "gather_ms": float(ms[1].item()) if gather is not None else 0.0, "gather": gstats,
+                "fallbacks": int(step.lib.pats_sinkhorn_fallback_count(1))}
+        return float(ms[0].item()), launches, sum(l3) / len(l3), clocks, info
 
     S = max(1, args.streams)
-    total_ms, launches, l3_avg, clocks, kf = timed_pass(S, args.steps, True)
+    from pats_b200 import _lib as _l0
+
+    _l0.load().pats_sinkhorn_fallback_count(1)
+    total_ms, launches, l3_avg, clocks, info = timed_pass(S, args.steps, True)
+    step = steps_by_kind[kind][0]
+    kf = info["kf"]
     value = world * B * args.steps / (total_ms * 1e-3)
     overlap = None
     if S == 1 and not args.no_overlap:
         o_ms, _, _, _, _ = timed_pass(2, args.steps, False)
         overlap = {"streams": 2, "value": world * B * args.steps / (o_ms * 1e-3), "unit": "pairs/s", "ms_per_step": o_ms / args.steps,
-                   "note": "same steps alternating over two CUDA streams (independent pairs overlap); informational"}
+                   "note": "same steps alternating over two CUDA streams (independent batches overlap); informational"}
+    diffuse = None
+    if kind == "planted" and not args.no_diffuse and world == 1:
+        n_d = max(3, min(args.steps, 20))
+        d_ms, _, d_l3, _, d_info = timed_pass(1, n_d, False, "diffuse")
+        diffuse = {"workload": WORKLOAD, "scores": "diffuse (0.1 * randn: flat plans, boxes grow to the iteration limit; the round-1 workload)",
+                   "value": world * B * n_d / (d_ms * 1e-3), "unit": "pairs/s", "ms_per_step": d_ms / n_d, "steps": n_d, "l3_ms_per_launch": d_l3,
+                   "matches_per_pair": d_info["kf"] // B}
+        del steps_by_kind["diffuse"]
+        torch.cuda.empty_cache()
 
     # ---- e2e: public API, host buffers ------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        es = E2EStep(torch, dev, B, step.host_inputs)
+        es = E2EStep(torch, dev, B, step.host_inputs, kind)
         es.run(2)
         barrier()
         n_e2e = max(3, min(args.steps, 400))  # the same K steps as the device-resident pass (2.3 ms each: the pipeline's fill and drain
@@ -621,14 +791,21 @@ def main():
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         fma_lane_peak = 148 * 128 * sm_mhz * 1e6                # FP32 FMA lanes/s
         fma_done = b3 * 65 * 65 * 2 * (ITERS - 1)               # two FMA passes over the plan per iteration
+        flops = 2.0 * fma_done / (l3_avg * 1e-3) / 1e12        # useful FP32 work of the scaling iterations, TFLOP/s
+        flops_peak = 2.0 * fma_lane_peak / 1e12                # 148 SMs x 128 FP32 lanes x 2 x f_SM (measured clock of this run)
         roofline = {
             "kernel": "sinkhorn_w65x2_kernel (level-3 OT, two warps per 65x65 problem, %d problems per launch)" % b3,
-            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
-            "peak_source": peak_src, "ms_per_launch": l3_avg, "algorithmic_bytes": alg_bytes,
-            "note": "plan is register-resident: HBM moves only the compulsory read+write, so the streaming-model fraction exceeds 1; "
-                    "the binding resources are FP32 FMA issue and shuffle/SFU latency (see frac_compulsory_hbm, frac_fp32_fma)",
-            "frac_compulsory_hbm": compulsory / (l3_avg * 1e-3) / 1e9 / peak,
-            "frac_fp32_fma": fma_done / (l3_avg * 1e-3) / fma_lane_peak,
+            # The plan is REGISTER-resident for all 100 iterations: HBM carries only the compulsory read + write (7 % of peak), so
+            # the HBM roofline does not bound this kernel.  What does: FP32 issue -- two FFMA passes over the plan per iteration
+            # plus the shuffle/FADD butterflies of the row and column sums (ncu: issue slots 51 %, FMA pipe 44 %).  `frac` is the
+            # useful-FMA fraction of the FP32 peak; the HBM-bound member of the family is under `roofline_streaming`.
+            "bound": "fp32_issue", "achieved": flops, "peak": flops_peak, "unit": "TFLOP/s", "frac": flops / flops_peak,
+            "traffic": ncu_traffic(), "peak_source": "148 SM x 128 FP32 lanes x 2 x SM clock sampled during this run (%.0f MHz)" % sm_mhz,
+            "ms_per_launch": l3_avg, "useful_fma": fma_done,
+            "hbm": {"compulsory_bytes": compulsory, "frac_of_hbm_peak": compulsory / (l3_avg * 1e-3) / 1e9 / peak, "hbm_peak_gbs": peak, "peak_source": peak_src,
+                    "streaming_model_bytes": alg_bytes, "streaming_model_gbs": achieved,
+                    "note": "streaming model (SURVEY.md 8d: one HBM pass per iteration) divided by the launch time exceeds the HBM peak "
+                            "because the kernel does not stream; it is listed for reference only"},
             "share_of_step": l3_avg * args.steps / total_ms,
         }
         # ---- the streaming member of the kernel family against the HBM roofline it is really bound by ------------------
@@ -699,7 +876,7 @@ def main():
             cores = os.cpu_count() or 1
             oracle.set_num_threads(cores)
             torch.set_num_threads(cores)
-            hin = make_inputs(torch, 1, SEED)
+            hin = make_inputs(torch, 1, SEED, kind)
             t0 = time.perf_counter()
             cpu_sample_step(torch, hin, 1.0 / 32, 1.0 / 16)  # warm-up and speed probe
             full = (time.perf_counter() - t0) < 1.0
@@ -710,15 +887,23 @@ def main():
             desc, parts = runs[-1][1], runs[-1][2]
             cpu = {"value": 1.0 / secs, "unit": "pairs/s", "cores": oracle.num_threads(), "kind": "port",
                    "sample": f"mean of {len(runs)} runs of: {desc}", "seconds_per_pair": secs, "parts_s": {k: round(v, 4) for k, v in parts.items()}}
+        fwd = None
+        if world == 1 and not args.no_forward:
+            try:
+                fwd = forward_leg(torch, dev, args)
+            except Exception as e:  # noqa: BLE001  (the leg needs the staged reference Python, oracle/_ref/py)
+                fwd = {"unavailable": f"{type(e).__name__}: {e}"}
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "pats_hot_path_pair640x480", "pairs_per_step": B, "streams": S, "P2": P2, "K3": K3, "sinkhorn_iters": ITERS,
-                       "host_numa": numa,
-                       "l2_flush": "not needed: one step streams > 300 MB of distinct plans per pair (L2 = 126 MB)",
-                       "matches_per_pair": kf // B, "exchange": "all_gather of match lists once after the pair loop (N>1)"},
+            "config": workload_config(B),
+            "run": {"streams": S, "host_numa": numa, "l2_flush": "not needed: one step streams > 300 MB of distinct plans per pair (L2 = 126 MB)",
+                    "matches_per_pair": kf // B, "windows_per_pair": info["windows"] // B, "sinkhorn_fallbacks": info["fallbacks"],
+                    "pairs_per_rank": B * args.steps,
+                    "exchange": "after the pair loop every step's match list of every rank is gathered to rank 0 (2 collectives, 1 host sync); inside the timed region",
+                    "gather_ms": info["gather_ms"], "gather": info["gather"]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_streaming": streaming, "cpu_baseline": cpu, "torch_cuda": torch_cuda,
-            "overlap": overlap,
+            "overlap": overlap, "diffuse": diffuse, "forward": fwd,
         }
         emit(line)
     if world > 1:

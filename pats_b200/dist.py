@@ -19,39 +19,62 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, min(n_items, lo + per)
 
 
-def gather_match_lists(matches: Sequence[torch.Tensor], group=None) -> List[List[torch.Tensor]]:
-    """All-gather per-pair match lists.
+def gather_match_lists(matches: Sequence[torch.Tensor], group=None, max_pairs: int | None = None, dst: int | None = None,
+                       stats: dict | None = None) -> List[List[torch.Tensor]]:
+    """Gather per-pair match lists (the path's ONE exchange: after the pair loop).
 
-    matches: this rank's list of [K_i, D] float tensors (one per local pair; D = 4 for (yl,xl,yr,xr)).
-    Returns, on every rank, a list over ranks of lists of tensors in pair order.
-    Two collectives: the per-pair counts, then one padded payload.
+    matches: this rank's list of [K_i, D] float tensors (one per local pair; D = 4 for (yl,xl,yr,xr)), any K_i >= 0.
+    max_pairs: an upper bound on the pairs per rank that every rank knows without talking (the shard size,
+        `shard_range`); None costs one extra all_reduce to find it.
+    dst: None -> every rank receives everything (all_gather); r -> only rank r does (what evaluate.py needs: metrics are
+        computed in one place), the others get [].
+    Returns a list over ranks of lists of tensors in pair order.
+
+    Exactly two collectives and ONE host synchronisation, whatever the world size: a fixed-size int64 header per rank
+    [n_pairs, K_0 .. K_{max_pairs-1}] (all_gather_into_tensor, read back with a single D2H copy), then one payload padded to
+    the largest rank total.  Nothing here runs inside the pair loop.  `stats` (optional dict) receives payload_bytes, rows.
     """
     world = dist.get_world_size(group)
-    dev = matches[0].device if len(matches) else torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    rank = dist.get_rank(group)
+    nccl = dist.get_backend(group) == "nccl"
+    dev = matches[0].device if len(matches) else (torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu"))
     D = matches[0].shape[1] if len(matches) else 4
-    n_local = torch.tensor([len(matches)], dtype=torch.int64, device=dev)
-    n_all = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(n_all, n_local, group=group)
-    max_pairs = max(int(t.item()) for t in n_all)
-    counts = torch.zeros(max(max_pairs, 1), dtype=torch.int64, device=dev)
+    if max_pairs is None:
+        n_max = torch.tensor([len(matches)], dtype=torch.int64, device=dev)
+        dist.all_reduce(n_max, op=dist.ReduceOp.MAX, group=group)
+        max_pairs = int(n_max.item())
+    if len(matches) > max_pairs:
+        raise ValueError(f"{len(matches)} local pairs exceed max_pairs = {max_pairs}")
+    header = torch.zeros(1 + max_pairs, dtype=torch.int64)
+    header[0] = len(matches)
+    for i, m in enumerate(matches):  # shapes are host integers: no device round trip
+        header[1 + i] = m.shape[0]
+    header = header.to(dev)
+    headers = torch.empty(world * (1 + max_pairs), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(headers, header, group=group)
+    heads = headers.cpu().reshape(world, 1 + max_pairs)  # the one host synchronisation
+    totals = heads[:, 1:].sum(1)
+    max_rows = max(1, int(totals.max()))
+    payload = torch.empty((max_rows, D), dtype=torch.float32, device=dev)
     if len(matches):
-        counts[: len(matches)] = torch.tensor([m.shape[0] for m in matches], dtype=torch.int64, device=dev)
-    counts_all = [torch.zeros_like(counts) for _ in range(world)]
-    dist.all_gather(counts_all, counts, group=group)
-    max_rows = max(1, max(int(c.sum().item()) for c in counts_all))
-    payload = torch.zeros((max_rows, D), dtype=torch.float32, device=dev)
-    if len(matches):
-        cat = torch.cat([m.to(torch.float32) for m in matches], 0)
-        payload[: cat.shape[0]] = cat
-    payload_all = [torch.zeros_like(payload) for _ in range(world)]
-    dist.all_gather(payload_all, payload, group=group)
+        torch.cat([m.to(torch.float32) for m in matches], 0, out=payload[: int(totals[rank])])
+    if stats is not None:
+        stats.update(payload_bytes_per_rank=max_rows * D * 4, rows_local=int(totals[rank]), rows_total=int(totals.sum()), collectives=2, host_syncs=1)
+    if dst is None:
+        recv = torch.empty((world * max_rows, D), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(recv, payload, group=group)
+        parts = recv.reshape(world, max_rows, D)
+    else:
+        parts = [torch.empty_like(payload) for _ in range(world)] if rank == dst else None
+        dist.gather(payload, parts, dst=dst, group=group)
+        if rank != dst:
+            return []
     out = []
     for r in range(world):
-        n = int(n_all[r].item())
-        cs = counts_all[r][:n].tolist()
+        n = int(heads[r, 0])
         rows, off = [], 0
-        for c in cs:
-            rows.append(payload_all[r][off:off + c])
+        for c in heads[r, 1:1 + n].tolist():
+            rows.append(parts[r][off:off + c])
             off += c
         out.append(rows)
     return out

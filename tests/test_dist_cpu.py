@@ -28,7 +28,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_pairs):
+def _worker(rank, world, port, n_pairs, mode="all"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -39,7 +39,17 @@ def _worker(rank, world, port, n_pairs):
             g = torch.Generator().manual_seed(i)
             k = int(torch.randint(0, 50, (1,), generator=g))
             mine.append(torch.rand(k, 4, generator=g))
-        allm = gather_match_lists(mine)
+        stats = {}
+        if mode == "all":
+            allm = gather_match_lists(mine, stats=stats)
+        elif mode == "bounded":  # the shard size is known to every rank: two collectives, no extra reduction
+            allm = gather_match_lists(mine, max_pairs=-(-n_pairs // world), stats=stats)
+        else:  # gather to rank 0 only (evaluate.py computes its metrics in one place)
+            allm = gather_match_lists(mine, max_pairs=-(-n_pairs // world), dst=0, stats=stats)
+            if rank != 0:
+                assert allm == []
+                return
+        assert stats["collectives"] == 2 and stats["host_syncs"] == 1
         assert len(allm) == world
         flat = [m for per_rank in allm for m in per_rank]
         assert len(flat) == n_pairs
@@ -58,6 +68,12 @@ def test_gather_match_lists_gloo_world2():
 
 def test_gather_match_lists_uneven_and_empty_rank():
     mp.spawn(_worker, args=(2, _free_port(), 1), nprocs=2, join=True)
+
+
+def test_gather_match_lists_bounded_header_and_gather_to_rank0():
+    mp.spawn(_worker, args=(2, _free_port(), 7, "bounded"), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), 7, "dst"), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), 0, "bounded"), nprocs=2, join=True)
 
 
 def test_parse_cpulist_and_numa_binding_never_raises():
