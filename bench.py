@@ -542,6 +542,38 @@ def forward_leg(torch, dev, args):
     return out
 
 
+def stress_leg(torch, dev, peak):
+    """BASELINE.json configs[4] ("stress: 1024x1024 pairs, 4096 coarse patches, 200 Sinkhorn iters, 8 x B200"): the level-1 solve of
+    a 1024 x 1024 pair (32 x 32 coarse patches -> one 1025 x 1025 plan, 100 iterations) and the synthetic N = 4096 plan at 200
+    iterations, ONE problem per GPU (under `--gpus 8` every rank solves its own).  Both run the grid-cooperative streaming kernel
+    (csrc/sinkhorn_grid.cu).  Algorithmic bytes as for `roofline_streaming`: 4 (N+1)^2 (iters + 2).  A single plan of these sizes
+    (4 MB / 67 MB) stays in the 126 MB L2 between iterations, so `gbs` may exceed the HBM peak: the bound is L2 / issue, not HBM;
+    `frac_of_hbm_peak` is listed because BASELINE.md section 4 defines the figure that way."""
+    from pats_b200 import modules as M
+
+    out = {}
+    one_d = torch.tensor(1.0, device=dev)
+    for name, N, iters, reps in (("pair1024_L1_1025x1025_it100", 1024, 100, 20), ("N4096_it200", 4096, 200, 5)):
+        g2 = torch.Generator().manual_seed(SEED + N)
+        sc = (0.1 * torch.randn(1, N, N, generator=g2)).to(dev)
+        nss = torch.exp((torch.rand(1, 1, N, generator=g2) * 2 - 1) * math.log(16.0)).to(dev)
+        for _ in range(3):
+            M.log_optimal_transport(sc, one_d, nss, iters)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for e0_, e1_ in evs:
+            e0_.record()
+            M.log_optimal_transport(sc, one_d, nss, iters)
+            e1_.record()
+        torch.cuda.synchronize(dev)
+        ms = sorted(a_.elapsed_time(b_) for a_, b_ in evs)[len(evs) // 2]
+        nbytes = 4 * (N + 1) * (N + 1) * (iters + 2)
+        out[name] = {"ms": ms, "problems_per_s_per_gpu": 1e3 / ms, "algorithmic_bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak, "plan_mb": 4 * (N + 1) * (N + 1) / 1e6}
+        del sc, nss
+    torch.cuda.empty_cache()
+    return out
+
+
 def workload_config(pairs_per_step: int) -> dict:
     """The `config` of BOTH arms (key for key: the driver compares them)."""
     return {"workload": WORKLOAD, "scores": "planted (peaked, area-consistent plans; make_inputs)", "pairs_per_step": pairs_per_step, "P2": P2, "K3": K3,
@@ -735,10 +767,34 @@ def main():
     from pats_b200 import _lib as _l0
 
     _l0.load().pats_sinkhorn_fallback_count(1)
-    total_ms, launches, l3_avg, clocks, info = timed_pass(S, args.steps, True)
+    _l0.load().pats_sinkhorn_iterations_skipped(1)
+    total_ms, launches, l3_avg_exit, clocks, info = timed_pass(S, args.steps, True)
+    skipped = int(_l0.load().pats_sinkhorn_iterations_skipped(1))
     step = steps_by_kind[kind][0]
     kf = info["kf"]
     value = world * B * args.steps / (total_ms * 1e-3)
+    # The same pass with the level-3 kernel's fixed-point exit switched off (every problem runs all 100 iterations): this is the
+    # launch time the roofline is quoted on (its useful-FMA count assumes every iteration), and the number to compare with round 1.
+    _l0.load().pats_sinkhorn_fixed_point_exit(0)
+    try:
+        n_full = max(3, min(args.steps, 40))
+        full_ms, _, l3_avg, _, _ = timed_pass(S, n_full, False)
+    finally:
+        _l0.load().pats_sinkhorn_fixed_point_exit(1)
+    # ... and with the level-3 problems loaded / stored by plain LDG / STG instead of the bulk-copy (TMA engine) staging
+    _l0.load().pats_sinkhorn_bulk_staging(0)
+    try:
+        direct_ms, _, l3_direct, _, _ = timed_pass(S, n_full, False)
+    finally:
+        _l0.load().pats_sinkhorn_bulk_staging(1)
+    bulk = {"enabled": True, "what": "65x65 problems staged by one cp.async.bulk of their 16-byte aligned superset (mbarrier), result formed in place, one bulk "
+                                     "store; persistent CTAs; bit-identical (tests/test_gpu_ot.py::test_bulk_staging_is_bit_identical)",
+            "l3_ms_per_launch": l3_avg_exit, "l3_ms_per_launch_direct_loads": l3_direct, "value_direct_loads": world * B * n_full / (direct_ms * 1e-3)}
+    fp_exit = {"enabled": True, "what": "65x65 kernel leaves its loop at a bitwise fixed point of beta; results identical to the full 100 iterations "
+                                        "(tests/test_gpu_ot.py::test_fixed_point_exit_is_bit_identical)",
+               "iters_executed_mean": ITERS - skipped / float(B * K3 * (args.steps + max(args.warmup, S))),
+               "l3_ms_per_launch": l3_avg_exit, "l3_ms_per_launch_without_exit": l3_avg,
+               "value_without_exit": world * B * n_full / (full_ms * 1e-3), "ms_per_step_without_exit": full_ms / n_full}
     overlap = None
     if S == 1 and not args.no_overlap:
         o_ms, _, _, _, _ = timed_pass(2, args.steps, False)
@@ -806,7 +862,8 @@ def main():
                     "streaming_model_bytes": alg_bytes, "streaming_model_gbs": achieved,
                     "note": "streaming model (SURVEY.md 8d: one HBM pass per iteration) divided by the launch time exceeds the HBM peak "
                             "because the kernel does not stream; it is listed for reference only"},
-            "share_of_step": l3_avg * args.steps / total_ms,
+            "share_of_step": l3_avg * n_full / full_ms,
+            "timed": "with the fixed-point exit OFF (all 100 iterations of every problem); see `fixed_point_exit` for the default",
         }
         # ---- the streaming member of the kernel family against the HBM roofline it is really bound by ------------------
         # BASELINE.json configs[2]: b = 32, N = 1536 (-> 1537 x 1537 plans, 302 MB in + 302 MB out: nothing fits on chip,
@@ -836,6 +893,9 @@ def main():
                          "algorithmic_bytes": bytes_s, "traffic": ncu_traffic("grid_dram_bytes_per_launch")}
             del sc, nss
             torch.cuda.empty_cache()
+        stress = None
+        if not args.no_streaming:
+            stress = stress_leg(torch, dev, peak)
         # ---- the reference's own formulation (log-domain, ~6 ATen ops per iteration: modules.py:137-182) on this GPU -------
         torch_cuda = None
         if world == 1 and not args.no_torch_baseline:
@@ -902,8 +962,8 @@ def main():
                     "pairs_per_rank": B * args.steps,
                     "exchange": "after the pair loop every step's match list of every rank is gathered to rank 0 (2 collectives, 1 host sync); inside the timed region",
                     "gather_ms": info["gather_ms"], "gather": info["gather"]},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_streaming": streaming, "cpu_baseline": cpu, "torch_cuda": torch_cuda,
-            "overlap": overlap, "diffuse": diffuse, "forward": fwd,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_streaming": streaming, "stress": stress, "cpu_baseline": cpu, "torch_cuda": torch_cuda,
+            "fixed_point_exit": fp_exit, "bulk_staging": bulk, "overlap": overlap, "diffuse": diffuse, "forward": fwd,
         }
         emit(line)
     if world > 1:

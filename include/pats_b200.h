@@ -94,6 +94,20 @@ void pats_sinkhorn_cluster_variant(int v);
  * (device counter, read with a synchronising copy; tests / diagnostics only). */
 int pats_sinkhorn_fallback_count(int reset);
 
+/* Fixed-point exit of the 65 x 65 kernel (default on).  log_sinkhorn_iterations (models/modules.py:139-142) runs a FIXED
+ * number of iterations; once a whole iteration leaves every beta_j bit-identical, all remaining iterations replay it and cannot
+ * change the result, so the kernel leaves its loop there.  The output is bit-identical to running all `iters` iterations
+ * (tests/test_gpu_ot.py::test_fixed_point_exit_is_bit_identical).  on = 0: always run every iteration.
+ * pats_sinkhorn_iterations_skipped: problem-iterations not executed since the last reset (device counter, synchronising read). */
+void pats_sinkhorn_fixed_point_exit(int on);
+
+/* Bulk-copy (TMA engine) staging of the 65 x 65 problems: persistent CTAs, one cp.async.bulk of each problem's 16-byte aligned
+ * superset into shared memory (completing on an mbarrier), the result formed in place and written back with one bulk store.
+ * Bit-identical to the direct kernel and 9 - 12 % faster (profiles/r02_ab_bulk_staging.json), so it is the default; 0 = direct
+ * loads (also taken automatically for log_optimal_transport's un-augmented input and for buffers that are not 16-byte aligned). */
+void pats_sinkhorn_bulk_staging(int on);
+long long pats_sinkhorn_iterations_skipped(int reset);
+
 /* HOST-buffer variants (end-to-end path: H2D, solve, D2H, synchronise). alpha / one by value. */
 int pats_log_optimal_transport_f32_host(const float *scores, float alpha, const float *ns, int b, int m, int n,
                                         int iters, float *out);

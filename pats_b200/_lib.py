@@ -35,6 +35,9 @@ SIGNATURES = {
     "pats_sinkhorn_disable_c145": [_I],
     "pats_sinkhorn_cluster_variant": [_I],
     "pats_sinkhorn_fallback_count": [_I],
+    "pats_sinkhorn_fixed_point_exit": [_I],
+    "pats_sinkhorn_bulk_staging": [_I],
+    "pats_sinkhorn_iterations_skipped": [_I],
     "pats_log_optimal_transport_f32_host": [_P, _F, _P, _I, _I, _I, _I, _P],
     "pats_log_optimal_transport2_f32_host": [_P, _F, _P, _I, _I, _I, _I, _P],
     "pats_tensor_resize_f32": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P],
@@ -56,7 +59,7 @@ SIGNATURES = {
     "pats_second_layer_match_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "pats_third_layer_match_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
 }
-_RESTYPE = {"pats_last_error": C.c_char_p, "pats_sinkhorn_force_generic": None, "pats_plan_handover": None, "pats_launch_chaining": None, "pats_sinkhorn_disable_w65": None, "pats_sinkhorn_disable_c145": None, "pats_sinkhorn_cluster_variant": None, "pats_sinkhorn_grid_ctas_per_problem": None, "pats_sinkhorn_grid_variant": None}
+_RESTYPE = {"pats_last_error": C.c_char_p, "pats_sinkhorn_bulk_staging": None, "pats_sinkhorn_fixed_point_exit": None, "pats_sinkhorn_iterations_skipped": C.c_longlong, "pats_sinkhorn_force_generic": None, "pats_plan_handover": None, "pats_launch_chaining": None, "pats_sinkhorn_disable_w65": None, "pats_sinkhorn_disable_c145": None, "pats_sinkhorn_cluster_variant": None, "pats_sinkhorn_grid_ctas_per_problem": None, "pats_sinkhorn_grid_variant": None}
 
 
 def library_path() -> str:

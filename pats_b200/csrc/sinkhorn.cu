@@ -793,22 +793,75 @@ __device__ __forceinline__ void ag_cols8(float (&v)[8]) {  // all-gather over pr
     for (int t = 0; t < 4; ++t) v[t + 4] = __shfl_xor_sync(0xffffffffu, v[t], 4);
 }
 
+// ---- bulk-copy (TMA engine) staging of a whole problem ----------------------------------------------------------------
+// A [b,65,65] plan is 16 900 B per problem: problem starts are only 4-byte aligned, so neither a tiled tensor map nor an exact
+// 1-D bulk copy applies (both need 16-byte aligned addresses and sizes).  The BULK variant copies the ALIGNED SUPERSET of the
+// problem -- [start & ~15, (end + 15) & ~15), at most 16 928 B -- into a 16-byte aligned shared buffer with ONE
+// cp.async.bulk (SASS UBLKCP) that completes on an mbarrier; element e of the problem then sits at float index
+// `sh + e`, sh = (start >> 2) & 3.  The result is formed IN PLACE in that buffer and leaves with one cp.async.bulk store
+// of the aligned interior (plus <= 3 + 3 scalar stores for the unaligned head / tail).  CTAs are persistent: the load of
+// the CTA's next problem is issued as soon as the store has read the buffer.
+constexpr int X2_STAGE_FLOATS = 4232 + 8;  // 16 928 B superset + slack, in floats
+__device__ __forceinline__ void bulk_load(unsigned dst_smem, const void *src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+                 "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, unsigned src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+
+template <bool BULK>
 __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_kernel(SinkArgs a) {
     constexpr int D = 64;
-    __shared__ float s_x[X2_PAIRS][2][2][68];  // [pair][parity][warp]: 64 owned-row values + scalars
+    static_assert(!BULK || X2_PAIRS == 1, "the bulk-copy variant stages one problem per CTA");
+    __shared__ __align__(16) float s_x[X2_PAIRS][2][2][68];  // [pair][parity][warp]: 64 owned-row values + scalars (64, 65: one float2)
     __shared__ float s_fb[X2_PAIRS][65 + 65 + 128];
+    __shared__ __align__(128) float s_stage[BULK ? X2_STAGE_FLOATS : 4];
+    __shared__ __align__(8) unsigned long long s_mbar;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int pair = wib >> 1, w = wib & 1;
-    const int p = blockIdx.x * X2_PAIRS + pair;
-    pdl_prologue();
-    if (p >= a.b) return;  // uniform over the pair; the named barrier below involves this pair only
+    // Launch chaining (common.cuh).  The persistent variant lets the next grid in only when a CTA begins its LAST problem: a
+    // hand-over consumer that became resident at the start would spin on its flag for the whole solve, next to the producers.
+    if constexpr (BULK) pdl_wait();
+    else pdl_prologue();
     const PairSync psync{1 + pair};
     const int pr = lane >> 2, qc = lane & 3;
     const int rmask = ((qc & 1) << 2) | ((qc >> 1) << 1);
     const int cmask = ((pr & 1) << 2) | (((pr >> 1) & 1) << 1) | (pr >> 2);
-    const Marg g = problem_marginals(a, p, lane);
 #define LROW(k) (pr + 8 * ((k) ^ rmask))
 #define LCOL(c) (32 * w + qc + 4 * ((c) ^ cmask))
+    [[maybe_unused]] unsigned mb = 0, stage_u32 = 0, phase = 0;
+    // first float of the aligned superset of problem q, its length in bytes, and the problem's offset inside it (floats)
+    auto superset = [&](int q, const float *&src, unsigned &bytes) {
+        const uintptr_t s0 = reinterpret_cast<uintptr_t>(a.Z + (size_t)q * 4225), e0 = s0 + 16900;
+        src = reinterpret_cast<const float *>(s0 & ~(uintptr_t)15);
+        bytes = (unsigned)(((e0 + 15) & ~(uintptr_t)15) - (s0 & ~(uintptr_t)15));
+        return (int)((s0 & 15) >> 2);
+    };
+    if constexpr (BULK) {
+        mb = smem_u32(&s_mbar), stage_u32 = smem_u32(s_stage);
+        if (threadIdx.x == 0) {
+            mbar_init(mb, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if ((int)blockIdx.x < a.b) {
+                const float *src;
+                unsigned bytes;
+                superset((int)blockIdx.x, src, bytes);
+                mbar_expect_tx(mb, bytes);
+                bulk_load(stage_u32, src, bytes, mb);
+            }
+        }
+        psync();
+    }
+    int p = BULK ? (int)blockIdx.x : (int)blockIdx.x * X2_PAIRS + pair;
+    if (p >= a.b) return;  // uniform over the pair; the named barrier involves this pair only
+    do {  // BULK: the problems of this persistent CTA; otherwise exactly one pass
+    if constexpr (BULK) {
+        if (p + (int)gridDim.x >= a.b) pdl_launch_dependents();
+    }
+    const Marg g = problem_marginals(a, p, lane);
     int par = 0;
     // exchange the two owned-row values and one scalar with the partner warp (double-buffered by parity).
     // (Precomputing the six smem addresses was measured SLOWER: +9% at 153.6 k problems -- more live registers.)
@@ -824,13 +877,47 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
         (osc) = oth_[64];                                                \
         par ^= 1;                                                        \
     } while (0)
+    // the loop's exchange: one more scalar (the fixed-point vote of the previous iteration) in the same barrier phase
+#define PAIR_XCHG_IT(v0, v1, sc, fx, o0, o1, osc, ofx)                   \
+    do {                                                                 \
+        float *mine_ = s_x[pair][par][w], *oth_ = s_x[pair][par][w ^ 1]; \
+        mine_[LROW(0)] = (v0);                                           \
+        mine_[LROW(1)] = (v1);                                           \
+        if (lane == 0) *reinterpret_cast<float2 *>(mine_ + 64) = make_float2((sc), (fx)); \
+        psync();                                                         \
+        (o0) = oth_[LROW(0)];                                            \
+        (o1) = oth_[LROW(1)];                                            \
+        {                                                                \
+            const float2 t_ = *reinterpret_cast<const float2 *>(oth_ + 64); \
+            (osc) = t_.x, (ofx) = t_.y;                                  \
+        }                                                                \
+        par ^= 1;                                                        \
+    } while (0)
 
     // ---- load ------------------------------------------------------------------------------------------------------
     float z[8][8], zc[2], zr, zcorner;
-#ifdef PATS_AB_RS2
-    float zr2;
-#endif
-    {
+    [[maybe_unused]] int sh = 0;
+    if constexpr (BULK) {
+        const float *src_;
+        unsigned bytes_;
+        sh = superset(p, src_, bytes_);
+        mbar_wait(mb, phase);  // the problem has landed in s_stage
+        phase ^= 1u;
+        const float *zs = s_stage + sh;
+        int coff[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) coff[c] = LCOL(c);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int roff = LROW(k) * 65;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) z[k][c] = zs[roff + coff[c]];
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) zc[t] = zs[LROW(t) * 65 + D];
+        zr = zs[D * 65 + LCOL(0)];
+        zcorner = zs[D * 65 + D];
+    } else {
         const PlanRef pl = plan_ref(a, g, p);
         int coff[8];
 #pragma unroll
@@ -845,18 +932,11 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
         for (int t = 0; t < 2; ++t) zc[t] = pl.edge(LROW(t), D);
         zr = pl.edge(D, LCOL(0));  // dustbin-row entry of the one column this lane owns
         zcorner = pl.edge(D, D);
-#ifdef PATS_AB_RS2
-        zr2 = pl.edge(D, LCOL(1));  // ... and of its twin's (lane ^ 16) column, finished redundantly by both (see the loop)
-#endif
     }
     float mu2[2];
 #pragma unroll
     for (int t = 0; t < 2; ++t) mu2[t] = expf(lmu_at(a, g, p, LROW(t)));
     const float nu1 = expf(lnu_at(a, g, p, LCOL(0)));
-#ifdef PATS_AB_RS2
-    const float nu1b = expf(lnu_at(a, g, p, LCOL(1)));
-    float Drb = 0.f;
-#endif
     const float mud = expf(lmu_at(a, g, p, D)), nud = expf(lnu_at(a, g, p, D));
     float u1o[2] = {0.f, 0.f}, v1o = 0.f, u1d = 0.f, v1d = 0.f;
     float Dc[2] = {0.f, 0.f}, Dr = 0.f, corner = 0.f;
@@ -888,9 +968,6 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
             for (int c = 0; c < 8; ++c) z[k][c] = fast_exp(z[k][c]);
         Dc[0] = fast_exp(zc[0]), Dc[1] = fast_exp(zc[1]);
         Dr = fast_exp(zr);
-#ifdef PATS_AB_RS2
-        Drb = fast_exp(zr2);
-#endif
         corner = fast_exp(zcorner);
     } else
 #endif
@@ -967,9 +1044,6 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
             u1o[t] = u1[t];
         }
         Dr = fast_exp((zr + u1d) + v1[0]);
-#ifdef PATS_AB_RS2
-        Drb = fast_exp((zr2 + u1d) + v1[1]);
-#endif
         v1o = v1[0];
         corner = fast_exp((zcorner + u1d) + v1d);
     }
@@ -997,6 +1071,11 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
     float Srp = warp_sum(Dr);  // this warp's half of sum_j K[D][j] beta_j
 #endif
     float lo = INFINITY, hi = 0.f;
+    // Fixed-point exit (SinkArgs::fp_exit).  beta_t == beta_{t-1} bit for bit -- every column of both warps and the dustbin -- makes
+    // iteration t+1 a replay of iteration t (same operands through the same instructions), and so every later one: the remaining
+    // iterations cannot change a bit of the result.  The vote of iteration t travels with iteration t+1's row exchange; the
+    // pair then finishes that iteration's alpha update (identical to iteration t's by the same argument) and leaves.
+    float pbe0 = 0.f, pbed = 0.f, fix = 0.f;  // a beta is never 0, so the first comparison fails
 
     for (int it = it0; it < a.iters; ++it) {
         float2 acc[8];
@@ -1014,11 +1093,17 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
 #pragma unroll
         for (int k = 0; k < 8; ++k) al[k] = acc[k].x + acc[k].y;
         rs_rows(al);
-        float o0, o1, oS;
-        PAIR_XCHG(al[0], al[1], Srp, o0, o1, oS);
+        float o0, o1, oS, ofix;
+        PAIR_XCHG_IT(al[0], al[1], Srp, fix, o0, o1, oS, ofix);
         al[0] = mu2[0] * fast_rcp(fmaf(Dc[0], bed, al[0] + o0));
         al[1] = mu2[1] * fast_rcp(fmaf(Dc[1], bed, al[1] + o1));
         ald = mud * fast_rcp(fmaf(corner, bed, Srp + oS));
+        if (fix != 0.f && ofix != 0.f) {  // both warps: beta did not change in the previous iteration
+            lo = fminf(fminf(fminf(lo, al[0]), fminf(al[1], ald)), fminf(be[0], bed));  // the sample the last iteration would have taken
+            hi = fmaxf(fmaxf(fmaxf(hi, al[0]), fmaxf(al[1], ald)), fmaxf(be[0], bed));
+            if (w == 0 && lane == 0 && a.fb_total) atomicAdd(a.fb_total + 1, a.iters - it);  // iterations not executed
+            break;
+        }
         // (deferring this butterfly and the beta_D update into the next row pass as well was measured 2.7 % SLOWER: beta_D's
         // reciprocal then sits in front of the alpha update)
         const float Sc = warp_sum(fmaf(Dc[0], al[0], Dc[1] * al[1]));
@@ -1034,25 +1119,11 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) be[2 * h] = s2[h].x, be[2 * h + 1] = s2[h].y;
-#ifdef PATS_AB_RS2
-        // reduce-scatter 8 -> 2 over lane bits 2, 3, then ONE all-reduce level over bit 4: the twins (lane, lane ^ 16) finish the
-        // same two columns redundantly (one more reciprocal), and the gather below starts from two slots -- a SHFL level less
-        // in each direction.  Operands are the base version's (a + b == b + a), so the betas are bit-identical.
-#pragma unroll
-        for (int t = 0; t < 4; ++t) be[t] += __shfl_xor_sync(0xffffffffu, be[t + 4], 4);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) be[t] += __shfl_xor_sync(0xffffffffu, be[t + 2], 8);
-        {
-            const float x0 = be[0] + __shfl_xor_sync(0xffffffffu, be[1], 16);
-            const float x1 = be[1] + __shfl_xor_sync(0xffffffffu, be[0], 16);
-            be[0] = nu1 * fast_rcp(fmaf(Dr, ald, x0));
-            be[1] = nu1b * fast_rcp(fmaf(Drb, ald, x1));
-        }
-#else
         rs_cols8_op(be, OpSum());
         be[0] = nu1 * fast_rcp(fmaf(Dr, ald, be[0]));
-#endif
         bed = nud * fast_rcp(fmaf(corner, ald, Sc));
+        fix = (a.fp_exit && __all_sync(0xffffffffu, be[0] == pbe0 && bed == pbed)) ? 1.f : 0.f;
+        pbe0 = be[0], pbed = bed;
 #ifndef PATS_AB_NO_PIPE_SRP
         Srp = Dr * be[0];
         Srp += __shfl_xor_sync(0xffffffffu, Srp, 16);
@@ -1064,14 +1135,7 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
             lo = fminf(fminf(fminf(lo, al[0]), fminf(al[1], ald)), fminf(be[0], bed));
             hi = fmaxf(fmaxf(fmaxf(hi, al[0]), fmaxf(al[1], ald)), fmaxf(be[0], bed));
         }
-#ifdef PATS_AB_RS2
-#pragma unroll
-        for (int t = 0; t < 2; ++t) be[t + 2] = __shfl_xor_sync(0xffffffffu, be[t], 8);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) be[t + 4] = __shfl_xor_sync(0xffffffffu, be[t], 4);
-#else
         ag_cols8(be);
-#endif
     }
 
     // ---- potentials, health check (agreed over the pair), output -----------------------------------------------------------
@@ -1112,38 +1176,89 @@ __global__ void __launch_bounds__(X2_PAIRS * 64, X2_MIN_CTAS) sinkhorn_w65x2_ker
         log_domain_solve<64>(a, g, p, s_fb[pair], s_fb[pair] + 65, s_fb[pair] + 130, w * 32 + lane, psync);
         psync();
         if (w == 0 && lane == 0) publish_problem(a, p);
-        return;
-    }
-    ag_rows(U);
-    ag_cols8(V);
-    float *o = a.out + (size_t)p * 65 * 65;
-    const PlanRef pl = plan_ref(a, g, opaque(p));  // recomputed: keeping the load-time copy alive costs registers in the loop
-    {
-        int coff[8];
+    } else {
+        ag_rows(U);
+        ag_cols8(V);
+        float *o = a.out + (size_t)p * 65 * 65;
+        if constexpr (BULK) {
+            // the result is formed in place in the staged copy (same expressions as the direct path: bit-identical) ...
+            float *zs = s_stage + sh;
+            int coff[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) coff[c] = LCOL(c);
+            for (int c = 0; c < 8; ++c) coff[c] = LCOL(c);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int row = LROW(k);
-            const int roff = row * pl.stride;
-            float zz[8];
+            for (int k = 0; k < 8; ++k) {
+                const int row = LROW(k);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) zz[c] = pl.core(roff, coff[c]);  // all eight loads of the row in flight (L2 hits)
+                for (int c = 0; c < 8; ++c) zs[row * 65 + coff[c]] = (zs[row * 65 + coff[c]] + U[k]) + V[c];
+                if (w == 0 && qc == 0) zs[row * 65 + D] = (zs[row * 65 + D] + U[k]) + Vd;
+            }
+            if (pr == 0) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) o[row * 65 + coff[c]] = (zz[c] + U[k]) + V[c];
-            if (w == 0 && qc == 0) o[row * 65 + D] = (pl.edge(row, D) + U[k]) + Vd;
+                for (int c = 0; c < 8; ++c) zs[D * 65 + coff[c]] = (zs[D * 65 + coff[c]] + Ud) + V[c];
+            }
+            if (w == 0 && lane == 0) zs[D * 65 + D] = (zs[D * 65 + D] + Ud) + Vd;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk store
+            psync();
+            // ... and leaves with ONE bulk store of its 16-byte aligned interior; <= 3 floats on either side go by hand.  (The host
+            // only picks this variant when input and output share their alignment phase, so the interior is aligned on both sides.)
+            if (threadIdx.x == 0) {
+                const int head = (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(o) & 15)) & 15u) >> 2);
+                const int body = (4225 - head) & ~3;
+                for (int e = 0; e < head; ++e) o[e] = zs[e];
+                for (int e = head + body; e < 4225; ++e) o[e] = zs[e];
+                bulk_store(o + head, stage_u32 + 4u * (unsigned)(sh + head), (unsigned)body * 4u);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (a.done) {
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // written, not just read: a consumer is waiting on the flag
+                    publish_problem(a, p);
+                } else {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the buffer may be overwritten
+                }
+            }
+        } else {
+            const PlanRef pl = plan_ref(a, g, opaque(p));  // recomputed: keeping the load-time copy alive costs registers in the loop
+            int coff[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) coff[c] = LCOL(c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int row = LROW(k);
+                const int roff = row * pl.stride;
+                float zz[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) zz[c] = pl.core(roff, coff[c]);  // all eight loads of the row in flight (L2 hits)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o[row * 65 + coff[c]] = (zz[c] + U[k]) + V[c];
+                if (w == 0 && qc == 0) o[row * 65 + D] = (pl.edge(row, D) + U[k]) + Vd;
+            }
+            if (pr == 0) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o[D * 65 + coff[c]] = (pl.edge(D, coff[c]) + Ud) + V[c];
+            }
+            if (w == 0 && lane == 0) o[D * 65 + D] = (pl.edge(D, D) + Ud) + Vd;
+            if (a.done) {  // both warps of the pair have stored their halves
+                psync();
+                if (w == 0 && lane == 0) publish_problem(a, p);
+            }
         }
-        if (pr == 0) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) o[D * 65 + coff[c]] = (pl.edge(D, coff[c]) + Ud) + V[c];
+    }
+    if constexpr (BULK) {  // stage the CTA's next problem (the buffer is free: every thread passed the barrier above)
+        if (threadIdx.x == 0) {
+            const int q = p + (int)gridDim.x;
+            if (q < a.b) {
+                const float *src;
+                unsigned bytes;
+                superset(q, src, bytes);
+                mbar_expect_tx(mb, bytes);
+                bulk_load(stage_u32, src, bytes, mb);
+            }
         }
     }
-    if (w == 0 && lane == 0) o[D * 65 + D] = (pl.edge(D, D) + Ud) + Vd;
-    if (a.done) {  // both warps of the pair have stored their halves
-        psync();
-        if (w == 0 && lane == 0) publish_problem(a, p);
-    }
+    if constexpr (BULK) p += (int)gridDim.x;
+    } while (BULK && p < a.b);
 #undef PAIR_XCHG
+#undef PAIR_XCHG_IT
 #undef LROW
 #undef LCOL
 }
@@ -1796,6 +1911,8 @@ static int g_disable_c145 = 0;  // 145 x 145 routing: 0 = 8-warp kernel, two CTA
                                 //                    2 = 9-warp kernel
 static int g_disable_w65 = 0;  // 65 x 65 routing: 0 = two warps per problem (default), 1 = padded 72 x 68 warp kernel,
                                //                  2 / 3 = one-warp 65 x 65 kernel at 2 / 3 CTAs per SM (tests / A-B timing)
+static int g_bulk_staging = 1;  // pats_sinkhorn_bulk_staging(): 65 x 65 problems staged by cp.async.bulk (persistent CTAs); 0 = direct loads
+static int g_fp_exit = 1;  // pats_sinkhorn_fixed_point_exit(): 65 x 65 kernel leaves its loop at a bitwise fixed point (results identical)
 static int *g_fb_total[kMaxDevices];  // per device: counter of problems that took the log-domain fallback
 static std::mutex g_mu;
 
@@ -1804,8 +1921,8 @@ static int ensure_counter(int **counter) {
     if (dev < 0) return PATS_E_CUDA;
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_fb_total[dev]) {
-        PATS_CUDA_TRY(cudaMalloc(&g_fb_total[dev], sizeof(int)));
-        PATS_CUDA_TRY(cudaMemset(g_fb_total[dev], 0, sizeof(int)));
+        PATS_CUDA_TRY(cudaMalloc(&g_fb_total[dev], 2 * sizeof(int)));  // [0] fallbacks, [1] iterations skipped by the fixed-point exit
+        PATS_CUDA_TRY(cudaMemset(g_fb_total[dev], 0, 2 * sizeof(int)));
     }
     *counter = g_fb_total[dev];
     return PATS_OK;
@@ -1987,6 +2104,7 @@ static int run_sinkhorn(SinkArgs a, void *stream, bool publish = false, const un
     if ((long long)a.M * a.N > 0x7fffffffLL / 2) return invalid("sinkhorn: problem too large");
     int rc = ensure_counter(&a.fb_total);
     if (rc) return rc;
+    a.fp_exit = g_fp_exit;
     cudaStream_t st = as_stream(stream);
     const bool c145b = kernel_kind(a.M, a.N) == 1 && a.M == 145 && a.N == 145 && g_disable_c145 == 0;
     if (a.edge_add != 0.f && !c145b && kernel_kind(a.M, a.N) != 2) {  // kernels without the edge epilogue: solve, then one more pass
@@ -2003,7 +2121,31 @@ static int run_sinkhorn(SinkArgs a, void *stream, bool publish = false, const un
         case 0:
             if (a.M == 65 && a.N == 65 && g_disable_w65 == 0) {
                 if (publish) a.done = handover_begin(st, a.b, &a.epoch);
-                PATS_CUDA_TRY(launch_chained(sinkhorn_w65x2_kernel, dim3((a.b + X2_PAIRS - 1) / X2_PAIRS), dim3(X2_PAIRS * 64), 0, st, a));
+                // bulk-copy staging (pats_sinkhorn_bulk_staging): contiguous [b,65,65] problems whose input and output share their
+                // 16-byte phase; a trailing problem whose aligned superset would reach past the tensor goes through the direct kernel
+                const bool bulk_ok = g_bulk_staging && X2_PAIRS == 1 && a.mode != MODE_OT && (reinterpret_cast<uintptr_t>(a.Z) & 15) == 0 &&
+                                     (reinterpret_cast<uintptr_t>(a.out) & 15) == 0;
+                if (bulk_ok) {
+                    const int tail = (a.b % 4 != 0) ? 1 : 0, main_b = a.b - tail;
+                    if (main_b > 0) {
+                        SinkArgs m = a;
+                        m.b = main_b;
+                        const int sms = sm_count() > 0 ? sm_count() : 148;
+                        const int grid = main_b < sms * X2_MIN_CTAS ? main_b : sms * X2_MIN_CTAS;
+                        PATS_CUDA_TRY(launch_chained(sinkhorn_w65x2_kernel<true>, dim3(grid), dim3(64), 0, st, m));
+                    }
+                    if (tail) {
+                        SinkArgs t = a;  // the last problem alone, flags and all
+                        const size_t off = (size_t)main_b;
+                        t.Z = a.Z + off * 4225, t.out = a.out + off * 4225, t.ns = a.ns ? a.ns + off * 64 : nullptr;
+                        t.log_mu = a.log_mu ? a.log_mu + off * 65 : nullptr, t.log_nu = a.log_nu ? a.log_nu + off * 65 : nullptr;
+                        t.done = a.done ? a.done + off : nullptr;
+                        t.b = 1;
+                        PATS_CUDA_TRY(launch_chained(sinkhorn_w65x2_kernel<false>, dim3(1), dim3(X2_PAIRS * 64), 0, st, t));
+                    }
+                    return PATS_OK;
+                }
+                PATS_CUDA_TRY(launch_chained(sinkhorn_w65x2_kernel<false>, dim3((a.b + X2_PAIRS - 1) / X2_PAIRS), dim3(X2_PAIRS * 64), 0, st, a));
                 return PATS_OK;
             }
             if (a.M == 65 && a.N == 65 && (g_disable_w65 == 2 || g_disable_w65 == 3)) {
@@ -2086,6 +2228,18 @@ int sinkhorn_ot2_publish(const float *scores, const float *one, const float *ns,
 PATS_API void pats_sinkhorn_cluster_variant(int v) { g_cluster_variant = (v >= 0 && v <= 4) ? v : 0; }
 PATS_API void pats_sinkhorn_disable_c145(int mode) { g_disable_c145 = (mode >= 0 && mode <= 2) ? mode : 0; }
 PATS_API void pats_sinkhorn_disable_w65(int mode) { g_disable_w65 = (mode >= 0 && mode <= 3) ? mode : 0; }
+
+PATS_API void pats_sinkhorn_fixed_point_exit(int on) { g_fp_exit = on ? 1 : 0; }
+PATS_API void pats_sinkhorn_bulk_staging(int on) { g_bulk_staging = on ? 1 : 0; }
+
+PATS_API long long pats_sinkhorn_iterations_skipped(int reset) {
+    int *counter = nullptr;  // of the current device
+    if (ensure_counter(&counter) != PATS_OK) return -1;
+    int v = 0;
+    if (cudaMemcpy(&v, counter + 1, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (reset) cudaMemset(counter + 1, 0, sizeof(int));
+    return (long long)v;
+}
 
 PATS_API int pats_sinkhorn_fallback_count(int reset) {
     int *counter = nullptr;  // of the current device

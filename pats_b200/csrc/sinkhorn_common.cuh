@@ -25,6 +25,7 @@ struct SinkArgs {
     // place right after the solve; the corner gets it twice).  Only the 145 x 145 kernel and the log-domain solver apply
     // it in their epilogue; run_sinkhorn() covers the other kernels with a separate pass.
     float edge_add;
+    int fp_exit;  // 65 x 65 kernel: leave the iteration loop at a bitwise fixed point of beta (bit-identical results; fb_total[1] counts the skipped iterations)
 };
 
 struct Marg {

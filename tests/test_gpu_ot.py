@@ -288,6 +288,96 @@ def test_cluster_kernel_fallback(M, lib, dev):
     assert n_fb == 1
 
 
+def _peaked(g, b, gw, peak, floor):
+    """[b, gw*gw+1, gw*gw+1]: affinity of a random affine warp of a gw x gw grid + dustbin row / column (plans a trained matcher produces)."""
+    n = gw * gw
+    ys, xs = torch.meshgrid(torch.arange(gw).float(), torch.arange(gw).float(), indexing="ij")
+    src = torch.stack([ys.reshape(-1), xs.reshape(-1)], 1)
+    A = torch.eye(2)[None] * (0.6 + 0.8 * torch.rand(b, 1, 1, generator=g)) + 0.1 * torch.randn(b, 2, 2, generator=g)
+    w = (src - gw / 2.0) @ A.transpose(1, 2) + gw / 2.0 + torch.randn(b, 1, 2, generator=g) * (0.12 * gw)
+    d2 = ((w[:, :, None, :] - src[None, None, :, :]) ** 2).sum(-1)
+    out = torch.empty(b, n + 1, n + 1)
+    out[:, :n, :n] = (peak - d2 / 1.5 + 0.3 * torch.randn(b, n, n, generator=g)).clamp_min(floor)
+    out[:, n, :] = -1.0 + 0.3 * torch.randn(b, n + 1, generator=g)
+    out[:, :, n] = -1.0 + 0.3 * torch.randn(b, n + 1, generator=g)
+    return out
+
+
+@pytest.mark.parametrize("kind", ["peaked_direct", "peaked_log_start", "diffuse", "ill_conditioned", "few_iterations"])
+def test_fixed_point_exit_is_bit_identical(M, lib, dev, kind):
+    """The 65 x 65 kernel leaves its loop once a whole iteration left every beta bit-identical (pats_sinkhorn_fixed_point_exit).
+    The reference runs a fixed 100 iterations (models/modules.py:139-142), so the exit is only legitimate if the result is
+    IDENTICAL, bit for bit, to running all of them -- on every kind of input, including problems that never converge, problems
+    that start in the log domain and problems that end in the log-domain fallback."""
+    g = torch.Generator().manual_seed(77)
+    b, iters = 1500, 100
+    if kind == "peaked_direct":
+        s = _peaked(g, b, 8, 7.0, -10.0)          # |z| <= 12: direct start
+    elif kind == "peaked_log_start":
+        s = _peaked(g, b, 8, 14.0, -25.0)         # log-domain first iteration
+    elif kind == "diffuse":
+        s = 0.1 * torch.randn(b, 65, 65, generator=g)
+    elif kind == "ill_conditioned":
+        s = 40.0 * torch.randn(b, 65, 65, generator=g)   # most problems end in the fallback
+    else:
+        s, iters = _peaked(g, b, 8, 7.0, -10.0), 7
+    ns = areas(g, b, 64, 4.0).to(dev)
+    s = s.to(dev)
+    one = torch.tensor(1.0, device=dev)
+    try:
+        lib.pats_sinkhorn_fixed_point_exit(0)
+        lib.pats_sinkhorn_iterations_skipped(1)
+        full = M.log_optimal_transport2(s, one, ns, iters)
+        torch.cuda.synchronize()
+        assert lib.pats_sinkhorn_iterations_skipped(1) == 0, "exit disabled, yet iterations were skipped"
+        lib.pats_sinkhorn_fixed_point_exit(1)
+        fast = M.log_optimal_transport2(s, one, ns, iters)
+        torch.cuda.synchronize()
+        skipped = lib.pats_sinkhorn_iterations_skipped(1)
+    finally:
+        lib.pats_sinkhorn_fixed_point_exit(1)
+    same = torch.equal(full, fast) or bool(((full == fast) | (full.isnan() & fast.isnan())).all())
+    assert same, f"{kind}: {int((full != fast).sum())} entries differ between the early exit and the full {iters} iterations"
+    if kind in ("peaked_direct", "diffuse"):
+        assert skipped > 0, f"{kind}: the exit never fired (it is not exercised by this test)"
+    print(f"{kind}: {skipped} of {b * iters} problem-iterations skipped")
+
+
+@pytest.mark.parametrize("b", [1, 4, 5, 63, 1187, 4800])
+def test_bulk_staging_is_bit_identical(M, lib, dev, b):
+    """pats_sinkhorn_bulk_staging(1): persistent CTAs, each 65 x 65 problem staged by one cp.async.bulk of its 16-byte aligned
+    superset and written back by one bulk store.  Same arithmetic, so the plans must be bit-identical to the direct kernel --
+    for batch sizes that end inside / outside a 16-byte boundary (b % 4), more problems than CTAs, ill-conditioned problems
+    (in-kernel fallback), raw marginals, and through the composite call (plan hand-over flags raised after the bulk store)."""
+    from pats_b200 import layers as Ly
+
+    g = torch.Generator().manual_seed(500 + b)
+    s = _peaked(g, b, 8, 7.0, -10.0)
+    if b >= 63:
+        s[7] *= 40.0  # one problem that ends in the log-domain fallback
+    s = s.to(dev)
+    ns = areas(g, b, 64, 4.0).to(dev)
+    one = torch.tensor(1.0, device=dev)
+    lmu = torch.log_softmax(torch.randn(b, 65, generator=g), 1).to(dev)
+    lnu = torch.log_softmax(torch.randn(b, 65, generator=g), 1).to(dev)
+    sxy = (ns.reshape(b, 64) + 1e-8).sqrt()
+    ps = (torch.randint(0, 24, (b, 2), generator=g) * 4).to(dev)
+    outs = {}
+    try:
+        for mode in (0, 1):
+            lib.pats_sinkhorn_bulk_staging(mode)
+            outs[mode] = (M.log_optimal_transport2(s, one, ns, 100), M.log_sinkhorn_iterations(s, lmu, lnu, 20),
+                          Ly.third_layer_match(s, 1.0, ns, sxy, sxy, ps, ps, 100))
+            torch.cuda.synchronize()
+    finally:
+        lib.pats_sinkhorn_bulk_staging(1)
+    eq = lambda x, y: bool(((x == y) | (x.isnan() & y.isnan())).all()) if x.is_floating_point() else torch.equal(x, y)  # noqa: E731
+    assert eq(outs[0][0], outs[1][0]), "log_optimal_transport2 differs with bulk staging"
+    assert eq(outs[0][1], outs[1][1]), "log_sinkhorn_iterations differs with bulk staging"
+    for x, y in zip(outs[0][2], outs[1][2]):
+        assert eq(x, y), "third_layer_match differs with bulk staging"
+
+
 def test_empty_batch(M, dev):
     out = M.log_optimal_transport2(torch.zeros(0, 65, 65, device=dev), 1.0, torch.zeros(0, 1, 64, device=dev), 100)
     assert out.shape == (0, 65, 65)
