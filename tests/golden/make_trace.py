@@ -304,11 +304,19 @@ def install_recorders(ref, rec):
     return restore
 
 
-def run(tag, if_local, caps, limit, merge_new=True, default_limit=3, hw=(480, 640)):
+def run(tag, if_local, caps, limit, merge_new=True, default_limit=3, hw=(480, 640), conditioned=False):
     ref = load_reference()
     torch.manual_seed(SEED)
     cfg = types.SimpleNamespace(if_local=if_local, if_outdoor=True, merge_new=merge_new)
-    model = ref.pats.PATS(cfg).eval()
+    if conditioned:
+        # the network scaled to realistic score magnitudes (tests/live_util.condition): |0.1 * scores| <= 12 .. 26, so the
+        # recorded transport calls are well conditioned and run through the register kernels, not the log-domain fallback
+        sys.path.insert(0, os.path.dirname(HERE))
+        import live_util
+
+        model = live_util.build_model(ref, cfg, device="cpu")
+    else:
+        model = ref.pats.PATS(cfg).eval()
     g = torch.Generator().manual_seed(SEED)
     image0 = torch.randint(0, 256, (1, hw[0], hw[1], 3), generator=g, dtype=torch.uint8)
     image1 = torch.roll(image0, (16, 24), dims=(1, 2)).contiguous()
@@ -322,7 +330,7 @@ def run(tag, if_local, caps, limit, merge_new=True, default_limit=3, hw=(480, 64
         for owner, name, orig in restore:
             setattr(owner, name, orig)
     print(f"[{tag}] forward {time.time() - t0:.1f} s; matches {tuple(out['matches_l'].shape)}; calls seen {rec.count}")
-    meta = {"tag": tag, "cfg": {"if_local": if_local, "if_outdoor": True, "merge_new": merge_new}, "seed": SEED, "image": list(hw),
+    meta = {"tag": tag, "cfg": {"if_local": if_local, "if_outdoor": True, "merge_new": merge_new}, "conditioned": bool(conditioned), "seed": SEED, "image": list(hw),
             "calls_seen": rec.count, "matches": int(out["matches_l"].shape[0]), "calls": rec.calls}
     path = os.path.join(HERE, f"trace_{tag}.npz")
     np.savez_compressed(path, __schema__=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **rec.store.arrays)
@@ -332,7 +340,18 @@ def run(tag, if_local, caps, limit, merge_new=True, default_limit=3, hw=(480, 64
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["global", "local", "mergeold", "portrait", "big"]
+    which = sys.argv[1:] or ["global", "local", "mergeold", "portrait", "big", "cond", "condlocal"]
+    if "cond" in which:
+        # the conditioned network, whole-image mode: every hot-path function once, transport calls of ordinary magnitude
+        run("cond", False, caps={301: 1, 145: 6, 65: 48},
+            limit={"log_sinkhorn_iterations": 1, "log_optimal_transport": 1, "log_optimal_transport2": 2, "tensor_resize": 1, "origin_extract": 1,
+                   "Iterative_expand_matrix": 2, "Compute_imgs": 1, "FirstLayer.est_position": 1, "SecondLayer.est_position": 1,
+                   "SecondLayer.merge_patches_new": 1, "ThirdLayer.Compute_result": 1, "get_result": 1, "split_patches": 1}, conditioned=True)
+    if "condlocal" in which:
+        # the conditioned network with configs/test_megadepth.yaml's flags (chunked): the per-chunk calls of the first three chunks
+        run("condlocal", True, caps={145: 4, 65: 24},
+            limit={"log_optimal_transport2": 6, "SecondLayer.est_position": 3, "SecondLayer.merge_patches_new": 3, "ThirdLayer.Compute_result": 3,
+                   "get_result": 3, "split_patches": 1}, default_limit=0, conditioned=True)
     if "global" in which:
         run("global", False, caps={301: 1, 145: 5, 65: 32},
             limit={"log_sinkhorn_iterations": 3, "log_optimal_transport2": 2, "tensor_resize": 1, "origin_extract": 1})

@@ -21,7 +21,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-TAGS = ("global", "local", "mergeold", "portrait", "big")   # replayed on the GPU (tests/test_gpu_trace.py) and on the oracle
+TAGS = ("global", "local", "mergeold", "portrait", "big", "cond", "condlocal")   # replayed on the GPU (tests/test_gpu_trace.py) and on the oracle
 
 EXACT = "exact"
 OT = ("ot", 1e-4, 2e-6)
