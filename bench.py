@@ -70,7 +70,8 @@ def emit(obj):
 # synthetic inputs of one step (seeded; host tensors)
 # ------------------------------------------------------------------------------------------------------------
 WORKLOAD = "pats_hot_path_pair640x480"
-SURVIVE = 0.05                         # fraction of fine points that end up in the match list (the live conditioned forward keeps 0.1 - 2 %)
+SURVIVE = 0.01                         # fraction of the 691 200 fine points of a pair that end up in its match list: ~6.9 k matches per pair
+                                       # (the live conditioned forward keeps 0.4 - 1.7 k, tests/test_gpu_live_forward.py; a trained PATS a few thousand)
 
 
 def planted_scores(torch, g, b, gh, gw, sharp, noise, floor, dustbin=False, peak=5.0):
@@ -248,12 +249,34 @@ class DeviceStep:
 # ------------------------------------------------------------------------------------------------------------
 # end-to-end step through the torch-facing public API with host (pinned) buffers
 # ------------------------------------------------------------------------------------------------------------
+_WC_KEEP = []
+
+
+def wc_pinned(torch, nbytes: int):
+    """A write-combined pinned host buffer as a uint8 tensor (cudaHostAlloc + cudaHostAllocWriteCombined), or None.  The CPU only
+    ever WRITES the staging arena; write-combined pages are not snooped during the device's reads over PCIe, which matters when
+    eight ranks pull from one host memory system at once (A/B: --wc-staging)."""
+    try:
+        import ctypes as C
+
+        rt = C.CDLL("libcudart.so.12")
+        ptr = C.c_void_p()
+        if rt.cudaHostAlloc(C.byref(ptr), C.c_size_t(nbytes), C.c_uint(0x04)) != 0 or not ptr.value:
+            return None
+        buf = (C.c_uint8 * nbytes).from_address(ptr.value)
+        t = torch.frombuffer(buf, dtype=torch.uint8)
+        _WC_KEEP.append((rt, ptr, buf))
+        return t if t.is_pinned() else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 class E2EStep:
     """One step = H2D of every stage input from pinned host memory, the reference-named wrappers, D2H of the results.
     Steps are software-pipelined over two device input buffers: the copies of step i+1 run on a copy stream while
     step i computes (every step still pays its own H2D and D2H inside the timed region)."""
 
-    def __init__(self, torch, dev, pairs: int, host_inputs, kind: str = "planted"):
+    def __init__(self, torch, dev, pairs: int, host_inputs, kind: str = "planted", wc: bool = False):
         self.torch, self.dev, self.B, self.kind = torch, dev, pairs, kind
         # every stage input lives in ONE pinned host arena and goes over in ONE cudaMemcpyAsync per step (a copy per
         # tensor costs ~17 DMA set-ups per step); the device-side tensors are views into the arena's device twin
@@ -262,7 +285,10 @@ class E2EStep:
             total = (total + 255) & ~255
             offs[k] = total
             total += v.numel() * v.element_size()
-        self.h_arena = torch.empty(total, dtype=torch.uint8).pin_memory()
+        self.h_arena = wc_pinned(torch, total) if wc else None
+        self.staging = "write-combined pinned (cudaHostAllocWriteCombined)" if self.h_arena is not None else "pinned"
+        if self.h_arena is None:
+            self.h_arena = torch.empty(total, dtype=torch.uint8).pin_memory()
         for k, v in host_inputs.items():
             self.h_arena[offs[k]:offs[k] + v.numel() * v.element_size()].view(v.dtype).reshape(v.shape).copy_(v)
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in host_inputs.values())
@@ -639,6 +665,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--wc-staging", action="store_true", help="A/B: write-combined pinned memory for the e2e staging arena")
     ap.add_argument("--no-numa", action="store_true", help="A/B: do not bind the process to the GPU's NUMA node before allocating pinned memory")
     ap.add_argument("--no-chain", action="store_true", help="A/B: plain kernel launches instead of launch chaining (pats_launch_chaining(0))")
     ap.add_argument("--no-handover", action="store_true", help="A/B: no plan hand-over inside the composite calls (pats_plan_handover(0))")
@@ -715,8 +742,16 @@ def main():
         # this rank's shard of the pair list: n_steps * B pairs; every step appends its match rows [yl, xl, yr, xr] to `acc`
         acc = torch.empty((sum(kfs[i % S] for i in range(n_steps)), 4), dtype=torch.float32, device=dev) if gather is not None else None
         gstats = {}
-        if gather is not None:  # warm-up of the exchange too (NCCL builds its communicator lazily on the first collective)
-            gather([acc[: kfs[0]]], max_pairs=1, dst=0)
+        def all_lists():
+            lists, o2 = [], 0
+            for i in range(n_steps):
+                lists.append(acc[o2:o2 + kfs[i % S]])
+                o2 += kfs[i % S]
+            return lists
+
+        if gather is not None:  # warm-up of the exchange with the real sizes: NCCL builds its channels lazily, and the receive buffers come
+            gather(all_lists(), max_pairs=n_steps, dst=0)  # out of torch's caching allocator afterwards instead of cudaMalloc
+            torch.cuda.synchronize(dev)
         l3_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if (i % L3_SAMPLE_EVERY) == L3_SAMPLE_EVERY - 1 or
                      n_steps < L3_SAMPLE_EVERY else None for i in range(n_steps)]
         sampler = ClockSampler(local_rank)
@@ -746,11 +781,7 @@ def main():
                 main_stream.wait_event(done[i])
         eg.record(main_stream)
         if gather is not None:  # one list per step (= per batch of B pairs), all of them, to rank 0
-            lists, o2 = [], 0
-            for i in range(n_steps):
-                lists.append(acc[o2:o2 + kfs[i % S]])
-                o2 += kfs[i % S]
-            gather(lists, max_pairs=n_steps, dst=0, stats=gstats)
+            gather(all_lists(), max_pairs=n_steps, dst=0, stats=gstats)
         e1.record(main_stream)
         barrier()
         t_wall1 = time.perf_counter()
@@ -813,7 +844,7 @@ def main():
     # ---- e2e: public API, host buffers ------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        es = E2EStep(torch, dev, B, step.host_inputs, kind)
+        es = E2EStep(torch, dev, B, step.host_inputs, kind, wc=args.wc_staging)
         es.run(2)
         barrier()
         n_e2e = max(3, min(args.steps, 400))  # the same K steps as the device-resident pass (2.3 ms each: the pipeline's fill and drain
@@ -834,6 +865,7 @@ def main():
         ce1.record()
         torch.cuda.synchronize(dev)
         link_ms = ce0.elapsed_time(ce1) / 5
+        e2e["staging"] = es.staging
         e2e["h2d_link_gbs"] = es.h_arena.numel() / (link_ms * 1e-3) / 1e9
         e2e["h2d_ms_per_step_alone"] = link_ms
         e2e["note"] = "bound by the host->device copy of the stage inputs (h2d_ms_per_step_alone vs ms_per_step of the device-resident path)"
