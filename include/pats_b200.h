@@ -249,6 +249,16 @@ int pats_third_layer_match_f32(const float *scores, const float *one, const floa
                                float *mkpts1_f, uint8_t *if_matching1, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Descriptor correlation feeding the Sinkhorn solves (tcgen05 tensor cores, 3xTF32)
+ *   models/first_layer.py:110-114, models/second_layer.py:100-104, models/third_layer.py:156-158
+ * ------------------------------------------------------------------------------------------- */
+
+/* out[p,i,j] = scale * sum_k d0[p,k,i] * d1[p,k,j]       torch.einsum('bdn,bdm->bnm', d0, d1) / d**.5 ; 0.1 * scores
+ *   d0 [b,d,n], d1 [b,d,m] f32 contiguous (d a multiple of 8), scale = 0.1 / sqrt(d) -> out [b,n,m] f32, the layout
+ *   pats_log_optimal_transport*_f32 reads.  FP32-accurate (operands split into two TF32 halves, three MMAs per K step). */
+int pats_correlation_f32(const float *d0, const float *d1, int b, int d, int n, int m, float scale, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Feature gathers next to the path                  (models/second_layer.py:71-80, models/third_layer.py:119-146)
  * ------------------------------------------------------------------------------------------- */
 

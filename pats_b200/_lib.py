@@ -53,6 +53,7 @@ SIGNATURES = {
     "pats_get_result_f32": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, C.c_longlong, _P, _P, _P],
     "pats_third_compute_result_f32": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
     "pats_third_result_from_log_f32": [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
+    "pats_correlation_f32": [_P, _P, _I, _I, _I, _I, _F, _P, _P],
     "pats_grid_sample12_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "pats_third_unfold_f32": [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P],
     "pats_est_position_f32": [_P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -1,0 +1,234 @@
+// N2 -- the descriptor correlation that feeds every Sinkhorn solve, on the 5th-generation tensor cores (tcgen05 + TMEM).
+// Replaces, from zju3dv/pats:
+//   models/first_layer.py:110-114    scores = einsum('bdn,bdm->bnm', mdesc0, mdesc1) / 448**.5 ;  0.1 * scores
+//   models/second_layer.py:100-104   ... / 264**.5 ;  0.1 * scores          (b = P windows, n = m = 145)
+//   models/third_layer.py:156-158    ... / 128**.5 ;  0.1 * scores          (b = K points,  n = m = 65)
+// i.e. one batched GEMM and two full elementwise passes over the [b,n,m] score tensor.  Here: one kernel that writes
+// Z = scale * d0^T d1 (scale = 0.1 / sqrt(d)) straight into the contiguous [b,n,m] layout the Sinkhorn kernels stage with one
+// bulk copy per problem.
+//
+// Arithmetic.  The reference multiplies in FP32 (cuBLAS SGEMM; torch's allow_tf32 is off by default) and the plans must agree
+// to 1e-4 with identical argmax, so plain TF32 (10-bit mantissa: ~5e-4 relative per product) is not enough.  Every operand is
+// split x = hi + lo with hi = x rounded to TF32 and lo = x - hi (exact in FP32) rounded to TF32, and three MMAs per K step accumulate hi*hi + hi*lo + lo*hi in the FP32 accumulator ("3xTF32"; the
+// dropped lo*lo term is ~2^-22 relative).  Measured against the FP32 einsum: tests/test_gpu_correlation.py.
+//
+// Structure (one CTA of 128 threads per (problem, 128-row block)):
+//   * operands are staged by all threads: global [d, n] rows (contiguous along n) -> registers -> split -> shared memory in the
+//     canonical K-major no-swizzle UMMA layout (core matrix = 8 rows x 16 B; the transposition happens in the store index, and
+//     lane = (k % 4) * 8 + (row % 8) makes the 32 stores of a warp hit 32 different banks).  TMA cannot do this copy: rows are
+//     65 / 145 / 300 floats, i.e. not 16-byte aligned.
+//   * ONE thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = a multiple of 16 up to 160, K = 8) per K step,
+//     accumulator in TMEM, and tcgen05.commit arrives on an mbarrier that the CTA waits on before restaging the buffers;
+//   * the four warps read their 32 TMEM lanes with tcgen05.ld (32x32b.x16), scale, and store the valid rows / columns.
+//   SASS: UTCMMA (the MMA), LDTM (TMEM load), UTCBAR (commit), STS / LDG for the staging.
+#include "common.cuh"
+
+namespace pats {
+namespace {
+
+constexpr int KC = 32;            // K extent staged per chunk
+constexpr int KC4 = KC / 4;       // core matrices along K per chunk
+constexpr int CORR_THREADS = 128;
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle: element (row, k) of a tile with KC4 core matrices along K lives at float index
+//   ((row / 8) * KC4 + k / 4) * 32 + (row % 8) * 4 + k % 4          LBO (K direction) = 128 B, SBO (row direction) = KC4 * 128 B
+__device__ __forceinline__ unsigned long long umma_desc(unsigned saddr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((saddr & 0x3FFFFu) >> 4);          // start address, bits [0,14)
+    d |= (unsigned long long)(128u >> 4) << 16;                  // leading byte offset, bits [16,30)
+    d |= (unsigned long long)((KC4 * 128u) >> 4) << 32;          // stride byte offset, bits [32,46)
+    d |= 1ull << 46;                                             // descriptor version (Blackwell)
+    return d;                                                    // base offset 0, layout type SWIZZLE_NONE
+}
+// kind::tf32, FP32 accumulate, both operands K-major, M = 128
+__device__ __forceinline__ unsigned umma_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long a, unsigned long long b, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_init1(unsigned mb) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory"); }
+__device__ __forceinline__ void mbar_wait_parity(unsigned mb, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(mb),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+struct CorrArgs {
+    const float *d0, *d1;  // [b,d,n], [b,d,m]
+    float *out;            // [b,n,m]
+    int b, d, n, m;
+    float scale;
+    int mblocks;           // ceil(n / 128)
+    int npad;              // m rounded up to 16
+    int tile_n, ntiles;    // N extent per MMA (multiple of 16, <= 160), tiles per accumulator row block
+    int tmem_cols;         // power of two >= max(32, npad)
+};
+
+// stage rows [r0, r0 + rows) x k in [k0, k0 + kn) of src[d, ld] into the hi / lo tiles (rows beyond `valid` and k beyond kn are zero)
+__device__ __forceinline__ void stage_tile(const float *__restrict__ src, int ld, int valid, int r0, int rows, int k0, int kn, float *hi,
+                                           float *lo, int warp, int lane, int nwarps) {
+    const int kq = lane >> 3, rr = lane & 7;  // lane = (k % 4) * 8 + row % 8
+    const int groups = (rows + 7) >> 3;
+    for (int blk = warp; blk < groups * KC4; blk += nwarps) {
+        const int g8 = blk / KC4, k4 = blk - g8 * KC4;
+        const int row = r0 + g8 * 8 + rr, k = k4 * 4 + kq;
+        float x = 0.f;
+        if (row < valid && k < kn) x = __ldg(src + (size_t)(k0 + k) * ld + row);
+        // hi = x rounded to TF32 (nearest), lo = the exact remainder, rounded to TF32 as well: the tensor core would TRUNCATE the
+        // low 13 bits of a 32-bit container, and a truncation error has one sign -- it adds up linearly over K instead of as sqrt(K)
+        const float h = tf32_rn(x);
+        const int idx = (g8 * KC4 + k4) * 32 + rr * 4 + kq;
+        hi[idx] = h;
+        lo[idx] = tf32_rn(x - h);
+    }
+}
+
+__global__ void __launch_bounds__(CORR_THREADS) correlation_tcgen05_kernel(CorrArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ unsigned s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *a_hi = smem, *a_lo = a_hi + 128 * KC;        // [16][KC4][8][4]
+    float *b_hi = a_lo + 128 * KC, *b_lo = b_hi + a.npad * KC;
+    const unsigned mb = smem_addr(&s_bar);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "r"((unsigned)a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init1(mb);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = s_tmem;
+    unsigned phase = 0;
+
+    for (int work = blockIdx.x; work < a.b * a.mblocks; work += gridDim.x) {
+        const int p = work / a.mblocks, mblk = work - p * a.mblocks;
+        const float *d0 = a.d0 + (size_t)p * a.d * a.n, *d1 = a.d1 + (size_t)p * a.d * a.m;
+        const int r0 = mblk * 128;
+        unsigned first = 1;
+        for (int k0 = 0; k0 < a.d; k0 += KC) {
+            const int kn = min(KC, a.d - k0);
+            // only the row groups that hold real rows are written; what the other accumulator rows / columns see is never stored
+            stage_tile(d0, a.n, a.n, r0, min(128, (a.n - r0 + 7) & ~7), k0, kn, a_hi, a_lo, warp, lane, CORR_THREADS / 32);
+            stage_tile(d1, a.m, a.m, 0, (a.m + 7) & ~7, k0, kn, b_hi, b_lo, warp, lane, CORR_THREADS / 32);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int steps = (kn + 7) >> 3;
+                for (int t = 0; t < a.ntiles; ++t) {
+                    const int c0 = t * a.tile_n, cn = min(a.tile_n, a.npad - c0);
+                    const unsigned idesc = umma_idesc(cn);
+                    const unsigned dcol = tmem + (unsigned)c0;
+                    // B rows c0.. of this tile: (c0 / 8) row groups further on
+                    const unsigned boff = (unsigned)((c0 >> 3) * KC4 * 128);
+                    for (int s = 0; s < steps; ++s) {
+                        const unsigned koff = (unsigned)s * 256u;  // two core matrices (K = 8) per step
+                        const unsigned long long ah = umma_desc(smem_addr(a_hi) + koff), al = umma_desc(smem_addr(a_lo) + koff);
+                        const unsigned long long bh = umma_desc(smem_addr(b_hi) + boff + koff), bl = umma_desc(smem_addr(b_lo) + boff + koff);
+                        umma_tf32(dcol, ah, bh, idesc, (first && s == 0) ? 0u : 1u);
+                        umma_tf32(dcol, ah, bl, idesc, 1u);
+                        umma_tf32(dcol, al, bh, idesc, 1u);
+                    }
+                }
+                // arrives on the mbarrier when every MMA issued so far has finished reading shared memory and writing TMEM
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb) : "memory");
+            }
+            first = 0;
+            mbar_wait_parity(mb, phase);
+            phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        // ---- epilogue: warp w owns TMEM lanes (= accumulator rows) 32w .. 32w+31 --------------------------------------
+        const int row = r0 + warp * 32 + lane;
+        float *orow = a.out + ((size_t)p * a.n + row) * a.m;
+        for (int c0 = 0; c0 < a.npad; c0 += 16) {
+            unsigned v[16];
+            const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < a.n) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j < a.m) orow[c0 + j] = __uint_as_float(v[j]) * a.scale;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // every warp has drained its accumulator rows before the next block's first MMA overwrites them
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)a.tmem_cols) : "memory");
+}
+
+}  // namespace
+}  // namespace pats
+
+using namespace pats;
+
+PATS_API int pats_correlation_f32(const float *d0, const float *d1, int b, int d, int n, int m, float scale, float *out, void *stream) {
+    if (b < 0 || d <= 0 || n <= 0 || m <= 0) return invalid("correlation: bad sizes b=%d d=%d n=%d m=%d", b, d, n, m);
+    if (b == 0) return PATS_OK;
+    if (!d0 || !d1 || !out) return invalid("correlation: null pointer");
+    if (d % 8 != 0) return invalid("correlation: d = %d is not a multiple of 8 (the K extent of one TF32 MMA)", d);
+    CorrArgs a;
+    a.d0 = d0, a.d1 = d1, a.out = out, a.b = b, a.d = d, a.n = n, a.m = m, a.scale = scale;
+    a.mblocks = (n + 127) / 128;
+    a.npad = (m + 15) & ~15;
+    if (a.npad > 512) return invalid("correlation: m = %d exceeds the 512 accumulator columns of tensor memory", m);
+    a.ntiles = (a.npad + 159) / 160;
+    a.tile_n = (((a.npad + a.ntiles - 1) / a.ntiles) + 15) & ~15;
+    a.tmem_cols = 32;
+    while (a.tmem_cols < a.npad) a.tmem_cols <<= 1;
+    const size_t smem = sizeof(float) * (size_t)KC * 2 * (128 + a.npad);
+    const int dev = current_device();
+    if (dev < 0) return PATS_E_CUDA;
+    static PerDeviceOnce configured;
+    if (!configured.done(dev)) {
+        PATS_CUDA_TRY(cudaFuncSetAttribute(correlation_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured.mark(dev);
+    }
+    // co-resident CTAs share the SM's 512 TMEM columns and its shared memory; a CTA that cannot allocate would wait for one that can
+    int per_sm = 512 / a.tmem_cols;
+    const int by_smem = (int)((200 * 1024) / (smem + 1024));
+    if (per_sm > by_smem) per_sm = by_smem;
+    if (per_sm < 1) per_sm = 1;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    long long grid = (long long)b * a.mblocks;
+    if (grid > (long long)sms * per_sm) grid = (long long)sms * per_sm;
+    correlation_tcgen05_kernel<<<(unsigned)grid, CORR_THREADS, smem, as_stream(stream)>>>(a);
+    PATS_LAUNCH_CHECK("correlation_tcgen05_kernel");
+    return PATS_OK;
+}

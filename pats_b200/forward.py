@@ -20,6 +20,14 @@ import torch
 
 from . import layers as _layers
 
+# The descriptor correlation in front of the Sinkhorn solves (second_layer.py:100-104, third_layer.py:156-158) on the tcgen05 kernel
+# (csrc/correlation.cu: scale folded in, FP32-accurate 3xTF32, one pass) instead of the reference's einsum, division and scaling.
+# Measured (tools/time_correlation.py, profiles/r02_ab_correlation.json): level 3 (K x 128 x 65 x 65) 0.365 vs 0.558 ms at K = 4800 and
+# 2.73 vs 4.37 ms at K = 38 400 -- on; level 2 (P x 264 x 145 x 145) 0.30 vs 0.13 ms at P = 300: the 128-row blocks waste 43 % of
+# the tensor-core tile on 145 rows and restage B per block -- off.
+TCGEN05_CORRELATION_L3 = True
+TCGEN05_CORRELATION_L2 = False
+
 
 def second_layer_forward(self, left, right, desc_l, original_image_shape, if_nomatching1_L1, scores_back, outdoor, merge_new):
     """SecondLayer.forward (models/second_layer.py:61-134)."""
@@ -44,11 +52,14 @@ def second_layer_forward(self, left, right, desc_l, original_image_shape, if_nom
     scale_x = torch.exp(self.sigmoid(scale_x) * math.log(256.0) - math.log(256.0) / 2)
     scale_y = torch.exp(self.sigmoid(scale_y) * math.log(256.0) - math.log(256.0) / 2)
     scale = scale_x * scale_y
-    scores = torch.einsum('bdn,bdm->bnm', mdesc0, mdesc1)
-    scores = scores / self.config['descriptor_dim'] ** .5
+    if TCGEN05_CORRELATION_L2:  # :100-103: einsum, / sqrt(d), * 0.1 in one tensor-core kernel
+        scores = _layers.correlation(mdesc0, mdesc1, 0.1 / self.config['descriptor_dim'] ** .5)
+    else:
+        scores = torch.einsum('bdn,bdm->bnm', mdesc0, mdesc1)
+        scores = 0.1 * (scores / self.config['descriptor_dim'] ** .5)
     # :103-116 in one call: Sinkhorn -> dustbin offsets (+log 2 outdoor / +log 3 indoor) -> est_position, handed over per window
     scores, trust_score_L2, pts, x_scale_reproj, y_scale_reproj, if_nomatching1, if_nomatching2 = _layers.second_layer_match(
-        0.1 * scores, self.one, scale, scale_x, scale_y, self.config['sinkhorn_iterations'], bool(outdoor), self.row_num)
+        scores, self.one, scale, scale_x, scale_y, self.config['sinkhorn_iterations'], bool(outdoor), self.row_num)
     patch_num = left.shape[0]
     if merge_new:
         if_nomatching1, scores_back = self.merge_patches_new(patch_num, trust_score_L2, original_image_shape, if_nomatching1_L1, if_nomatching1, scores_back)
@@ -96,10 +107,13 @@ def third_layer_forward(self, new_left, new_right, mkpts0_c, mkpts1_c, b_ids, de
     scale = torch.exp(self.sigmoid(scale) * math.log(256.0) - math.log(256.0) / 2)
     scale_x = (scale + 1e-8).sqrt()
     scale_y = (scale + 1e-8).sqrt()
-    scores = torch.einsum('bdn,bdm->bnm', feat_f0_unfold, feat_f1_unfold)
-    scores = scores / 128 ** .5
+    if TCGEN05_CORRELATION_L3:  # :156-158
+        scores = _layers.correlation(feat_f0_unfold, feat_f1_unfold, 0.1 / 128 ** .5)
+    else:
+        scores = torch.einsum('bdn,bdm->bnm', feat_f0_unfold, feat_f1_unfold)
+        scores = 0.1 * (scores / 128 ** .5)
     # :158-167 in one call: Sinkhorn -> exp -> Compute_result + the "best target is not the dustbin" test
-    _, mkpts0_f, mkpts1_f, if_matching1 = _layers.third_layer_match(0.1 * scores, self.one, scale, scale_x, scale_y, p_s, p_t, 100)
+    _, mkpts0_f, mkpts1_f, if_matching1 = _layers.third_layer_match(scores, self.one, scale, scale_x, scale_y, p_s, p_t, 100)
     K = p_t.shape[0]
     label = torch.full((K * 16, 2), 1e8, dtype=torch.float32, device=dev)
     if not outdoor:

@@ -279,3 +279,23 @@ def third_unfold(feat, mkpts_c, b_ids, kenc_out, rubbish, mkpts0_c, clamp96: boo
 
 
 __all__ += ["grid_sample12", "third_unfold"]
+
+
+def correlation(desc0, desc1, scale: float):
+    """scale * einsum('bdn,bdm->bnm', desc0, desc1): the descriptor correlation in front of every Sinkhorn solve
+    (first_layer.py:110-114, second_layer.py:100-104, third_layer.py:156-158 with scale = 0.1 / sqrt(d)), on the tcgen05 tensor cores
+    with FP32-level accuracy (3xTF32).  desc0 [b,d,n], desc1 [b,d,m] -> [b,n,m]."""
+    d0 = cuda_f32(desc0, "desc0")
+    d1 = cuda_f32(desc1, "desc1")
+    if d0.dim() != 3 or d1.dim() != 3 or d0.shape[:2] != d1.shape[:2]:
+        raise ValueError(f"correlation: expected [b,d,n] and [b,d,m], got {tuple(d0.shape)} and {tuple(d1.shape)}")
+    b, d, n = d0.shape
+    m = d1.shape[2]
+    out = torch.empty((b, n, m), dtype=torch.float32, device=d0.device)
+    with torch.cuda.device(d0.device):
+        rc = _lib.load().pats_correlation_f32(d0.data_ptr(), d1.data_ptr(), b, d, n, m, float(scale), out.data_ptr(), stream_ptr(d0.device))
+    _lib.check(rc, "correlation")
+    return out
+
+
+__all__ += ["correlation"]

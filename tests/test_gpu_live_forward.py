@@ -40,12 +40,14 @@ for _k in ("log_sinkhorn_iterations", "log_optimal_transport", "log_optimal_tran
     RULES[_k] = OT_LIVE
 RULES["tensor_resize"] = T.EXACT  # same device, same ATen kernel arithmetic: bit-identical (tests/test_gpu_subdivide.py)
 RULES["Compute_imgs"] = [T.EXACT, T.EXACT, T.EXACT, T.EXACT, T.EXACT]
-# layer-level mirrors (pats_b200.forward): the returned dictionaries, key by key
+# layer-level mirrors (pats_b200.forward): the returned dictionaries, key by key.  The third layer's scores come from the tcgen05
+# correlation (FP32-accurate, not bit-identical to cuBLAS), so the sub-pixel points -- a weighted mean around an ARGMAX -- carry a
+# budget of 1e-4 of their entries for neighbourhoods that moved by one cell; everything else is as strict as at the function level.
 _F = (2e-5, 2e-5)
 RULES["SecondLayer.forward"] = {"scales": T.EXACT, "scales_reproj": [(2e-5, 1e-6), (2e-5, 1e-6)], "scores": OT_LIVE, "features": T.EXACT,
                                 "features_before": T.EXACT, "pts": _F, "if_nomatching1": T.EXACT, "if_nomatching2": T.EXACT,
                                 "trust_score": (2e-4, 2e-6), "scores_back": (2e-4, 2e-6)}
-RULES["ThirdLayer.forward"] = {"mkpts0_f": T.EXACT, "mkpts1_f": (1e-5, 2e-5), "label": T.EXACT}
+RULES["ThirdLayer.forward"] = {"mkpts0_f": T.EXACT, "mkpts1_f": (1e-5, 2e-5, 1e-4), "label": T.EXACT}
 MATCH_R_TOL_PX = 5e-4
 MUTATORS = ("SecondLayer.merge_patches_new", "SecondLayer.merge_patches_old")
 

@@ -127,8 +127,12 @@ def compare_leaf(label, got, want, rule):
         mx = float(d.max()) if d.size else 0.0
         assert not (excess > 0).any(), f"{label}: {int((excess > 0).sum())} entries beyond {rule[1]:g} + {rule[2]:g}|ref| (max |d| = {mx:.3e})"
         return mx
-    rtol, atol = rule
+    rtol, atol = rule[0], rule[1]
     bad = d > atol + rtol * np.abs(wf[fin])
+    if len(rule) > 2 and bad.any():  # (rtol, atol, budget): a float output that sits behind a discrete decision (a box that grew one step
+        # further, a neighbourhood centred one cell over) may differ outright in at most `budget` of its entries
+        assert bad.mean() <= rule[2], f"{label}: {int(bad.sum())} of {d.size} entries differ ({bad.mean():.2e} > budget {rule[2]:g})"
+        return float(d[~bad].max()) if (~bad).any() else 0.0
     assert not bad.any(), f"{label}: {int(bad.sum())} of {d.size} entries beyond rtol {rtol:g} / atol {atol:g} (max |d| {float(d.max()):.3e})"
     return float(d.max()) if d.size else 0.0
 
