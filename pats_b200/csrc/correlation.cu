@@ -12,14 +12,15 @@
 // split x = hi + lo with hi = x rounded to TF32 and lo = x - hi (exact in FP32) rounded to TF32, and three MMAs per K step accumulate hi*hi + hi*lo + lo*hi in the FP32 accumulator ("3xTF32"; the
 // dropped lo*lo term is ~2^-22 relative).  Measured against the FP32 einsum: tests/test_gpu_correlation.py.
 //
-// Structure (one CTA of 128 threads per (problem, 128-row block)):
+// Structure (one CTA of 256 threads per (problem, 128-row block)):
 //   * operands are staged by all threads: global [d, n] rows (contiguous along n) -> registers -> split -> shared memory in the
 //     canonical K-major no-swizzle UMMA layout (core matrix = 8 rows x 16 B; the transposition happens in the store index, and
 //     lane = (k % 4) * 8 + (row % 8) makes the 32 stores of a warp hit 32 different banks).  TMA cannot do this copy: rows are
 //     65 / 145 / 300 floats, i.e. not 16-byte aligned.
 //   * ONE thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = a multiple of 16 up to 160, K = 8) per K step,
 //     accumulator in TMEM, and tcgen05.commit arrives on an mbarrier that the CTA waits on before restaging the buffers;
-//   * the four warps read their 32 TMEM lanes with tcgen05.ld (32x32b.x16), scale, and store the valid rows / columns.
+//   * the eight warps read the 32 TMEM lanes of their quadrant with tcgen05.ld (32x32b.x16; warps w and w + 4 alternate over the
+//     16-column groups), scale, and store the valid rows / columns.
 //   SASS: UTCMMA (the MMA), LDTM (TMEM load), UTCBAR (commit), STS / LDG for the staging.
 #include "common.cuh"
 
@@ -28,7 +29,7 @@ namespace {
 
 constexpr int KC = 32;            // K extent staged per chunk
 constexpr int KC4 = KC / 4;       // core matrices along K per chunk
-constexpr int CORR_THREADS = 128;
+constexpr int CORR_THREADS = 256;  // 8 warps stage; warps w and w + 4 share a TMEM lane quadrant and split the accumulator columns
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -88,22 +89,36 @@ struct CorrArgs {
     int tmem_cols;         // power of two >= max(32, npad)
 };
 
-// stage rows [r0, r0 + rows) x k in [k0, k0 + kn) of src[d, ld] into the hi / lo tiles (rows beyond `valid` and k beyond kn are zero)
+// stage rows [r0, r0 + rows) x k in [k0, k0 + kn) of src[d, ld] into the hi / lo tiles (rows beyond `valid` and k beyond kn are zero).
+// A warp moves one 8-row x 4-k core matrix per step; UN steps are in flight together (the loop is latency-bound otherwise: one
+// dependent LDG -> split -> 2 STS chain per thread at a time kept a CTA at ~60 us per 145-row problem).
+template <int UN>
 __device__ __forceinline__ void stage_tile(const float *__restrict__ src, int ld, int valid, int r0, int rows, int k0, int kn, float *hi,
                                            float *lo, int warp, int lane, int nwarps) {
     const int kq = lane >> 3, rr = lane & 7;  // lane = (k % 4) * 8 + row % 8
-    const int groups = (rows + 7) >> 3;
-    for (int blk = warp; blk < groups * KC4; blk += nwarps) {
-        const int g8 = blk / KC4, k4 = blk - g8 * KC4;
-        const int row = r0 + g8 * 8 + rr, k = k4 * 4 + kq;
-        float x = 0.f;
-        if (row < valid && k < kn) x = __ldg(src + (size_t)(k0 + k) * ld + row);
-        // hi = x rounded to TF32 (nearest), lo = the exact remainder, rounded to TF32 as well: the tensor core would TRUNCATE the
-        // low 13 bits of a 32-bit container, and a truncation error has one sign -- it adds up linearly over K instead of as sqrt(K)
-        const float h = tf32_rn(x);
-        const int idx = (g8 * KC4 + k4) * 32 + rr * 4 + kq;
-        hi[idx] = h;
-        lo[idx] = tf32_rn(x - h);
+    const int groups = (rows + 7) >> 3, nblk = groups * KC4;
+    for (int blk0 = warp; blk0 < nblk; blk0 += nwarps * UN) {
+        float x[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int blk = blk0 + u * nwarps;
+            const int g8 = blk / KC4, k4 = blk - g8 * KC4;
+            const int row = r0 + g8 * 8 + rr, k = k4 * 4 + kq;
+            x[u] = (blk < nblk && row < valid && k < kn) ? __ldg(src + (size_t)(k0 + k) * ld + row) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int blk = blk0 + u * nwarps;
+            if (blk < nblk) {
+                const int g8 = blk / KC4, k4 = blk - g8 * KC4;
+                // hi = x rounded to TF32 (nearest), lo = the exact remainder, rounded to TF32 as well: the tensor core would TRUNCATE
+                // the low 13 bits of a 32-bit container, and a truncation error has one sign -- it adds up linearly over K
+                const float h = tf32_rn(x[u]);
+                const int idx = (g8 * KC4 + k4) * 32 + rr * 4 + kq;
+                hi[idx] = h;
+                lo[idx] = tf32_rn(x[u] - h);
+            }
+        }
     }
 }
 
@@ -137,8 +152,8 @@ __global__ void __launch_bounds__(CORR_THREADS) correlation_tcgen05_kernel(CorrA
         for (int k0 = 0; k0 < a.d; k0 += KC) {
             const int kn = min(KC, a.d - k0);
             // only the row groups that hold real rows are written; what the other accumulator rows / columns see is never stored
-            stage_tile(d0, a.n, a.n, r0, min(128, (a.n - r0 + 7) & ~7), k0, kn, a_hi, a_lo, warp, lane, CORR_THREADS / 32);
-            stage_tile(d1, a.m, a.m, 0, (a.m + 7) & ~7, k0, kn, b_hi, b_lo, warp, lane, CORR_THREADS / 32);
+            stage_tile<16>(d0, a.n, a.n, r0, min(128, (a.n - r0 + 7) & ~7), k0, kn, a_hi, a_lo, warp, lane, CORR_THREADS / 32);
+            stage_tile<16>(d1, a.m, a.m, 0, (a.m + 7) & ~7, k0, kn, b_hi, b_lo, warp, lane, CORR_THREADS / 32);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
             __syncthreads();
             if (tid == 0) {
@@ -168,11 +183,12 @@ __global__ void __launch_bounds__(CORR_THREADS) correlation_tcgen05_kernel(CorrA
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         // ---- epilogue: warp w owns TMEM lanes (= accumulator rows) 32w .. 32w+31 --------------------------------------
-        const int row = r0 + warp * 32 + lane;
+        const int quad = warp & 3;  // a warp may only touch the TMEM lanes of its quadrant (warp id % 4)
+        const int row = r0 + quad * 32 + lane;
         float *orow = a.out + ((size_t)p * a.n + row) * a.m;
-        for (int c0 = 0; c0 < a.npad; c0 += 16) {
+        for (int c0 = (warp >> 2) * 16; c0 < a.npad; c0 += 32) {
             unsigned v[16];
-            const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
+            const unsigned taddr = tmem + ((unsigned)(quad * 32) << 16) + (unsigned)c0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),

@@ -22,8 +22,8 @@ from . import layers as _layers
 
 # The descriptor correlation in front of the Sinkhorn solves (second_layer.py:100-104, third_layer.py:156-158) on the tcgen05 kernel
 # (csrc/correlation.cu: scale folded in, FP32-accurate 3xTF32, one pass) instead of the reference's einsum, division and scaling.
-# Measured (tools/time_correlation.py, profiles/r02_ab_correlation.json): level 3 (K x 128 x 65 x 65) 0.365 vs 0.558 ms at K = 4800 and
-# 2.73 vs 4.37 ms at K = 38 400 -- on; level 2 (P x 264 x 145 x 145) 0.30 vs 0.13 ms at P = 300: the 128-row blocks waste 43 % of
+# Measured (tools/time_correlation.py, profiles/r02_ab_correlation.json): level 3 (K x 128 x 65 x 65) 0.291 vs 0.558 ms at K = 4800 and
+# 2.19 vs 4.38 ms at K = 38 400 -- on; level 2 (P x 264 x 145 x 145) 0.18 vs 0.13 ms at P = 300: the 128-row blocks waste 43 % of
 # the tensor-core tile on 145 rows and restage B per block -- off.
 TCGEN05_CORRELATION_L3 = True
 TCGEN05_CORRELATION_L2 = False
