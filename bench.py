@@ -600,6 +600,51 @@ def stress_leg(torch, dev, peak):
     return out
 
 
+def correlation_leg(torch, dev, B):
+    """N2: the level-3 correlation in front of the solve (third_layer.py:156-158: einsum('bdn,bdm->bnm') / sqrt(128), then 0.1 *) as the
+    reference formulates it (cuBLAS FP32 GEMM + two elementwise passes) against pats_correlation_f32 (tcgen05, 3xTF32), each followed
+    by the level-3 Sinkhorn, on B pairs' worth of problems.  Descriptors are synthetic (unit normal)."""
+    from pats_b200 import layers as Ly
+    from pats_b200 import modules as M
+
+    g = torch.Generator().manual_seed(SEED)
+    K = B * K3
+    d0 = torch.randn(K, 128, 65, generator=g).to(dev)
+    d1 = torch.randn(K, 128, 65, generator=g).to(dev)
+    ns = torch.exp((torch.rand(K, 1, 64, generator=g) * 2 - 1) * math.log(2.0)).to(dev)
+    one = torch.tensor(1.0, device=dev)
+    sc = 0.1 / math.sqrt(128.0)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for a_, b_ in evs:
+            a_.record()
+            fn()
+            b_.record()
+        torch.cuda.synchronize(dev)
+        return sorted(a_.elapsed_time(b_) for a_, b_ in evs)[5]
+
+    try:
+        ref_corr = timed(lambda: 0.1 * (torch.einsum('bdn,bdm->bnm', d0, d1) / 128 ** .5))
+        our_corr = timed(lambda: Ly.correlation(d0, d1, sc))
+        ref_both = timed(lambda: M.log_optimal_transport2(0.1 * (torch.einsum('bdn,bdm->bnm', d0, d1) / 128 ** .5), one, ns, ITERS))
+        our_both = timed(lambda: M.log_optimal_transport2(Ly.correlation(d0, d1, sc), one, ns, ITERS))
+        Za = M.log_optimal_transport2(Ly.correlation(d0, d1, sc), one, ns, ITERS)
+        Zb = M.log_optimal_transport2(0.1 * (torch.einsum('bdn,bdm->bnm', d0, d1) / 128 ** .5), one, ns, ITERS)
+        out = {"problems": K, "shape": "[K,128,65] x [K,128,65] -> [K,65,65]", "reference_formulation_ms": ref_corr, "tcgen05_ms": our_corr,
+               "reference_formulation_plus_sinkhorn_ms": ref_both, "tcgen05_plus_sinkhorn_ms": our_both,
+               "plans_max_abs_diff": float((Za - Zb).abs().max()), "argmax_equal": bool(torch.equal(Za.argmax(2), Zb.argmax(2)) and torch.equal(Za.argmax(1), Zb.argmax(1)))}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    del d0, d1
+    torch.cuda.empty_cache()
+    return out
+
+
 def workload_config(pairs_per_step: int) -> dict:
     """The `config` of BOTH arms (key for key: the driver compares them)."""
     return {"workload": WORKLOAD, "scores": "planted (peaked, area-consistent plans; make_inputs)", "pairs_per_step": pairs_per_step, "P2": P2, "K3": K3,
@@ -928,6 +973,12 @@ def main():
         stress = None
         if not args.no_streaming:
             stress = stress_leg(torch, dev, peak)
+        corr = None
+        if world == 1 and not args.no_streaming:
+            try:
+                corr = correlation_leg(torch, dev, B)
+            except Exception as e:  # noqa: BLE001
+                corr = {"unavailable": f"{type(e).__name__}: {e}"}
         # ---- the reference's own formulation (log-domain, ~6 ATen ops per iteration: modules.py:137-182) on this GPU -------
         torch_cuda = None
         if world == 1 and not args.no_torch_baseline:
@@ -994,7 +1045,7 @@ def main():
                     "pairs_per_rank": B * args.steps,
                     "exchange": "after the pair loop every step's match list of every rank is gathered to rank 0 (2 collectives, 1 host sync); inside the timed region",
                     "gather_ms": info["gather_ms"], "gather": info["gather"]},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_streaming": streaming, "stress": stress, "cpu_baseline": cpu, "torch_cuda": torch_cuda,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_streaming": streaming, "stress": stress, "correlation": corr, "cpu_baseline": cpu, "torch_cuda": torch_cuda,
             "fixed_point_exit": fp_exit, "bulk_staging": bulk, "overlap": overlap, "diffuse": diffuse, "forward": fwd,
         }
         emit(line)

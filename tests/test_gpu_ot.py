@@ -378,6 +378,20 @@ def test_bulk_staging_is_bit_identical(M, lib, dev, b):
         assert eq(x, y), "third_layer_match differs with bulk staging"
 
 
+def test_unaligned_views_take_the_direct_kernel_and_agree(M, dev):
+    """A [1:] view of a [b,65,65] tensor starts 16 900 B into the allocation (4-byte phase): the bulk-copy staging needs 16-byte
+    aligned tensors, so the dispatch falls back to the direct loads.  Same bits either way."""
+    g = torch.Generator().manual_seed(91)
+    s = _peaked(g, 41, 8, 7.0, -10.0).to(dev)
+    ns = areas(g, 41, 64, 4.0).to(dev)
+    one = torch.tensor(1.0, device=dev)
+    view = s[1:]
+    assert view.data_ptr() % 16 != 0 and view.is_contiguous()
+    a = M.log_optimal_transport2(view, one, ns[1:], 100)
+    b = M.log_optimal_transport2(view.clone(), one, ns[1:].clone(), 100)
+    assert torch.equal(a, b)
+
+
 def test_empty_batch(M, dev):
     out = M.log_optimal_transport2(torch.zeros(0, 65, 65, device=dev), 1.0, torch.zeros(0, 1, 64, device=dev), 100)
     assert out.shape == (0, 65, 65)
