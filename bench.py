@@ -912,6 +912,11 @@ def main():
         link_ms = ce0.elapsed_time(ce1) / 5
         e2e["staging"] = es.staging
         e2e["h2d_link_gbs"] = es.h_arena.numel() / (link_ms * 1e-3) / 1e9
+        if world > 1:  # every rank's host link, measured while all ranks copy at once: attributes the e2e scaling to the shared host path
+            links = torch.zeros(world, device=dev, dtype=torch.float64)
+            links[rank] = e2e["h2d_link_gbs"]
+            dist.all_reduce(links)
+            e2e["h2d_link_gbs_per_rank"] = [round(float(x), 1) for x in links.tolist()]
         e2e["h2d_ms_per_step_alone"] = link_ms
         e2e["note"] = "bound by the host->device copy of the stage inputs (h2d_ms_per_step_alone vs ms_per_step of the device-resident path)"
 

@@ -2,6 +2,9 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#ifdef __cplusplus
+#include <atomic>
+#endif
 #include <math.h>
 #include <stdint.h>
 
@@ -136,8 +139,10 @@ __device__ __forceinline__ void await_problem(const unsigned *done, unsigned epo
 // publish -- launch the consumer in plain stream order.  edge_add: see SinkArgs::edge_add.
 int sinkhorn_ot2_publish(const float *scores, const float *one, const float *ns, int b, int m, int n, int iters, float edge_add,
                          float *out, cudaStream_t st, const unsigned **done, unsigned *epoch);
-extern int g_handover;  // pats_plan_handover(): 0 = never publish (plain stream order everywhere)
-extern int g_chain;     // pats_launch_chaining(): 0 = plain launches
+// Process-wide switches (A/B timing and tests).  Atomics: a call samples each switch once, on entry; flipping one from another host
+// thread never tears, it just applies to that thread's later calls.  They select between bit-identical code paths.
+extern std::atomic<int> g_handover;  // pats_plan_handover(): 0 = never publish (plain stream order everywhere)
+extern std::atomic<int> g_chain;     // pats_launch_chaining(): 0 = plain launches
 
 // launch with programmatic stream serialization (see pdl_prologue); the kernel MUST start with pdl_prologue() (or, for
 // the hand-over consumers, wait on the per-problem flags instead)
@@ -152,7 +157,7 @@ inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_chain ? 1 : 0;
+    cfg.numAttrs = g_chain.load(std::memory_order_relaxed) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -23,6 +23,7 @@
 //     No CPU path exists.
 #include <cooperative_groups.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 
@@ -1904,15 +1905,15 @@ using CfgCl320b = RegCfg<16, 5, 5, 10, 1, 4>;  // <= 320 x 320, cluster of 4 CTA
 using CfgCl320z = RegCfg<8, 5, 4, 10, 1, 10>;
 using CfgCl512 = RegCfg<16, 5, 4, 16, 1, 8>;   // <= 512 x 512, cluster of 8 CTAs x 512 threads
 
-static int g_force_generic = 0;
-static int g_cluster_variant = 0;  // <= 320 x 320 plans: 0 = auto (10 x 256 for b <= 8, else 8 x 256), 1 = 4 CTAs x 512 threads, 2 = 8 x 256 one-hop exchange,
+static std::atomic<int> g_force_generic{0};
+static std::atomic<int> g_cluster_variant{0};  // <= 320 x 320 plans: 0 = auto (10 x 256 for b <= 8, else 8 x 256), 1 = 4 CTAs x 512 threads, 2 = 8 x 256 one-hop exchange,
                                    // 3 = 8 x 256, 4 = 10 x 256
-static int g_disable_c145 = 0;  // 145 x 145 routing: 0 = 8-warp kernel, two CTAs per SM (default), 1 = padded 160 x 160 CTA kernel,
+static std::atomic<int> g_disable_c145{0};  // 145 x 145 routing: 0 = 8-warp kernel, two CTAs per SM (default), 1 = padded 160 x 160 CTA kernel,
                                 //                    2 = 9-warp kernel
-static int g_disable_w65 = 0;  // 65 x 65 routing: 0 = two warps per problem (default), 1 = padded 72 x 68 warp kernel,
+static std::atomic<int> g_disable_w65{0};  // 65 x 65 routing: 0 = two warps per problem (default), 1 = padded 72 x 68 warp kernel,
                                //                  2 / 3 = one-warp 65 x 65 kernel at 2 / 3 CTAs per SM (tests / A-B timing)
-static int g_bulk_staging = 1;  // pats_sinkhorn_bulk_staging(): 65 x 65 problems staged by cp.async.bulk (persistent CTAs); 0 = direct loads
-static int g_fp_exit = 1;  // pats_sinkhorn_fixed_point_exit(): 65 x 65 kernel leaves its loop at a bitwise fixed point (results identical)
+static std::atomic<int> g_bulk_staging{1};  // pats_sinkhorn_bulk_staging(): 65 x 65 problems staged by cp.async.bulk (persistent CTAs); 0 = direct loads
+static std::atomic<int> g_fp_exit{1};  // pats_sinkhorn_fixed_point_exit(): 65 x 65 kernel leaves its loop at a bitwise fixed point (results identical)
 static int *g_fb_total[kMaxDevices];  // per device: counter of problems that took the log-domain fallback
 static std::mutex g_mu;
 
@@ -2215,8 +2216,8 @@ PATS_API void pats_plan_handover(int on) { g_handover = on ? 1 : 0; }
 PATS_API void pats_launch_chaining(int on) { g_chain = on ? 1 : 0; }
 
 namespace pats {
-int g_handover = 1;
-int g_chain = 1;
+std::atomic<int> g_handover{1};
+std::atomic<int> g_chain{1};
 int sinkhorn_ot2_publish(const float *scores, const float *one, const float *ns, int b, int m, int n, int iters, float edge_add,
                          float *out, cudaStream_t st, const unsigned **done, unsigned *epoch) {
     if (b > 0 && (!one || !ns)) return invalid("log_optimal_transport2: null one / ns");

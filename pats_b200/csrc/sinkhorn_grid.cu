@@ -17,6 +17,7 @@
 //   86 % of the measured HBM peak (the one-CTA-per-problem log-domain kernel needs > 1 s); 1025 x 1025, b = 1: 0.65 ms.
 //   Variants that lost the A/B and were removed: register prefetch of the next row across the exchange (register
 //   pressure), a one-barrier exchange where every CTA sums all partials, 16 warps x 1 CTA per SM (kept as a hook).
+#include <atomic>
 #include <map>
 #include <mutex>
 
@@ -467,8 +468,8 @@ void *grid_workspace(cudaStream_t st, size_t bytes) {
     return e.first;
 }
 
-int g_grid_ctas_per_problem = 0;  // test hook: 0 = automatic
-int g_grid_variant = 0;            // A/B hook: 1 = 16 warps x 1 CTA per SM instead of 8 warps x 2 CTAs per SM
+std::atomic<int> g_grid_ctas_per_problem{0};  // test hook: 0 = automatic
+std::atomic<int> g_grid_variant{0};            // A/B hook: 1 = 16 warps x 1 CTA per SM instead of 8 warps x 2 CTAs per SM
 
 template <int CPL, int W, int OCC, bool KEEP, bool FULLONLY = false>
 int launch_grid_cfg(const SinkArgs &a, cudaStream_t st) {
@@ -486,8 +487,8 @@ int launch_grid_cfg(const SinkArgs &a, cudaStream_t st) {
         G = slots / a.b;
         if (G < 1) G = 1;
         if (G > gmax) G = gmax;
-        if (g_grid_ctas_per_problem > 0 && g_grid_ctas_per_problem <= slots)
-            G = g_grid_ctas_per_problem < gmax ? g_grid_ctas_per_problem : gmax;
+        const int forced = g_grid_ctas_per_problem.load(std::memory_order_relaxed);
+        if (forced > 0 && forced <= slots) G = forced < gmax ? forced : gmax;
         smem = GridSmem<CPL, W>::bytes((a.M + G - 1) / G);
         if (smem > 227 * 1024) continue;
         PATS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -55,6 +55,16 @@ M.log_optimal_transport2(s3, one, ns3, IT)
 # ill-conditioned problems: the in-kernel log-domain fallback of the register kernels
 M.log_optimal_transport2(s3 * 400.0, one, ns3, IT)
 M.log_optimal_transport2(s2 * 400.0, one, (sx * sy).reshape(5, 1, 144), IT)
+# tcgen05 correlation (TMEM allocation, mbarrier commit, shared-memory operand staging) on the three shapes, feeding a solve
+for (bb, dd, nn) in ((5, 128, 65), (2, 264, 145), (1, 448, 300)):
+    c0 = torch.randn(bb, dd, nn, generator=g).to(dev)
+    c1 = torch.randn(bb, dd, nn, generator=g).to(dev)
+    zc = Ly.correlation(c0, c1, 0.1 / dd ** 0.5)
+    if nn == 65:
+        M.log_optimal_transport2(zc, one, areas(bb, 1, 64), IT)
+# the bulk-staged 65 x 65 kernel with more problems than resident CTAs would need is covered above (19 problems, one CTA each);
+# an unaligned view takes the direct kernel
+M.log_optimal_transport2(s3[1:], one, ns3[1:], IT)
 # streaming (grid-cooperative) kernel and the generic log-domain kernel
 sb = (0.3 * torch.randn(2, 600, 600, generator=g)).to(dev)
 M.log_optimal_transport(sb, one, areas(2, 1, 600), 3)
