@@ -37,3 +37,32 @@ def test_install_rebinds_callers_and_uninstall_restores():
         inst.uninstall()
     assert ref.first_layer.log_optimal_transport is orig
     assert ref.second_layer.SecondLayer.merge_patches_new is orig_merge
+
+
+def test_install_fused_rebinds_the_layer_forwards_with_the_reference_signatures():
+    """install(fused=True) also swaps SecondLayer.forward / ThirdLayer.forward for pats_b200.forward's mirrors: same parameter
+    names in the same order as the reference's methods (models/second_layer.py:61, models/third_layer.py:112), restored by
+    uninstall()."""
+    import inspect
+
+    ref = ref_loader.load_reference()
+    from pats_b200 import forward as fwd
+    from pats_b200 import install as inst
+
+    o2, o3 = ref.second_layer.SecondLayer.forward, ref.third_layer.ThirdLayer.forward
+    assert list(inspect.signature(fwd.second_layer_forward).parameters) == list(inspect.signature(o2).parameters)
+    assert list(inspect.signature(fwd.third_layer_forward).parameters) == list(inspect.signature(o3).parameters)
+    done = inst.install(fused=True)
+    try:
+        assert ("models.second_layer", "SecondLayer.forward") in done and ("models.third_layer", "ThirdLayer.forward") in done
+        assert ref.second_layer.SecondLayer.forward is fwd.second_layer_forward
+        assert ref.third_layer.ThirdLayer.forward is fwd.third_layer_forward
+    finally:
+        inst.uninstall()
+    assert ref.second_layer.SecondLayer.forward is o2 and ref.third_layer.ThirdLayer.forward is o3
+    plain = inst.install()
+    try:
+        assert ("models.second_layer", "SecondLayer.forward") not in plain
+        assert ref.second_layer.SecondLayer.forward is o2
+    finally:
+        inst.uninstall()
