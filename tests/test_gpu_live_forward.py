@@ -139,10 +139,16 @@ def run_case(name, dev="cuda:0"):
         try:
             model(data)
             torch.cuda.synchronize()
+            from pats_b200 import _lib as _pl
+
+            _pl.load().pats_sinkhorn_iterations_skipped(1)
             t0 = time.perf_counter()
             our_out = model(data)
             torch.cuda.synchronize()
             log["installed_s"] = time.perf_counter() - t0
+            # how often the bit-exact fixed-point exit fires on real call data: problem-iterations not executed in one forward pass
+            log["sinkhorn_iterations_skipped"] = int(_pl.load().pats_sinkhorn_iterations_skipped(1))
+            log["sinkhorn_problem_iterations"] = 100 * int(log["calls"].get("log_optimal_transport2", {}).get("problems", 0))
         finally:
             inst.uninstall()
         # (iii) layer-level drop-ins too: SecondLayer.forward / ThirdLayer.forward on the fused entry points
