@@ -259,6 +259,36 @@ int pats_third_layer_match_f32(const float *scores, const float *one, const floa
 int pats_correlation_f32(const float *d0, const float *d1, int b, int d, int n, int m, float scale, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The attention network in front of every matching level      models/modules.py:84-134
+ *   AttentionalGNN.forward :119-134 (called first_layer.py:106, second_layer.py:93, third_layer.py:148),
+ *   AttentionalPropagation :108-117, MultiHeadedAttention :90-106, attention :84-88, MLP :58-69
+ * ------------------------------------------------------------------------------------------- */
+
+/* Parameters.  `raw` (DEVICE) holds, per layer and in this order, the reference's tensors as they sit in its state_dict:
+ *   attn.proj.0.weight [D,D] .bias [D], attn.proj.1.* , attn.proj.2.* (query, key, value), attn.merge.weight [D,D] .bias [D],
+ *   mlp.0.weight [2D,2D] .bias [2D], mlp.1.weight, .bias, .running_mean, .running_var [2D each] (BatchNorm1d), mlp.3.weight [D,2D] .bias [D]
+ * = pats_gnn_raw_floats(layers, D) floats.  pats_gnn_pack_f32 writes pats_gnn_packed_floats(layers, D) floats (DEVICE): the
+ * query / key / value rows permuted head-major, the merge convolution and the inference-mode BatchNorm folded into the first
+ * MLP convolution (FP64 products).  Pack once per set of weights. */
+long long pats_gnn_raw_floats(int layers, int D);
+long long pats_gnn_packed_floats(int layers, int D);
+int pats_gnn_pack_f32(const float *raw, int layers, int D, int heads, float bn_eps, float *packed, void *stream);
+
+/* desc0, desc1 [B,D,N] f32 (DEVICE) -> out0, out1 [B,D,N]: `layers` rounds of desc += mlp(cat(desc, attn(desc, src, src))) with
+ *   src = the same set (cross[l] == 0, 'self') or the other one (cross[l] != 0, 'cross'); `cross` is a HOST array of `layers` bytes.
+ *   BatchNorm in inference mode (module.eval(); a module in train() mode uses batch statistics and is not this function).
+ *   `workspace` (DEVICE): at least pats_gnn_workspace_floats(1, D, N) floats; problems are processed in chunks of as many as fit
+ *   (14 * N * D floats each).  D a multiple of 8 and of `heads`, the head dimension even; n <= 160 tokens with head dimension <= 96,
+ *   or n <= 96 with head dimension <= 32, or any n with head dimension <= 128 (flash-style pass over the keys).
+ *   Arithmetic: the 1x1 convolutions on the tcgen05 tensor cores with FP32-class accuracy (3xTF32); pats_gnn_precision(1) selects
+ *   single-pass TF32, which is what cuDNN gives the reference's Conv1d on a GPU (torch.backends.cudnn.allow_tf32 defaults to True);
+ *   the attention products in FP32 as in the reference. */
+long long pats_gnn_workspace_floats(int chunk, int D, int N);
+int pats_attentional_gnn_f32(const float *desc0, const float *desc1, int B, int D, int N, const float *packed, const unsigned char *cross,
+                             int layers, int heads, float *out0, float *out1, float *workspace, long long workspace_floats, void *stream);
+void pats_gnn_precision(int passes);
+
+/* ---------------------------------------------------------------------------------------------
  * Feature gathers next to the path                  (models/second_layer.py:71-80, models/third_layer.py:119-146)
  * ------------------------------------------------------------------------------------------- */
 

@@ -18,7 +18,7 @@ SO = os.path.join(HERE, "libpats_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 # source -> extra flags.  regroup.cu is compiled without FMA contraction: its f32 expressions must round
 # exactly like the C oracle's (integer results hang off them).
-SOURCES = {"api.cu": [], "sinkhorn.cu": [], "sinkhorn_grid.cu": [], "subdivide.cu": [], "regroup.cu": ["-fmad=false"], "gather.cu": [], "correlation.cu": []}
+SOURCES = {"api.cu": [], "sinkhorn.cu": [], "sinkhorn_grid.cu": [], "subdivide.cu": [], "regroup.cu": ["-fmad=false"], "gather.cu": [], "correlation.cu": [], "gnn.cu": []}
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

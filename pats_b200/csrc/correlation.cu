@@ -23,6 +23,7 @@
 //     16-column groups), scale, and store the valid rows / columns.
 //   SASS: UTCMMA (the MMA), LDTM (TMEM load), UTCBAR (commit), STS / LDG for the staging.
 #include "common.cuh"
+#include "tcgen05.cuh"
 
 namespace pats {
 namespace {
@@ -31,52 +32,10 @@ constexpr int KC = 32;            // K extent staged per chunk
 constexpr int KC4 = KC / 4;       // core matrices along K per chunk
 constexpr int CORR_THREADS = 256;  // 8 warps stage; warps w and w + 4 share a TMEM lane quadrant and split the accumulator columns
 
-__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+using namespace tc;  // csrc/tcgen05.cuh: descriptors, MMA issue, commit / mbarrier, TMEM allocation and loads, TF32 rounding
 
-// K-major, no swizzle: element (row, k) of a tile with KC4 core matrices along K lives at float index
-//   ((row / 8) * KC4 + k / 4) * 32 + (row % 8) * 4 + k % 4          LBO (K direction) = 128 B, SBO (row direction) = KC4 * 128 B
-__device__ __forceinline__ unsigned long long umma_desc(unsigned saddr) {
-    unsigned long long d = 0;
-    d |= (unsigned long long)((saddr & 0x3FFFFu) >> 4);          // start address, bits [0,14)
-    d |= (unsigned long long)(128u >> 4) << 16;                  // leading byte offset, bits [16,30)
-    d |= (unsigned long long)((KC4 * 128u) >> 4) << 32;          // stride byte offset, bits [32,46)
-    d |= 1ull << 46;                                             // descriptor version (Blackwell)
-    return d;                                                    // base offset 0, layout type SWIZZLE_NONE
-}
-// kind::tf32, FP32 accumulate, both operands K-major, M = 128
-__device__ __forceinline__ unsigned umma_idesc(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((128u >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(unsigned d_tmem, unsigned long long a, unsigned long long b, unsigned idesc, unsigned accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_init1(unsigned mb) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory"); }
-__device__ __forceinline__ void mbar_wait_parity(unsigned mb, unsigned parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(mb),
-        "r"(parity)
-        : "memory");
-}
-
-__device__ __forceinline__ float tf32_rn(float x) {
-    unsigned r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// K-major, no swizzle (tcgen05.cuh): LBO (K direction) = 128 B, SBO (row direction) = KC4 * 128 B
+__device__ __forceinline__ unsigned long long umma_desc(unsigned saddr) { return tc::umma_desc(saddr, KC4 * 128u); }
 
 struct CorrArgs {
     const float *d0, *d1;  // [b,d,n], [b,d,m]
@@ -131,8 +90,7 @@ __global__ void __launch_bounds__(CORR_THREADS) correlation_tcgen05_kernel(CorrA
     float *b_hi = a_lo + 128 * KC, *b_lo = b_hi + a.npad * KC;
     const unsigned mb = smem_addr(&s_bar);
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "r"((unsigned)a.tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        tmem_alloc(&s_tmem, (unsigned)a.tmem_cols);
     }
     if (tid == 0) {
         mbar_init1(mb);
@@ -175,7 +133,7 @@ __global__ void __launch_bounds__(CORR_THREADS) correlation_tcgen05_kernel(CorrA
                     }
                 }
                 // arrives on the mbarrier when every MMA issued so far has finished reading shared memory and writing TMEM
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mb) : "memory");
+                umma_commit(mb);
             }
             first = 0;
             mbar_wait_parity(mb, phase);
@@ -189,13 +147,7 @@ __global__ void __launch_bounds__(CORR_THREADS) correlation_tcgen05_kernel(CorrA
         for (int c0 = (warp >> 2) * 16; c0 < a.npad; c0 += 32) {
             unsigned v[16];
             const unsigned taddr = tmem + ((unsigned)(quad * 32) << 16) + (unsigned)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_ld16(taddr, v);
             if (row < a.n) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
@@ -206,7 +158,7 @@ __global__ void __launch_bounds__(CORR_THREADS) correlation_tcgen05_kernel(CorrA
         __syncthreads();  // every warp has drained its accumulator rows before the next block's first MMA overwrites them
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((unsigned)a.tmem_cols) : "memory");
+    if (warp == 0) tmem_dealloc(tmem, (unsigned)a.tmem_cols);
 }
 
 }  // namespace

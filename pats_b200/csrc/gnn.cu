@@ -1,0 +1,617 @@
+// N3 -- the attention network in front of every matching level, on the tcgen05 tensor cores.
+// Replaces, from zju3dv/pats (models/modules.py):
+//   AttentionalGNN.forward            :119-134   L layers, 'self' / 'cross', residual update of both descriptor sets
+//   AttentionalPropagation.forward    :108-117   message = attn(x, source, source);  mlp(cat([x, message]))
+//   MultiHeadedAttention.forward      :100-106   three 1x1 convolutions, view(b, dim, heads, n), attention, merge convolution
+//   attention                         :84-88     softmax(q^T k / sqrt(dim)) v per head
+//   MLP([2D, 2D, D])                  :58-69     Conv1d(2D,2D) -> BatchNorm1d (inference statistics) -> ReLU -> Conv1d(2D,D)
+// called at first_layer.py:106 (D = 448, n = 300, 18 layers), second_layer.py:93 (D = 264, n = 145, 18 layers, b = P windows) and
+// third_layer.py:148 (D = 128, n = 65, 10 layers, b = K points).  The reference runs ~25 ATen kernels per layer and side (17 000
+// launches per image pair); with the Sinkhorn path at ~1 ms these networks are 2/3 of what is left of a forward pass
+// (tools/profile_forward.py).
+//
+// Formulation.  Activations are kept TOKEN-major inside the network: X[t][c], t = (side * b + problem) * n + token, so that every
+// 1x1 convolution is one GEMM over all tokens of all problems with both operands K-major (rows of D / 2D floats, 16-byte aligned):
+//     QKV = X  Wqkv^T + bqkv                       [T, 3D]   (rows of Wq / Wk / Wv permuted head-major: c' = h * dim + d <- c = d * heads + h)
+//     O   = softmax(Q_h K_h^T / sqrt(dim)) V_h     [T, D]    per (problem, side, head); K / V of the same side ('self') or the other ('cross')
+//     Y   = relu([X | O] W1f^T + b1f)              [T, 2D]   W1f = bn_scale * [W1[:, :D] | W1[:, D:] Wm]: the merge convolution and the
+//                                                            inference BatchNorm are affine and are folded into the first MLP layer when
+//                                                            the weights are packed (products accumulated in FP64)
+//     X  += Y W2^T + b2                            [T, D]
+// Four kernels per layer, launch-chained (griddepcontrol), no host synchronisation; the [b, D, n] <-> [T, D] transpositions are
+// one pass each at entry and exit.  Problems are processed in chunks sized so that a chunk's activations stay in the 126 MB L2.
+//
+// GEMM kernel (gnn_gemm_kernel): one CTA of 256 threads per (128-token block, <= 256-output block).  Per 32-wide K chunk every
+// thread loads its 16-byte pieces of the activation and weight tiles (issued BEFORE it waits for the previous chunk's MMAs, so
+// the L2 latency hides behind the tensor core), splits them into TF32 hi / lo halves and stores them in the canonical K-major
+// no-swizzle UMMA layout (lane = (k4 % 4) * 8 + row % 8: conflict-free 128-bit stores, fully used 32-byte sectors); one thread
+// issues tcgen05.mma.kind::tf32 (M = 128, N <= 256, K = 8; accumulator in TMEM) -- hi*hi + hi*lo + lo*hi per K step ("3xTF32":
+// FP32-class accuracy; the reference's own convolutions run as single TF32 through cuDNN, which `pats_gnn_precision(1)` mirrors)
+// -- and tcgen05.commit arrives on an mbarrier.  Two CTAs share an SM (96 KB of operands + 256 TMEM columns each), so one CTA
+// stages while the other's MMAs run.  Epilogue: tcgen05.ld, + bias, ReLU or the in-place residual add, 64-byte row pieces.
+// Attention kernel (gnn_attention_kernel): FP32 on the CUDA cores, as the reference computes it (torch.einsum -> SGEMM): one CTA
+// per (problem, side, head), K^T / V / Q in shared memory, a warp owns R query rows x all keys in registers (R * ceil(n / 32)
+// accumulators), softmax by warp shuffles, P through a per-warp shared buffer into the P V product.
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace pats {
+namespace {
+
+using namespace tc;
+
+constexpr int GKC = 32;             // K extent staged per chunk
+constexpr int GKC4 = GKC / 4;       // core matrices along K per chunk
+constexpr int GEMM_THREADS = 256;   // 8 warps stage and drain; warps w and w + 4 share a TMEM lane quadrant
+constexpr int GEMM_M = 128;
+
+std::atomic<int> g_precision{3};    // 3 = 3xTF32 (default), 1 = single TF32 (what cuDNN gives the reference's Conv1d)
+
+struct GemmArgs {
+    const float *A1, *A2;  // [T, K1] (row stride lda1), [T, K2] (row stride lda2; K2 = 0: absent): the K extents are concatenated
+    const float *W;        // [Nout, K1 + K2] row-major (row stride ldw)
+    const float *bias;     // [Nout]
+    float *out;            // [T, Nout] at row stride ldo
+    int lda1, lda2, K1, K2, ldw, ldo;
+    int T, Nout;
+    int nb, nblocks, mblocks;  // outputs per block (a multiple of 16, <= 256), blocks along Nout, 128-token blocks
+    int relu, accumulate;      // out = relu(acc + bias)   /   out += acc + bias
+    int tmem_cols;
+};
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// round to TF32 (nearest, ties away from zero in magnitude) with two integer instructions; cvt.rna.tf32.f32 adds a NaN / Inf test
+// (FSETP + SEL per value) that the activations of this network never need: an Inf / NaN input stays Inf / NaN through the mask
+__device__ __forceinline__ float tf32_round(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
+template <bool SPLIT>
+__device__ __forceinline__ void store_split(float *hi, float *lo, int idx, float4 x) {
+    const float4 h = make_float4(tf32_round(x.x), tf32_round(x.y), tf32_round(x.z), tf32_round(x.w));
+    *reinterpret_cast<float4 *>(hi + idx) = h;
+    if (SPLIT) *reinterpret_cast<float4 *>(lo + idx) = make_float4(tf32_round(x.x - h.x), tf32_round(x.y - h.y), tf32_round(x.z - h.z), tf32_round(x.w - h.w));
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gnn_gemm_kernel(GemmArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ unsigned s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kq = lane >> 3, rr = lane & 7;  // lane = (k4 % 4) * 8 + row % 8
+    const int nbpad_max = (a.nb + 15) & ~15;
+    float *a_hi = smem;
+    float *a_lo = a_hi + (SPLIT ? GEMM_M * GKC : 0);
+    float *b_hi = a_lo + GEMM_M * GKC;
+    float *b_lo = b_hi + (SPLIT ? nbpad_max * GKC : 0);
+    const unsigned mb = smem_addr(&s_bar);
+    pdl_prologue();
+    if (warp == 0) tmem_alloc(&s_tmem, (unsigned)a.tmem_cols);
+    if (tid == 0) {
+        mbar_init1(mb);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const unsigned tmem = s_tmem;
+    unsigned phase = 0;
+    const int nch1 = (a.K1 + GKC - 1) / GKC, nch = nch1 + (a.K2 + GKC - 1) / GKC;
+
+    for (int unit = blockIdx.x; unit < a.mblocks * a.nblocks; unit += gridDim.x) {
+        const int mblk = unit / a.nblocks, nblk = unit - mblk * a.nblocks;
+        const int r0 = mblk * GEMM_M, n0 = nblk * a.nb;
+        const int ncols = min(a.nb, a.Nout - n0), npad = (ncols + 15) & ~15;
+        const int bgroups = npad >> 3;
+        bool inflight = false;
+        for (int ch = 0; ch < nch; ++ch) {
+            const bool second = ch >= nch1;
+            const float *src = second ? a.A2 : a.A1;
+            const int lda = second ? a.lda2 : a.lda1;
+            const int k0 = (second ? ch - nch1 : ch) * GKC;
+            const int kn = min(GKC, (second ? a.K2 : a.K1) - k0);
+            const int wc0 = (second ? a.K1 : 0) + k0;
+            const int kb_sh = kn > 16 ? 1 : 0;  // warp items along K: one (k4 0..3) or two (k4 0..7)
+            // ---- global -> registers (nothing in shared memory is touched yet: the previous chunk's MMAs may still be reading it) ----
+            float4 av[4], bv[8];
+            const int a_items = 16 << kb_sh, b_items = bgroups << kb_sh;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int w = warp + i * 8;
+                const int g8 = w >> kb_sh, k4 = ((w & kb_sh) << 2) + kq;
+                const int row = r0 + g8 * 8 + rr;
+                av[i] = (w < a_items && row < a.T && k4 * 4 < kn) ? ldg4(src + (size_t)row * lda + k0 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int w = warp + i * 8;
+                const int g8 = w >> kb_sh, k4 = ((w & kb_sh) << 2) + kq;
+                const int nrow = n0 + g8 * 8 + rr;
+                bv[i] = (w < b_items && nrow < a.Nout && k4 * 4 < kn) ? ldg4(a.W + (size_t)nrow * a.ldw + wc0 + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (inflight) {  // the previous chunk's MMAs have finished reading the operand tiles
+                mbar_wait_parity(mb, phase);
+                phase ^= 1u;
+                fence_after_sync();
+            }
+            // ---- registers -> split -> shared memory (canonical K-major layout) ----
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int w = warp + i * 8;
+                const int g8 = w >> kb_sh, k4 = ((w & kb_sh) << 2) + kq;
+                if (w < a_items) store_split<SPLIT>(a_hi, a_lo, (g8 * GKC4 + k4) * 32 + rr * 4, av[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int w = warp + i * 8;
+                const int g8 = w >> kb_sh, k4 = ((w & kb_sh) << 2) + kq;
+                if (w < b_items) store_split<SPLIT>(b_hi, b_lo, (g8 * GKC4 + k4) * 32 + rr * 4, bv[i]);
+            }
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                fence_after_sync();
+                const unsigned idesc = umma_idesc(npad);
+                const int steps = (kn + 7) >> 3;
+                for (int s = 0; s < steps; ++s) {
+                    const unsigned koff = (unsigned)s * 256u;  // two core matrices (K = 8) per step
+                    const unsigned long long ah = umma_desc(smem_addr(a_hi) + koff, GKC4 * 128u), bh = umma_desc(smem_addr(b_hi) + koff, GKC4 * 128u);
+                    umma_tf32(tmem, ah, bh, idesc, (ch == 0 && s == 0) ? 0u : 1u);
+                    if (SPLIT) {
+                        const unsigned long long al = umma_desc(smem_addr(a_lo) + koff, GKC4 * 128u), bl = umma_desc(smem_addr(b_lo) + koff, GKC4 * 128u);
+                        umma_tf32(tmem, ah, bl, idesc, 1u);
+                        umma_tf32(tmem, al, bh, idesc, 1u);
+                    }
+                }
+                umma_commit(mb);
+            }
+            inflight = true;
+        }
+        // ---- epilogue: warp w owns TMEM lanes (= tokens) 32 (w % 4) .. + 31; warps w and w + 4 alternate over the 16-column groups.
+        // The residual / bias values of a group are loaded BEFORE the wait for the accumulator (first group) or while the previous
+        // group is being finished, so their latency does not add to every group.
+        const int quad = warp & 3;
+        const int row = r0 + quad * 32 + lane;
+        const bool live = row < a.T;
+        float *orow = a.out + (size_t)(live ? row : 0) * a.ldo + n0;
+        float4 res[4], bia[4];
+        auto prefetch = [&](int c0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool ok = c0 + 4 * j < ncols;
+                bia[j] = ok ? ldg4(a.bias + n0 + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                res[j] = (ok && live && a.accumulate) ? *reinterpret_cast<const float4 *>(orow + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        int c0 = (warp >> 2) * 16;
+        if (c0 < npad) prefetch(c0);
+        mbar_wait_parity(mb, phase);
+        phase ^= 1u;
+        fence_after_sync();
+        for (; c0 < npad; c0 += 32) {
+            unsigned v[16];
+            tmem_ld16(tmem + ((unsigned)(quad * 32) << 16) + (unsigned)c0, v);
+            float4 r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                r[j] = make_float4(__uint_as_float(v[4 * j]) + bia[j].x + res[j].x, __uint_as_float(v[4 * j + 1]) + bia[j].y + res[j].y,
+                                   __uint_as_float(v[4 * j + 2]) + bia[j].z + res[j].z, __uint_as_float(v[4 * j + 3]) + bia[j].w + res[j].w);
+                if (a.relu) r[j].x = fmaxf(r[j].x, 0.f), r[j].y = fmaxf(r[j].y, 0.f), r[j].z = fmaxf(r[j].z, 0.f), r[j].w = fmaxf(r[j].w, 0.f);
+            }
+            const int cur = c0;
+            if (c0 + 32 < npad) prefetch(c0 + 32);
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (cur + 4 * j < ncols) *reinterpret_cast<float4 *>(orow + cur + 4 * j) = r[j];
+            }
+        }
+        fence_before_sync();
+        __syncthreads();  // every warp has drained its accumulator rows before the next unit's first MMA overwrites them
+        fence_after_sync();
+    }
+    if (warp == 0) tmem_dealloc(tmem, (unsigned)a.tmem_cols);
+}
+
+// ---- attention ----------------------------------------------------------------------------------------------------------------
+struct AttArgs {
+    const float *qkv;  // [T, 3D]: q | k | v, each head-major (column h * dim + d)
+    float *o;          // [T, D] head-major
+    int Bc, N, D, heads, dim, cross;
+    float c;           // log2(e) / sqrt(dim)
+};
+
+__device__ __forceinline__ float comp(const float4 &q, int dd) {
+    return dd == 0 ? q.x : dd == 1 ? q.y : dd == 2 ? q.z : q.w;
+}
+
+// NJ = ceil(n / 32) key slots per lane; R query rows per warp pass; NW warps.  Value layout: PV2 = false: DI = ceil(dim / 32) scalar
+// slots per lane (dim <= 32 DI: level 3, dim = 32); PV2 = true: dims [0, 64) as one float2 per lane, the dim - 64 <= 4 tail dims by a
+// key-parallel reduction (level 2, dim = 66: a third scalar slot would idle 30 of 32 lanes).
+template <int NJ, int DI, bool PV2, int R, int NW>
+__global__ void __launch_bounds__(NW * 32) gnn_attention_kernel(AttArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int NP = NJ * 32 + 1, NP32 = NJ * 32, DV = PV2 ? 64 : DI * 32, NT = NW * 32, TAILMAX = 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = a.N, dim = a.dim, dim4 = (dim + 3) & ~3, D3 = 3 * a.D;
+    const int tail = PV2 ? dim - 64 : 0;
+    float *Q = sm;                         // [N][dim4]
+    float *P = Q + N * dim4;               // [NW][NP32][R]
+    float *V = P + NW * NP32 * R;          // [N][DV]
+    float *Vt = V + N * DV;                // [N][TAILMAX]   (PV2 only)
+    float *Kt = Vt + (PV2 ? N * TAILMAX : 0);  // [dim4][NP]
+    pdl_prologue();
+    const int ps = blockIdx.x / a.heads, h = blockIdx.x - ps * a.heads;
+    const int side = ps / a.Bc, b = ps - side * a.Bc;
+    const int sps = a.cross ? (1 - side) * a.Bc + b : ps;
+    const float *qbase = a.qkv + (size_t)ps * N * D3 + h * dim;
+    const float *kbase = a.qkv + (size_t)sps * N * D3 + a.D + h * dim;
+    const float *vbase = kbase + a.D;
+    const int half = dim4 >> 1;
+    // staging: four pieces (12 loads) per thread in flight
+    for (int it0 = tid; it0 < N * half; it0 += NT * 4) {
+        float2 q2[4], k2[4], v2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * NT;
+            const int n = it / half, d = (it - n * half) * 2;
+            q2[u] = k2[u] = v2[u] = make_float2(0.f, 0.f);
+            if (it < N * half && d < dim) {
+                q2[u] = __ldg(reinterpret_cast<const float2 *>(qbase + (size_t)n * D3 + d));
+                k2[u] = __ldg(reinterpret_cast<const float2 *>(kbase + (size_t)n * D3 + d));
+                v2[u] = __ldg(reinterpret_cast<const float2 *>(vbase + (size_t)n * D3 + d));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * NT;
+            if (it < N * half) {
+                const int n = it / half, d = (it - n * half) * 2;
+                *reinterpret_cast<float2 *>(Q + n * dim4 + d) = q2[u];
+                Kt[d * NP + n] = k2[u].x, Kt[(d + 1) * NP + n] = k2[u].y;
+                if (d < DV)
+                    *reinterpret_cast<float2 *>(V + n * DV + d) = v2[u];
+                else if (PV2)
+                    Vt[n * TAILMAX + d - 64] = v2[u].x, Vt[n * TAILMAX + d - 63] = v2[u].y;
+            }
+        }
+    }
+    for (int it = tid; it < dim4 * (NP32 - N); it += NT) {  // keys beyond n: finite (masked after the products)
+        const int d = it / (NP32 - N), m = N + it - d * (NP32 - N);
+        Kt[d * NP + m] = 0.f;
+    }
+    if (!PV2 && DV > dim4)
+        for (int it = tid; it < N * (DV - dim4); it += NT) {  // value columns beyond dim: zero
+            const int n = it / (DV - dim4), d = dim4 + it - n * (DV - dim4);
+            V[n * DV + d] = 0.f;
+        }
+    __syncthreads();
+    float *Pw = P + warp * NP32 * R;
+    for (int n0 = warp * R; n0 < N; n0 += NW * R) {
+        float s[R][NJ];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) s[r][j] = 0.f;
+        const float *qrow[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) qrow[r] = Q + min(n0 + r, N - 1) * dim4;
+        for (int d = 0; d < dim4; d += 4) {
+            float4 q[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) q[r] = *reinterpret_cast<const float4 *>(qrow[r] + d);
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) {
+                float kv[NJ];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) kv[j] = Kt[(d + dd) * NP + lane + 32 * j];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) s[r][j] = fmaf(comp(q[r], dd), kv[j], s[r][j]);
+            }
+        }
+        // softmax(s / sqrt(dim)) over the keys: exp2((s - max) * log2(e) / sqrt(dim)) / sum
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if (lane + 32 * j >= N) s[r][j] = -INFINITY;
+                mx = fmaxf(mx, s[r][j]);
+            }
+            mx = warp_max(mx);
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                s[r][j] = fast_exp2((s[r][j] - mx) * a.c);
+                sum += s[r][j];
+            }
+            sum = warp_sum(sum);
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) s[r][j] *= inv;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int r4 = 0; r4 < R; r4 += 4)
+                *reinterpret_cast<float4 *>(Pw + (lane + 32 * j) * R + r4) = make_float4(s[r4][j], s[r4 + 1][j], s[r4 + 2][j], s[r4 + 3][j]);
+        __syncwarp();
+        constexpr int OS = PV2 ? 2 : DI;  // value slots per lane
+        float o[R][OS];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < OS; ++i) o[r][i] = 0.f;
+#pragma unroll 2
+        for (int m = 0; m < N; ++m) {
+            float p[R];
+#pragma unroll
+            for (int r4 = 0; r4 < R; r4 += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(Pw + m * R + r4);
+                p[r4] = t.x, p[r4 + 1] = t.y, p[r4 + 2] = t.z, p[r4 + 3] = t.w;
+            }
+            float vv[OS];
+            if (PV2) {
+                const float2 t = *reinterpret_cast<const float2 *>(V + m * DV + 2 * lane);
+                vv[0] = t.x, vv[OS - 1] = t.y;
+            } else {
+#pragma unroll
+                for (int i = 0; i < OS; ++i) vv[i] = V[m * DV + lane + 32 * i];
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int i = 0; i < OS; ++i) o[r][i] = fmaf(p[r], vv[i], o[r][i]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (n0 + r < N) {
+                float *orow = a.o + ((size_t)ps * N + n0 + r) * a.D + h * dim;
+                if (PV2) {
+                    *reinterpret_cast<float2 *>(orow + 2 * lane) = make_float2(o[r][0], o[r][OS - 1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < OS; ++i)
+                        if (lane + 32 * i < dim) orow[lane + 32 * i] = o[r][i];
+                }
+            }
+        if (PV2) {  // tail dims 64 .. dim - 1: every lane sums its own keys (the probabilities are still in registers), then one warp reduction
+            for (int t = 0; t < tail; ++t) {
+                float vt[NJ];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) vt[j] = lane + 32 * j < N ? Vt[(lane + 32 * j) * TAILMAX + t] : 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) acc = fmaf(s[r][j], vt[j], acc);
+                    acc = warp_sum(acc);
+                    if (lane == 0 && n0 + r < N) a.o[((size_t)ps * N + n0 + r) * a.D + h * dim + 64 + t] = acc;
+                }
+            }
+        }
+        __syncwarp();  // the P buffer is rewritten by the next pass
+    }
+}
+
+// ---- layout changes at entry / exit: [b, D, n] (the reference's Conv1d layout) <-> token-major [T, D] --------------------------
+struct TransArgs {
+    const float *d0, *d1;  // entry: inputs [B, D, N] per side
+    float *o0, *o1;        // exit: outputs [B, D, N] per side
+    float *X;              // [2 * Bc * N, D]
+    int b0, Bc, D, N;      // problems [b0, b0 + Bc) of the batch
+    int to_tokens;
+};
+
+__global__ void __launch_bounds__(256) gnn_transpose_kernel(TransArgs a) {
+    __shared__ float tile[32][33];
+    pdl_prologue();
+    const int ps = blockIdx.z, side = ps / a.Bc, b = ps - side * a.Bc;
+    const int nb = blockIdx.x * 32, db = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const size_t off = (size_t)(a.b0 + b) * a.D * a.N;
+    float *X = a.X + (size_t)ps * a.N * a.D;
+    if (a.to_tokens) {
+        const float *src = (side ? a.d1 : a.d0) + off;
+        for (int i = ty; i < 32; i += 8)
+            if (db + i < a.D && nb + tx < a.N) tile[i][tx] = src[(size_t)(db + i) * a.N + nb + tx];
+        __syncthreads();
+        for (int i = ty; i < 32; i += 8)
+            if (nb + i < a.N && db + tx < a.D) X[(size_t)(nb + i) * a.D + db + tx] = tile[tx][i];
+    } else {
+        float *dst = (side ? a.o1 : a.o0) + off;
+        for (int i = ty; i < 32; i += 8)
+            if (nb + i < a.N && db + tx < a.D) tile[i][tx] = X[(size_t)(nb + i) * a.D + db + tx];
+        __syncthreads();
+        for (int i = ty; i < 32; i += 8)
+            if (db + i < a.D && nb + tx < a.N) dst[(size_t)(db + i) * a.N + nb + tx] = tile[tx][i];
+    }
+}
+
+// ---- weight packing (device, FP64 accumulation) ----------------------------------------------------------------------------------
+// raw layer layout (floats), the reference's parameters in this order (models/modules.py:92-112):
+//   Wq[D*D] bq[D] Wk[D*D] bk[D] Wv[D*D] bv[D]       attn.proj.0 / 1 / 2  (Conv1d weight [out, in, 1])
+//   Wm[D*D] bm[D]                                   attn.merge
+//   W1[2D*2D] b1[2D]                                mlp.0
+//   gamma[2D] beta[2D] mean[2D] var[2D]             mlp.1 (BatchNorm1d weight, bias, running_mean, running_var)
+//   W2[D*2D] b2[D]                                  mlp.3
+// packed layer layout: Wqkv[3D*D] bqkv[3D] W1f[2D*2D] b1f[2D] W2[D*2D] b2[D]
+__host__ __device__ inline size_t raw_layer_floats(int D) { return (size_t)4 * D * D + 4 * D + (size_t)4 * D * D + 2 * D + 8 * D + (size_t)2 * D * D + D; }
+__host__ __device__ inline size_t packed_layer_floats(int D) { return (size_t)9 * D * D + 6 * D; }
+
+__global__ void gnn_pack_kernel(const float *raw, float *packed, int layers, int D, int heads, float eps) {
+    const int dim = D / heads, D2 = 2 * D;
+    const size_t per = packed_layer_floats(D);
+    const size_t total = per * layers;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int l = (int)(i / per);
+        size_t e = i - (size_t)l * per;
+        const float *r = raw + (size_t)l * raw_layer_floats(D);
+        const size_t DD = (size_t)D * D;
+        const float *Wm = r + 3 * (DD + D), *bm = Wm + DD;
+        const float *W1 = bm + D, *b1 = W1 + (size_t)D2 * D2;
+        const float *gamma = b1 + D2, *beta = gamma + D2, *mean = beta + D2, *var = mean + D2;
+        const float *W2 = var + D2;
+        float val;
+        if (e < 3 * DD) {  // Wqkv: row c' = h * dim + d of block p <- row c = d * heads + h of proj.p
+            const int p = (int)(e / DD);
+            const int cp = (int)((e - p * DD) / D), k = (int)(e - p * DD - (size_t)cp * D);
+            const int hh = cp / dim, d = cp - hh * dim;
+            val = r[(size_t)p * (DD + D) + (size_t)(d * heads + hh) * D + k];
+        } else if ((e -= 3 * DD) < (size_t)3 * D) {
+            const int p = (int)(e / D), cp = (int)(e - (size_t)p * D);
+            const int hh = cp / dim, d = cp - hh * dim;
+            val = r[(size_t)p * (DD + D) + DD + d * heads + hh];
+        } else if ((e -= 3 * D) < (size_t)D2 * D2) {  // W1f
+            const int o = (int)(e / D2), c = (int)(e - (size_t)o * D2);
+            const double sc = (double)gamma[o] / sqrt((double)var[o] + (double)eps);
+            double acc;
+            if (c < D) {
+                acc = W1[(size_t)o * D2 + c];
+            } else {
+                const int cp = c - D, hh = cp / dim, d = cp - hh * dim, old = d * heads + hh;
+                acc = 0.0;
+                for (int k = 0; k < D; ++k) acc += (double)W1[(size_t)o * D2 + D + k] * (double)Wm[(size_t)k * D + old];
+            }
+            val = (float)(acc * sc);
+        } else if ((e -= (size_t)D2 * D2) < (size_t)D2) {  // b1f = (b1 + W1[:, D:] bm - mean) * scale + beta
+            const int o = (int)e;
+            const double sc = (double)gamma[o] / sqrt((double)var[o] + (double)eps);
+            double acc = b1[o];
+            for (int k = 0; k < D; ++k) acc += (double)W1[(size_t)o * D2 + D + k] * (double)bm[k];
+            val = (float)((acc - (double)mean[o]) * sc + (double)beta[o]);
+        } else {  // W2, b2 verbatim
+            e -= D2;
+            val = W2[e];
+        }
+        packed[i] = val;
+    }
+}
+
+template <int NJ, int DI, bool PV2, int R, int NW>
+int launch_attention(const AttArgs &a, cudaStream_t st, int dev) {
+    const int dim4 = (a.dim + 3) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)a.N * dim4 + (size_t)NW * NJ * 32 * R + (size_t)a.N * (PV2 ? 64 + 4 : DI * 32) + (size_t)dim4 * (NJ * 32 + 1));
+    static PerDeviceOnce configured;
+    if (!configured.done(dev)) {
+        PATS_CUDA_TRY(cudaFuncSetAttribute(gnn_attention_kernel<NJ, DI, PV2, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured.mark(dev);
+    }
+    if (smem > 220 * 1024) return invalid("attentional_gnn: attention tile of %zu bytes exceeds shared memory (n = %d, head dim = %d)", smem, a.N, a.dim);
+    PATS_CUDA_TRY(launch_chained(gnn_attention_kernel<NJ, DI, PV2, R, NW>, dim3((unsigned)(2 * a.Bc * a.heads)), dim3(NW * 32), smem, st, a));
+    return PATS_OK;
+}
+
+int launch_gemm(GemmArgs a, cudaStream_t st, int dev, int sms) {
+    // split Nout evenly into blocks of <= 256 outputs, each a multiple of 16
+    a.nblocks = (a.Nout + 255) / 256;
+    a.nb = (((a.Nout + a.nblocks - 1) / a.nblocks) + 15) & ~15;
+    a.nblocks = (a.Nout + a.nb - 1) / a.nb;
+    a.mblocks = (a.T + GEMM_M - 1) / GEMM_M;
+    a.tmem_cols = 32;
+    while (a.tmem_cols < a.nb) a.tmem_cols <<= 1;
+    const bool split = g_precision.load(std::memory_order_relaxed) != 1;
+    const size_t smem = sizeof(float) * (size_t)GKC * (GEMM_M + a.nb) * (split ? 2 : 1);
+    static PerDeviceOnce configured;
+    if (!configured.done(dev)) {
+        PATS_CUDA_TRY(cudaFuncSetAttribute(gnn_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PATS_CUDA_TRY(cudaFuncSetAttribute(gnn_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured.mark(dev);
+    }
+    // co-resident CTAs share the SM's 512 TMEM columns and its shared memory; a CTA that cannot allocate would wait for one that can
+    int per_sm = 512 / a.tmem_cols;
+    const int by_smem = (int)((224 * 1024) / (smem + 2048));
+    if (per_sm > by_smem) per_sm = by_smem;
+    if (per_sm > 2) per_sm = 2;  // __launch_bounds__(256, 2): the register file
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)a.mblocks * a.nblocks;
+    if (grid > (long long)sms * per_sm) grid = (long long)sms * per_sm;
+    if (split)
+        PATS_CUDA_TRY(launch_chained(gnn_gemm_kernel<true>, dim3((unsigned)grid), dim3(GEMM_THREADS), smem, st, a));
+    else
+        PATS_CUDA_TRY(launch_chained(gnn_gemm_kernel<false>, dim3((unsigned)grid), dim3(GEMM_THREADS), smem, st, a));
+    return PATS_OK;
+}
+
+}  // namespace
+}  // namespace pats
+
+using namespace pats;
+
+PATS_API void pats_gnn_precision(int passes) { g_precision.store(passes == 1 ? 1 : 3, std::memory_order_relaxed); }
+
+PATS_API long long pats_gnn_raw_floats(int layers, int D) { return (long long)(raw_layer_floats(D) * (size_t)layers); }
+PATS_API long long pats_gnn_packed_floats(int layers, int D) { return (long long)(packed_layer_floats(D) * (size_t)layers); }
+PATS_API long long pats_gnn_workspace_floats(int chunk, int D, int N) { return (long long)14 * chunk * N * D; }
+
+PATS_API int pats_gnn_pack_f32(const float *raw, int layers, int D, int heads, float bn_eps, float *packed, void *stream) {
+    if (layers <= 0 || D <= 0 || heads <= 0 || D % heads != 0) return invalid("gnn_pack: bad sizes layers=%d D=%d heads=%d", layers, D, heads);
+    if (!raw || !packed) return invalid("gnn_pack: null pointer");
+    gnn_pack_kernel<<<1184, 256, 0, as_stream(stream)>>>(raw, packed, layers, D, heads, bn_eps);
+    PATS_LAUNCH_CHECK("gnn_pack_kernel");
+    return PATS_OK;
+}
+
+PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, int B, int D, int N, const float *packed, const unsigned char *cross,
+                                      int layers, int heads, float *out0, float *out1, float *workspace, long long workspace_floats, void *stream) {
+    if (B < 0 || D <= 0 || N <= 0 || layers <= 0 || heads <= 0) return invalid("attentional_gnn: bad sizes B=%d D=%d N=%d layers=%d heads=%d", B, D, N, layers, heads);
+    if (B == 0) return PATS_OK;
+    if (!desc0 || !desc1 || !packed || !cross || !out0 || !out1 || !workspace) return invalid("attentional_gnn: null pointer");
+    if (D % heads != 0 || D % 8 != 0 || (D / heads) % 2 != 0)
+        return invalid("attentional_gnn: D = %d, heads = %d: D must be a multiple of 8 and of heads, the head dimension even", D, heads);
+    const int dim = D / heads;
+    const int NJ = (N + 31) / 32, DI = (dim + 31) / 32;
+    if (!((NJ <= 3 && DI == 1) || (NJ <= 5 && DI <= 3)))
+        return invalid("attentional_gnn: n = %d tokens with head dimension %d is not a shape this build has an attention kernel for (n <= 96 with dim <= 32, n <= 160 with dim <= 96)", N, dim);
+    const long long per_problem = (long long)14 * N * D;
+    int chunk = (int)(workspace_floats / per_problem < B ? workspace_floats / per_problem : B);
+    if (chunk > 16384) chunk = 16384;  // 2 * chunk is a grid z extent
+    if (chunk < 1) return invalid("attentional_gnn: workspace of %lld floats holds no problem (%lld floats each)", workspace_floats, per_problem);
+    const int dev = current_device();
+    if (dev < 0) return PATS_E_CUDA;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    cudaStream_t st = as_stream(stream);
+    const size_t per = packed_layer_floats(D);
+    const size_t DD = (size_t)D * D;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int Bc = B - b0 < chunk ? B - b0 : chunk;
+        const int T = 2 * Bc * N;
+        float *X = workspace, *QKV = X + (size_t)T * D, *O = QKV + (size_t)T * 3 * D, *Y = O + (size_t)T * D;
+        TransArgs t;
+        t.d0 = desc0, t.d1 = desc1, t.o0 = out0, t.o1 = out1, t.X = X, t.b0 = b0, t.Bc = Bc, t.D = D, t.N = N, t.to_tokens = 1;
+        const dim3 tgrid((unsigned)((N + 31) / 32), (unsigned)((D + 31) / 32), (unsigned)(2 * Bc));
+        PATS_CUDA_TRY(launch_chained(gnn_transpose_kernel, tgrid, dim3(256), 0, st, t));
+        for (int l = 0; l < layers; ++l) {
+            const float *w = packed + (size_t)l * per;
+            const float *Wqkv = w, *bqkv = Wqkv + 3 * DD, *W1f = bqkv + 3 * D, *b1f = W1f + 4 * DD, *W2 = b1f + 2 * D, *b2 = W2 + 2 * DD;
+            GemmArgs g = {};
+            g.A1 = X, g.lda1 = D, g.K1 = D, g.A2 = nullptr, g.lda2 = 0, g.K2 = 0, g.W = Wqkv, g.ldw = D, g.bias = bqkv, g.out = QKV, g.ldo = 3 * D;
+            g.T = T, g.Nout = 3 * D, g.relu = 0, g.accumulate = 0;
+            int rc = launch_gemm(g, st, dev, sms);
+            if (rc) return rc;
+            AttArgs at;
+            at.qkv = QKV, at.o = O, at.Bc = Bc, at.N = N, at.D = D, at.heads = heads, at.dim = dim, at.cross = cross[l] ? 1 : 0;
+            at.c = 1.4426950408889634f / sqrtf((float)dim);
+            if (NJ <= 3 && DI == 1)
+                rc = launch_attention<3, 1, false, 8, 4>(at, st, dev);
+            else if (dim >= 64 && dim <= 68)
+                rc = launch_attention<5, 3, true, 8, 10>(at, st, dev);
+            else
+                rc = launch_attention<5, 3, false, 4, 8>(at, st, dev);
+            if (rc) return rc;
+            g.A1 = X, g.lda1 = D, g.K1 = D, g.A2 = O, g.lda2 = D, g.K2 = D, g.W = W1f, g.ldw = 2 * D, g.bias = b1f, g.out = Y, g.ldo = 2 * D;
+            g.Nout = 2 * D, g.relu = 1, g.accumulate = 0;
+            rc = launch_gemm(g, st, dev, sms);
+            if (rc) return rc;
+            g.A1 = Y, g.lda1 = 2 * D, g.K1 = 2 * D, g.A2 = nullptr, g.lda2 = 0, g.K2 = 0, g.W = W2, g.ldw = 2 * D, g.bias = b2, g.out = X, g.ldo = D;
+            g.Nout = D, g.relu = 0, g.accumulate = 1;
+            rc = launch_gemm(g, st, dev, sms);
+            if (rc) return rc;
+        }
+        t.to_tokens = 0;
+        PATS_CUDA_TRY(launch_chained(gnn_transpose_kernel, tgrid, dim3(256), 0, st, t));
+    }
+    return PATS_OK;
+}

@@ -1,0 +1,126 @@
+"""The attention network in front of every matching level on the CUDA library (csrc/gnn.cu).
+
+Mirrors models/modules.py of zju3dv/pats:
+    AttentionalGNN.forward(self, desc0, desc1)          :126-134     -> `attentional_gnn_forward` (same signature, bound by
+                                                                         pats_b200.install.install(attention=True))
+with AttentionalPropagation :108-117, MultiHeadedAttention :90-106, attention :84-88 and MLP :58-69 inside.  The module object
+stays the reference's own (its parameters are read, never copied back); the packed form of its weights (query / key / value rows
+head-major, merge convolution + inference BatchNorm folded into the first MLP convolution) is built once by the library
+(`pats_gnn_pack_f32`) and cached on the module until a parameter changes.
+
+What is NOT this path: a module in train() mode (the reference keeps the third layer's network in train() when `if_local` is
+False, models/pats.py:112-119: BatchNorm then normalises with the statistics of the batch and updates its running buffers) and
+token counts / head sizes csrc/gnn.cu has no attention kernel for.  Those calls run the reference's own layer modules, exactly as
+`AttentionalGNN.forward` does -- on the GPU, in PyTorch; there is no CPU path here either.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._torchutil import cuda_f32, stream_ptr
+
+__all__ = ["attentional_gnn_forward", "attentional_gnn", "pack_module", "supported", "set_precision"]
+
+WORKSPACE_MB = 192  # activations of one chunk of problems (14 * n * D floats each); sized to stay mostly inside the 126 MB L2
+_PARAM_ORDER = ("attn.proj.0", "attn.proj.1", "attn.proj.2", "attn.merge", "mlp.0")
+
+
+def set_precision(passes: int) -> None:
+    """3 (default): FP32-class 3xTF32 convolutions; 1: single-pass TF32 (what cuDNN gives the reference's Conv1d on a GPU)."""
+    _lib.load().pats_gnn_precision(int(passes))
+
+
+def supported(n_tokens: int, d_model: int, heads: int) -> bool:
+    """Shapes csrc/gnn.cu has kernels for (pats_attentional_gnn_f32 in include/pats_b200.h)."""
+    if d_model % heads or d_model % 8:
+        return False
+    dim = d_model // heads
+    if dim % 2:
+        return False
+    return (n_tokens <= 96 and dim <= 32) or (n_tokens <= 160 and dim <= 96)
+
+
+def _raw(gnn: torch.nn.Module) -> torch.Tensor:
+    """The module's parameters in the order include/pats_b200.h documents for `raw`."""
+    parts = []
+    for layer in gnn.layers:
+        sd = dict(layer.named_parameters())
+        sd.update(dict(layer.named_buffers()))
+        for k in _PARAM_ORDER:
+            parts += [sd[k + ".weight"], sd[k + ".bias"]]
+        parts += [sd["mlp.1.weight"], sd["mlp.1.bias"], sd["mlp.1.running_mean"], sd["mlp.1.running_var"], sd["mlp.3.weight"], sd["mlp.3.bias"]]
+    return torch.cat([p.detach().reshape(-1).float() for p in parts])
+
+
+def _key(gnn: torch.nn.Module):
+    return tuple((t.data_ptr(), t._version) for layer in gnn.layers for t in list(layer.parameters()) + list(layer.buffers()))
+
+
+def pack_module(gnn: torch.nn.Module):
+    """(packed weights, cross flags, D, heads, layers) of a reference `AttentionalGNN`, cached on the module."""
+    key = _key(gnn)
+    cached = getattr(gnn, "_pats_b200_pack", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    layer0 = gnn.layers[0]
+    D = layer0.attn.merge.weight.shape[0]
+    heads = layer0.attn.num_heads
+    L = len(gnn.layers)
+    raw = _raw(gnn)
+    lib = _lib.load()
+    if raw.numel() != lib.pats_gnn_raw_floats(L, D):
+        raise RuntimeError(f"pats_b200.gnn: the module holds {raw.numel()} parameters, the packed layout expects {lib.pats_gnn_raw_floats(L, D)}")
+    if not raw.is_cuda:
+        raise RuntimeError("pats_b200.gnn: the module is on the CPU; pats_b200 is CUDA-only (no CPU fallback)")
+    packed = torch.empty(lib.pats_gnn_packed_floats(L, D), dtype=torch.float32, device=raw.device)
+    with torch.cuda.device(raw.device):
+        rc = lib.pats_gnn_pack_f32(raw.data_ptr(), L, D, heads, float(layer0.mlp[1].eps), packed.data_ptr(), stream_ptr(raw.device))
+    _lib.check(rc, "gnn_pack")
+    cross = bytes(1 if n == "cross" else 0 for n in gnn.names)
+    out = (packed, cross, D, heads, L)
+    gnn._pats_b200_pack = (key, out)
+    return out
+
+
+def attentional_gnn(packed: torch.Tensor, cross: bytes, heads: int, desc0: torch.Tensor, desc1: torch.Tensor, workspace_mb: int | None = None):
+    """desc0, desc1 [B,D,N] -> the two updated descriptor sets (fresh tensors)."""
+    d0 = cuda_f32(desc0, "desc0")
+    d1 = cuda_f32(desc1, "desc1")
+    if d0.dim() != 3 or d0.shape != d1.shape:
+        raise ValueError(f"attentional_gnn: expected two [b,d,n] tensors of one shape, got {tuple(d0.shape)} and {tuple(d1.shape)}")
+    B, D, N = d0.shape
+    lib = _lib.load()
+    per = lib.pats_gnn_workspace_floats(1, D, N)
+    budget = (WORKSPACE_MB if workspace_mb is None else workspace_mb) * (1 << 20) // 4
+    chunk = max(1, min(B, budget // per))
+    ws = torch.empty(per * chunk, dtype=torch.float32, device=d0.device)
+    out0, out1 = torch.empty_like(d0), torch.empty_like(d1)
+    with torch.cuda.device(d0.device):
+        rc = lib.pats_attentional_gnn_f32(d0.data_ptr(), d1.data_ptr(), B, D, N, packed.data_ptr(), cross, len(cross), heads, out0.data_ptr(),
+                                          out1.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(d0.device))
+    _lib.check(rc, "attentional_gnn")
+    return out0, out1
+
+
+def _layerwise(self, desc0, desc1):
+    """AttentionalGNN.forward as the reference composes it (models/modules.py:126-134), on the module's own layers."""
+    for layer, name in zip(self.layers, self.names):
+        if name == 'cross':
+            src0, src1 = desc1, desc0
+        else:
+            src0, src1 = desc0, desc1
+        delta0, delta1 = layer(desc0, src0), layer(desc1, src1)
+        desc0, desc1 = (desc0 + delta0), (desc1 + delta1)
+    return desc0, desc1
+
+
+def attentional_gnn_forward(self, desc0, desc1):
+    """AttentionalGNN.forward (models/modules.py:126-134)."""
+    if not desc0.is_cuda:
+        raise RuntimeError(f"desc0 is on {desc0.device}: pats_b200 is CUDA-only (no CPU fallback)")
+    heads = self.layers[0].attn.num_heads
+    if self.training or desc0.dim() != 3 or not supported(desc0.shape[2], desc0.shape[1], heads):
+        return _layerwise(self, desc0, desc1)
+    packed, cross, _, heads, _ = pack_module(self)
+    return attentional_gnn(packed, cross, heads, desc0, desc1)
