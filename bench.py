@@ -492,6 +492,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def tensor_peak_bf16():
+    """dense BF16 TFLOP/s measured on this pool's B200s (MEASURED_PEAKS.json, burst figure), else the recipe's fallback"""
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["bf16_tflops"])
+    except Exception:  # noqa: BLE001
+        return 2250.0
+
+
 def ncu_traffic(key="sinkhorn_warp_dram_bytes_per_launch"):
     path = os.path.join(REPO, "profiles", "roofline_traffic.json")
     if os.path.exists(path):
@@ -509,6 +518,7 @@ def forward_leg(torch, dev, args):
         reference_cuda   the stock reference on CUDA tensors (ATen ops + its compiled setup/library.cpp) -- how it really runs
         installed        + pats_b200.install.install(): every hot-path function on the CUDA library
         installed_fused  + install(fused=True): the two layer forwards on the fused entry points as well
+        installed_fused_attention  + install(fused=True, attention=True): the attention networks on csrc/gnn.cu too
         reference_cpu    the stock reference on CPU tensors, all host threads (one pair; --no-forward-cpu skips it)
     The ResNet / attention networks are NOT part of the path (they stay the reference's own PyTorch modules in every arm), so
     this leg bounds what the hot path is worth inside the whole forward pass; `value` / `e2e` above isolate the path itself."""
@@ -536,7 +546,8 @@ def forward_leg(torch, dev, args):
 
     with torch.no_grad():
         model = L.build_model(ref, cfg, device=dev)
-        for name, setup in (("reference_cuda", None), ("installed", dict(fused=False)), ("installed_fused", dict(fused=True))):
+        for name, setup in (("reference_cuda", None), ("installed", dict(fused=False)), ("installed_fused", dict(fused=True)),
+                            ("installed_fused_attention", dict(fused=True, attention=True))):
             if setup is not None:
                 inst.install(**setup)
             try:
@@ -565,6 +576,7 @@ def forward_leg(torch, dev, args):
             out["reference_cpu"] = {"value": 1.0 / dt, "s_per_pair": dt, "matches": m, "cores": cores, "pairs_timed": 1}
     out["speedup_installed_vs_reference_cuda"] = out["installed"]["value"] / out["reference_cuda"]["value"]
     out["speedup_fused_vs_reference_cuda"] = out["installed_fused"]["value"] / out["reference_cuda"]["value"]
+    out["speedup_fused_attention_vs_reference_cuda"] = out["installed_fused_attention"]["value"] / out["reference_cuda"]["value"]
     return out
 
 
@@ -597,6 +609,65 @@ def stress_leg(torch, dev, peak):
                      "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peak, "plan_mb": 4 * (N + 1) * (N + 1) / 1e6}
         del sc, nss
     torch.cuda.empty_cache()
+    return out
+
+
+def attention_leg(torch, dev, peak_bf16_tflops):
+    """N3: the attention network in front of each matching level (models/modules.py:119-134) at the shapes of ONE 640x480 pair --
+    level 1: 1 x 448 x 300, 18 layers; level 2: 300 x 264 x 145, 18 layers; level 3: 4800 x 128 x 65, 10 layers -- the reference's own
+    module on this GPU (cuDNN Conv1d = single-pass TF32, cuBLAS FP32 einsum; ~25 ATen launches per layer and side) against
+    pats_attentional_gnn_f32 (csrc/gnn.cu) in its default 3xTF32 mode and in single-pass TF32.  Weights: torch's default
+    initialisation (seeded); inputs: unit normal.  `useful_tflops` counts each multiply-add of the network once (2 T 9 D^2 per layer
+    for the convolutions, 4 n^2 D per problem side for the attention); the tensor peak is half the measured BF16 figure (TF32)."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import live_util as L
+
+    if L.reference_root() is None:
+        return {"unavailable": "reference Python not staged (oracle/_ref/py)"}
+    ref = L.load_reference()
+    from pats_b200 import gnn as G
+
+    out = {"tensor_peak_tflops_tf32": peak_bf16_tflops / 2.0, "levels": {}}
+    total_ref = total_ours = 0.0
+    with torch.no_grad():
+        for name, B, D, N, layers in (("L1", 1, 448, 300, 18), ("L2", P2, 264, 145, 18), ("L3", K3, 128, 65, 10)):
+            torch.manual_seed(SEED)
+            mod = ref.modules.AttentionalGNN(D, ["self", "cross"] * (layers // 2)).eval().to(dev)
+            g = torch.Generator().manual_seed(SEED + D)
+            x0, x1 = torch.randn(B, D, N, generator=g).to(dev), torch.randn(B, D, N, generator=g).to(dev)
+
+            def timed(fn, reps=3):
+                fn()
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize(dev)
+                return e0.elapsed_time(e1) / reps
+
+            T = 2 * B * N
+            flops = layers * (2.0 * T * 9 * D * D + 2 * B * 4.0 * N * N * D)
+            rec = {"shape": [B, D, N], "layers": layers, "reference_module_ms": timed(lambda: mod(x0, x1))}
+            try:
+                for passes in (3, 1):
+                    G.set_precision(passes)
+                    rec[f"ours_{passes}xtf32_ms"] = timed(lambda: G.attentional_gnn_forward(mod, x0, x1))
+            finally:
+                G.set_precision(3)
+            a0, _ = G.attentional_gnn_forward(mod, x0, x1)
+            b0, _ = mod(x0, x1)
+            rec["max_abs_diff_vs_reference_module"] = float((a0 - b0).abs().max())
+            rec["output_scale"] = float(b0.abs().max())
+            rec["useful_tflops"] = flops / (rec["ours_3xtf32_ms"] * 1e-3) / 1e12
+            rec["speedup"] = rec["reference_module_ms"] / rec["ours_3xtf32_ms"]
+            total_ref += rec["reference_module_ms"]
+            total_ours += rec["ours_3xtf32_ms"]
+            out["levels"][name] = rec
+    out["reference_module_ms_per_pair"] = total_ref
+    out["ours_ms_per_pair"] = total_ours
+    out["speedup"] = total_ref / total_ours
     return out
 
 
@@ -1041,6 +1112,12 @@ def main():
                 fwd = forward_leg(torch, dev, args)
             except Exception as e:  # noqa: BLE001  (the leg needs the staged reference Python, oracle/_ref/py)
                 fwd = {"unavailable": f"{type(e).__name__}: {e}"}
+        att = None
+        if world == 1 and not args.no_forward:
+            try:
+                att = attention_leg(torch, dev, tensor_peak_bf16())
+            except Exception as e:  # noqa: BLE001
+                att = {"unavailable": f"{type(e).__name__}: {e}"}
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -1051,7 +1128,7 @@ def main():
                     "exchange": "after the pair loop every step's match list of every rank is gathered to rank 0 (2 collectives, 1 host sync); inside the timed region",
                     "gather_ms": info["gather_ms"], "gather": info["gather"]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_streaming": streaming, "stress": stress, "correlation": corr, "cpu_baseline": cpu, "torch_cuda": torch_cuda,
-            "fixed_point_exit": fp_exit, "bulk_staging": bulk, "overlap": overlap, "diffuse": diffuse, "forward": fwd,
+            "fixed_point_exit": fp_exit, "bulk_staging": bulk, "overlap": overlap, "diffuse": diffuse, "forward": fwd, "attention": att,
         }
         emit(line)
     if world > 1:

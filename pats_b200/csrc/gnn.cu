@@ -396,6 +396,160 @@ __global__ void __launch_bounds__(NW * 32) gnn_attention_kernel(AttArgs a) {
     }
 }
 
+// Any token count (level 1: n = 300 at 640 x 480, 1024 at 1024 x 1024; head dimension 112): one CTA per (problem, side, head, tile of
+// NW * R * RB query rows), the keys in chunks of NJ * 32 with the running maximum / sum of an online softmax, the output rescaled when
+// the maximum moves ("flash" formulation; identical to the plain softmax up to FP32 rounding).
+template <int NJ, int DI, int R, int NW, int RB>
+__global__ void __launch_bounds__(NW * 32) gnn_attention_flash_kernel(AttArgs a, int qtiles) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int NP = NJ * 32 + 1, NP32 = NJ * 32, DV = DI * 32, NT = NW * 32, QT = NW * R * RB;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = a.N, dim = a.dim, dim4 = (dim + 3) & ~3, D3 = 3 * a.D;
+    float *Q = sm;                     // [QT][dim4]
+    float *P = Q + QT * dim4;          // [NW][NP32][R]
+    float *V = P + NW * NP32 * R;      // [NP32][DV]
+    float *Kt = V + NP32 * DV;         // [dim4][NP]
+    pdl_prologue();
+    const int qt = blockIdx.x % qtiles, rest = blockIdx.x / qtiles;
+    const int ps = rest / a.heads, h = rest - ps * a.heads;
+    const int side = ps / a.Bc, b = ps - side * a.Bc;
+    const int sps = a.cross ? (1 - side) * a.Bc + b : ps;
+    const float *qbase = a.qkv + (size_t)ps * N * D3 + h * dim;
+    const float *kbase = a.qkv + (size_t)sps * N * D3 + a.D + h * dim;
+    const float *vbase = kbase + a.D;
+    const int q0 = qt * QT, half = dim4 >> 1;
+    for (int it = tid; it < QT * half; it += NT) {
+        const int n = it / half, d = (it - n * half) * 2;
+        float2 q2 = make_float2(0.f, 0.f);
+        if (q0 + n < N && d < dim) q2 = __ldg(reinterpret_cast<const float2 *>(qbase + (size_t)(q0 + n) * D3 + d));
+        *reinterpret_cast<float2 *>(Q + n * dim4 + d) = q2;
+    }
+    float o[RB][R][DI], mrun[RB][R], lrun[RB][R];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            mrun[rb][r] = -INFINITY, lrun[rb][r] = 0.f;
+#pragma unroll
+            for (int i = 0; i < DI; ++i) o[rb][r][i] = 0.f;
+        }
+    float *Pw = P + warp * NP32 * R;
+    for (int kc0 = 0; kc0 < N; kc0 += NP32) {
+        const int kn = min(NP32, N - kc0);
+        __syncthreads();  // the previous chunk's K / V are no longer read
+        for (int it0 = tid; it0 < NP32 * half; it0 += NT * 4) {
+            float2 k2[4], v2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int it = it0 + u * NT;
+                const int n = it / half, d = (it - n * half) * 2;
+                k2[u] = v2[u] = make_float2(0.f, 0.f);
+                if (it < NP32 * half && n < kn && d < dim) {
+                    k2[u] = __ldg(reinterpret_cast<const float2 *>(kbase + (size_t)(kc0 + n) * D3 + d));
+                    v2[u] = __ldg(reinterpret_cast<const float2 *>(vbase + (size_t)(kc0 + n) * D3 + d));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int it = it0 + u * NT;
+                if (it < NP32 * half) {
+                    const int n = it / half, d = (it - n * half) * 2;
+                    Kt[d * NP + n] = k2[u].x, Kt[(d + 1) * NP + n] = k2[u].y;
+                    *reinterpret_cast<float2 *>(V + n * DV + d) = v2[u];
+                }
+            }
+        }
+        if (DV > dim4)
+            for (int it = tid; it < NP32 * (DV - dim4); it += NT) {
+                const int n = it / (DV - dim4), d = dim4 + it - n * (DV - dim4);
+                V[n * DV + d] = 0.f;
+            }
+        __syncthreads();
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+            const int l0 = (rb * NW + warp) * R;  // first row of this block inside the tile
+            if (q0 + l0 >= N) continue;
+            float s[R][NJ];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) s[r][j] = 0.f;
+            for (int d = 0; d < dim4; d += 4) {
+                float4 q[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) q[r] = *reinterpret_cast<const float4 *>(Q + (l0 + r) * dim4 + d);
+#pragma unroll
+                for (int dd = 0; dd < 4; ++dd) {
+                    float kv[NJ];
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) kv[j] = Kt[(d + dd) * NP + lane + 32 * j];
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) s[r][j] = fmaf(comp(q[r], dd), kv[j], s[r][j]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    if (lane + 32 * j >= kn) s[r][j] = -INFINITY;
+                    mx = fmaxf(mx, s[r][j]);
+                }
+                const float mnew = fmaxf(mrun[rb][r], warp_max(mx));
+                const float sc = fast_exp2((mrun[rb][r] - mnew) * a.c);  // 0 on the first chunk (running maximum -inf)
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    s[r][j] = fast_exp2((s[r][j] - mnew) * a.c);
+                    sum += s[r][j];
+                }
+                lrun[rb][r] = lrun[rb][r] * sc + warp_sum(sum);
+                mrun[rb][r] = mnew;
+#pragma unroll
+                for (int i = 0; i < DI; ++i) o[rb][r][i] *= sc;
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int r4 = 0; r4 < R; r4 += 4)
+                    *reinterpret_cast<float4 *>(Pw + (lane + 32 * j) * R + r4) = make_float4(s[r4][j], s[r4 + 1][j], s[r4 + 2][j], s[r4 + 3][j]);
+            __syncwarp();
+#pragma unroll 2
+            for (int m = 0; m < kn; ++m) {
+                float p[R];
+#pragma unroll
+                for (int r4 = 0; r4 < R; r4 += 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(Pw + m * R + r4);
+                    p[r4] = t.x, p[r4 + 1] = t.y, p[r4 + 2] = t.z, p[r4 + 3] = t.w;
+                }
+                float vv[DI];
+#pragma unroll
+                for (int i = 0; i < DI; ++i) vv[i] = V[m * DV + lane + 32 * i];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int i = 0; i < DI; ++i) o[rb][r][i] = fmaf(p[r], vv[i], o[rb][r][i]);
+            }
+            __syncwarp();  // the P buffer is rewritten by the next block
+        }
+    }
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int n = q0 + (rb * NW + warp) * R + r;
+            if (n < N) {
+                const float inv = 1.0f / lrun[rb][r];
+                float *orow = a.o + ((size_t)ps * N + n) * a.D + h * dim;
+#pragma unroll
+                for (int i = 0; i < DI; ++i)
+                    if (lane + 32 * i < dim) orow[lane + 32 * i] = o[rb][r][i] * inv;
+            }
+        }
+}
+
 // ---- layout changes at entry / exit: [b, D, n] (the reference's Conv1d layout) <-> token-major [T, D] --------------------------
 struct TransArgs {
     const float *d0, *d1;  // entry: inputs [B, D, N] per side
@@ -504,6 +658,22 @@ int launch_attention(const AttArgs &a, cudaStream_t st, int dev) {
     return PATS_OK;
 }
 
+template <int NJ, int DI, int R, int NW, int RB>
+int launch_attention_flash(const AttArgs &a, cudaStream_t st, int dev) {
+    constexpr int QT = NW * R * RB;
+    const int dim4 = (a.dim + 3) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)QT * dim4 + (size_t)NW * NJ * 32 * R + (size_t)NJ * 32 * DI * 32 + (size_t)dim4 * (NJ * 32 + 1));
+    static PerDeviceOnce configured;
+    if (!configured.done(dev)) {
+        PATS_CUDA_TRY(cudaFuncSetAttribute(gnn_attention_flash_kernel<NJ, DI, R, NW, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured.mark(dev);
+    }
+    if (smem > 220 * 1024) return invalid("attentional_gnn: attention tile of %zu bytes exceeds shared memory (head dim = %d)", smem, a.dim);
+    const int qtiles = (a.N + QT - 1) / QT;
+    PATS_CUDA_TRY(launch_chained(gnn_attention_flash_kernel<NJ, DI, R, NW, RB>, dim3((unsigned)(2 * a.Bc * a.heads * qtiles)), dim3(NW * 32), smem, st, a, qtiles));
+    return PATS_OK;
+}
+
 int launch_gemm(GemmArgs a, cudaStream_t st, int dev, int sms) {
     // split Nout evenly into blocks of <= 256 outputs, each a multiple of 16
     a.nblocks = (a.Nout + 255) / 256;
@@ -563,8 +733,7 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
         return invalid("attentional_gnn: D = %d, heads = %d: D must be a multiple of 8 and of heads, the head dimension even", D, heads);
     const int dim = D / heads;
     const int NJ = (N + 31) / 32, DI = (dim + 31) / 32;
-    if (!((NJ <= 3 && DI == 1) || (NJ <= 5 && DI <= 3)))
-        return invalid("attentional_gnn: n = %d tokens with head dimension %d is not a shape this build has an attention kernel for (n <= 96 with dim <= 32, n <= 160 with dim <= 96)", N, dim);
+    if (DI > 4) return invalid("attentional_gnn: head dimension %d exceeds the 128 this build has attention kernels for", dim);
     const long long per_problem = (long long)14 * N * D;
     int chunk = (int)(workspace_floats / per_problem < B ? workspace_floats / per_problem : B);
     if (chunk > 16384) chunk = 16384;  // 2 * chunk is a grid z extent
@@ -596,10 +765,12 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
             at.c = 1.4426950408889634f / sqrtf((float)dim);
             if (NJ <= 3 && DI == 1)
                 rc = launch_attention<3, 1, false, 8, 4>(at, st, dev);
-            else if (dim >= 64 && dim <= 68)
+            else if (NJ <= 5 && dim >= 64 && dim <= 68)
                 rc = launch_attention<5, 3, true, 8, 10>(at, st, dev);
-            else
+            else if (NJ <= 5 && DI <= 3)
                 rc = launch_attention<5, 3, false, 4, 8>(at, st, dev);
+            else
+                rc = launch_attention_flash<5, 4, 4, 8, 2>(at, st, dev);
             if (rc) return rc;
             g.A1 = X, g.lda1 = D, g.K1 = D, g.A2 = O, g.lda2 = D, g.K2 = D, g.W = W1f, g.ldw = 2 * D, g.bias = b1f, g.out = Y, g.ldo = 2 * D;
             g.Nout = 2 * D, g.relu = 1, g.accumulate = 0;

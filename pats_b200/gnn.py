@@ -38,7 +38,7 @@ def supported(n_tokens: int, d_model: int, heads: int) -> bool:
     dim = d_model // heads
     if dim % 2:
         return False
-    return (n_tokens <= 96 and dim <= 32) or (n_tokens <= 160 and dim <= 96)
+    return dim <= 128  # n <= 96 / dim <= 32 and n <= 160 / dim <= 96: keys resident; anything else: chunked keys, online softmax
 
 
 def _raw(gnn: torch.nn.Module) -> torch.Tensor:

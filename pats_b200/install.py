@@ -47,12 +47,17 @@ _METHODS = {
 _saved: dict = {}
 
 
-def install(only=None, fused: bool = False) -> list:
+def install(only=None, fused: bool = False, attention: bool = False) -> list:
     """Rebind the hot-path names; returns the list of (module, name) pairs that were replaced.
 
     fused=True additionally rebinds `SecondLayer.forward` and `ThirdLayer.forward` to pats_b200.forward's mirrors, which
     reach the pieces of the path that are inline statements in the reference (12 x 12 grid sampling, 8 x 8 window unfold)
-    and the composite Sinkhorn -> consumer calls."""
+    and the composite Sinkhorn -> consumer calls.
+
+    attention=True additionally rebinds `AttentionalGNN.forward` (models/modules.py:126-134, the network in front of every
+    matching level: SURVEY.md 8f N3) to pats_b200.gnn.attentional_gnn_forward.  Its 1x1 convolutions then run with FP32-class
+    accuracy on the tensor cores, whereas the stock reference on a GPU runs them as single-pass TF32 through cuDNN: the match
+    lists agree with the stock GPU run only as far as the stock run agrees with its own CPU execution (tests/test_gpu_gnn.py)."""
     done = []
     sys.modules.setdefault("tensor_resize", _tensor_resize)
     for modname, table in _TABLE.items():
@@ -72,6 +77,10 @@ def install(only=None, fused: bool = False) -> list:
         from .forward import FORWARDS
 
         methods.update(FORWARDS)
+    if attention:
+        from .gnn import attentional_gnn_forward
+
+        methods[("models.modules", "AttentionalGNN", "forward")] = attentional_gnn_forward
     for (modname, clsname, meth), repl in methods.items():
         if only is not None and meth not in only:
             continue

@@ -66,3 +66,33 @@ def test_install_fused_rebinds_the_layer_forwards_with_the_reference_signatures(
         assert ref.second_layer.SecondLayer.forward is o2
     finally:
         inst.uninstall()
+
+
+def test_install_attention_rebinds_the_network_forward_and_refuses_the_cpu():
+    """install(attention=True) swaps AttentionalGNN.forward (models/modules.py:126-134) for pats_b200.gnn's mirror -- same parameters,
+    visible through every caller module's star import -- and uninstall() restores it; on CPU tensors the mirror raises (no fallback)."""
+    import inspect
+
+    import pytest
+    import torch
+
+    ref = ref_loader.load_reference()
+    from pats_b200 import gnn as G
+    from pats_b200 import install as inst
+
+    orig = ref.modules.AttentionalGNN.forward
+    assert list(inspect.signature(G.attentional_gnn_forward).parameters) == list(inspect.signature(orig).parameters)
+    done = inst.install(attention=True)
+    try:
+        assert ("models.modules", "AttentionalGNN.forward") in done
+        assert ref.second_layer.AttentionalGNN.forward is G.attentional_gnn_forward  # the class object the layers construct
+        gnn = ref.modules.AttentionalGNN(16, ["self", "cross"]).eval()
+        with pytest.raises(RuntimeError, match="CUDA-only"):
+            gnn(torch.zeros(1, 16, 5), torch.zeros(1, 16, 5))
+    finally:
+        inst.uninstall()
+    assert ref.modules.AttentionalGNN.forward is orig
+    assert ("models.modules", "AttentionalGNN.forward") not in inst.install()
+    inst.uninstall()
+    assert G.supported(145, 264, 4) and G.supported(65, 128, 4) and G.supported(300, 448, 4) and G.supported(1024, 448, 4)
+    assert not G.supported(65, 130, 4) and not G.supported(65, 1024, 4)

@@ -28,7 +28,9 @@ def main():
     out = {}
     with torch.no_grad():
         model = L.build_model(ref, cfg, device=dev)
-        inst.install(fused=True)
+        attention = "attention" in sys.argv[1:]
+        inst.install(fused=True, attention=attention)
+        out["attention"] = attention
         try:
             def run(p):
                 r = model({"image0": p[0].to(dev), "image1": p[1].to(dev)})
@@ -84,7 +86,7 @@ def main():
         finally:
             inst.uninstall()
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(REPO, "gpurun_out", "profile_forward.json"), "w") as f:
+    with open(os.path.join(REPO, "gpurun_out", "profile_forward_attention.json" if out["attention"] else "profile_forward.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps({k: out[k] for k in ("s_per_pair_free_running", "s_per_pair_synchronised", "cuda_kernel_total_ms", "cuda_kernel_launches", "cpu_self_total_ms")}))
 
