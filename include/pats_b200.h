@@ -287,6 +287,9 @@ long long pats_gnn_workspace_floats(int chunk, int D, int N);
 int pats_attentional_gnn_f32(const float *desc0, const float *desc1, int B, int D, int N, const float *packed, const unsigned char *cross,
                              int layers, int heads, float *out0, float *out1, float *workspace, long long workspace_floats, void *stream);
 void pats_gnn_precision(int passes);
+/* A/B switch (timing only; every variant computes the same sums in the same order per row): tiling of the level-2 attention kernel.
+ *   0 = 4 query rows per warp, 20 warps (default); 1 = 8 rows, 10 warps; 2 = 4 rows, 16 warps. */
+void pats_gnn_attention_variant(int v);
 
 /* ---------------------------------------------------------------------------------------------
  * Feature gathers next to the path                  (models/second_layer.py:71-80, models/third_layer.py:119-146)

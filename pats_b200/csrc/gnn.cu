@@ -46,6 +46,7 @@ constexpr int GEMM_THREADS = 256;   // 8 warps stage and drain; warps w and w + 
 constexpr int GEMM_M = 128;
 
 std::atomic<int> g_precision{3};    // 3 = 3xTF32 (default), 1 = single TF32 (what cuDNN gives the reference's Conv1d)
+std::atomic<int> g_att_variant{0};  // A/B of the level-2 attention tiling (pats_gnn_attention_variant)
 
 struct GemmArgs {
     const float *A1, *A2;  // [T, K1] (row stride lda1), [T, K2] (row stride lda2; K2 = 0: absent): the K extents are concatenated
@@ -710,6 +711,7 @@ int launch_gemm(GemmArgs a, cudaStream_t st, int dev, int sms) {
 
 using namespace pats;
 
+PATS_API void pats_gnn_attention_variant(int v) { g_att_variant.store(v, std::memory_order_relaxed); }
 PATS_API void pats_gnn_precision(int passes) { g_precision.store(passes == 1 ? 1 : 3, std::memory_order_relaxed); }
 
 PATS_API long long pats_gnn_raw_floats(int layers, int D) { return (long long)(raw_layer_floats(D) * (size_t)layers); }
@@ -765,8 +767,12 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
             at.c = 1.4426950408889634f / sqrtf((float)dim);
             if (NJ <= 3 && DI == 1)
                 rc = launch_attention<3, 1, false, 8, 4>(at, st, dev);
-            else if (NJ <= 5 && dim >= 64 && dim <= 68)
-                rc = launch_attention<5, 3, true, 8, 10>(at, st, dev);
+            else if (NJ <= 5 && dim >= 64 && dim <= 68) {
+                const int v = g_att_variant.load(std::memory_order_relaxed);
+                // measured (tools/gnn_kernels.py, 89 problems per launch): 4 rows x 20 warps 206 us, 8 rows x 10 warps 232 us, 4 rows x 16 warps 225 us
+                rc = v == 1 ? launch_attention<5, 3, true, 8, 10>(at, st, dev) : v == 2 ? launch_attention<5, 3, true, 4, 16>(at, st, dev)
+                            : launch_attention<5, 3, true, 4, 20>(at, st, dev);
+            }
             else if (NJ <= 5 && DI <= 3)
                 rc = launch_attention<5, 3, false, 4, 8>(at, st, dev);
             else
