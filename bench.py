@@ -580,6 +580,57 @@ def forward_leg(torch, dev, args):
     return out
 
 
+def forward_sharded_leg(torch, dist, dev, rank, world, pairs_per_rank=4):
+    """SURVEY.md 8(d) / BASELINE configs[3] at driver size: image-pairs/s through the UNMODIFIED `PATS.forward` with the whole path
+    installed (install(fused=True, attention=True)) on N GPUs.  Pairs are independent (evaluate.py:25-35): rank r runs its contiguous
+    shard of the seeded synthetic pair list (pats_b200.dist.shard_range; images host -> device inside the timed region), keeps the
+    match lists on the device, and after the pair loop every list is gathered to rank 0 (dist.gather_match_lists: 2 collectives,
+    1 host sync).  Time = barrier .. barrier, max over ranks; weights replicated (same seed on every rank)."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import live_util as L
+
+    if L.reference_root() is None:
+        return {"unavailable": "reference Python not staged (oracle/_ref/py)"}
+    ref = L.load_reference()
+    import pats_b200.install as inst
+    from pats_b200 import dist as pdist
+
+    cfg = L.config(if_local=True, merge_new=True, if_outdoor=True)  # configs/test_megadepth.yaml
+    n_total, n_warm = pairs_per_rank * world, 2
+    lo, hi = pdist.shard_range(n_total, rank, world)
+    host = {i: tuple(t.pin_memory() for t in L.synthetic_pair((H, W_IMG), seed=SEED + i)) for i in list(range(lo, hi)) + [n_total + k for k in range(n_warm)]}
+
+    def one(i):
+        i0, i1 = host[i]
+        r = model({"image0": i0.to(dev, non_blocking=True), "image1": i1.to(dev, non_blocking=True)})
+        return torch.cat([r["matches_l"].float(), r["matches_r"].float()], 1)
+
+    with torch.no_grad():
+        model = L.build_model(ref, cfg, device=dev)
+        inst.install(fused=True, attention=True)
+        try:
+            for k in range(n_warm):
+                one(n_total + k)
+            torch.cuda.synchronize(dev)
+            dist.barrier(device_ids=[dev.index])
+            t0 = time.perf_counter()
+            lists = [one(i) for i in range(lo, hi)]
+            stats = {}
+            gathered = pdist.gather_match_lists(lists, max_pairs=pairs_per_rank, dst=0, stats=stats)
+            torch.cuda.synchronize(dev)
+            dist.barrier(device_ids=[dev.index])
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        finally:
+            inst.uninstall()
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    out = {"config": "configs/test_megadepth.yaml flags, 640x480, install(fused=True, attention=True), conditioned random-init weights (tests/live_util.py)",
+           "pairs": n_total, "pairs_per_rank": pairs_per_rank, "seconds": float(dt.item()), "value": n_total / float(dt.item()), "unit": "pairs/s",
+           "exchange": stats}
+    if rank == 0:
+        out["matches_gathered"] = int(sum(m.shape[0] for per_rank in gathered for m in per_rank))
+    return out
+
+
 def stress_leg(torch, dev, peak):
     """BASELINE.json configs[4] ("stress: 1024x1024 pairs, 4096 coarse patches, 200 Sinkhorn iters, 8 x B200"): the level-1 solve of
     a 1024 x 1024 pair (32 x 32 coarse patches -> one 1025 x 1025 plan, 100 iterations) and the synthetic N = 4096 plan at 200
@@ -991,6 +1042,13 @@ def main():
         e2e["h2d_ms_per_step_alone"] = link_ms
         e2e["note"] = "bound by the host->device copy of the stage inputs (h2d_ms_per_step_alone vs ms_per_step of the device-resident path)"
 
+    fwd_sharded = None
+    if world > 1 and not args.no_forward:
+        try:
+            fwd_sharded = forward_sharded_leg(torch, dist, dev, rank, world)
+        except Exception as e:  # noqa: BLE001  (needs the staged reference Python on every rank)
+            fwd_sharded = {"unavailable": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         peak, peak_src = peaks()
         b3 = B * K3
@@ -1128,7 +1186,7 @@ def main():
                     "exchange": "after the pair loop every step's match list of every rank is gathered to rank 0 (2 collectives, 1 host sync); inside the timed region",
                     "gather_ms": info["gather_ms"], "gather": info["gather"]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_streaming": streaming, "stress": stress, "correlation": corr, "cpu_baseline": cpu, "torch_cuda": torch_cuda,
-            "fixed_point_exit": fp_exit, "bulk_staging": bulk, "overlap": overlap, "diffuse": diffuse, "forward": fwd, "attention": att,
+            "fixed_point_exit": fp_exit, "bulk_staging": bulk, "overlap": overlap, "diffuse": diffuse, "forward": fwd, "attention": att, "forward_sharded": fwd_sharded,
         }
         emit(line)
     if world > 1:
