@@ -631,6 +631,70 @@ def forward_sharded_leg(torch, dist, dev, rank, world, pairs_per_rank=4):
     return out
 
 
+def tail_leg(torch, dev, n_pairs=6):
+    """N4: the evaluation loop of evaluate.py:20-39 -- dataset item (image decode / resize stand-in: tests/pose_util.py), PATS.forward with
+    the whole path installed, the reference's compute_pose_error (utils/metrics.py:21-66: OpenCV essential-matrix RANSAC + recoverPose)
+    -- run stage after stage as the reference does, and as pats_b200.pipeline.evaluate_pairs' three-stage pipeline (same calls, same
+    order, bit-identical pose errors: tests/test_gpu_pipeline.py).  The forward pass runs on the real (random-init, conditioned)
+    network; RANSAC is fed planted two-view correspondences with 30 % outliers (random-init matches fit no essential matrix and would
+    make RANSAC run to its iteration cap)."""
+    import threading
+
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import live_util as L
+    import pose_util as P
+
+    m = P.reference_metrics()
+    if m is None or L.reference_root() is None:
+        return {"unavailable": "reference Python not staged (oracle/_ref/py)"}
+    ref = L.load_reference()
+    import pats_b200.install as inst
+    from pats_b200 import pipeline as PL
+
+    ds = P.SyntheticTwoView(n_pairs=n_pairs + 2, hw=(H, W_IMG), n_points=1500, outliers=0.3, load_cost=6)
+    out = {"pairs_timed": n_pairs, "unit": "pairs/s"}
+    with torch.no_grad():
+        real = L.build_model(ref, L.config(if_local=True, merge_new=True, if_outdoor=True), device=dev)
+        inst.install(fused=True, attention=True)
+        try:
+            model = P.PlantedModel(real=real)
+            PL.evaluate_pairs_sequential(model, ds, m.compute_pose_error, 1.0, 0.5, device=dev, indices=[n_pairs, n_pairs + 1])  # warm-up
+            torch.cuda.synchronize(dev)
+            # the GPU stage alone (forward pass incl. host -> device of the images and device -> host of the match lists)
+            model.real_matches = 0
+            t0 = time.perf_counter()
+            for i in range(n_pairs):
+                data = PL._collate(ds[i])
+                data["image0"], data["image1"] = data["image0"].to(dev), data["image1"].to(dev)
+                model(data)["matches_l"].cpu()
+            torch.cuda.synchronize(dev)
+            out["forward_only_s_per_pair"] = (time.perf_counter() - t0) / n_pairs
+            out["forward_matches_per_pair"] = model.real_matches / n_pairs
+            box = {}
+
+            def seq():
+                t0 = time.perf_counter()
+                box["r"] = PL.evaluate_pairs_sequential(model, ds, m.compute_pose_error, 1.0, 0.5, device=dev, indices=range(n_pairs))
+                torch.cuda.synchronize(dev)
+                box["s"] = time.perf_counter() - t0
+
+            th = threading.Thread(target=seq)  # a fresh thread, like the pipeline's metrics thread: same OpenCV generator state
+            th.start()
+            th.join()
+            stats = {}
+            t0 = time.perf_counter()
+            par = PL.evaluate_pairs(model, ds, m.compute_pose_error, 1.0, 0.5, device=dev, indices=list(range(n_pairs)), stats=stats)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+        finally:
+            inst.uninstall()
+    out["sequential"] = {"value": n_pairs / box["s"], "s_per_pair": box["s"] / n_pairs}
+    out["pipelined"] = {"value": n_pairs / dt, "s_per_pair": dt / n_pairs, "load_s_per_pair": stats["load_s"] / n_pairs, "pose_s_per_pair": stats["pose_s"] / n_pairs}
+    out["speedup"] = box["s"] / dt
+    out["pose_errors_identical"] = bool(box["r"] == par)
+    return out
+
+
 def stress_leg(torch, dev, peak):
     """BASELINE.json configs[4] ("stress: 1024x1024 pairs, 4096 coarse patches, 200 Sinkhorn iters, 8 x B200"): the level-1 solve of
     a 1024 x 1024 pair (32 x 32 coarse patches -> one 1025 x 1025 plan, 100 iterations) and the synthetic N = 4096 plan at 200
@@ -1176,6 +1240,12 @@ def main():
                 att = attention_leg(torch, dev, tensor_peak_bf16())
             except Exception as e:  # noqa: BLE001
                 att = {"unavailable": f"{type(e).__name__}: {e}"}
+        tail = None
+        if world == 1 and not args.no_forward:
+            try:
+                tail = tail_leg(torch, dev)
+            except Exception as e:  # noqa: BLE001
+                tail = {"unavailable": f"{type(e).__name__}: {e}"}
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -1186,7 +1256,7 @@ def main():
                     "exchange": "after the pair loop every step's match list of every rank is gathered to rank 0 (2 collectives, 1 host sync); inside the timed region",
                     "gather_ms": info["gather_ms"], "gather": info["gather"]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_streaming": streaming, "stress": stress, "correlation": corr, "cpu_baseline": cpu, "torch_cuda": torch_cuda,
-            "fixed_point_exit": fp_exit, "bulk_staging": bulk, "overlap": overlap, "diffuse": diffuse, "forward": fwd, "attention": att, "forward_sharded": fwd_sharded,
+            "fixed_point_exit": fp_exit, "bulk_staging": bulk, "overlap": overlap, "diffuse": diffuse, "forward": fwd, "attention": att, "forward_sharded": fwd_sharded, "tail": tail,
         }
         emit(line)
     if world > 1:
