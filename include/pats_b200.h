@@ -278,7 +278,7 @@ int pats_gnn_pack_f32(const float *raw, int layers, int D, int heads, float bn_e
  *   src = the same set (cross[l] == 0, 'self') or the other one (cross[l] != 0, 'cross'); `cross` is a HOST array of `layers` bytes.
  *   BatchNorm in inference mode (module.eval(); a module in train() mode uses batch statistics and is not this function).
  *   `workspace` (DEVICE): at least pats_gnn_workspace_floats(1, D, N) floats; problems are processed in chunks of as many as fit
- *   (14 * N * D floats each).  D a multiple of 8 and of `heads`, the head dimension even; n <= 160 tokens with head dimension <= 96,
+ *   (24 * N * D floats each).  D a multiple of 8 and of `heads`, the head dimension even; n <= 160 tokens with head dimension <= 96,
  *   or n <= 96 with head dimension <= 32, or any n with head dimension <= 128 (flash-style pass over the keys).
  *   Arithmetic: the 1x1 convolutions on the tcgen05 tensor cores with FP32-class accuracy (3xTF32); pats_gnn_precision(1) selects
  *   single-pass TF32, which is what cuDNN gives the reference's Conv1d on a GPU (torch.backends.cudnn.allow_tf32 defaults to True);
@@ -290,6 +290,9 @@ void pats_gnn_precision(int passes);
 /* A/B switch (timing only; every variant computes the same sums in the same order per row): tiling of the level-2 attention kernel.
  *   0 = 4 query rows per warp, 20 warps (default); 1 = 8 rows, 10 warps; 2 = 4 rows, 16 warps. */
 void pats_gnn_attention_variant(int v);
+/* A/B switch: 0 = the TMA-fed, warp-specialised GEMM (operands pre-split into TF32 halves by their producers; default),
+ *             1 = the register-staged GEMM (operands split while they are staged).  Same products, same accumulation order. */
+void pats_gnn_gemm_variant(int v);
 
 /* ---------------------------------------------------------------------------------------------
  * Feature gathers next to the path                  (models/second_layer.py:71-80, models/third_layer.py:119-146)

@@ -61,13 +61,14 @@ SIGNATURES = {
     "pats_attentional_gnn_f32": [_P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, C.c_longlong, _P],
     "pats_gnn_precision": [_I],
     "pats_gnn_attention_variant": [_I],
+    "pats_gnn_gemm_variant": [_I],
     "pats_grid_sample12_f32": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
     "pats_third_unfold_f32": [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P],
     "pats_est_position_f32": [_P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "pats_second_layer_match_f32": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "pats_third_layer_match_f32": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
 }
-_RESTYPE = {"pats_last_error": C.c_char_p, "pats_gnn_raw_floats": C.c_longlong, "pats_gnn_packed_floats": C.c_longlong, "pats_gnn_workspace_floats": C.c_longlong, "pats_gnn_precision": None, "pats_gnn_attention_variant": None, "pats_sinkhorn_bulk_staging": None, "pats_sinkhorn_fixed_point_exit": None, "pats_sinkhorn_iterations_skipped": C.c_longlong, "pats_sinkhorn_force_generic": None, "pats_plan_handover": None, "pats_launch_chaining": None, "pats_sinkhorn_disable_w65": None, "pats_sinkhorn_disable_c145": None, "pats_sinkhorn_cluster_variant": None, "pats_sinkhorn_grid_ctas_per_problem": None, "pats_sinkhorn_grid_variant": None}
+_RESTYPE = {"pats_last_error": C.c_char_p, "pats_gnn_raw_floats": C.c_longlong, "pats_gnn_packed_floats": C.c_longlong, "pats_gnn_workspace_floats": C.c_longlong, "pats_gnn_precision": None, "pats_gnn_attention_variant": None, "pats_gnn_gemm_variant": None, "pats_sinkhorn_bulk_staging": None, "pats_sinkhorn_fixed_point_exit": None, "pats_sinkhorn_iterations_skipped": C.c_longlong, "pats_sinkhorn_force_generic": None, "pats_plan_handover": None, "pats_launch_chaining": None, "pats_sinkhorn_disable_w65": None, "pats_sinkhorn_disable_c145": None, "pats_sinkhorn_cluster_variant": None, "pats_sinkhorn_grid_ctas_per_problem": None, "pats_sinkhorn_grid_variant": None}
 
 
 def library_path() -> str:

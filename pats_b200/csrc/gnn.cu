@@ -32,6 +32,8 @@
 // Attention kernel (gnn_attention_kernel): FP32 on the CUDA cores, as the reference computes it (torch.einsum -> SGEMM): one CTA
 // per (problem, side, head), K^T / V / Q in shared memory, a warp owns R query rows x all keys in registers (R * ceil(n / 32)
 // accumulators), softmax by warp shuffles, P through a per-warp shared buffer into the P V product.
+#include <cuda.h>  // CUtensorMap and its enums only: cuTensorMapEncodeTiled is looked up at run time (no link against libcuda)
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -46,6 +48,7 @@ constexpr int GEMM_THREADS = 256;   // 8 warps stage and drain; warps w and w + 
 constexpr int GEMM_M = 128;
 
 std::atomic<int> g_precision{3};    // 3 = 3xTF32 (default), 1 = single TF32 (what cuDNN gives the reference's Conv1d)
+std::atomic<int> g_gemm_variant{0}; // 0 = TMA-fed warp-specialised GEMM, 1 = register-staged GEMM (pats_gnn_gemm_variant)
 std::atomic<int> g_att_variant{0};  // A/B of the level-2 attention tiling (pats_gnn_attention_variant)
 
 struct GemmArgs {
@@ -214,13 +217,214 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gnn_gemm_kernel(GemmArgs a) {
     if (warp == 0) tmem_dealloc(tmem, (unsigned)a.tmem_cols);
 }
 
+// ---- second GEMM generation: TMA-fed, warp-specialised --------------------------------------------------------------------------
+// The register pass of gnn_gemm_kernel (LDG -> round -> STS) is what bounds it: 12 LDG.128 + 24 STS.128 + ~100 ALU instructions per
+// thread and K chunk, all CTAs pulling their tiles through L2 at once.  Here the operands arrive ALREADY split: every producer of an
+// activation (transposition, attention, the epilogues below) writes its TF32 halves, the weights are packed as halves, and the
+// tiles go global -> shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle = the K-major UMMA layout) with no thread touching
+// them.  One persistent CTA per SM, six warps:
+//     warp 0   producer: waits for a free stage, arms its mbarrier with the byte count, issues the 2 (single-pass) or 4 tile loads
+//     warp 1   MMA: waits for a full stage, issues the tcgen05.mma of its K steps, tcgen05.commit -> "stage free"; after a unit's last
+//              chunk a second commit -> "accumulator full".  Two accumulators of 256 TMEM columns alternate between units.
+//     warps 2-5 epilogue: wait for "accumulator full", tcgen05.ld their lane quadrant, bias / ReLU / residual, store FP32 and / or
+//              the TF32 halves the next GEMM reads, arrive on "accumulator free" -- while the MMA warp is already in the next unit.
+constexpr int TMA_THREADS = 192;
+constexpr int ACC_COLS = 256;
+
+struct TmaGemmArgs {
+    const float *bias;
+    float *out;            // FP32 result (QKV; the residual stream X, read and written in place) or nullptr
+    float *out_h, *out_l;  // TF32 halves of the result or nullptr
+    int ldo, T, Nout, K1, K2;
+    int nb, nblocks, mblocks, layer, stages, split, relu, accumulate;
+};
+
+__device__ __forceinline__ void mbar_init(unsigned mb, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned mb, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned mb) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mb) : "memory"); }
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map, int c0, int c1, unsigned mb) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(mb),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned mb) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map),
+                 "r"(mb), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// K-major tile with 128-byte rows, SWIZZLE_128B (8-row atoms of 1024 bytes): start address, LBO unused (1), SBO = 1024 B, layout type 2
+__device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned saddr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((saddr & 0x3FFFFu) >> 4);
+    d |= 1ull << 16;
+    d |= (unsigned long long)(1024u >> 4) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+gnn_gemm_tma_kernel(const __grid_constant__ CUtensorMap a1h, const __grid_constant__ CUtensorMap a1l, const __grid_constant__ CUtensorMap a2h,
+                    const __grid_constant__ CUtensorMap a2l, const __grid_constant__ CUtensorMap wh, const __grid_constant__ CUtensorMap wl, TmaGemmArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_full[6], s_empty[6], s_accf[2], s_acce[2];
+    __shared__ unsigned s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // stage layout: A hi | A lo | B hi | B lo (the lo tiles only when split), every tile 1024-byte aligned
+    const unsigned sbase = (smem_addr(smem_raw) + 1023u) & ~1023u;
+    const int nbpad = (a.nb + 15) & ~15;
+    const unsigned a_bytes = GEMM_M * 128u, b_bytes = (unsigned)((nbpad + 7) & ~7) * 128u;
+    const unsigned stage_bytes = (a_bytes + b_bytes) * (a.split ? 2u : 1u);
+    pdl_prologue();
+    if (warp == 1) tmem_alloc(&s_tmem, 2 * ACC_COLS);
+    if (tid == 0) {
+        for (int i = 0; i < a.stages; ++i) mbar_init(smem_addr(&s_full[i]), 1), mbar_init(smem_addr(&s_empty[i]), 1);
+        for (int i = 0; i < 2; ++i) mbar_init(smem_addr(&s_accf[i]), 1), mbar_init(smem_addr(&s_acce[i]), 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const unsigned tmem = s_tmem;
+    const int nch1 = (a.K1 + GKC - 1) / GKC, nch = nch1 + (a.K2 + GKC - 1) / GKC;
+    const int units = a.mblocks * a.nblocks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int q = 0;
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+                const int mblk = unit / a.nblocks, nblk = unit - mblk * a.nblocks;
+                const int r0 = mblk * GEMM_M, n0 = nblk * a.nb;
+                for (int ch = 0; ch < nch; ++ch, ++q) {
+                    const int s = q % a.stages;
+                    if (q >= a.stages) mbar_wait_parity(smem_addr(&s_empty[s]), (unsigned)(((q / a.stages) - 1) & 1));
+                    const bool second = ch >= nch1;
+                    const int k0 = (second ? ch - nch1 : ch) * GKC;
+                    const unsigned mb = smem_addr(&s_full[s]);
+                    const unsigned st = sbase + (unsigned)s * stage_bytes;
+                    mbar_expect_tx(mb, stage_bytes);
+                    tma_load_2d(st, second ? &a2h : &a1h, k0, r0, mb);
+                    tma_load_3d(st + (a.split ? 2u : 1u) * a_bytes, &wh, (second ? a.K1 : 0) + k0, n0, a.layer, mb);
+                    if (a.split) {
+                        tma_load_2d(st + a_bytes, second ? &a2l : &a1l, k0, r0, mb);
+                        tma_load_3d(st + 2u * a_bytes + b_bytes, &wl, (second ? a.K1 : 0) + k0, n0, a.layer, mb);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int q = 0, u = 0;
+            for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++u) {
+                const int nblk = unit % a.nblocks;
+                const int ncols = min(a.nb, a.Nout - nblk * a.nb), npad = (ncols + 15) & ~15;
+                const unsigned idesc = umma_idesc(npad);
+                const int t = u & 1;
+                if (u >= 2) mbar_wait_parity(smem_addr(&s_acce[t]), (unsigned)(((u >> 1) - 1) & 1));  // the epilogue has drained this accumulator
+                fence_after_sync();
+                const unsigned acc = tmem + (unsigned)(t * ACC_COLS);
+                for (int ch = 0; ch < nch; ++ch, ++q) {
+                    const int s = q % a.stages;
+                    mbar_wait_parity(smem_addr(&s_full[s]), (unsigned)((q / a.stages) & 1));
+                    fence_after_sync();
+                    const bool second = ch >= nch1;
+                    const int kn = min(GKC, (second ? a.K2 : a.K1) - (second ? ch - nch1 : ch) * GKC);
+                    const unsigned st = sbase + (unsigned)s * stage_bytes;
+                    const unsigned ah0 = st, al0 = st + a_bytes, bh0 = st + (a.split ? 2u : 1u) * a_bytes, bl0 = bh0 + b_bytes;
+                    const int steps = (kn + 7) >> 3;
+                    for (int k = 0; k < steps; ++k) {
+                        const unsigned koff = (unsigned)k * 32u;  // 8 TF32 values along K inside the 128-byte swizzle row
+                        const unsigned long long ah = umma_desc_sw128(ah0 + koff), bh = umma_desc_sw128(bh0 + koff);
+                        umma_tf32(acc, ah, bh, idesc, (ch == 0 && k == 0) ? 0u : 1u);
+                        if (a.split) {
+                            umma_tf32(acc, ah, umma_desc_sw128(bl0 + koff), idesc, 1u);
+                            umma_tf32(acc, umma_desc_sw128(al0 + koff), bh, idesc, 1u);
+                        }
+                    }
+                    umma_commit(smem_addr(&s_empty[s]));  // the stage is free once these MMAs have read it
+                }
+                umma_commit(smem_addr(&s_accf[t]));  // ... and the accumulator complete once they have written it
+            }
+        }
+    } else {
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        int u = 0;
+        for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++u) {
+            const int mblk = unit / a.nblocks, nblk = unit - mblk * a.nblocks;
+            const int r0 = mblk * GEMM_M, n0 = nblk * a.nb;
+            const int ncols = min(a.nb, a.Nout - n0), npad = (ncols + 15) & ~15;
+            const int t = u & 1;
+            const int row = r0 + quad * 32 + lane;
+            const bool live = row < a.T;
+            const size_t obase = (size_t)(live ? row : 0) * a.ldo + n0;
+            float4 res[4], bia[4];
+            auto prefetch = [&](int c0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool ok = c0 + 4 * j < ncols;
+                    bia[j] = ok ? ldg4(a.bias + n0 + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    res[j] = (ok && live && a.accumulate) ? *reinterpret_cast<const float4 *>(a.out + obase + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            prefetch(0);
+            mbar_wait_parity(smem_addr(&s_accf[t]), (unsigned)((u >> 1) & 1));
+            fence_after_sync();
+            for (int c0 = 0; c0 < npad; c0 += 16) {
+                unsigned v[16];
+                tmem_ld16(tmem + ((unsigned)(quad * 32) << 16) + (unsigned)(t * ACC_COLS + c0), v);
+                float4 r[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    r[j] = make_float4(__uint_as_float(v[4 * j]) + bia[j].x + res[j].x, __uint_as_float(v[4 * j + 1]) + bia[j].y + res[j].y,
+                                       __uint_as_float(v[4 * j + 2]) + bia[j].z + res[j].z, __uint_as_float(v[4 * j + 3]) + bia[j].w + res[j].w);
+                    if (a.relu) r[j].x = fmaxf(r[j].x, 0.f), r[j].y = fmaxf(r[j].y, 0.f), r[j].z = fmaxf(r[j].z, 0.f), r[j].w = fmaxf(r[j].w, 0.f);
+                }
+                const int cur = c0;
+                if (c0 + 16 < npad) prefetch(c0 + 16);
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (cur + 4 * j < ncols) {
+                            if (a.out) *reinterpret_cast<float4 *>(a.out + obase + cur + 4 * j) = r[j];
+                            if (a.out_h) {
+                                const float4 h = make_float4(tf32_round(r[j].x), tf32_round(r[j].y), tf32_round(r[j].z), tf32_round(r[j].w));
+                                *reinterpret_cast<float4 *>(a.out_h + obase + cur + 4 * j) = h;
+                                *reinterpret_cast<float4 *>(a.out_l + obase + cur + 4 * j) =
+                                    make_float4(tf32_round(r[j].x - h.x), tf32_round(r[j].y - h.y), tf32_round(r[j].z - h.z), tf32_round(r[j].w - h.w));
+                            }
+                        }
+                }
+            }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_addr(&s_acce[t]));
+        }
+    }
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 2 * ACC_COLS);
+}
+
 // ---- attention ----------------------------------------------------------------------------------------------------------------
 struct AttArgs {
     const float *qkv;  // [T, 3D]: q | k | v, each head-major (column h * dim + d)
     float *o;          // [T, D] head-major
+    float *oh, *ol;    // when set: O as its TF32 halves (the operand form the TMA-fed GEMM reads) instead of `o`
     int Bc, N, D, heads, dim, cross;
     float c;           // log2(e) / sqrt(dim)
 };
+
+// one value of O: FP32, or split into its TF32 halves
+__device__ __forceinline__ void put_o(const AttArgs &a, size_t idx, float v) {
+    if (a.oh) {
+        const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+        a.oh[idx] = h;
+        a.ol[idx] = __uint_as_float((__float_as_uint(v - h) + 0x1000u) & 0xffffe000u);
+    } else {
+        a.o[idx] = v;
+    }
+}
 
 __device__ __forceinline__ float comp(const float4 &q, int dd) {
     return dd == 0 ? q.x : dd == 1 ? q.y : dd == 2 ? q.z : q.w;
@@ -369,13 +573,14 @@ __global__ void __launch_bounds__(NW * 32) gnn_attention_kernel(AttArgs a) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
             if (n0 + r < N) {
-                float *orow = a.o + ((size_t)ps * N + n0 + r) * a.D + h * dim;
+                const size_t obase = ((size_t)ps * N + n0 + r) * a.D + h * dim;
                 if (PV2) {
-                    *reinterpret_cast<float2 *>(orow + 2 * lane) = make_float2(o[r][0], o[r][OS - 1]);
+                    put_o(a, obase + 2 * lane, o[r][0]);
+                    put_o(a, obase + 2 * lane + 1, o[r][OS - 1]);
                 } else {
 #pragma unroll
                     for (int i = 0; i < OS; ++i)
-                        if (lane + 32 * i < dim) orow[lane + 32 * i] = o[r][i];
+                        if (lane + 32 * i < dim) put_o(a, obase + lane + 32 * i, o[r][i]);
                 }
             }
         if (PV2) {  // tail dims 64 .. dim - 1: every lane sums its own keys (the probabilities are still in registers), then one warp reduction
@@ -389,7 +594,7 @@ __global__ void __launch_bounds__(NW * 32) gnn_attention_kernel(AttArgs a) {
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) acc = fmaf(s[r][j], vt[j], acc);
                     acc = warp_sum(acc);
-                    if (lane == 0 && n0 + r < N) a.o[((size_t)ps * N + n0 + r) * a.D + h * dim + 64 + t] = acc;
+                    if (lane == 0 && n0 + r < N) put_o(a, ((size_t)ps * N + n0 + r) * a.D + h * dim + 64 + t, acc);
                 }
             }
         }
@@ -543,10 +748,10 @@ __global__ void __launch_bounds__(NW * 32) gnn_attention_flash_kernel(AttArgs a,
             const int n = q0 + (rb * NW + warp) * R + r;
             if (n < N) {
                 const float inv = 1.0f / lrun[rb][r];
-                float *orow = a.o + ((size_t)ps * N + n) * a.D + h * dim;
+                const size_t obase = ((size_t)ps * N + n) * a.D + h * dim;
 #pragma unroll
                 for (int i = 0; i < DI; ++i)
-                    if (lane + 32 * i < dim) orow[lane + 32 * i] = o[rb][r][i] * inv;
+                    if (lane + 32 * i < dim) put_o(a, obase + lane + 32 * i, o[rb][r][i] * inv);
             }
         }
 }
@@ -556,6 +761,7 @@ struct TransArgs {
     const float *d0, *d1;  // entry: inputs [B, D, N] per side
     float *o0, *o1;        // exit: outputs [B, D, N] per side
     float *X;              // [2 * Bc * N, D]
+    float *Xh, *Xl;        // entry, when set: the TF32 halves of X as well
     int b0, Bc, D, N;      // problems [b0, b0 + Bc) of the batch
     int to_tokens;
 };
@@ -574,7 +780,16 @@ __global__ void __launch_bounds__(256) gnn_transpose_kernel(TransArgs a) {
             if (db + i < a.D && nb + tx < a.N) tile[i][tx] = src[(size_t)(db + i) * a.N + nb + tx];
         __syncthreads();
         for (int i = ty; i < 32; i += 8)
-            if (nb + i < a.N && db + tx < a.D) X[(size_t)(nb + i) * a.D + db + tx] = tile[tx][i];
+            if (nb + i < a.N && db + tx < a.D) {
+                const size_t idx = (size_t)(nb + i) * a.D + db + tx;
+                const float v = tile[tx][i];
+                X[idx] = v;
+                if (a.Xh) {
+                    const float h = tf32_round(v);
+                    a.Xh[(size_t)ps * a.N * a.D + idx] = h;
+                    a.Xl[(size_t)ps * a.N * a.D + idx] = tf32_round(v - h);
+                }
+            }
     } else {
         float *dst = (side ? a.o1 : a.o0) + off;
         for (int i = ty; i < 32; i += 8)
@@ -595,6 +810,8 @@ __global__ void __launch_bounds__(256) gnn_transpose_kernel(TransArgs a) {
 // packed layer layout: Wqkv[3D*D] bqkv[3D] W1f[2D*2D] b1f[2D] W2[D*2D] b2[D]
 __host__ __device__ inline size_t raw_layer_floats(int D) { return (size_t)4 * D * D + 4 * D + (size_t)4 * D * D + 2 * D + 8 * D + (size_t)2 * D * D + D; }
 __host__ __device__ inline size_t packed_layer_floats(int D) { return (size_t)9 * D * D + 6 * D; }
+// behind the FP32 layers: per layer Wqkv_hi[3DD] Wqkv_lo[3DD] W1f_hi[4DD] W1f_lo[4DD] W2_hi[2DD] W2_lo[2DD] -- the TF32 halves the TMA-fed GEMM reads
+__host__ __device__ inline size_t halves_layer_floats(int D) { return (size_t)18 * D * D; }
 
 __global__ void gnn_pack_kernel(const float *raw, float *packed, int layers, int D, int heads, float eps) {
     const int dim = D / heads, D2 = 2 * D;
@@ -643,6 +860,79 @@ __global__ void gnn_pack_kernel(const float *raw, float *packed, int layers, int
         }
         packed[i] = val;
     }
+}
+
+__global__ void gnn_split_weights_kernel(float *packed, int layers, int D) {
+    const size_t DD = (size_t)D * D, per = packed_layer_floats(D), per2 = halves_layer_floats(D);
+    const size_t total = (size_t)layers * 9 * DD;
+    float *halves = packed + (size_t)layers * per;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int l = (int)(i / (9 * DD));
+        const size_t e = i - (size_t)l * 9 * DD;
+        const float *w = packed + (size_t)l * per;
+        float *h = halves + (size_t)l * per2;
+        float x;
+        size_t hi_at, lo_at;
+        if (e < 3 * DD) x = w[e], hi_at = e, lo_at = 3 * DD + e;                                              // Wqkv
+        else if (e < 7 * DD) x = w[3 * DD + 3 * D + (e - 3 * DD)], hi_at = 6 * DD + (e - 3 * DD), lo_at = 10 * DD + (e - 3 * DD);  // W1f
+        else x = w[7 * DD + 5 * D + (e - 7 * DD)], hi_at = 14 * DD + (e - 7 * DD), lo_at = 16 * DD + (e - 7 * DD);                  // W2
+        const float hv = tf32_round(x);
+        h[hi_at] = hv;
+        h[lo_at] = tf32_round(x - hv);
+    }
+}
+
+// ---- tensor maps (host) ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static std::atomic<void *> cached{nullptr};
+    void *fn = cached.load(std::memory_order_acquire);
+    if (!fn) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        cached.store(fn, std::memory_order_release);
+    }
+    return reinterpret_cast<EncodeTiledFn>(fn);
+}
+// [rows, cols] FP32, row stride ld floats; box = 32 columns (128 bytes, the swizzle span) x box_rows; out-of-range elements read as zero
+int make_map_2d(CUtensorMap *m, const float *base, int rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return invalid("attentional_gnn: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows}, strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows}, es[2] = {1u, 1u};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PATS_OK : invalid("attentional_gnn: cuTensorMapEncodeTiled failed (%d) for a [%d, %d] tensor", (int)r, rows, cols);
+}
+// [layers, rows, cols] weights, one layer every `layer_stride` floats
+int make_map_3d(CUtensorMap *m, const float *base, int layers, int rows, int cols, size_t layer_stride, int box_rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return invalid("attentional_gnn: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)layers}, strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)layer_stride * 4};
+    const cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u}, es[3] = {1u, 1u, 1u};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PATS_OK : invalid("attentional_gnn: cuTensorMapEncodeTiled failed (%d) for [%d, %d, %d] weights", (int)r, layers, rows, cols);
+}
+
+// block size along Nout for the TMA-fed kernel and the number of stages that fit
+struct TmaShape {
+    int nb, nblocks, stages;
+    size_t smem;
+};
+TmaShape tma_shape(int Nout, bool split) {
+    TmaShape t;
+    const size_t budget = 225 * 1024;
+    const int max_nb = split ? 160 : 256;  // three stages of (128 + nb) x 128 B x 2 halves must fit
+    t.nblocks = (Nout + max_nb - 1) / max_nb;
+    t.nb = (((Nout + t.nblocks - 1) / t.nblocks) + 15) & ~15;
+    t.nblocks = (Nout + t.nb - 1) / t.nb;
+    const size_t stage = (size_t)(GEMM_M + t.nb) * 128 * (split ? 2 : 1);
+    t.stages = (int)((budget - 1024) / stage);
+    if (t.stages > 6) t.stages = 6;
+    t.smem = (size_t)t.stages * stage + 1024;
+    return t;
 }
 
 template <int NJ, int DI, bool PV2, int R, int NW>
@@ -715,16 +1005,36 @@ PATS_API void pats_gnn_attention_variant(int v) { g_att_variant.store(v, std::me
 PATS_API void pats_gnn_precision(int passes) { g_precision.store(passes == 1 ? 1 : 3, std::memory_order_relaxed); }
 
 PATS_API long long pats_gnn_raw_floats(int layers, int D) { return (long long)(raw_layer_floats(D) * (size_t)layers); }
-PATS_API long long pats_gnn_packed_floats(int layers, int D) { return (long long)(packed_layer_floats(D) * (size_t)layers); }
-PATS_API long long pats_gnn_workspace_floats(int chunk, int D, int N) { return (long long)14 * chunk * N * D; }
+PATS_API long long pats_gnn_packed_floats(int layers, int D) { return (long long)((packed_layer_floats(D) + halves_layer_floats(D)) * (size_t)layers); }
+PATS_API long long pats_gnn_workspace_floats(int chunk, int D, int N) { return (long long)24 * chunk * N * D; }
+PATS_API void pats_gnn_gemm_variant(int v) { g_gemm_variant.store(v, std::memory_order_relaxed); }
 
 PATS_API int pats_gnn_pack_f32(const float *raw, int layers, int D, int heads, float bn_eps, float *packed, void *stream) {
     if (layers <= 0 || D <= 0 || heads <= 0 || D % heads != 0) return invalid("gnn_pack: bad sizes layers=%d D=%d heads=%d", layers, D, heads);
     if (!raw || !packed) return invalid("gnn_pack: null pointer");
     gnn_pack_kernel<<<1184, 256, 0, as_stream(stream)>>>(raw, packed, layers, D, heads, bn_eps);
     PATS_LAUNCH_CHECK("gnn_pack_kernel");
+    gnn_split_weights_kernel<<<1184, 256, 0, as_stream(stream)>>>(packed, layers, D);
+    PATS_LAUNCH_CHECK("gnn_split_weights_kernel");
     return PATS_OK;
 }
+
+namespace {
+int launch_gemm_tma(const CUtensorMap &a1h, const CUtensorMap &a1l, const CUtensorMap &a2h, const CUtensorMap &a2l, const CUtensorMap &wh, const CUtensorMap &wl,
+                    TmaGemmArgs a, const TmaShape &shape, cudaStream_t st, int dev, int sms) {
+    a.nb = shape.nb, a.nblocks = shape.nblocks, a.stages = shape.stages;
+    a.mblocks = (a.T + GEMM_M - 1) / GEMM_M;
+    static PerDeviceOnce configured;
+    if (!configured.done(dev)) {
+        PATS_CUDA_TRY(cudaFuncSetAttribute(gnn_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        configured.mark(dev);
+    }
+    long long grid = (long long)a.mblocks * a.nblocks;
+    if (grid > sms) grid = sms;
+    PATS_CUDA_TRY(launch_chained(gnn_gemm_tma_kernel, dim3((unsigned)grid), dim3(TMA_THREADS), shape.smem, st, a1h, a1l, a2h, a2l, wh, wl, a));
+    return PATS_OK;
+}
+}  // namespace
 
 PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, int B, int D, int N, const float *packed, const unsigned char *cross,
                                       int layers, int heads, float *out0, float *out1, float *workspace, long long workspace_floats, void *stream) {
@@ -736,7 +1046,7 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
     const int dim = D / heads;
     const int NJ = (N + 31) / 32, DI = (dim + 31) / 32;
     if (DI > 4) return invalid("attentional_gnn: head dimension %d exceeds the 128 this build has attention kernels for", dim);
-    const long long per_problem = (long long)14 * N * D;
+    const long long per_problem = (long long)24 * N * D;
     int chunk = (int)(workspace_floats / per_problem < B ? workspace_floats / per_problem : B);
     if (chunk > 16384) chunk = 16384;  // 2 * chunk is a grid z extent
     if (chunk < 1) return invalid("attentional_gnn: workspace of %lld floats holds no problem (%lld floats each)", workspace_floats, per_problem);
@@ -744,26 +1054,64 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
     if (dev < 0) return PATS_E_CUDA;
     const int sms = sm_count() > 0 ? sm_count() : 148;
     cudaStream_t st = as_stream(stream);
-    const size_t per = packed_layer_floats(D);
+    const size_t per = packed_layer_floats(D), per2 = halves_layer_floats(D);
     const size_t DD = (size_t)D * D;
+    const bool tma = g_gemm_variant.load(std::memory_order_relaxed) == 0;
+    const bool split = g_precision.load(std::memory_order_relaxed) != 1;
+    // weights as TF32 halves, one 3-D tensor map per matrix over all layers
+    CUtensorMap m_qkv_h, m_qkv_l, m_w1_h, m_w1_l, m_w2_h, m_w2_l;
+    TmaShape s_qkv = {}, s_w1 = {}, s_w2 = {};
+    if (tma) {
+        const float *halves = packed + (size_t)layers * per;
+        s_qkv = tma_shape(3 * D, split), s_w1 = tma_shape(2 * D, split), s_w2 = tma_shape(D, split);
+        int rc = make_map_3d(&m_qkv_h, halves, layers, 3 * D, D, per2, s_qkv.nb);
+        if (!rc) rc = make_map_3d(&m_qkv_l, halves + 3 * DD, layers, 3 * D, D, per2, s_qkv.nb);
+        if (!rc) rc = make_map_3d(&m_w1_h, halves + 6 * DD, layers, 2 * D, 2 * D, per2, s_w1.nb);
+        if (!rc) rc = make_map_3d(&m_w1_l, halves + 10 * DD, layers, 2 * D, 2 * D, per2, s_w1.nb);
+        if (!rc) rc = make_map_3d(&m_w2_h, halves + 14 * DD, layers, D, 2 * D, per2, s_w2.nb);
+        if (!rc) rc = make_map_3d(&m_w2_l, halves + 16 * DD, layers, D, 2 * D, per2, s_w2.nb);
+        if (rc) return rc;
+    }
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int Bc = B - b0 < chunk ? B - b0 : chunk;
         const int T = 2 * Bc * N;
-        float *X = workspace, *QKV = X + (size_t)T * D, *O = QKV + (size_t)T * 3 * D, *Y = O + (size_t)T * D;
+        const size_t TD = (size_t)T * D;
+        // X | Xh | Xl | QKV (3) | O or Oh, Ol (2) | Y or Yh, Yl (4)
+        float *X = workspace, *Xh = X + TD, *Xl = Xh + TD, *QKV = Xl + TD, *O = QKV + 3 * TD, *Oh = O, *Ol = O + TD, *Y = Ol + TD, *Yh = Y, *Yl = Y + 2 * TD;
+        CUtensorMap m_xh, m_xl, m_oh, m_ol, m_yh, m_yl;
+        if (tma) {
+            int rc = make_map_2d(&m_xh, Xh, T, D, D, GEMM_M);
+            if (!rc) rc = make_map_2d(&m_xl, Xl, T, D, D, GEMM_M);
+            if (!rc) rc = make_map_2d(&m_oh, Oh, T, D, D, GEMM_M);
+            if (!rc) rc = make_map_2d(&m_ol, Ol, T, D, D, GEMM_M);
+            if (!rc) rc = make_map_2d(&m_yh, Yh, T, 2 * D, 2 * D, GEMM_M);
+            if (!rc) rc = make_map_2d(&m_yl, Yl, T, 2 * D, 2 * D, GEMM_M);
+            if (rc) return rc;
+        }
         TransArgs t;
-        t.d0 = desc0, t.d1 = desc1, t.o0 = out0, t.o1 = out1, t.X = X, t.b0 = b0, t.Bc = Bc, t.D = D, t.N = N, t.to_tokens = 1;
+        t.d0 = desc0, t.d1 = desc1, t.o0 = out0, t.o1 = out1, t.X = X, t.Xh = tma ? Xh : nullptr, t.Xl = tma ? Xl : nullptr;
+        t.b0 = b0, t.Bc = Bc, t.D = D, t.N = N, t.to_tokens = 1;
         const dim3 tgrid((unsigned)((N + 31) / 32), (unsigned)((D + 31) / 32), (unsigned)(2 * Bc));
         PATS_CUDA_TRY(launch_chained(gnn_transpose_kernel, tgrid, dim3(256), 0, st, t));
         for (int l = 0; l < layers; ++l) {
             const float *w = packed + (size_t)l * per;
             const float *Wqkv = w, *bqkv = Wqkv + 3 * DD, *W1f = bqkv + 3 * D, *b1f = W1f + 4 * DD, *W2 = b1f + 2 * D, *b2 = W2 + 2 * DD;
+            int rc;
             GemmArgs g = {};
-            g.A1 = X, g.lda1 = D, g.K1 = D, g.A2 = nullptr, g.lda2 = 0, g.K2 = 0, g.W = Wqkv, g.ldw = D, g.bias = bqkv, g.out = QKV, g.ldo = 3 * D;
-            g.T = T, g.Nout = 3 * D, g.relu = 0, g.accumulate = 0;
-            int rc = launch_gemm(g, st, dev, sms);
+            TmaGemmArgs ta = {};
+            ta.T = T, ta.layer = l, ta.split = split ? 1 : 0;
+            if (tma) {
+                ta.bias = bqkv, ta.out = QKV, ta.out_h = ta.out_l = nullptr, ta.ldo = 3 * D, ta.Nout = 3 * D, ta.K1 = D, ta.K2 = 0, ta.relu = 0, ta.accumulate = 0;
+                rc = launch_gemm_tma(m_xh, m_xl, m_xh, m_xl, m_qkv_h, m_qkv_l, ta, s_qkv, st, dev, sms);
+            } else {
+                g.A1 = X, g.lda1 = D, g.K1 = D, g.A2 = nullptr, g.lda2 = 0, g.K2 = 0, g.W = Wqkv, g.ldw = D, g.bias = bqkv, g.out = QKV, g.ldo = 3 * D;
+                g.T = T, g.Nout = 3 * D, g.relu = 0, g.accumulate = 0;
+                rc = launch_gemm(g, st, dev, sms);
+            }
             if (rc) return rc;
             AttArgs at;
-            at.qkv = QKV, at.o = O, at.Bc = Bc, at.N = N, at.D = D, at.heads = heads, at.dim = dim, at.cross = cross[l] ? 1 : 0;
+            at.qkv = QKV, at.o = O, at.oh = tma ? Oh : nullptr, at.ol = tma ? Ol : nullptr;
+            at.Bc = Bc, at.N = N, at.D = D, at.heads = heads, at.dim = dim, at.cross = cross[l] ? 1 : 0;
             at.c = 1.4426950408889634f / sqrtf((float)dim);
             if (NJ <= 3 && DI == 1)
                 rc = launch_attention<3, 1, false, 8, 4>(at, st, dev);
@@ -772,19 +1120,28 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
                 // measured (tools/gnn_kernels.py, 89 problems per launch): 4 rows x 20 warps 206 us, 8 rows x 10 warps 232 us, 4 rows x 16 warps 225 us
                 rc = v == 1 ? launch_attention<5, 3, true, 8, 10>(at, st, dev) : v == 2 ? launch_attention<5, 3, true, 4, 16>(at, st, dev)
                             : launch_attention<5, 3, true, 4, 20>(at, st, dev);
-            }
-            else if (NJ <= 5 && DI <= 3)
+            } else if (NJ <= 5 && DI <= 3)
                 rc = launch_attention<5, 3, false, 4, 8>(at, st, dev);
             else
                 rc = launch_attention_flash<5, 4, 4, 8, 2>(at, st, dev);
             if (rc) return rc;
-            g.A1 = X, g.lda1 = D, g.K1 = D, g.A2 = O, g.lda2 = D, g.K2 = D, g.W = W1f, g.ldw = 2 * D, g.bias = b1f, g.out = Y, g.ldo = 2 * D;
-            g.Nout = 2 * D, g.relu = 1, g.accumulate = 0;
-            rc = launch_gemm(g, st, dev, sms);
+            if (tma) {
+                ta.bias = b1f, ta.out = nullptr, ta.out_h = Yh, ta.out_l = Yl, ta.ldo = 2 * D, ta.Nout = 2 * D, ta.K1 = D, ta.K2 = D, ta.relu = 1, ta.accumulate = 0;
+                rc = launch_gemm_tma(m_xh, m_xl, m_oh, m_ol, m_w1_h, m_w1_l, ta, s_w1, st, dev, sms);
+            } else {
+                g.A1 = X, g.lda1 = D, g.K1 = D, g.A2 = O, g.lda2 = D, g.K2 = D, g.W = W1f, g.ldw = 2 * D, g.bias = b1f, g.out = Y, g.ldo = 2 * D;
+                g.Nout = 2 * D, g.relu = 1, g.accumulate = 0;
+                rc = launch_gemm(g, st, dev, sms);
+            }
             if (rc) return rc;
-            g.A1 = Y, g.lda1 = 2 * D, g.K1 = 2 * D, g.A2 = nullptr, g.lda2 = 0, g.K2 = 0, g.W = W2, g.ldw = 2 * D, g.bias = b2, g.out = X, g.ldo = D;
-            g.Nout = D, g.relu = 0, g.accumulate = 1;
-            rc = launch_gemm(g, st, dev, sms);
+            if (tma) {
+                ta.bias = b2, ta.out = X, ta.out_h = Xh, ta.out_l = Xl, ta.ldo = D, ta.Nout = D, ta.K1 = 2 * D, ta.K2 = 0, ta.relu = 0, ta.accumulate = 1;
+                rc = launch_gemm_tma(m_yh, m_yl, m_yh, m_yl, m_w2_h, m_w2_l, ta, s_w2, st, dev, sms);
+            } else {
+                g.A1 = Y, g.lda1 = 2 * D, g.K1 = 2 * D, g.A2 = nullptr, g.lda2 = 0, g.K2 = 0, g.W = W2, g.ldw = 2 * D, g.bias = b2, g.out = X, g.ldo = D;
+                g.Nout = D, g.relu = 0, g.accumulate = 1;
+                rc = launch_gemm(g, st, dev, sms);
+            }
             if (rc) return rc;
         }
         t.to_tokens = 0;

@@ -19,6 +19,7 @@ def main():
     G.set_precision(int(sys.argv[1]) if len(sys.argv) > 1 else 3)
     from pats_b200 import _lib
     _lib.load().pats_gnn_attention_variant(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    _lib.load().pats_gnn_gemm_variant(int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     dev = torch.device("cuda:0")
     ref = L.load_reference()
     with torch.no_grad():
