@@ -111,6 +111,34 @@ def test_gnn_chunking_and_repeat_are_bit_identical():
     assert torch.equal(a0, c0) and torch.equal(a1, c1)
 
 
+@pytest.mark.parametrize("name", ["tiny", "l3", "l2", "l1"])
+def test_gnn_gemm_generations_are_bit_identical(name):
+    """The TMA-fed GEMM (operands pre-split by their producers, tiles loaded by cp.async.bulk.tensor with the 128-byte swizzle) and the
+    register-staged GEMM (operands split while staged into the no-swizzle layout) issue the same products in the same order: the two
+    must agree bit for bit, in both precisions -- which cross-checks tensor maps, swizzle and descriptors against plain loads."""
+    dev = _need_gpu()
+    import live_util as L
+    from pats_b200 import _lib, gnn as G
+
+    if L.reference_root() is None:
+        pytest.skip("reference Python not staged")
+    lib = _lib.load()
+    with torch.no_grad():
+        mod, x0, x1 = _module(name, dev)
+        try:
+            for passes in (3, 1):
+                G.set_precision(passes)
+                lib.pats_gnn_gemm_variant(0)
+                a0, a1 = G.attentional_gnn_forward(mod, x0, x1)
+                lib.pats_gnn_gemm_variant(1)
+                b0, b1 = G.attentional_gnn_forward(mod, x0, x1)
+                torch.cuda.synchronize()
+                assert torch.equal(a0, b0) and torch.equal(a1, b1), (name, passes, float((a0 - b0).abs().max()))
+        finally:
+            lib.pats_gnn_gemm_variant(0)
+            G.set_precision(3)
+
+
 def test_gnn_pack_follows_the_parameters_and_modes():
     dev = _need_gpu()
     import live_util as L
@@ -147,7 +175,7 @@ def test_gnn_argument_validation():
     rc = lib.pats_attentional_gnn_f32(None, None, 1, 12, 7, None, None, 2, 4, None, None, None, 0, None)
     assert rc != 0
     assert lib.pats_gnn_raw_floats(2, 16) == 2 * (4 * 256 + 4 * 16 + 4 * 256 + 2 * 16 + 8 * 16 + 2 * 256 + 16)
-    assert lib.pats_gnn_packed_floats(2, 16) == 2 * (9 * 256 + 6 * 16)
+    assert lib.pats_gnn_packed_floats(2, 16) == 2 * (9 * 256 + 6 * 16 + 18 * 256)  # FP32 layers + their TF32 halves
 
 
 @pytest.mark.parametrize("if_local", [True, False])
