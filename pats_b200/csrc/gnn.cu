@@ -21,14 +21,13 @@
 // Four kernels per layer, launch-chained (griddepcontrol), no host synchronisation; the [b, D, n] <-> [T, D] transpositions are
 // one pass each at entry and exit.  Problems are processed in chunks sized so that a chunk's activations stay in the 126 MB L2.
 //
-// GEMM kernel (gnn_gemm_kernel): one CTA of 256 threads per (128-token block, <= 256-output block).  Per 32-wide K chunk every
-// thread loads its 16-byte pieces of the activation and weight tiles (issued BEFORE it waits for the previous chunk's MMAs, so
-// the L2 latency hides behind the tensor core), splits them into TF32 hi / lo halves and stores them in the canonical K-major
-// no-swizzle UMMA layout (lane = (k4 % 4) * 8 + row % 8: conflict-free 128-bit stores, fully used 32-byte sectors); one thread
-// issues tcgen05.mma.kind::tf32 (M = 128, N <= 256, K = 8; accumulator in TMEM) -- hi*hi + hi*lo + lo*hi per K step ("3xTF32":
-// FP32-class accuracy; the reference's own convolutions run as single TF32 through cuDNN, which `pats_gnn_precision(1)` mirrors)
-// -- and tcgen05.commit arrives on an mbarrier.  Two CTAs share an SM (96 KB of operands + 256 TMEM columns each), so one CTA
-// stages while the other's MMAs run.  Epilogue: tcgen05.ld, + bias, ReLU or the in-place residual add, 64-byte row pieces.
+// GEMM kernels: gnn_gemm_tma_kernel (default; operands pre-split into TF32 halves by their producers, tiles by TMA, warp-specialised --
+// see its header below) and gnn_gemm_kernel, the first generation (one CTA of 256 threads per (128-token block, <= 256-output block),
+// two CTAs per SM: per 32-wide K chunk every thread loads its 16-byte pieces of the FP32 activation and weight tiles -- issued BEFORE it
+// waits for the previous chunk's MMAs -- rounds them to TF32, forms the remainder tile and stores both in the canonical K-major
+// no-swizzle UMMA layout, lane = (k4 % 4) * 8 + row % 8: conflict-free 128-bit stores; one thread issues tcgen05.mma.kind::tf32, M = 128,
+// N <= 256, K = 8, accumulator in TMEM).  Both issue hi*hi + hi*lo + lo*hi per K step ("3xTF32": FP32-class accuracy; the reference's
+// own convolutions run as single TF32 through cuDNN, which `pats_gnn_precision(1)` mirrors) in the same order and agree bit for bit.
 // Attention kernel (gnn_attention_kernel): FP32 on the CUDA cores, as the reference computes it (torch.einsum -> SGEMM): one CTA
 // per (problem, side, head), K^T / V / Q in shared memory, a warp owns R query rows x all keys in registers (R * ceil(n / 32)
 // accumulators), softmax by warp shuffles, P through a per-warp shared buffer into the P V product.
