@@ -287,8 +287,8 @@ long long pats_gnn_workspace_floats(int chunk, int D, int N);
 int pats_attentional_gnn_f32(const float *desc0, const float *desc1, int B, int D, int N, const float *packed, const unsigned char *cross,
                              int layers, int heads, float *out0, float *out1, float *workspace, long long workspace_floats, void *stream);
 void pats_gnn_precision(int passes);
-/* A/B switch (timing only; every variant computes the same sums in the same order per row): tiling of the level-2 attention kernel.
- *   0 = 4 query rows per warp, 20 warps (default); 1 = 8 rows, 10 warps; 2 = 4 rows, 16 warps. */
+/* A/B switch: 0 = the packed-FP32 (fma.rn.f32x2) generation of the resident-key attention kernels (default), 1 = the first
+ *   generation.  Same sums in the same order: bit-identical results. */
 void pats_gnn_attention_variant(int v);
 /* A/B switch: 0 = the TMA-fed, warp-specialised GEMM (operands pre-split into TF32 halves by their producers; default),
  *             1 = the register-staged GEMM (operands split while they are staged).  Same products, same accumulation order. */

@@ -601,6 +601,180 @@ __global__ void __launch_bounds__(NW * 32) gnn_attention_kernel(AttArgs a) {
     }
 }
 
+// Second generation of the resident-key kernel: the same sums in the same order (bit-identical to gnn_attention_kernel), on the packed
+// FP32 pipe.  A warp owns 8 query rows as 4 row PAIRS: Q of its block sits transposed in the warp's own buffer ([dim][8 rows]: two
+// broadcast LDS.128 per dimension deliver the four (q_r, q_r+1) pairs), every accumulator is a float2 over a row pair, and one
+// fma.rn.f32x2 (SASS FFMA2) does the work of two FFMAs -- the key / value element is duplicated into a register pair with one MOV that
+// serves four FFMA2.  Per dimension and 8 rows x 160 keys: 2 + 5 loads, 5 MOVs, 20 FFMA2 (first generation: 52 instructions, this: 32);
+// per key in P V: 13 instead of 20.  The warp's buffer holds Q^T during Q K^T and P afterwards; Q is no longer staged for the CTA.
+// VMODE 0: dim <= 32, one value slot per lane; VMODE 1: dims [0, 64) as a float2 per lane + the <= 4 tail dims by a key-parallel reduction.
+template <int NJ, int VMODE, int NW>
+__global__ void __launch_bounds__(NW * 32) gnn_attention2_kernel(AttArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int R = 8, NP = NJ * 32 + 1, NP32 = NJ * 32, DV = VMODE ? 64 : 32, NT = NW * 32, TAILMAX = 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = a.N, dim = a.dim, dim4 = (dim + 3) & ~3, D3 = 3 * a.D;
+    const int tail = VMODE ? dim - 64 : 0;
+    float *P = sm;                               // [NW][NP32][R]   (Q^T of the warp's block first: [dim4][R])
+    float *V = P + NW * NP32 * R;                // [N][DV]
+    float *Vt = V + N * DV;                      // [N][TAILMAX]    (VMODE 1 only)
+    float *Kt = Vt + (VMODE ? N * TAILMAX : 0);  // [dim4][NP]
+    pdl_prologue();
+    const int ps = blockIdx.x / a.heads, h = blockIdx.x - ps * a.heads;
+    const int side = ps / a.Bc, b = ps - side * a.Bc;
+    const int sps = a.cross ? (1 - side) * a.Bc + b : ps;
+    const float *qbase = a.qkv + (size_t)ps * N * D3 + h * dim;
+    const float *kbase = a.qkv + (size_t)sps * N * D3 + a.D + h * dim;
+    const float *vbase = kbase + a.D;
+    const int half = dim4 >> 1;
+    for (int it0 = tid; it0 < N * half; it0 += NT * 4) {
+        float2 k2[4], v2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * NT;
+            const int n = it / half, d = (it - n * half) * 2;
+            k2[u] = v2[u] = make_float2(0.f, 0.f);
+            if (it < N * half && d < dim) {
+                k2[u] = __ldg(reinterpret_cast<const float2 *>(kbase + (size_t)n * D3 + d));
+                v2[u] = __ldg(reinterpret_cast<const float2 *>(vbase + (size_t)n * D3 + d));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int it = it0 + u * NT;
+            if (it < N * half) {
+                const int n = it / half, d = (it - n * half) * 2;
+                Kt[d * NP + n] = k2[u].x, Kt[(d + 1) * NP + n] = k2[u].y;
+                if (d < DV)
+                    *reinterpret_cast<float2 *>(V + n * DV + d) = v2[u];
+                else if (VMODE)
+                    Vt[n * TAILMAX + d - 64] = v2[u].x, Vt[n * TAILMAX + d - 63] = v2[u].y;
+            }
+        }
+    }
+    for (int it = tid; it < dim4 * (NP32 - N); it += NT) {  // keys beyond n: finite (masked after the products)
+        const int d = it / (NP32 - N), m = N + it - d * (NP32 - N);
+        Kt[d * NP + m] = 0.f;
+    }
+    if (!VMODE && DV > dim4)
+        for (int it = tid; it < N * (DV - dim4); it += NT) {  // value columns beyond dim: zero
+            const int n = it / (DV - dim4), d = dim4 + it - n * (DV - dim4);
+            V[n * DV + d] = 0.f;
+        }
+    __syncthreads();
+    float *Pw = P + warp * NP32 * R;
+    for (int n0 = warp * R; n0 < N; n0 += NW * R) {
+        // ---- Q^T of this block into the warp's buffer: Pw[d * 8 + r] ----
+        for (int it = lane; it < R * half; it += 32) {
+            const int r = it / half, d = (it - r * half) * 2;
+            float2 q2 = make_float2(0.f, 0.f);
+            if (d < dim) q2 = __ldg(reinterpret_cast<const float2 *>(qbase + (size_t)min(n0 + r, N - 1) * D3 + d));
+            Pw[d * R + r] = q2.x, Pw[(d + 1) * R + r] = q2.y;
+        }
+        __syncwarp();
+        float2 s2[R / 2][NJ];
+#pragma unroll
+        for (int rp = 0; rp < R / 2; ++rp)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) s2[rp][j] = make_float2(0.f, 0.f);
+        for (int d = 0; d < dim4; ++d) {
+            const float4 qa = *reinterpret_cast<const float4 *>(Pw + d * R), qb = *reinterpret_cast<const float4 *>(Pw + d * R + 4);
+            const float2 qp[4] = {make_float2(qa.x, qa.y), make_float2(qa.z, qa.w), make_float2(qb.x, qb.y), make_float2(qb.z, qb.w)};
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const float kv = Kt[d * NP + lane + 32 * j];
+                const float2 kk = make_float2(kv, kv);
+#pragma unroll
+                for (int rp = 0; rp < R / 2; ++rp) s2[rp][j] = ffma2(qp[rp], kk, s2[rp][j]);
+            }
+        }
+        __syncwarp();  // Q^T has been read; the buffer becomes P
+        float s[R][NJ];
+#pragma unroll
+        for (int rp = 0; rp < R / 2; ++rp)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) s[2 * rp][j] = s2[rp][j].x, s[2 * rp + 1][j] = s2[rp][j].y;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if (lane + 32 * j >= N) s[r][j] = -INFINITY;
+                mx = fmaxf(mx, s[r][j]);
+            }
+            mx = warp_max(mx);
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                s[r][j] = fast_exp2((s[r][j] - mx) * a.c);
+                sum += s[r][j];
+            }
+            sum = warp_sum(sum);
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) s[r][j] *= inv;
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            *reinterpret_cast<float4 *>(Pw + (lane + 32 * j) * R) = make_float4(s[0][j], s[1][j], s[2][j], s[3][j]);
+            *reinterpret_cast<float4 *>(Pw + (lane + 32 * j) * R + 4) = make_float4(s[4][j], s[5][j], s[6][j], s[7][j]);
+        }
+        __syncwarp();
+        constexpr int OS = VMODE ? 2 : 1;  // value slots per lane
+        float2 o2[R / 2][OS];
+#pragma unroll
+        for (int rp = 0; rp < R / 2; ++rp)
+#pragma unroll
+            for (int i = 0; i < OS; ++i) o2[rp][i] = make_float2(0.f, 0.f);
+#pragma unroll 2
+        for (int m = 0; m < N; ++m) {
+            const float4 pa = *reinterpret_cast<const float4 *>(Pw + m * R), pb = *reinterpret_cast<const float4 *>(Pw + m * R + 4);
+            const float2 pp[4] = {make_float2(pa.x, pa.y), make_float2(pa.z, pa.w), make_float2(pb.x, pb.y), make_float2(pb.z, pb.w)};
+            float vv[OS];
+            if (VMODE) {
+                const float2 t = *reinterpret_cast<const float2 *>(V + m * DV + 2 * lane);
+                vv[0] = t.x, vv[OS - 1] = t.y;
+            } else {
+                vv[0] = V[m * DV + lane];
+            }
+#pragma unroll
+            for (int i = 0; i < OS; ++i) {
+                const float2 vd = make_float2(vv[i], vv[i]);
+#pragma unroll
+                for (int rp = 0; rp < R / 2; ++rp) o2[rp][i] = ffma2(pp[rp], vd, o2[rp][i]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (n0 + r < N) {
+                const size_t obase = ((size_t)ps * N + n0 + r) * a.D + h * dim;
+                const float2 *op = o2[r >> 1];
+                if (VMODE) {
+                    put_o(a, obase + 2 * lane, (r & 1) ? op[0].y : op[0].x);
+                    put_o(a, obase + 2 * lane + 1, (r & 1) ? op[OS - 1].y : op[OS - 1].x);
+                } else if (lane < dim) {
+                    put_o(a, obase + lane, (r & 1) ? op[0].y : op[0].x);
+                }
+            }
+        if (VMODE) {  // tail dims 64 .. dim - 1: every lane sums its own keys (the probabilities are still in registers), then one warp reduction
+            for (int t = 0; t < tail; ++t) {
+                float vt[NJ];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) vt[j] = lane + 32 * j < N ? Vt[(lane + 32 * j) * TAILMAX + t] : 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) acc = fmaf(s[r][j], vt[j], acc);
+                    acc = warp_sum(acc);
+                    if (lane == 0 && n0 + r < N) put_o(a, ((size_t)ps * N + n0 + r) * a.D + h * dim + 64 + t, acc);
+                }
+            }
+        }
+        __syncwarp();  // the buffer is rewritten by the next pass
+    }
+}
+
 // Any token count (level 1: n = 300 at 640 x 480, 1024 at 1024 x 1024; head dimension 112): one CTA per (problem, side, head, tile of
 // NW * R * RB query rows), the keys in chunks of NJ * 32 with the running maximum / sum of an online softmax, the output rescaled when
 // the maximum moves ("flash" formulation; identical to the plain softmax up to FP32 rounding).
@@ -948,6 +1122,20 @@ int launch_attention(const AttArgs &a, cudaStream_t st, int dev) {
     return PATS_OK;
 }
 
+template <int NJ, int VMODE, int NW>
+int launch_attention2(const AttArgs &a, cudaStream_t st, int dev) {
+    const int dim4 = (a.dim + 3) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)NW * NJ * 32 * 8 + (size_t)a.N * (VMODE ? 64 + 4 : 32) + (size_t)dim4 * (NJ * 32 + 1));
+    static PerDeviceOnce configured;
+    if (!configured.done(dev)) {
+        PATS_CUDA_TRY(cudaFuncSetAttribute(gnn_attention2_kernel<NJ, VMODE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured.mark(dev);
+    }
+    if (smem > 220 * 1024) return invalid("attentional_gnn: attention tile of %zu bytes exceeds shared memory (n = %d, head dim = %d)", smem, a.N, a.dim);
+    PATS_CUDA_TRY(launch_chained(gnn_attention2_kernel<NJ, VMODE, NW>, dim3((unsigned)(2 * a.Bc * a.heads)), dim3(NW * 32), smem, st, a));
+    return PATS_OK;
+}
+
 template <int NJ, int DI, int R, int NW, int RB>
 int launch_attention_flash(const AttArgs &a, cudaStream_t st, int dev) {
     constexpr int QT = NW * R * RB;
@@ -1112,14 +1300,13 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
             at.qkv = QKV, at.o = O, at.oh = tma ? Oh : nullptr, at.ol = tma ? Ol : nullptr;
             at.Bc = Bc, at.N = N, at.D = D, at.heads = heads, at.dim = dim, at.cross = cross[l] ? 1 : 0;
             at.c = 1.4426950408889634f / sqrtf((float)dim);
+            const int av = g_att_variant.load(std::memory_order_relaxed);  // 0: packed-FP32 generation; 1: first generation (same sums, same order)
             if (NJ <= 3 && DI == 1)
-                rc = launch_attention<3, 1, false, 8, 4>(at, st, dev);
-            else if (NJ <= 5 && dim >= 64 && dim <= 68) {
-                const int v = g_att_variant.load(std::memory_order_relaxed);
-                // measured (tools/gnn_kernels.py, 89 problems per launch): 4 rows x 20 warps 206 us, 8 rows x 10 warps 232 us, 4 rows x 16 warps 225 us
-                rc = v == 1 ? launch_attention<5, 3, true, 8, 10>(at, st, dev) : v == 2 ? launch_attention<5, 3, true, 4, 16>(at, st, dev)
-                            : launch_attention<5, 3, true, 4, 20>(at, st, dev);
-            } else if (NJ <= 5 && DI <= 3)
+                rc = av == 0 ? launch_attention2<3, 0, 4>(at, st, dev) : launch_attention<3, 1, false, 8, 4>(at, st, dev);
+            else if (NJ <= 5 && dim >= 64 && dim <= 68)
+                // first generation, measured (tools/gnn_kernels.py, 89 windows per launch): 4 rows x 20 warps 206 us, 8 rows x 10 warps 232 us
+                rc = av == 0 ? launch_attention2<5, 1, 20>(at, st, dev) : launch_attention<5, 3, true, 4, 20>(at, st, dev);
+            else if (NJ <= 5 && DI <= 3)
                 rc = launch_attention<5, 3, false, 4, 8>(at, st, dev);
             else
                 rc = launch_attention_flash<5, 4, 4, 8, 2>(at, st, dev);

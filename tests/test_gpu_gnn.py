@@ -139,6 +139,29 @@ def test_gnn_gemm_generations_are_bit_identical(name):
             G.set_precision(3)
 
 
+@pytest.mark.parametrize("name", ["tiny", "l3", "l2"])
+def test_gnn_attention_generations_are_bit_identical(name):
+    """The packed-FP32 (fma.rn.f32x2) attention kernels accumulate the same products in the same order as the first generation."""
+    dev = _need_gpu()
+    import live_util as L
+    from pats_b200 import _lib, gnn as G
+
+    if L.reference_root() is None:
+        pytest.skip("reference Python not staged")
+    lib = _lib.load()
+    with torch.no_grad():
+        mod, x0, x1 = _module(name, dev)
+        try:
+            lib.pats_gnn_attention_variant(0)
+            a0, a1 = G.attentional_gnn_forward(mod, x0, x1)
+            lib.pats_gnn_attention_variant(1)
+            b0, b1 = G.attentional_gnn_forward(mod, x0, x1)
+            torch.cuda.synchronize()
+        finally:
+            lib.pats_gnn_attention_variant(0)
+    assert torch.equal(a0, b0) and torch.equal(a1, b1), (name, float((a0 - b0).abs().max()))
+
+
 def test_gnn_pack_follows_the_parameters_and_modes():
     dev = _need_gpu()
     import live_util as L
