@@ -1094,18 +1094,29 @@ struct TmaShape {
     int nb, nblocks, stages;
     size_t smem;
 };
-TmaShape tma_shape(int Nout, bool split) {
-    TmaShape t;
+// The widest block that fits three stages moves the fewest operand bytes per flop -- what counts when there are many waves of units.
+// With few token blocks (the chunked calls of an `if_local` forward: 91 blocks at 40 windows) the last wave decides: among the block
+// widths that fit, take the one with the smallest  waves x (128 + nb)  -- rounds of the persistent CTAs times operand bytes per K chunk.
+TmaShape tma_shape(int Nout, bool split, int mblocks, int sms) {
     const size_t budget = 225 * 1024;
     const int max_nb = split ? 160 : 256;  // three stages of (128 + nb) x 128 B x 2 halves must fit
-    t.nblocks = (Nout + max_nb - 1) / max_nb;
-    t.nb = (((Nout + t.nblocks - 1) / t.nblocks) + 15) & ~15;
-    t.nblocks = (Nout + t.nb - 1) / t.nb;
-    const size_t stage = (size_t)(GEMM_M + t.nb) * 128 * (split ? 2 : 1);
-    t.stages = (int)((budget - 1024) / stage);
-    if (t.stages > 6) t.stages = 6;
-    t.smem = (size_t)t.stages * stage + 1024;
-    return t;
+    long long best_cost = -1;
+    TmaShape best = {};
+    const int first = (Nout + max_nb - 1) / max_nb;
+    for (int nblocks = first; nblocks <= first + 6; ++nblocks) {
+        TmaShape t;
+        t.nb = (((Nout + nblocks - 1) / nblocks) + 15) & ~15;
+        t.nblocks = (Nout + t.nb - 1) / t.nb;
+        const long long units = (long long)mblocks * t.nblocks, waves = (units + sms - 1) / sms;
+        const long long cost = waves * (GEMM_M + t.nb);
+        if (best_cost < 0 || cost < best_cost) best_cost = cost, best = t;
+        if (t.nb <= 48) break;
+    }
+    const size_t stage = (size_t)(GEMM_M + best.nb) * 128 * (split ? 2 : 1);
+    best.stages = (int)((budget - 1024) / stage);
+    if (best.stages > 6) best.stages = 6;
+    best.smem = (size_t)best.stages * stage + 1024;
+    return best;
 }
 
 template <int NJ, int DI, bool PV2, int R, int NW>
@@ -1245,20 +1256,10 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
     const size_t DD = (size_t)D * D;
     const bool tma = g_gemm_variant.load(std::memory_order_relaxed) == 0;
     const bool split = g_precision.load(std::memory_order_relaxed) != 1;
-    // weights as TF32 halves, one 3-D tensor map per matrix over all layers
+    // weights as TF32 halves, one 3-D tensor map per matrix over all layers (box height = the output block of the call's shape)
     CUtensorMap m_qkv_h, m_qkv_l, m_w1_h, m_w1_l, m_w2_h, m_w2_l;
     TmaShape s_qkv = {}, s_w1 = {}, s_w2 = {};
-    if (tma) {
-        const float *halves = packed + (size_t)layers * per;
-        s_qkv = tma_shape(3 * D, split), s_w1 = tma_shape(2 * D, split), s_w2 = tma_shape(D, split);
-        int rc = make_map_3d(&m_qkv_h, halves, layers, 3 * D, D, per2, s_qkv.nb);
-        if (!rc) rc = make_map_3d(&m_qkv_l, halves + 3 * DD, layers, 3 * D, D, per2, s_qkv.nb);
-        if (!rc) rc = make_map_3d(&m_w1_h, halves + 6 * DD, layers, 2 * D, 2 * D, per2, s_w1.nb);
-        if (!rc) rc = make_map_3d(&m_w1_l, halves + 10 * DD, layers, 2 * D, 2 * D, per2, s_w1.nb);
-        if (!rc) rc = make_map_3d(&m_w2_h, halves + 14 * DD, layers, D, 2 * D, per2, s_w2.nb);
-        if (!rc) rc = make_map_3d(&m_w2_l, halves + 16 * DD, layers, D, 2 * D, per2, s_w2.nb);
-        if (rc) return rc;
-    }
+    int maps_for_mblocks = -1;
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int Bc = B - b0 < chunk ? B - b0 : chunk;
         const int T = 2 * Bc * N;
@@ -1267,6 +1268,19 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
         float *X = workspace, *Xh = X + TD, *Xl = Xh + TD, *QKV = Xl + TD, *O = QKV + 3 * TD, *Oh = O, *Ol = O + TD, *Y = Ol + TD, *Yh = Y, *Yl = Y + 2 * TD;
         CUtensorMap m_xh, m_xl, m_oh, m_ol, m_yh, m_yl;
         if (tma) {
+            const int mblocks = (T + GEMM_M - 1) / GEMM_M;
+            if (mblocks != maps_for_mblocks) {  // first chunk, and a shorter last one
+                const float *halves = packed + (size_t)layers * per;
+                s_qkv = tma_shape(3 * D, split, mblocks, sms), s_w1 = tma_shape(2 * D, split, mblocks, sms), s_w2 = tma_shape(D, split, mblocks, sms);
+                int rcw = make_map_3d(&m_qkv_h, halves, layers, 3 * D, D, per2, s_qkv.nb);
+                if (!rcw) rcw = make_map_3d(&m_qkv_l, halves + 3 * DD, layers, 3 * D, D, per2, s_qkv.nb);
+                if (!rcw) rcw = make_map_3d(&m_w1_h, halves + 6 * DD, layers, 2 * D, 2 * D, per2, s_w1.nb);
+                if (!rcw) rcw = make_map_3d(&m_w1_l, halves + 10 * DD, layers, 2 * D, 2 * D, per2, s_w1.nb);
+                if (!rcw) rcw = make_map_3d(&m_w2_h, halves + 14 * DD, layers, D, 2 * D, per2, s_w2.nb);
+                if (!rcw) rcw = make_map_3d(&m_w2_l, halves + 16 * DD, layers, D, 2 * D, per2, s_w2.nb);
+                if (rcw) return rcw;
+                maps_for_mblocks = mblocks;
+            }
             int rc = make_map_2d(&m_xh, Xh, T, D, D, GEMM_M);
             if (!rc) rc = make_map_2d(&m_xl, Xl, T, D, D, GEMM_M);
             if (!rc) rc = make_map_2d(&m_oh, Oh, T, D, D, GEMM_M);
