@@ -20,7 +20,7 @@ import torch
 from . import _lib
 from ._torchutil import cuda_f32, stream_ptr
 
-__all__ = ["attentional_gnn_forward", "attentional_gnn", "pack_module", "supported", "set_precision"]
+__all__ = ["attentional_gnn_forward", "attentional_gnn", "pack_module", "pack_raw", "supported", "set_precision"]
 
 WORKSPACE_MB = 512  # activations of one chunk of problems (24 * n * D floats each: FP32 and TF32-half copies); larger chunks measured faster (fewer tails)
 _PARAM_ORDER = ("attn.proj.0", "attn.proj.1", "attn.proj.2", "attn.merge", "mlp.0")
@@ -57,6 +57,22 @@ def _key(gnn: torch.nn.Module):
     return tuple((t.data_ptr(), t._version) for layer in gnn.layers for t in list(layer.parameters()) + list(layer.buffers()))
 
 
+def pack_raw(raw: torch.Tensor, layers: int, d_model: int, heads: int, bn_eps: float = 1e-5) -> torch.Tensor:
+    """`raw` (CUDA, float32): the parameters of `layers` AttentionalPropagation layers in the order include/pats_b200.h documents
+    -> the packed weights `attentional_gnn` takes."""
+    lib = _lib.load()
+    if not raw.is_cuda:
+        raise RuntimeError("pats_b200.gnn: the parameters are on the CPU; pats_b200 is CUDA-only (no CPU fallback)")
+    raw = raw.detach().float().contiguous()
+    if raw.numel() != lib.pats_gnn_raw_floats(layers, d_model):
+        raise RuntimeError(f"pats_b200.gnn: {raw.numel()} parameters given, the packed layout expects {lib.pats_gnn_raw_floats(layers, d_model)}")
+    packed = torch.empty(lib.pats_gnn_packed_floats(layers, d_model), dtype=torch.float32, device=raw.device)
+    with torch.cuda.device(raw.device):
+        rc = lib.pats_gnn_pack_f32(raw.data_ptr(), layers, d_model, heads, float(bn_eps), packed.data_ptr(), stream_ptr(raw.device))
+    _lib.check(rc, "gnn_pack")
+    return packed
+
+
 def pack_module(gnn: torch.nn.Module):
     """(packed weights, cross flags, D, heads, layers) of a reference `AttentionalGNN`, cached on the module."""
     key = _key(gnn)
@@ -67,16 +83,7 @@ def pack_module(gnn: torch.nn.Module):
     D = layer0.attn.merge.weight.shape[0]
     heads = layer0.attn.num_heads
     L = len(gnn.layers)
-    raw = _raw(gnn)
-    lib = _lib.load()
-    if raw.numel() != lib.pats_gnn_raw_floats(L, D):
-        raise RuntimeError(f"pats_b200.gnn: the module holds {raw.numel()} parameters, the packed layout expects {lib.pats_gnn_raw_floats(L, D)}")
-    if not raw.is_cuda:
-        raise RuntimeError("pats_b200.gnn: the module is on the CPU; pats_b200 is CUDA-only (no CPU fallback)")
-    packed = torch.empty(lib.pats_gnn_packed_floats(L, D), dtype=torch.float32, device=raw.device)
-    with torch.cuda.device(raw.device):
-        rc = lib.pats_gnn_pack_f32(raw.data_ptr(), L, D, heads, float(layer0.mlp[1].eps), packed.data_ptr(), stream_ptr(raw.device))
-    _lib.check(rc, "gnn_pack")
+    packed = pack_raw(_raw(gnn), L, D, heads, float(layer0.mlp[1].eps))
     cross = bytes(1 if n == "cross" else 0 for n in gnn.names)
     out = (packed, cross, D, heads, L)
     gnn._pats_b200_pack = (key, out)
