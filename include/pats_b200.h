@@ -290,8 +290,11 @@ void pats_gnn_precision(int passes);
 /* A/B switch: 0 = the packed-FP32 (fma.rn.f32x2) generation of the resident-key attention kernels (default), 1 = the first
  *   generation.  Same sums in the same order: bit-identical results. */
 void pats_gnn_attention_variant(int v);
-/* A/B switch: 0 = the TMA-fed, warp-specialised GEMM (operands pre-split into TF32 halves by their producers; default),
- *             1 = the register-staged GEMM (operands split while they are staged).  Same products, same accumulation order. */
+/* A/B switch: 0 = the TMA-fed, warp-specialised GEMM (operands pre-split into TF32 halves by their producers) in thread-block
+ *                 clusters of two CTAs: two token blocks of one output block, each CTA loads half of the weight tile and multicasts
+ *                 it into both (default),
+ *             1 = the register-staged GEMM (operands split while they are staged),
+ *             2 = as 0 without clusters.  Same products, same accumulation order: bit-identical results. */
 void pats_gnn_gemm_variant(int v);
 
 /* ---------------------------------------------------------------------------------------------

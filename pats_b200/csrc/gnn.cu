@@ -31,6 +31,8 @@
 // Attention kernel (gnn_attention_kernel): FP32 on the CUDA cores, as the reference computes it (torch.einsum -> SGEMM): one CTA
 // per (problem, side, head), K^T / V / Q in shared memory, a warp owns R query rows x all keys in registers (R * ceil(n / 32)
 // accumulators), softmax by warp shuffles, P through a per-warp shared buffer into the P V product.
+#include <stdlib.h>
+
 #include <cuda.h>  // CUtensorMap and its enums only: cuTensorMapEncodeTiled is looked up at run time (no link against libcuda)
 
 #include "common.cuh"
@@ -47,7 +49,7 @@ constexpr int GEMM_THREADS = 256;   // 8 warps stage and drain; warps w and w + 
 constexpr int GEMM_M = 128;
 
 std::atomic<int> g_precision{3};    // 3 = 3xTF32 (default), 1 = single TF32 (what cuDNN gives the reference's Conv1d)
-std::atomic<int> g_gemm_variant{0}; // 0 = TMA-fed warp-specialised GEMM, 1 = register-staged GEMM (pats_gnn_gemm_variant)
+std::atomic<int> g_gemm_variant{0}; // 0 = TMA-fed warp-specialised GEMM in CTA pairs, 1 = register-staged GEMM, 2 = TMA-fed, single CTAs (pats_gnn_gemm_variant)
 std::atomic<int> g_att_variant{0};  // A/B of the level-2 attention tiling (pats_gnn_attention_variant)
 
 struct GemmArgs {
@@ -236,6 +238,8 @@ struct TmaGemmArgs {
     float *out_h, *out_l;  // TF32 halves of the result or nullptr
     int ldo, T, Nout, K1, K2;
     int nb, nblocks, mblocks, layer, stages, split, relu, accumulate;
+    int cluster;  // 1, or 2: CTA pairs (a thread-block cluster) work on two token blocks of the same output block and each loads HALF of the
+                  // weight tile, multicast into both CTAs' shared memory -- the weight bytes pulled through L2 per CTA halve
 };
 
 __device__ __forceinline__ void mbar_init(unsigned mb, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mb), "r"(count) : "memory"); }
@@ -252,6 +256,25 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(map),
                  "r"(mb), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_multicast(unsigned dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned mb, unsigned short mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+        "l"(map), "r"(mb), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the mbarrier at this shared-memory offset in EVERY CTA of the mask
+__device__ __forceinline__ void umma_commit_multicast(unsigned mb, unsigned short mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mb), "h"(mask) : "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // K-major tile with 128-byte rows, SWIZZLE_128B (8-row atoms of 1024 bytes): start address, LBO unused (1), SBO = 1024 B, layout type 2
 __device__ __forceinline__ unsigned long long umma_desc_sw128(unsigned saddr) {
@@ -279,7 +302,7 @@ gnn_gemm_tma_kernel(const __grid_constant__ CUtensorMap a1h, const __grid_consta
     pdl_prologue();
     if (warp == 1) tmem_alloc(&s_tmem, 2 * ACC_COLS);
     if (tid == 0) {
-        for (int i = 0; i < a.stages; ++i) mbar_init(smem_addr(&s_full[i]), 1), mbar_init(smem_addr(&s_empty[i]), 1);
+        for (int i = 0; i < a.stages; ++i) mbar_init(smem_addr(&s_full[i]), 1), mbar_init(smem_addr(&s_empty[i]), (unsigned)a.cluster);
         for (int i = 0; i < 2; ++i) mbar_init(smem_addr(&s_accf[i]), 1), mbar_init(smem_addr(&s_acce[i]), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -288,27 +311,42 @@ gnn_gemm_tma_kernel(const __grid_constant__ CUtensorMap a1h, const __grid_consta
     fence_after_sync();
     const unsigned tmem = s_tmem;
     const int nch1 = (a.K1 + GKC - 1) / GKC, nch = nch1 + (a.K2 + GKC - 1) / GKC;
-    const int units = a.mblocks * a.nblocks;
+    // cluster == 2: the two CTAs of a pair walk the same sequence of (token-block pair, output block) units in lock step (the stage
+    // barriers tie them together); CTA `crank` takes token block 2 * pair + crank (beyond the last block: all rows out of range -> zero
+    // tiles, nothing stored).  unit_of() maps a position of that sequence to this CTA's (token block, output block).
+    const int crank = a.cluster == 2 ? (int)cluster_ctarank() : 0;
+    const unsigned short cmask = (unsigned short)((1u << a.cluster) - 1u);
+    if (a.cluster == 2) cluster_sync_all();  // the peer's barriers exist before anything of ours can reach them
+    const int mgroups = (a.mblocks + a.cluster - 1) / a.cluster;
+    const int units = mgroups * a.nblocks;
+    const int first_unit = (int)blockIdx.x / a.cluster, unit_step = (int)gridDim.x / a.cluster;
+    const unsigned b_half_bytes = b_bytes / (unsigned)a.cluster;
 
     if (warp == 0) {
         if (lane == 0) {
             int q = 0;
-            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-                const int mblk = unit / a.nblocks, nblk = unit - mblk * a.nblocks;
-                const int r0 = mblk * GEMM_M, n0 = nblk * a.nb;
+            for (int unit = first_unit; unit < units; unit += unit_step) {
+                const int mgrp = unit / a.nblocks, nblk = unit - mgrp * a.nblocks;
+                const int r0 = (mgrp * a.cluster + crank) * GEMM_M, n0 = nblk * a.nb;
                 for (int ch = 0; ch < nch; ++ch, ++q) {
                     const int s = q % a.stages;
+                    // free in BOTH CTAs of a pair: our half of the weight tile lands in the peer's stage as well
                     if (q >= a.stages) mbar_wait_parity(smem_addr(&s_empty[s]), (unsigned)(((q / a.stages) - 1) & 1));
                     const bool second = ch >= nch1;
-                    const int k0 = (second ? ch - nch1 : ch) * GKC;
+                    const int k0 = (second ? ch - nch1 : ch) * GKC, wk = (second ? a.K1 : 0) + k0;
                     const unsigned mb = smem_addr(&s_full[s]);
                     const unsigned st = sbase + (unsigned)s * stage_bytes;
-                    mbar_expect_tx(mb, stage_bytes);
+                    const unsigned bh = st + (a.split ? 2u : 1u) * a_bytes, bl = bh + b_bytes;
+                    mbar_expect_tx(mb, stage_bytes);  // own activation tiles + the whole weight tile (our half and the peer's)
                     tma_load_2d(st, second ? &a2h : &a1h, k0, r0, mb);
-                    tma_load_3d(st + (a.split ? 2u : 1u) * a_bytes, &wh, (second ? a.K1 : 0) + k0, n0, a.layer, mb);
-                    if (a.split) {
-                        tma_load_2d(st + a_bytes, second ? &a2l : &a1l, k0, r0, mb);
-                        tma_load_3d(st + 2u * a_bytes + b_bytes, &wl, (second ? a.K1 : 0) + k0, n0, a.layer, mb);
+                    if (a.split) tma_load_2d(st + a_bytes, second ? &a2l : &a1l, k0, r0, mb);
+                    if (a.cluster == 2) {
+                        const int nh = (int)(b_half_bytes / 128u);  // rows of half a weight tile
+                        tma_load_3d_multicast(bh + (unsigned)crank * b_half_bytes, &wh, wk, n0 + crank * nh, a.layer, mb, cmask);
+                        if (a.split) tma_load_3d_multicast(bl + (unsigned)crank * b_half_bytes, &wl, wk, n0 + crank * nh, a.layer, mb, cmask);
+                    } else {
+                        tma_load_3d(bh, &wh, wk, n0, a.layer, mb);
+                        if (a.split) tma_load_3d(bl, &wl, wk, n0, a.layer, mb);
                     }
                 }
             }
@@ -316,7 +354,7 @@ gnn_gemm_tma_kernel(const __grid_constant__ CUtensorMap a1h, const __grid_consta
     } else if (warp == 1) {
         if (lane == 0) {
             int q = 0, u = 0;
-            for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++u) {
+            for (int unit = first_unit; unit < units; unit += unit_step, ++u) {
                 const int nblk = unit % a.nblocks;
                 const int ncols = min(a.nb, a.Nout - nblk * a.nb), npad = (ncols + 15) & ~15;
                 const unsigned idesc = umma_idesc(npad);
@@ -342,7 +380,10 @@ gnn_gemm_tma_kernel(const __grid_constant__ CUtensorMap a1h, const __grid_consta
                             umma_tf32(acc, umma_desc_sw128(al0 + koff), bh, idesc, 1u);
                         }
                     }
-                    umma_commit(smem_addr(&s_empty[s]));  // the stage is free once these MMAs have read it
+                    if (a.cluster == 2)
+                        umma_commit_multicast(smem_addr(&s_empty[s]), cmask);  // ... in both CTAs' books: either may refill the other's stage
+                    else
+                        umma_commit(smem_addr(&s_empty[s]));  // the stage is free once these MMAs have read it
                 }
                 umma_commit(smem_addr(&s_accf[t]));  // ... and the accumulator complete once they have written it
             }
@@ -350,9 +391,9 @@ gnn_gemm_tma_kernel(const __grid_constant__ CUtensorMap a1h, const __grid_consta
     } else {
         const int quad = warp & 3;  // TMEM lane quadrant this warp may read
         int u = 0;
-        for (int unit = blockIdx.x; unit < units; unit += gridDim.x, ++u) {
-            const int mblk = unit / a.nblocks, nblk = unit - mblk * a.nblocks;
-            const int r0 = mblk * GEMM_M, n0 = nblk * a.nb;
+        for (int unit = first_unit; unit < units; unit += unit_step, ++u) {
+            const int mgrp = unit / a.nblocks, nblk = unit - mgrp * a.nblocks;
+            const int r0 = (mgrp * a.cluster + crank) * GEMM_M, n0 = nblk * a.nb;
             const int ncols = min(a.nb, a.Nout - n0), npad = (ncols + 15) & ~15;
             const int t = u & 1;
             const int row = r0 + quad * 32 + lane;
@@ -402,6 +443,7 @@ gnn_gemm_tma_kernel(const __grid_constant__ CUtensorMap a1h, const __grid_consta
         }
     }
     __syncthreads();
+    if (a.cluster == 2) cluster_sync_all();  // the peer may still be arriving on our barriers
     if (warp == 1) tmem_dealloc(tmem, 2 * ACC_COLS);
 }
 
@@ -1099,7 +1141,11 @@ struct TmaShape {
 // widths that fit, take the one with the smallest  waves x (128 + nb)  -- rounds of the persistent CTAs times operand bytes per K chunk.
 TmaShape tma_shape(int Nout, bool split, int mblocks, int sms) {
     const size_t budget = 225 * 1024;
-    const int max_nb = split ? 160 : 256;  // three stages of (128 + nb) x 128 B x 2 halves must fit
+    int max_nb = split ? 160 : 256;  // three stages of (128 + nb) x 128 B x 2 halves must fit
+    if (const char *e = getenv("PATS_GNN_MAX_NB")) {  // A/B of the block width (tools/gnn_small.py)
+        const int v = atoi(e);
+        if (v >= 16 && v < max_nb) max_nb = v & ~15;
+    }
     long long best_cost = -1;
     TmaShape best = {};
     const int first = (Nout + max_nb - 1) / max_nb;
@@ -1219,17 +1265,37 @@ PATS_API int pats_gnn_pack_f32(const float *raw, int layers, int D, int heads, f
 
 namespace {
 int launch_gemm_tma(const CUtensorMap &a1h, const CUtensorMap &a1l, const CUtensorMap &a2h, const CUtensorMap &a2l, const CUtensorMap &wh, const CUtensorMap &wl,
-                    TmaGemmArgs a, const TmaShape &shape, cudaStream_t st, int dev, int sms) {
-    a.nb = shape.nb, a.nblocks = shape.nblocks, a.stages = shape.stages;
+                    TmaGemmArgs a, const TmaShape &shape, int cluster, cudaStream_t st, int dev, int sms) {
+    a.nb = shape.nb, a.nblocks = shape.nblocks, a.stages = shape.stages, a.cluster = cluster;
     a.mblocks = (a.T + GEMM_M - 1) / GEMM_M;
     static PerDeviceOnce configured;
     if (!configured.done(dev)) {
         PATS_CUDA_TRY(cudaFuncSetAttribute(gnn_gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         configured.mark(dev);
     }
-    long long grid = (long long)a.mblocks * a.nblocks;
-    if (grid > sms) grid = sms;
-    PATS_CUDA_TRY(launch_chained(gnn_gemm_tma_kernel, dim3((unsigned)grid), dim3(TMA_THREADS), shape.smem, st, a1h, a1l, a2h, a2l, wh, wl, a));
+    const long long groups = (long long)((a.mblocks + cluster - 1) / cluster) * a.nblocks;
+    long long clusters = sms / cluster;
+    if (clusters > groups) clusters = groups;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * cluster));
+    cfg.blockDim = dim3(TMA_THREADS);
+    cfg.dynamicSmemBytes = shape.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (g_chain.load(std::memory_order_relaxed)) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster, attr[n].val.clusterDim.y = 1, attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    PATS_CUDA_TRY(cudaLaunchKernelEx(&cfg, gnn_gemm_tma_kernel, a1h, a1l, a2h, a2l, wh, wl, a));
     return PATS_OK;
 }
 }  // namespace
@@ -1254,7 +1320,9 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
     cudaStream_t st = as_stream(stream);
     const size_t per = packed_layer_floats(D), per2 = halves_layer_floats(D);
     const size_t DD = (size_t)D * D;
-    const bool tma = g_gemm_variant.load(std::memory_order_relaxed) == 0;
+    const int gv = g_gemm_variant.load(std::memory_order_relaxed);
+    const bool tma = gv != 1;
+    const int cluster = gv == 0 ? 2 : 1;  // default: CTA pairs with the weight tile multicast (level 2, 300 windows: GEMMs 22.2 -> 20.5 ms)
     const bool split = g_precision.load(std::memory_order_relaxed) != 1;
     // weights as TF32 halves, one 3-D tensor map per matrix over all layers (box height = the output block of the call's shape)
     CUtensorMap m_qkv_h, m_qkv_l, m_w1_h, m_w1_l, m_w2_h, m_w2_l;
@@ -1272,12 +1340,12 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
             if (mblocks != maps_for_mblocks) {  // first chunk, and a shorter last one
                 const float *halves = packed + (size_t)layers * per;
                 s_qkv = tma_shape(3 * D, split, mblocks, sms), s_w1 = tma_shape(2 * D, split, mblocks, sms), s_w2 = tma_shape(D, split, mblocks, sms);
-                int rcw = make_map_3d(&m_qkv_h, halves, layers, 3 * D, D, per2, s_qkv.nb);
-                if (!rcw) rcw = make_map_3d(&m_qkv_l, halves + 3 * DD, layers, 3 * D, D, per2, s_qkv.nb);
-                if (!rcw) rcw = make_map_3d(&m_w1_h, halves + 6 * DD, layers, 2 * D, 2 * D, per2, s_w1.nb);
-                if (!rcw) rcw = make_map_3d(&m_w1_l, halves + 10 * DD, layers, 2 * D, 2 * D, per2, s_w1.nb);
-                if (!rcw) rcw = make_map_3d(&m_w2_h, halves + 14 * DD, layers, D, 2 * D, per2, s_w2.nb);
-                if (!rcw) rcw = make_map_3d(&m_w2_l, halves + 16 * DD, layers, D, 2 * D, per2, s_w2.nb);
+                int rcw = make_map_3d(&m_qkv_h, halves, layers, 3 * D, D, per2, s_qkv.nb / cluster);
+                if (!rcw) rcw = make_map_3d(&m_qkv_l, halves + 3 * DD, layers, 3 * D, D, per2, s_qkv.nb / cluster);
+                if (!rcw) rcw = make_map_3d(&m_w1_h, halves + 6 * DD, layers, 2 * D, 2 * D, per2, s_w1.nb / cluster);
+                if (!rcw) rcw = make_map_3d(&m_w1_l, halves + 10 * DD, layers, 2 * D, 2 * D, per2, s_w1.nb / cluster);
+                if (!rcw) rcw = make_map_3d(&m_w2_h, halves + 14 * DD, layers, D, 2 * D, per2, s_w2.nb / cluster);
+                if (!rcw) rcw = make_map_3d(&m_w2_l, halves + 16 * DD, layers, D, 2 * D, per2, s_w2.nb / cluster);
                 if (rcw) return rcw;
                 maps_for_mblocks = mblocks;
             }
@@ -1303,7 +1371,7 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
             ta.T = T, ta.layer = l, ta.split = split ? 1 : 0;
             if (tma) {
                 ta.bias = bqkv, ta.out = QKV, ta.out_h = ta.out_l = nullptr, ta.ldo = 3 * D, ta.Nout = 3 * D, ta.K1 = D, ta.K2 = 0, ta.relu = 0, ta.accumulate = 0;
-                rc = launch_gemm_tma(m_xh, m_xl, m_xh, m_xl, m_qkv_h, m_qkv_l, ta, s_qkv, st, dev, sms);
+                rc = launch_gemm_tma(m_xh, m_xl, m_xh, m_xl, m_qkv_h, m_qkv_l, ta, s_qkv, cluster, st, dev, sms);
             } else {
                 g.A1 = X, g.lda1 = D, g.K1 = D, g.A2 = nullptr, g.lda2 = 0, g.K2 = 0, g.W = Wqkv, g.ldw = D, g.bias = bqkv, g.out = QKV, g.ldo = 3 * D;
                 g.T = T, g.Nout = 3 * D, g.relu = 0, g.accumulate = 0;
@@ -1327,7 +1395,7 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
             if (rc) return rc;
             if (tma) {
                 ta.bias = b1f, ta.out = nullptr, ta.out_h = Yh, ta.out_l = Yl, ta.ldo = 2 * D, ta.Nout = 2 * D, ta.K1 = D, ta.K2 = D, ta.relu = 1, ta.accumulate = 0;
-                rc = launch_gemm_tma(m_xh, m_xl, m_oh, m_ol, m_w1_h, m_w1_l, ta, s_w1, st, dev, sms);
+                rc = launch_gemm_tma(m_xh, m_xl, m_oh, m_ol, m_w1_h, m_w1_l, ta, s_w1, cluster, st, dev, sms);
             } else {
                 g.A1 = X, g.lda1 = D, g.K1 = D, g.A2 = O, g.lda2 = D, g.K2 = D, g.W = W1f, g.ldw = 2 * D, g.bias = b1f, g.out = Y, g.ldo = 2 * D;
                 g.Nout = 2 * D, g.relu = 1, g.accumulate = 0;
@@ -1336,7 +1404,7 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
             if (rc) return rc;
             if (tma) {
                 ta.bias = b2, ta.out = X, ta.out_h = Xh, ta.out_l = Xl, ta.ldo = D, ta.Nout = D, ta.K1 = 2 * D, ta.K2 = 0, ta.relu = 0, ta.accumulate = 1;
-                rc = launch_gemm_tma(m_yh, m_yl, m_yh, m_yl, m_w2_h, m_w2_l, ta, s_w2, st, dev, sms);
+                rc = launch_gemm_tma(m_yh, m_yl, m_yh, m_yl, m_w2_h, m_w2_l, ta, s_w2, cluster, st, dev, sms);
             } else {
                 g.A1 = Y, g.lda1 = 2 * D, g.K1 = 2 * D, g.A2 = nullptr, g.lda2 = 0, g.K2 = 0, g.W = W2, g.ldw = 2 * D, g.bias = b2, g.out = X, g.ldo = D;
                 g.Nout = D, g.relu = 0, g.accumulate = 1;

@@ -130,10 +130,11 @@ def test_gnn_gemm_generations_are_bit_identical(name):
                 G.set_precision(passes)
                 lib.pats_gnn_gemm_variant(0)
                 a0, a1 = G.attentional_gnn_forward(mod, x0, x1)
-                lib.pats_gnn_gemm_variant(1)
-                b0, b1 = G.attentional_gnn_forward(mod, x0, x1)
-                torch.cuda.synchronize()
-                assert torch.equal(a0, b0) and torch.equal(a1, b1), (name, passes, float((a0 - b0).abs().max()))
+                for other in (1, 2):  # 1: register-staged; 2: TMA-fed with CTA pairs and the weight tile multicast
+                    lib.pats_gnn_gemm_variant(other)
+                    b0, b1 = G.attentional_gnn_forward(mod, x0, x1)
+                    torch.cuda.synchronize()
+                    assert torch.equal(a0, b0) and torch.equal(a1, b1), (name, passes, other, float((a0 - b0).abs().max()))
         finally:
             lib.pats_gnn_gemm_variant(0)
             G.set_precision(3)
