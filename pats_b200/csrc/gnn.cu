@@ -1384,7 +1384,8 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
             at.c = 1.4426950408889634f / sqrtf((float)dim);
             const int av = g_att_variant.load(std::memory_order_relaxed);  // 0: packed-FP32 generation; 1: first generation (same sums, same order)
             if (NJ <= 3 && DI == 1)
-                rc = av == 0 ? launch_attention2<3, 0, 4>(at, st, dev) : launch_attention<3, 1, false, 8, 4>(at, st, dev);
+                // 65 rows = 9 blocks of 8: one pass per warp.  Measured (2800 points, 560 per launch): 9 warps 158 us, 5 warps 165 us, 4 warps 188 us, 3 warps 242 us
+                rc = av == 0 ? launch_attention2<3, 0, 9>(at, st, dev) : launch_attention<3, 1, false, 8, 4>(at, st, dev);
             else if (NJ <= 5 && dim >= 64 && dim <= 68)
                 // first generation, measured (tools/gnn_kernels.py, 89 windows per launch): 4 rows x 20 warps 206 us, 8 rows x 10 warps 232 us
                 rc = av == 0 ? launch_attention2<5, 1, 20>(at, st, dev) : launch_attention<5, 3, true, 4, 20>(at, st, dev);
