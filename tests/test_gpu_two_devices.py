@@ -62,3 +62,36 @@ def test_second_device_in_one_process_gives_identical_results():
                 assert same, f"{which}, stream {si}, output {i}: differs from the first run on device 0"
     assert int(a[0][-1]) >= 1, "the ill-conditioned problem did not reach the per-device fallback counter"
     assert np.isfinite(a[0][0].numpy()).all()
+
+
+def test_attention_network_on_a_second_device():
+    """csrc/gnn.cu: kernel attributes (dynamic shared memory of the GEMM / attention kernels) are set per device, tensor maps carry the
+    device's pointers, cluster launches go to the current device -- the same network on device 1 after device 0 gives the same bits."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from oracle import gnn as O
+    from pats_b200 import gnn as G
+
+    L_, D_, N_, B_ = 4, 264, 145, 5
+    params = O.seeded_params(3, L_, D_)
+    order = ("attn.proj.0", "attn.proj.1", "attn.proj.2", "attn.merge", "mlp.0")
+    raw = np.concatenate([np.concatenate([np.concatenate([p[k + ".weight"].reshape(-1), p[k + ".bias"]]) for k in order]
+                                         + [p["mlp.1.weight"], p["mlp.1.bias"], p["mlp.1.running_mean"], p["mlp.1.running_var"],
+                                            p["mlp.3.weight"].reshape(-1), p["mlp.3.bias"]]) for p in params])
+    g = torch.Generator().manual_seed(4)
+    x0, x1 = torch.randn(B_, D_, N_, generator=g), torch.randn(B_, D_, N_, generator=g)
+    cross = bytes([0, 1] * (L_ // 2))
+
+    def run(dev):
+        d = torch.device("cuda", dev)
+        with torch.cuda.device(d):
+            packed = G.pack_raw(torch.from_numpy(raw).to(d), L_, D_, 4, O.BN_EPS)
+            o0, o1 = G.attentional_gnn(packed, cross, 4, x0.to(d), x1.to(d))
+            torch.cuda.synchronize(d)
+        return o0.cpu(), o1.cpu()
+
+    a, b, again = run(0), run(1), run(0)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert torch.equal(a[0], again[0]) and torch.equal(a[1], again[1])
+    r0, _ = O.attentional_gnn(params, ["self", "cross"] * (L_ // 2), x0.numpy(), x1.numpy())
+    assert float(np.abs(a[0].numpy() - r0).max()) <= 3e-5 * float(np.abs(r0).max())
