@@ -276,9 +276,9 @@ int pats_gnn_pack_f32(const float *raw, int layers, int D, int heads, float bn_e
 
 /* desc0, desc1 [B,D,N] f32 (DEVICE) -> out0, out1 [B,D,N]: `layers` rounds of desc += mlp(cat(desc, attn(desc, src, src))) with
  *   src = the same set (cross[l] == 0, 'self') or the other one (cross[l] != 0, 'cross'); `cross` is a HOST array of `layers` bytes.
- *   BatchNorm in inference mode (module.eval(); a module in train() mode uses batch statistics and is not this function).
+ *   BatchNorm in inference mode (module.eval(); for train() mode see pats_attentional_gnn_train_f32).
  *   `workspace` (DEVICE): at least pats_gnn_workspace_floats(1, D, N) floats; problems are processed in chunks of as many as fit
- *   (24 * N * D floats each).  D a multiple of 8 and of `heads`, the head dimension even; n <= 160 tokens with head dimension <= 96,
+ *   (28 * N * D floats each).  D a multiple of 8 and of `heads`, the head dimension even; n <= 160 tokens with head dimension <= 96,
  *   or n <= 96 with head dimension <= 32, or any n with head dimension <= 128 (flash-style pass over the keys).
  *   Arithmetic: the 1x1 convolutions on the tcgen05 tensor cores with FP32-class accuracy (3xTF32); pats_gnn_precision(1) selects
  *   single-pass TF32, which is what cuDNN gives the reference's Conv1d on a GPU (torch.backends.cudnn.allow_tf32 defaults to True);
@@ -286,6 +286,18 @@ int pats_gnn_pack_f32(const float *raw, int layers, int D, int heads, float bn_e
 long long pats_gnn_workspace_floats(int chunk, int D, int N);
 int pats_attentional_gnn_f32(const float *desc0, const float *desc1, int B, int D, int N, const float *packed, const unsigned char *cross,
                              int layers, int heads, float *out0, float *out1, float *workspace, long long workspace_floats, void *stream);
+/* The same network with its BatchNorm layers in train() mode (models/pats.py:112-119 keeps the third layer's network in train()
+ * when `if_local` is False -- three of the reference's four configurations): each of the two BatchNorm calls of a layer
+ * (models/modules.py:131: layer(desc0, src0), layer(desc1, src1)) normalises with the statistics of ITS batch (all tokens of all
+ * problems of that side) and updates the running statistics as torch does (momentum, unbiased variance; side 0 first).
+ *   packed   from pats_gnn_pack_train_f32 (as pats_gnn_pack_f32 without folding the BatchNorm)
+ *   raw      the parameters as for pats_gnn_pack_f32 (gamma / beta are read from here)
+ *   running  [layers][2][2D] f32 (DEVICE): running_mean, running_var of every layer -- updated in place
+ *   workspace must hold the whole batch: pats_gnn_workspace_floats(B, D, N) floats. */
+int pats_gnn_pack_train_f32(const float *raw, int layers, int D, int heads, float *packed, void *stream);
+int pats_attentional_gnn_train_f32(const float *desc0, const float *desc1, int B, int D, int N, const float *packed, const float *raw, float *running,
+                                   float momentum, float bn_eps, const unsigned char *cross, int layers, int heads, float *out0, float *out1,
+                                   float *workspace, long long workspace_floats, void *stream);
 void pats_gnn_precision(int passes);
 /* A/B switch: 0 = the packed-FP32 (fma.rn.f32x2) generation of the resident-key attention kernels (default), 1 = the first
  *   generation.  Same sums in the same order: bit-identical results. */

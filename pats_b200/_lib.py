@@ -59,6 +59,8 @@ SIGNATURES = {
     "pats_gnn_workspace_floats": [_I, _I, _I],
     "pats_gnn_pack_f32": [_P, _I, _I, _I, _F, _P, _P],
     "pats_attentional_gnn_f32": [_P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, C.c_longlong, _P],
+    "pats_gnn_pack_train_f32": [_P, _I, _I, _I, _P, _P],
+    "pats_attentional_gnn_train_f32": [_P, _P, _I, _I, _I, _P, _P, _P, _F, _F, _P, _I, _I, _P, _P, _P, C.c_longlong, _P],
     "pats_gnn_precision": [_I],
     "pats_gnn_attention_variant": [_I],
     "pats_gnn_gemm_variant": [_I],

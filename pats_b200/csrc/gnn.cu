@@ -1028,7 +1028,7 @@ __host__ __device__ inline size_t packed_layer_floats(int D) { return (size_t)9 
 // behind the FP32 layers: per layer Wqkv_hi[3DD] Wqkv_lo[3DD] W1f_hi[4DD] W1f_lo[4DD] W2_hi[2DD] W2_lo[2DD] -- the TF32 halves the TMA-fed GEMM reads
 __host__ __device__ inline size_t halves_layer_floats(int D) { return (size_t)18 * D * D; }
 
-__global__ void gnn_pack_kernel(const float *raw, float *packed, int layers, int D, int heads, float eps) {
+__global__ void gnn_pack_kernel(const float *raw, float *packed, int layers, int D, int heads, float eps, int fold_bn) {
     const int dim = D / heads, D2 = 2 * D;
     const size_t per = packed_layer_floats(D);
     const size_t total = per * layers;
@@ -1053,7 +1053,7 @@ __global__ void gnn_pack_kernel(const float *raw, float *packed, int layers, int
             val = r[(size_t)p * (DD + D) + DD + d * heads + hh];
         } else if ((e -= 3 * D) < (size_t)D2 * D2) {  // W1f
             const int o = (int)(e / D2), c = (int)(e - (size_t)o * D2);
-            const double sc = (double)gamma[o] / sqrt((double)var[o] + (double)eps);
+            const double sc = fold_bn ? (double)gamma[o] / sqrt((double)var[o] + (double)eps) : 1.0;  // train(): the BatchNorm stays a separate step
             double acc;
             if (c < D) {
                 acc = W1[(size_t)o * D2 + c];
@@ -1068,12 +1068,81 @@ __global__ void gnn_pack_kernel(const float *raw, float *packed, int layers, int
             const double sc = (double)gamma[o] / sqrt((double)var[o] + (double)eps);
             double acc = b1[o];
             for (int k = 0; k < D; ++k) acc += (double)W1[(size_t)o * D2 + D + k] * (double)bm[k];
-            val = (float)((acc - (double)mean[o]) * sc + (double)beta[o]);
+            val = fold_bn ? (float)((acc - (double)mean[o]) * sc + (double)beta[o]) : (float)acc;
         } else {  // W2, b2 verbatim
             e -= D2;
             val = W2[e];
         }
         packed[i] = val;
+    }
+}
+
+// ---- BatchNorm1d in train() mode (models/pats.py:112-119 keeps the third layer's network in train() when `if_local` is False): the
+// first MLP convolution writes its FP32 result Z, the statistics of each side's batch -- `layer(desc0, src0)` and `layer(desc1, src1)`
+// are two BatchNorm calls (models/modules.py:131) -- are taken over all its tokens, and the normalisation + ReLU produces the TF32
+// halves the second convolution reads.  Running statistics are updated as torch does (momentum, unbiased variance), side 0 first.
+struct BnArgs {
+    const float *Z;          // [T, C] pre-normalisation, T = 2 * Th (side-major)
+    double *stats;           // [2 sides][C][2]: sum, sum of squares (zero on entry of the statistics kernel)
+    const float *gamma, *beta;
+    float *running;          // [2][C]: running_mean, running_var of this layer (updated in place)
+    float *Yh, *Yl;          // [T, C] TF32 halves of relu(bn(Z))
+    int Th, C;
+    float eps, momentum;
+};
+
+constexpr int BN_ROWS = 128;
+
+__global__ void __launch_bounds__(256) gnn_bn_stats_kernel(BnArgs a) {
+    pdl_prologue();
+    const int side = blockIdx.y, r0 = blockIdx.x * BN_ROWS, r1 = min(r0 + BN_ROWS, a.Th);
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+        const float *z = a.Z + ((size_t)side * a.Th + r0) * a.C + c;
+        double s = 0.0, q = 0.0;
+        for (int r = r0; r < r1; ++r, z += a.C) {
+            const double v = (double)__ldg(z);
+            s += v, q += v * v;
+        }
+        atomicAdd(a.stats + ((size_t)side * a.C + c) * 2, s);
+        atomicAdd(a.stats + ((size_t)side * a.C + c) * 2 + 1, q);
+    }
+}
+
+__global__ void __launch_bounds__(256) gnn_bn_apply_kernel(BnArgs a) {
+    pdl_prologue();
+    const int side = blockIdx.y, r0 = blockIdx.x * BN_ROWS, r1 = min(r0 + BN_ROWS, a.Th);
+    const double n = (double)a.Th;
+    for (int c4 = threadIdx.x * 4; c4 < a.C; c4 += blockDim.x * 4) {
+        float sc[4], sh[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double *st = a.stats + ((size_t)side * a.C + c4 + j) * 2;
+            const double mean = st[0] / n, var = fmax(st[1] / n - mean * mean, 0.0);
+            const double scale = (double)a.gamma[c4 + j] / sqrt(var + (double)a.eps);
+            sc[j] = (float)scale, sh[j] = (float)((double)a.beta[c4 + j] - mean * scale);
+        }
+        for (int r = r0; r < r1; ++r) {
+            const size_t idx = ((size_t)side * a.Th + r) * a.C + c4;
+            const float4 z = *reinterpret_cast<const float4 *>(a.Z + idx);
+            const float4 y = make_float4(fmaxf(fmaf(z.x, sc[0], sh[0]), 0.f), fmaxf(fmaf(z.y, sc[1], sh[1]), 0.f), fmaxf(fmaf(z.z, sc[2], sh[2]), 0.f),
+                                         fmaxf(fmaf(z.w, sc[3], sh[3]), 0.f));
+            const float4 h = make_float4(tf32_round(y.x), tf32_round(y.y), tf32_round(y.z), tf32_round(y.w));
+            *reinterpret_cast<float4 *>(a.Yh + idx) = h;
+            *reinterpret_cast<float4 *>(a.Yl + idx) = make_float4(tf32_round(y.x - h.x), tf32_round(y.y - h.y), tf32_round(y.z - h.z), tf32_round(y.w - h.w));
+        }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0) {  // running statistics: the two BatchNorm calls of the layer in the reference's order
+        for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+            float rm = a.running[c], rv = a.running[a.C + c];
+            for (int sd = 0; sd < 2; ++sd) {
+                const double *st = a.stats + ((size_t)sd * a.C + c) * 2;
+                const double mean = st[0] / n, var = fmax(st[1] / n - mean * mean, 0.0);
+                const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
+                rm = (1.0f - a.momentum) * rm + a.momentum * (float)mean;
+                rv = (1.0f - a.momentum) * rv + a.momentum * (float)unbiased;
+            }
+            a.running[c] = rm, a.running[a.C + c] = rv;
+        }
     }
 }
 
@@ -1250,17 +1319,26 @@ PATS_API void pats_gnn_precision(int passes) { g_precision.store(passes == 1 ? 1
 
 PATS_API long long pats_gnn_raw_floats(int layers, int D) { return (long long)(raw_layer_floats(D) * (size_t)layers); }
 PATS_API long long pats_gnn_packed_floats(int layers, int D) { return (long long)((packed_layer_floats(D) + halves_layer_floats(D)) * (size_t)layers); }
-PATS_API long long pats_gnn_workspace_floats(int chunk, int D, int N) { return (long long)24 * chunk * N * D; }
+PATS_API long long pats_gnn_workspace_floats(int chunk, int D, int N) { return (long long)28 * chunk * N * D + 32 * D; }
 PATS_API void pats_gnn_gemm_variant(int v) { g_gemm_variant.store(v, std::memory_order_relaxed); }
 
-PATS_API int pats_gnn_pack_f32(const float *raw, int layers, int D, int heads, float bn_eps, float *packed, void *stream) {
+namespace {
+int pack_impl(const float *raw, int layers, int D, int heads, float bn_eps, int fold_bn, float *packed, void *stream) {
     if (layers <= 0 || D <= 0 || heads <= 0 || D % heads != 0) return invalid("gnn_pack: bad sizes layers=%d D=%d heads=%d", layers, D, heads);
     if (!raw || !packed) return invalid("gnn_pack: null pointer");
-    gnn_pack_kernel<<<1184, 256, 0, as_stream(stream)>>>(raw, packed, layers, D, heads, bn_eps);
+    gnn_pack_kernel<<<1184, 256, 0, as_stream(stream)>>>(raw, packed, layers, D, heads, bn_eps, fold_bn);
     PATS_LAUNCH_CHECK("gnn_pack_kernel");
     gnn_split_weights_kernel<<<1184, 256, 0, as_stream(stream)>>>(packed, layers, D);
     PATS_LAUNCH_CHECK("gnn_split_weights_kernel");
     return PATS_OK;
+}
+}  // namespace
+
+PATS_API int pats_gnn_pack_f32(const float *raw, int layers, int D, int heads, float bn_eps, float *packed, void *stream) {
+    return pack_impl(raw, layers, D, heads, bn_eps, 1, packed, stream);
+}
+PATS_API int pats_gnn_pack_train_f32(const float *raw, int layers, int D, int heads, float *packed, void *stream) {
+    return pack_impl(raw, layers, D, heads, 0.f, 0, packed, stream);
 }
 
 namespace {
@@ -1300,8 +1378,15 @@ int launch_gemm_tma(const CUtensorMap &a1h, const CUtensorMap &a1l, const CUtens
 }
 }  // namespace
 
-PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, int B, int D, int N, const float *packed, const unsigned char *cross,
-                                      int layers, int heads, float *out0, float *out1, float *workspace, long long workspace_floats, void *stream) {
+namespace {
+struct TrainBn {
+    const float *raw;  // the reference's parameters (gamma / beta of every layer's BatchNorm are read from here)
+    float *running;    // [layers][2][2D] running_mean, running_var -- updated in place
+    float momentum, eps;
+};
+
+int gnn_impl(const float *desc0, const float *desc1, int B, int D, int N, const float *packed, const unsigned char *cross, int layers, int heads, float *out0,
+             float *out1, float *workspace, long long workspace_floats, void *stream, const TrainBn *train) {
     if (B < 0 || D <= 0 || N <= 0 || layers <= 0 || heads <= 0) return invalid("attentional_gnn: bad sizes B=%d D=%d N=%d layers=%d heads=%d", B, D, N, layers, heads);
     if (B == 0) return PATS_OK;
     if (!desc0 || !desc1 || !packed || !cross || !out0 || !out1 || !workspace) return invalid("attentional_gnn: null pointer");
@@ -1310,8 +1395,12 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
     const int dim = D / heads;
     const int NJ = (N + 31) / 32, DI = (dim + 31) / 32;
     if (DI > 4) return invalid("attentional_gnn: head dimension %d exceeds the 128 this build has attention kernels for", dim);
-    const long long per_problem = (long long)24 * N * D;
-    int chunk = (int)(workspace_floats / per_problem < B ? workspace_floats / per_problem : B);
+    const long long per_problem = (long long)28 * N * D;
+    const long long ws_problems = (workspace_floats - 32 * D) / per_problem;
+    int chunk = (int)(ws_problems < B ? ws_problems : B);
+    if (train && chunk < B)
+        return invalid("attentional_gnn (train): batch statistics need the whole batch in one chunk: workspace of %lld floats, %lld needed", workspace_floats,
+                       per_problem * B + 32 * D);
     if (chunk > 16384) chunk = 16384;  // 2 * chunk is a grid z extent
     if (chunk < 1) return invalid("attentional_gnn: workspace of %lld floats holds no problem (%lld floats each)", workspace_floats, per_problem);
     const int dev = current_device();
@@ -1321,7 +1410,7 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
     const size_t per = packed_layer_floats(D), per2 = halves_layer_floats(D);
     const size_t DD = (size_t)D * D;
     const int gv = g_gemm_variant.load(std::memory_order_relaxed);
-    const bool tma = gv != 1;
+    const bool tma = gv != 1 || train != nullptr;
     const int cluster = gv == 0 ? 2 : 1;  // default: CTA pairs with the weight tile multicast (level 2, 300 windows: GEMMs 22.2 -> 20.5 ms)
     const bool split = g_precision.load(std::memory_order_relaxed) != 1;
     // weights as TF32 halves, one 3-D tensor map per matrix over all layers (box height = the output block of the call's shape)
@@ -1332,8 +1421,9 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
         const int Bc = B - b0 < chunk ? B - b0 : chunk;
         const int T = 2 * Bc * N;
         const size_t TD = (size_t)T * D;
-        // X | Xh | Xl | QKV (3) | O or Oh, Ol (2) | Y or Yh, Yl (4)
-        float *X = workspace, *Xh = X + TD, *Xl = Xh + TD, *QKV = Xl + TD, *O = QKV + 3 * TD, *Oh = O, *Ol = O + TD, *Y = Ol + TD, *Yh = Y, *Yl = Y + 2 * TD;
+        // stats (32 D) | X | Xh | Xl | QKV (3) | O or Oh, Ol (2) | Y or Yh, Yl (4) | Z (4, train only)
+        double *stats = reinterpret_cast<double *>(workspace);
+        float *X = workspace + 32 * D, *Xh = X + TD, *Xl = Xh + TD, *QKV = Xl + TD, *O = QKV + 3 * TD, *Oh = O, *Ol = O + TD, *Y = Ol + TD, *Yh = Y, *Yl = Y + 2 * TD, *Z = Yl + 2 * TD;
         CUtensorMap m_xh, m_xl, m_oh, m_ol, m_yh, m_yl;
         if (tma) {
             const int mblocks = (T + GEMM_M - 1) / GEMM_M;
@@ -1394,7 +1484,21 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
             else
                 rc = launch_attention_flash<5, 4, 4, 8, 2>(at, st, dev);
             if (rc) return rc;
-            if (tma) {
+            if (train) {
+                // Z = [X | O] W1f^T + b1f (BatchNorm not folded), batch statistics per side, normalise + ReLU -> the halves of Y
+                ta.bias = b1f, ta.out = Z, ta.out_h = ta.out_l = nullptr, ta.ldo = 2 * D, ta.Nout = 2 * D, ta.K1 = D, ta.K2 = D, ta.relu = 0, ta.accumulate = 0;
+                rc = launch_gemm_tma(m_xh, m_xl, m_oh, m_ol, m_w1_h, m_w1_l, ta, s_w1, cluster, st, dev, sms);
+                if (rc) return rc;
+                PATS_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(double) * 8 * D, st));
+                BnArgs bn;
+                const float *rl = train->raw + (size_t)l * raw_layer_floats(D);
+                bn.Z = Z, bn.stats = stats, bn.gamma = rl + 4 * (DD + D) + 4 * DD + 2 * D, bn.beta = bn.gamma + 2 * D;
+                bn.running = train->running + (size_t)l * 4 * D, bn.Yh = Yh, bn.Yl = Yl, bn.Th = T / 2, bn.C = 2 * D, bn.eps = train->eps, bn.momentum = train->momentum;
+                const dim3 bgrid((unsigned)((T / 2 + BN_ROWS - 1) / BN_ROWS), 2u);
+                gnn_bn_stats_kernel<<<bgrid, 256, 0, st>>>(bn);
+                PATS_LAUNCH_CHECK("gnn_bn_stats_kernel");
+                PATS_CUDA_TRY(launch_chained(gnn_bn_apply_kernel, bgrid, dim3(256), 0, st, bn));
+            } else if (tma) {
                 ta.bias = b1f, ta.out = nullptr, ta.out_h = Yh, ta.out_l = Yl, ta.ldo = 2 * D, ta.Nout = 2 * D, ta.K1 = D, ta.K2 = D, ta.relu = 1, ta.accumulate = 0;
                 rc = launch_gemm_tma(m_xh, m_xl, m_oh, m_ol, m_w1_h, m_w1_l, ta, s_w1, cluster, st, dev, sms);
             } else {
@@ -1417,4 +1521,19 @@ PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, in
         PATS_CUDA_TRY(launch_chained(gnn_transpose_kernel, tgrid, dim3(256), 0, st, t));
     }
     return PATS_OK;
+}
+}  // namespace
+
+PATS_API int pats_attentional_gnn_f32(const float *desc0, const float *desc1, int B, int D, int N, const float *packed, const unsigned char *cross,
+                                      int layers, int heads, float *out0, float *out1, float *workspace, long long workspace_floats, void *stream) {
+    return gnn_impl(desc0, desc1, B, D, N, packed, cross, layers, heads, out0, out1, workspace, workspace_floats, stream, nullptr);
+}
+
+PATS_API int pats_attentional_gnn_train_f32(const float *desc0, const float *desc1, int B, int D, int N, const float *packed, const float *raw, float *running,
+                                            float momentum, float bn_eps, const unsigned char *cross, int layers, int heads, float *out0, float *out1,
+                                            float *workspace, long long workspace_floats, void *stream) {
+    if (!raw || !running) return invalid("attentional_gnn (train): null pointer");
+    if (D % 4 != 0) return invalid("attentional_gnn (train): D = %d", D);
+    TrainBn t = {raw, running, momentum, bn_eps};
+    return gnn_impl(desc0, desc1, B, D, N, packed, cross, layers, heads, out0, out1, workspace, workspace_floats, stream, &t);
 }

@@ -8,10 +8,12 @@ stays the reference's own (its parameters are read, never copied back); the pack
 head-major, merge convolution + inference BatchNorm folded into the first MLP convolution) is built once by the library
 (`pats_gnn_pack_f32`) and cached on the module until a parameter changes.
 
-What is NOT this path: a module in train() mode (the reference keeps the third layer's network in train() when `if_local` is
-False, models/pats.py:112-119: BatchNorm then normalises with the statistics of the batch and updates its running buffers) and
-token counts / head sizes csrc/gnn.cu has no attention kernel for.  Those calls run the reference's own layer modules, exactly as
-`AttentionalGNN.forward` does -- on the GPU, in PyTorch; there is no CPU path here either.
+A module in train() mode is this path too (the reference keeps the third layer's network in train() when `if_local` is False,
+models/pats.py:112-119 -- three of its four configurations): each BatchNorm call then normalises with the statistics of its batch,
+and the module's running buffers and `num_batches_tracked` are updated exactly as the two calls per layer of the reference update
+them (`pats_attentional_gnn_train_f32`).  What is NOT this path: head sizes csrc/gnn.cu has no attention kernel for and a BatchNorm
+with `momentum=None`; those calls run the reference's own layer modules, exactly as `AttentionalGNN.forward` does -- on the GPU, in
+PyTorch; there is no CPU path here either.
 """
 from __future__ import annotations
 
@@ -51,6 +53,11 @@ def _raw(gnn: torch.nn.Module) -> torch.Tensor:
             parts += [sd[k + ".weight"], sd[k + ".bias"]]
         parts += [sd["mlp.1.weight"], sd["mlp.1.bias"], sd["mlp.1.running_mean"], sd["mlp.1.running_var"], sd["mlp.3.weight"], sd["mlp.3.bias"]]
     return torch.cat([p.detach().reshape(-1).float() for p in parts])
+
+
+def _key_params(gnn: torch.nn.Module):
+    """train(): the packed weights do not depend on the running buffers (which every call updates)"""
+    return tuple((t.data_ptr(), t._version) for layer in gnn.layers for t in layer.parameters())
 
 
 def _key(gnn: torch.nn.Module):
@@ -122,12 +129,53 @@ def _layerwise(self, desc0, desc1):
     return desc0, desc1
 
 
+def _train_forward(self, desc0, desc1):
+    """train(): batch-statistics BatchNorm, running buffers updated as the reference's two calls per layer do."""
+    lib = _lib.load()
+    key = _key_params(self)
+    cached = getattr(self, "_pats_b200_pack_train", None)
+    if cached is None or cached[0] != key:
+        layer0 = self.layers[0]
+        D, heads, L = layer0.attn.merge.weight.shape[0], layer0.attn.num_heads, len(self.layers)
+        raw = _raw(self)
+        if not raw.is_cuda:
+            raise RuntimeError("pats_b200.gnn: the module is on the CPU; pats_b200 is CUDA-only (no CPU fallback)")
+        packed = torch.empty(lib.pats_gnn_packed_floats(L, D), dtype=torch.float32, device=raw.device)
+        with torch.cuda.device(raw.device):
+            rc = lib.pats_gnn_pack_train_f32(raw.data_ptr(), L, D, heads, packed.data_ptr(), stream_ptr(raw.device))
+        _lib.check(rc, "gnn_pack_train")
+        cached = (key, (packed, raw, bytes(1 if n == "cross" else 0 for n in self.names), D, heads, L))
+        self._pats_b200_pack_train = cached
+    packed, raw, cross, D, heads, L = cached[1]
+    d0, d1 = cuda_f32(desc0, "desc0"), cuda_f32(desc1, "desc1")
+    B, _, N = d0.shape
+    bns = [layer.mlp[1] for layer in self.layers]
+    running = torch.stack([torch.stack([bn.running_mean, bn.running_var]) for bn in bns]).float().contiguous()  # [L, 2, 2D]
+    ws = torch.empty(lib.pats_gnn_workspace_floats(B, D, N), dtype=torch.float32, device=d0.device)
+    out0, out1 = torch.empty_like(d0), torch.empty_like(d1)
+    with torch.cuda.device(d0.device):
+        rc = lib.pats_attentional_gnn_train_f32(d0.data_ptr(), d1.data_ptr(), B, D, N, packed.data_ptr(), raw.data_ptr(), running.data_ptr(),
+                                                float(bns[0].momentum), float(bns[0].eps), cross, L, heads, out0.data_ptr(), out1.data_ptr(),
+                                                ws.data_ptr(), ws.numel(), stream_ptr(d0.device))
+    _lib.check(rc, "attentional_gnn_train")
+    for bn, r in zip(bns, running):  # the side effects of the 2 L BatchNorm calls
+        bn.running_mean.copy_(r[0])
+        bn.running_var.copy_(r[1])
+        bn.num_batches_tracked += 2
+    return out0, out1
+
+
 def attentional_gnn_forward(self, desc0, desc1):
     """AttentionalGNN.forward (models/modules.py:126-134)."""
     if not desc0.is_cuda:
         raise RuntimeError(f"desc0 is on {desc0.device}: pats_b200 is CUDA-only (no CPU fallback)")
     heads = self.layers[0].attn.num_heads
-    if self.training or desc0.dim() != 3 or not supported(desc0.shape[2], desc0.shape[1], heads):
+    if desc0.dim() != 3 or not supported(desc0.shape[2], desc0.shape[1], heads):
         return _layerwise(self, desc0, desc1)
+    if self.training:
+        bn = self.layers[0].mlp[1]
+        if bn.momentum is None or not bn.track_running_stats or desc0.shape[0] * desc0.shape[2] < 2:
+            return _layerwise(self, desc0, desc1)
+        return _train_forward(self, desc0, desc1)
     packed, cross, _, heads, _ = pack_module(self)
     return attentional_gnn(packed, cross, heads, desc0, desc1)

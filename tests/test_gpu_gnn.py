@@ -163,6 +163,46 @@ def test_gnn_attention_generations_are_bit_identical(name):
     assert torch.equal(a0, b0) and torch.equal(a1, b1), (name, float((a0 - b0).abs().max()))
 
 
+@pytest.mark.parametrize("name", ["tiny", "l3", "l2"])
+def test_gnn_train_mode_matches_the_reference_module(name):
+    """train(): BatchNorm with the statistics of each call's batch (models/pats.py:112-119 runs the third layer's network this way
+    when `if_local` is False).  Truth: the same module in float64; compared: both outputs, every layer's running_mean / running_var
+    after the 2 L BatchNorm calls, num_batches_tracked."""
+    dev = _need_gpu()
+    import copy
+
+    import live_util as L
+    from pats_b200 import gnn as G
+
+    if L.reference_root() is None:
+        pytest.skip("reference Python not staged")
+    with torch.no_grad():
+        mod, x0, x1 = _module(name, dev)
+        mod.train()
+        m64 = copy.deepcopy(mod).double()
+        m32 = copy.deepcopy(mod)
+        t0, t1 = m64(x0.double(), x1.double())
+        r0, r1 = m32(x0, x1)  # the stock module on this GPU (cuDNN: TF32 convolutions, FP32 batch statistics)
+        o0, o1 = G.attentional_gnn_forward(mod, x0, x1)
+        torch.cuda.synchronize()
+    scale = float(max(t0.abs().max(), t1.abs().max()))
+    ours = float(max((o0 - t0).abs().max(), (o1 - t1).abs().max())) / scale
+    stock = float(max((r0 - t0).abs().max(), (r1 - t1).abs().max())) / scale
+    assert ours <= TOL_3X, (ours, stock)
+    for la, lb in zip(mod.layers, m64.layers):
+        a, b = la.mlp[1], lb.mlp[1]
+        assert int(a.num_batches_tracked) == int(b.num_batches_tracked) == 2
+        assert float((a.running_mean - b.running_mean).abs().max()) <= 2e-5 * max(1.0, float(b.running_mean.abs().max()))
+        assert float((a.running_var - b.running_var).abs().max()) <= 2e-5 * max(1.0, float(b.running_var.abs().max()))
+    json.dump({"ours_vs_f64": ours, "stock_cuda_vs_f64": stock}, open(os.path.join(REPO, "gpurun_out", f"gnn_train_accuracy_{name}.json"), "w"))
+    # back in eval(): the packed copy follows the updated running statistics
+    with torch.no_grad():
+        mod.eval(), m64.eval()
+        e0, _ = G.attentional_gnn_forward(mod, x0, x1)
+        f0, _ = m64(x0.double(), x1.double())
+    assert float((e0 - f0).abs().max()) <= TOL_3X * float(f0.abs().max())
+
+
 def test_gnn_pack_follows_the_parameters_and_modes():
     dev = _need_gpu()
     import live_util as L
@@ -181,7 +221,7 @@ def test_gnn_pack_follows_the_parameters_and_modes():
         assert mod._pats_b200_pack[1][0] is not first
         r0, _ = mod(x0, x1)
         assert float((b0 - r0).abs().max()) < 5e-3 and float((a0 - b0).abs().max()) > 1e-2
-        # train(): BatchNorm uses batch statistics and updates its buffers -- the module's own layers run (models/pats.py:112-119)
+        # train(): BatchNorm uses batch statistics and updates its buffers (models/pats.py:112-119)
         mod.train()
         before = mod.layers[0].mlp[1].running_mean.clone()
         G.attentional_gnn_forward(mod, x0, x1)
