@@ -511,7 +511,7 @@ def ncu_traffic(key="sinkhorn_warp_dram_bytes_per_launch"):
     return None
 
 
-def forward_leg(torch, dev, args):
+def forward_leg(torch, dev, args, if_local=True, arms=None):
     """image-pairs/s through the UNMODIFIED reference `PATS.forward` (models/pats.py:18-85, driven like evaluate.py:25-33: uint8
     images host -> device, forward, match lists device -> host), three ways on the same seeded random-init network
     (tests/live_util: conditioned to realistic score magnitudes) and the same synthetic 640x480 pairs:
@@ -530,10 +530,12 @@ def forward_leg(torch, dev, args):
     ref = L.load_reference()
     import pats_b200.install as inst
 
-    cfg = L.config(if_local=True, merge_new=True, if_outdoor=True)  # configs/test_megadepth.yaml
-    n_pairs, n_warm = 6, 2
+    cfg = L.config(if_local=if_local, merge_new=True, if_outdoor=True)  # configs/test_megadepth.yaml (if_local) / test_yfcc.yaml, test_demo.yaml
+    n_pairs, n_warm = (6, 2) if if_local else (5, 2)
     host = [tuple(t.pin_memory() for t in L.synthetic_pair((H, W_IMG), seed=SEED + i)) for i in range(n_pairs)]
-    out = {"config": "configs/test_megadepth.yaml flags (if_local, merge_new, if_outdoor), 640x480, seeded random-init weights conditioned by tests/live_util.py",
+    out = {"config": ("configs/test_megadepth.yaml flags (if_local, merge_new, if_outdoor)" if if_local else
+                      "configs/test_yfcc.yaml / test_demo.yaml flags (if_local False: no chunking, the third layer's network in train() mode; merge_new, if_outdoor)")
+                     + ", 640x480, seeded random-init weights conditioned by tests/live_util.py",
            "pairs_timed": n_pairs - n_warm, "unit": "pairs/s"}
 
     def run(model, device, pairs):
@@ -548,6 +550,8 @@ def forward_leg(torch, dev, args):
         model = L.build_model(ref, cfg, device=dev)
         for name, setup in (("reference_cuda", None), ("installed", dict(fused=False)), ("installed_fused", dict(fused=True)),
                             ("installed_fused_attention", dict(fused=True, attention=True))):
+            if arms is not None and name not in arms:
+                continue
             if setup is not None:
                 inst.install(**setup)
             try:
@@ -561,7 +565,7 @@ def forward_leg(torch, dev, args):
                 if setup is not None:
                     inst.uninstall()
             out[name] = {"value": (n_pairs - n_warm) / dt, "s_per_pair": dt / (n_pairs - n_warm), "matches": m}
-        if not args.no_forward_cpu:
+        if not args.no_forward_cpu and arms is None:
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             cpu_model = L.build_model(ref, cfg, device="cpu")
@@ -574,9 +578,10 @@ def forward_leg(torch, dev, args):
             finally:
                 torch.Tensor.cuda = orig_cuda
             out["reference_cpu"] = {"value": 1.0 / dt, "s_per_pair": dt, "matches": m, "cores": cores, "pairs_timed": 1}
-    out["speedup_installed_vs_reference_cuda"] = out["installed"]["value"] / out["reference_cuda"]["value"]
-    out["speedup_fused_vs_reference_cuda"] = out["installed_fused"]["value"] / out["reference_cuda"]["value"]
-    out["speedup_fused_attention_vs_reference_cuda"] = out["installed_fused_attention"]["value"] / out["reference_cuda"]["value"]
+    for arm, key in (("installed", "speedup_installed_vs_reference_cuda"), ("installed_fused", "speedup_fused_vs_reference_cuda"),
+                     ("installed_fused_attention", "speedup_fused_attention_vs_reference_cuda")):
+        if arm in out and "reference_cuda" in out:
+            out[key] = out[arm]["value"] / out["reference_cuda"]["value"]
     return out
 
 
@@ -1234,6 +1239,12 @@ def main():
                 fwd = forward_leg(torch, dev, args)
             except Exception as e:  # noqa: BLE001  (the leg needs the staged reference Python, oracle/_ref/py)
                 fwd = {"unavailable": f"{type(e).__name__}: {e}"}
+        fwd_global = None
+        if world == 1 and not args.no_forward:
+            try:
+                fwd_global = forward_leg(torch, dev, args, if_local=False, arms=("reference_cuda", "installed_fused", "installed_fused_attention"))
+            except Exception as e:  # noqa: BLE001
+                fwd_global = {"unavailable": f"{type(e).__name__}: {e}"}
         att = None
         if world == 1 and not args.no_forward:
             try:
@@ -1256,7 +1267,7 @@ def main():
                     "exchange": "after the pair loop every step's match list of every rank is gathered to rank 0 (2 collectives, 1 host sync); inside the timed region",
                     "gather_ms": info["gather_ms"], "gather": info["gather"]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "roofline_streaming": streaming, "stress": stress, "correlation": corr, "cpu_baseline": cpu, "torch_cuda": torch_cuda,
-            "fixed_point_exit": fp_exit, "bulk_staging": bulk, "overlap": overlap, "diffuse": diffuse, "forward": fwd, "attention": att, "forward_sharded": fwd_sharded, "tail": tail,
+            "fixed_point_exit": fp_exit, "bulk_staging": bulk, "overlap": overlap, "diffuse": diffuse, "forward": fwd, "forward_global": fwd_global, "attention": att, "forward_sharded": fwd_sharded, "tail": tail,
         }
         emit(line)
     if world > 1:
