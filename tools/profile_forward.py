@@ -23,7 +23,7 @@ def main():
 
     dev = torch.device("cuda:0")
     ref = L.load_reference()
-    cfg = L.config(if_local=True, merge_new=True, if_outdoor=True)
+    cfg = L.config(if_local="global" not in sys.argv[1:], merge_new=True, if_outdoor=True)
     pairs = [L.synthetic_pair((480, 640), seed=L.SEED + i) for i in range(4)]
     out = {}
     with torch.no_grad():
@@ -86,7 +86,7 @@ def main():
         finally:
             inst.uninstall()
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(REPO, "gpurun_out", "profile_forward_attention.json" if out["attention"] else "profile_forward.json"), "w") as f:
+    with open(os.path.join(REPO, "gpurun_out", ("profile_forward_global" if "global" in sys.argv[1:] else "profile_forward") + ("_attention.json" if out["attention"] else ".json")), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps({k: out[k] for k in ("s_per_pair_free_running", "s_per_pair_synchronised", "cuda_kernel_total_ms", "cuda_kernel_launches", "cpu_self_total_ms")}))
 
