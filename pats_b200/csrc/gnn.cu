@@ -719,6 +719,7 @@ __global__ void __launch_bounds__(NW * 32) gnn_attention2_kernel(AttArgs a) {
         for (int rp = 0; rp < R / 2; ++rp)
 #pragma unroll
             for (int j = 0; j < NJ; ++j) s2[rp][j] = make_float2(0.f, 0.f);
+#pragma unroll 4
         for (int d = 0; d < dim4; ++d) {
             const float4 qa = *reinterpret_cast<const float4 *>(Pw + d * R), qb = *reinterpret_cast<const float4 *>(Pw + d * R + 4);
             const float2 qp[4] = {make_float2(qa.x, qa.y), make_float2(qa.z, qa.w), make_float2(qb.x, qb.y), make_float2(qb.z, qb.w)};
@@ -768,7 +769,7 @@ __global__ void __launch_bounds__(NW * 32) gnn_attention2_kernel(AttArgs a) {
         for (int rp = 0; rp < R / 2; ++rp)
 #pragma unroll
             for (int i = 0; i < OS; ++i) o2[rp][i] = make_float2(0.f, 0.f);
-#pragma unroll 2
+#pragma unroll 4
         for (int m = 0; m < N; ++m) {
             const float4 pa = *reinterpret_cast<const float4 *>(Pw + m * R), pb = *reinterpret_cast<const float4 *>(Pw + m * R + 4);
             const float2 pp[4] = {make_float2(pa.x, pa.y), make_float2(pa.z, pa.w), make_float2(pb.x, pb.y), make_float2(pb.z, pb.w)};
