@@ -369,15 +369,17 @@ gnn_gemm_tma_kernel(const __grid_constant__ CUtensorMap a1h, const __grid_consta
                     const bool second = ch >= nch1;
                     const int kn = min(GKC, (second ? a.K2 : a.K1) - (second ? ch - nch1 : ch) * GKC);
                     const unsigned st = sbase + (unsigned)s * stage_bytes;
-                    const unsigned ah0 = st, al0 = st + a_bytes, bh0 = st + (a.split ? 2u : 1u) * a_bytes, bl0 = bh0 + b_bytes;
+                    // the four tile descriptors once per stage; a K step (8 TF32 values = 32 bytes inside the 128-byte swizzle row) advances
+                    // the start-address field (16-byte units) by 2
+                    const unsigned long long ah0 = umma_desc_sw128(st), al0 = umma_desc_sw128(st + a_bytes);
+                    const unsigned long long bh0 = umma_desc_sw128(st + (a.split ? 2u : 1u) * a_bytes), bl0 = umma_desc_sw128(st + (a.split ? 2u : 1u) * a_bytes + b_bytes);
                     const int steps = (kn + 7) >> 3;
                     for (int k = 0; k < steps; ++k) {
-                        const unsigned koff = (unsigned)k * 32u;  // 8 TF32 values along K inside the 128-byte swizzle row
-                        const unsigned long long ah = umma_desc_sw128(ah0 + koff), bh = umma_desc_sw128(bh0 + koff);
-                        umma_tf32(acc, ah, bh, idesc, (ch == 0 && k == 0) ? 0u : 1u);
+                        const unsigned long long kadv = (unsigned long long)(2 * k);
+                        umma_tf32(acc, ah0 + kadv, bh0 + kadv, idesc, (ch == 0 && k == 0) ? 0u : 1u);
                         if (a.split) {
-                            umma_tf32(acc, ah, umma_desc_sw128(bl0 + koff), idesc, 1u);
-                            umma_tf32(acc, umma_desc_sw128(al0 + koff), bh, idesc, 1u);
+                            umma_tf32(acc, ah0 + kadv, bl0 + kadv, idesc, 1u);
+                            umma_tf32(acc, al0 + kadv, bh0 + kadv, idesc, 1u);
                         }
                     }
                     if (a.cluster == 2)
