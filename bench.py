@@ -781,6 +781,12 @@ def attention_leg(torch, dev, peak_bf16_tflops):
             rec["max_abs_diff_vs_reference_module"] = float((a0 - b0).abs().max())
             rec["output_scale"] = float(b0.abs().max())
             rec["useful_tflops"] = flops / (rec["ours_3xtf32_ms"] * 1e-3) / 1e12
+            # tensor-core work actually issued in the default mode (three TF32 MMAs per product) over the WHOLE call's time, attention and
+            # transpositions included: a lower bound of the GEMM kernels' rate (ncu: tensor pipe 50 % active inside them)
+            gemm_flops = layers * 2.0 * T * 9 * D * D
+            rec["roofline"] = {"bound": "tensor", "achieved": 3.0 * gemm_flops / (rec["ours_3xtf32_ms"] * 1e-3) / 1e12, "peak": peak_bf16_tflops / 2.0, "unit": "TFLOP/s",
+                               "frac": 3.0 * gemm_flops / (rec["ours_3xtf32_ms"] * 1e-3) / 1e12 / (peak_bf16_tflops / 2.0),
+                               "note": "TF32 MMA flops issued (3 passes) / time of the whole network call; peak = measured BF16 TFLOP/s / 2"}
             rec["speedup"] = rec["reference_module_ms"] / rec["ours_3xtf32_ms"]
             total_ref += rec["reference_module_ms"]
             total_ours += rec["ours_3xtf32_ms"]
