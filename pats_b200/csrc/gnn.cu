@@ -1216,7 +1216,7 @@ TmaShape tma_shape(int Nout, bool split, int mblocks, int sms) {
     int max_nb = split ? 160 : 256;  // three stages of (128 + nb) x 128 B x 2 halves must fit
     if (const char *e = getenv("PATS_GNN_MAX_NB")) {  // A/B of the block width (tools/gnn_small.py)
         const int v = atoi(e);
-        if (v >= 16 && v < max_nb) max_nb = v & ~15;
+        if (v >= 16 && v <= 256) max_nb = v & ~15;
     }
     long long best_cost = -1;
     TmaShape best = {};
