@@ -4,7 +4,7 @@
 //   AttentionalPropagation.forward    :108-117   message = attn(x, source, source);  mlp(cat([x, message]))
 //   MultiHeadedAttention.forward      :100-106   three 1x1 convolutions, view(b, dim, heads, n), attention, merge convolution
 //   attention                         :84-88     softmax(q^T k / sqrt(dim)) v per head
-//   MLP([2D, 2D, D])                  :58-69     Conv1d(2D,2D) -> BatchNorm1d (inference statistics) -> ReLU -> Conv1d(2D,D)
+//   MLP([2D, 2D, D])                  :58-69     Conv1d(2D,2D) -> BatchNorm1d (inference or batch statistics) -> ReLU -> Conv1d(2D,D)
 // called at first_layer.py:106 (D = 448, n = 300, 18 layers), second_layer.py:93 (D = 264, n = 145, 18 layers, b = P windows) and
 // third_layer.py:148 (D = 128, n = 65, 10 layers, b = K points).  The reference runs ~25 ATen kernels per layer and side (17 000
 // launches per image pair); with the Sinkhorn path at ~1 ms these networks are 2/3 of what is left of a forward pass
@@ -19,7 +19,8 @@
 //                                                            the weights are packed (products accumulated in FP64)
 //     X  += Y W2^T + b2                            [T, D]
 // Four kernels per layer, launch-chained (griddepcontrol), no host synchronisation; the [b, D, n] <-> [T, D] transpositions are
-// one pass each at entry and exit.  Problems are processed in chunks sized so that a chunk's activations stay in the 126 MB L2.
+// one pass each at entry and exit.  Problems are processed in chunks of as many as fit the caller's workspace (28 n D floats each);
+// larger chunks measured faster (fewer kernel tails) than chunks that would stay inside the 126 MB L2.
 //
 // GEMM kernels: gnn_gemm_tma_kernel (default; operands pre-split into TF32 halves by their producers, tiles by TMA, warp-specialised --
 // see its header below) and gnn_gemm_kernel, the first generation (one CTA of 256 threads per (128-token block, <= 256-output block),
@@ -28,9 +29,12 @@
 // no-swizzle UMMA layout, lane = (k4 % 4) * 8 + row % 8: conflict-free 128-bit stores; one thread issues tcgen05.mma.kind::tf32, M = 128,
 // N <= 256, K = 8, accumulator in TMEM).  Both issue hi*hi + hi*lo + lo*hi per K step ("3xTF32": FP32-class accuracy; the reference's
 // own convolutions run as single TF32 through cuDNN, which `pats_gnn_precision(1)` mirrors) in the same order and agree bit for bit.
-// Attention kernel (gnn_attention_kernel): FP32 on the CUDA cores, as the reference computes it (torch.einsum -> SGEMM): one CTA
-// per (problem, side, head), K^T / V / Q in shared memory, a warp owns R query rows x all keys in registers (R * ceil(n / 32)
-// accumulators), softmax by warp shuffles, P through a per-warp shared buffer into the P V product.
+// Attention kernels: FP32 on the CUDA cores, as the reference computes it (torch.einsum -> SGEMM): one CTA per (problem, side, head),
+// K^T / V in shared memory, a warp owns 8 query rows x all keys in registers, softmax by warp shuffles, P through a per-warp shared
+// buffer into the P V product.  gnn_attention2_kernel (default: row pairs on the packed FP32 pipe), gnn_attention_kernel (first
+// generation, bit-identical), gnn_attention_flash_kernel (any token count: keys in chunks, online softmax).
+// train() mode (batch-statistics BatchNorm, pats_attentional_gnn_train_f32): the first MLP GEMM writes FP32, gnn_bn_stats_kernel and
+// gnn_bn_apply_kernel normalise per side and update the running statistics.
 #include <stdlib.h>
 
 #include <cuda.h>  // CUtensorMap and its enums only: cuTensorMapEncodeTiled is looked up at run time (no link against libcuda)
