@@ -85,3 +85,24 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "libpats_oracle" not in text, f
+
+
+def test_attention_network_sizes_and_validation_need_no_gpu():
+    """pats_gnn_*: the size functions follow the layouts include/pats_b200.h documents; bad arguments are refused before any CUDA call."""
+    from pats_b200 import _lib
+
+    lib = _lib.load()
+    L, D = 18, 264
+    DD = D * D
+    assert lib.pats_gnn_raw_floats(L, D) == L * (4 * (DD + D) + 4 * DD + 2 * D + 8 * D + 2 * DD + D)
+    assert lib.pats_gnn_packed_floats(L, D) == L * (9 * DD + 6 * D + 18 * DD)  # FP32 layers, then their TF32 halves
+    assert lib.pats_gnn_workspace_floats(3, D, 145) == 28 * 3 * 145 * D + 32 * D
+    rc = lib.pats_attentional_gnn_f32(None, None, 1, 264, 145, None, None, 18, 4, None, None, None, 0, None)
+    assert rc == -1 and b"null" in lib.pats_last_error()
+    rc = lib.pats_attentional_gnn_f32(None, None, -1, 264, 145, None, None, 18, 4, None, None, None, 0, None)
+    assert rc == -1 and b"bad sizes" in lib.pats_last_error()
+    assert lib.pats_attentional_gnn_f32(None, None, 0, 264, 145, None, None, 18, 4, None, None, None, 0, None) == 0  # empty batch
+    rc = lib.pats_gnn_pack_f32(None, 18, 264, 5, 1e-5, None, None)
+    assert rc == -1 and b"bad sizes" in lib.pats_last_error()
+    rc = lib.pats_attentional_gnn_train_f32(None, None, 1, 264, 145, None, None, None, 0.1, 1e-5, None, 18, 4, None, None, None, 0, None)
+    assert rc == -1
