@@ -72,13 +72,30 @@ def _raw(gnn: torch.nn.Module) -> torch.Tensor:
     return torch.cat([p.detach().reshape(-1).float() for p in parts])
 
 
+def _slots(gnn: torch.nn.Module):
+    """(dict, name) of every parameter / buffer of the network's layers, in module order, cached on the module.  Looking a tensor up
+    through its owner's `_parameters` / `_buffers` dict follows replacements (`module.to()` swaps buffer objects, a user may assign a new
+    Parameter) at the price of a dict access; walking `layer.parameters()` on every call cost 1.1 ms per call -- 19 ms per image pair."""
+    slots = getattr(gnn, "_pats_b200_slots", None)
+    if slots is None or slots[0] != len(gnn.layers):
+        par, buf = [], []
+        for layer in gnn.layers:
+            for m in layer.modules():
+                par += [(m._parameters, n) for n, p in m._parameters.items() if p is not None]
+                buf += [(m._buffers, n) for n, b in m._buffers.items() if b is not None and b.is_floating_point()]
+        slots = (len(gnn.layers), par, buf)
+        gnn._pats_b200_slots = slots
+    return slots
+
+
 def _key_params(gnn: torch.nn.Module):
     """train(): the packed weights do not depend on the running buffers (which every call updates)"""
-    return tuple((t.data_ptr(), t._version) for layer in gnn.layers for t in layer.parameters())
+    return tuple([(d[n].data_ptr(), d[n]._version) for d, n in _slots(gnn)[1]])
 
 
 def _key(gnn: torch.nn.Module):
-    return tuple((t.data_ptr(), t._version) for layer in gnn.layers for t in list(layer.parameters()) + list(layer.buffers()))
+    _, par, buf = _slots(gnn)
+    return tuple([(d[n].data_ptr(), d[n]._version) for d, n in par]) + tuple([(d[n].data_ptr(), d[n]._version) for d, n in buf])
 
 
 def pack_raw(raw: torch.Tensor, layers: int, d_model: int, heads: int, bn_eps: float = 1e-5) -> torch.Tensor:
