@@ -84,3 +84,54 @@ def test_parse_cpulist_and_numa_binding_never_raises():
     assert _parse_cpulist("") == set()
     info = bind_host_to_gpu(0)
     assert info["bound"] is False and "why" in info
+
+
+def _pipeline_worker(rank, world, port, n_pairs, out_dir):
+    """Each rank runs its shard of the pair list through the overlapped evaluation loop (pats_b200.pipeline, N4); the pose errors are
+    gathered with all_gather_object and compared, on rank 0, with ONE sequential loop over its own shard (the RANSAC stream is per
+    shard: a rank starts a fresh metrics thread)."""
+    import sys
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import pose_util as P
+    from pats_b200 import pipeline as PL
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = P.reference_metrics()
+        ds = P.SyntheticTwoView(n_pairs=n_pairs, n_points=200, outliers=0.3)
+        lo, hi = shard_range(n_pairs, rank, world)
+        mine = PL.evaluate_pairs(P.PlantedModel(), ds, m.compute_pose_error, 1.0, 0.5, device="cpu", indices=list(range(lo, hi)))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, (lo, hi, mine))
+        if rank == 0:
+            assert [e[0] for e in everyone] == [shard_range(n_pairs, r, world)[0] for r in range(world)]
+            assert sum(len(e[2][0]) for e in everyone) == n_pairs
+            import threading
+
+            box = {}
+            t = threading.Thread(target=lambda: box.setdefault("r", PL.evaluate_pairs_sequential(P.PlantedModel(), ds, m.compute_pose_error, 1.0, 0.5,
+                                                                                              device="cpu", indices=range(lo, hi))))
+            t.start()
+            t.join()
+            assert np.array_equal(np.array(box["r"][0]), np.array(mine[0])) and np.array_equal(np.array(box["r"][1]), np.array(mine[1]))
+            errs = [x for e in everyone for x in e[2][0]]
+            assert all(np.isfinite(errs)) and max(errs) < 5.0
+            open(os.path.join(out_dir, "ok"), "w").write("1")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_evaluation_loop_gloo_world2(tmp_path):
+    import pytest
+
+    import pose_util as P
+
+    if P.reference_metrics() is None:
+        pytest.skip("reference Python not available")
+    mp.spawn(_pipeline_worker, args=(2, _free_port(), 5, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
