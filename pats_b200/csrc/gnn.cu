@@ -656,10 +656,10 @@ __global__ void __launch_bounds__(NW * 32) gnn_attention_kernel(AttArgs a) {
 // serves four FFMA2.  Per dimension and 8 rows x 160 keys: 2 + 5 loads, 5 MOVs, 20 FFMA2 (first generation: 52 instructions, this: 32);
 // per key in P V: 13 instead of 20.  The warp's buffer holds Q^T during Q K^T and P afterwards; Q is no longer staged for the CTA.
 // VMODE 0: dim <= 32, one value slot per lane; VMODE 1: dims [0, 64) as a float2 per lane + the <= 4 tail dims by a key-parallel reduction.
-template <int NJ, int VMODE, int NW>
+template <int NJ, int VMODE, int NW, int R>
 __global__ void __launch_bounds__(NW * 32) gnn_attention2_kernel(AttArgs a) {
     extern __shared__ __align__(16) float sm[];
-    constexpr int R = 8, NP = NJ * 32 + 1, NP32 = NJ * 32, DV = VMODE ? 64 : 32, NT = NW * 32, TAILMAX = 4;
+    constexpr int NP = NJ * 32 + 1, NP32 = NJ * 32, DV = VMODE ? 64 : 32, NT = NW * 32, TAILMAX = 4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = a.N, dim = a.dim, dim4 = (dim + 3) & ~3, D3 = 3 * a.D;
     const int tail = VMODE ? dim - 64 : 0;
@@ -727,8 +727,12 @@ __global__ void __launch_bounds__(NW * 32) gnn_attention2_kernel(AttArgs a) {
             for (int j = 0; j < NJ; ++j) s2[rp][j] = make_float2(0.f, 0.f);
 #pragma unroll 4
         for (int d = 0; d < dim4; ++d) {
-            const float4 qa = *reinterpret_cast<const float4 *>(Pw + d * R), qb = *reinterpret_cast<const float4 *>(Pw + d * R + 4);
-            const float2 qp[4] = {make_float2(qa.x, qa.y), make_float2(qa.z, qa.w), make_float2(qb.x, qb.y), make_float2(qb.z, qb.w)};
+            float2 qp[R / 2];
+#pragma unroll
+            for (int r4 = 0; r4 < R; r4 += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(Pw + d * R + r4);
+                qp[r4 / 2] = make_float2(t.x, t.y), qp[r4 / 2 + 1] = make_float2(t.z, t.w);
+            }
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 const float kv = Kt[d * NP + lane + 32 * j];
@@ -764,10 +768,10 @@ __global__ void __launch_bounds__(NW * 32) gnn_attention2_kernel(AttArgs a) {
             for (int j = 0; j < NJ; ++j) s[r][j] *= inv;
         }
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            *reinterpret_cast<float4 *>(Pw + (lane + 32 * j) * R) = make_float4(s[0][j], s[1][j], s[2][j], s[3][j]);
-            *reinterpret_cast<float4 *>(Pw + (lane + 32 * j) * R + 4) = make_float4(s[4][j], s[5][j], s[6][j], s[7][j]);
-        }
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int r4 = 0; r4 < R; r4 += 4)
+                *reinterpret_cast<float4 *>(Pw + (lane + 32 * j) * R + r4) = make_float4(s[r4][j], s[r4 + 1][j], s[r4 + 2][j], s[r4 + 3][j]);
         __syncwarp();
         constexpr int OS = VMODE ? 2 : 1;  // value slots per lane
         float2 o2[R / 2][OS];
@@ -777,8 +781,12 @@ __global__ void __launch_bounds__(NW * 32) gnn_attention2_kernel(AttArgs a) {
             for (int i = 0; i < OS; ++i) o2[rp][i] = make_float2(0.f, 0.f);
 #pragma unroll 4
         for (int m = 0; m < N; ++m) {
-            const float4 pa = *reinterpret_cast<const float4 *>(Pw + m * R), pb = *reinterpret_cast<const float4 *>(Pw + m * R + 4);
-            const float2 pp[4] = {make_float2(pa.x, pa.y), make_float2(pa.z, pa.w), make_float2(pb.x, pb.y), make_float2(pb.z, pb.w)};
+            float2 pp[R / 2];
+#pragma unroll
+            for (int r4 = 0; r4 < R; r4 += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(Pw + m * R + r4);
+                pp[r4 / 2] = make_float2(t.x, t.y), pp[r4 / 2 + 1] = make_float2(t.z, t.w);
+            }
             float vv[OS];
             if (VMODE) {
                 const float2 t = *reinterpret_cast<const float2 *>(V + m * DV + 2 * lane);
@@ -1255,17 +1263,17 @@ int launch_attention(const AttArgs &a, cudaStream_t st, int dev) {
     return PATS_OK;
 }
 
-template <int NJ, int VMODE, int NW>
+template <int NJ, int VMODE, int NW, int R = 8>
 int launch_attention2(const AttArgs &a, cudaStream_t st, int dev) {
     const int dim4 = (a.dim + 3) & ~3;
-    const size_t smem = sizeof(float) * ((size_t)NW * NJ * 32 * 8 + (size_t)a.N * (VMODE ? 64 + 4 : 32) + (size_t)dim4 * (NJ * 32 + 1));
+    const size_t smem = sizeof(float) * ((size_t)NW * NJ * 32 * R + (size_t)a.N * (VMODE ? 64 + 4 : 32) + (size_t)dim4 * (NJ * 32 + 1));
     static PerDeviceOnce configured;
     if (!configured.done(dev)) {
-        PATS_CUDA_TRY(cudaFuncSetAttribute(gnn_attention2_kernel<NJ, VMODE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        PATS_CUDA_TRY(cudaFuncSetAttribute(gnn_attention2_kernel<NJ, VMODE, NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         configured.mark(dev);
     }
     if (smem > 220 * 1024) return invalid("attentional_gnn: attention tile of %zu bytes exceeds shared memory (n = %d, head dim = %d)", smem, a.N, a.dim);
-    PATS_CUDA_TRY(launch_chained(gnn_attention2_kernel<NJ, VMODE, NW>, dim3((unsigned)(2 * a.Bc * a.heads)), dim3(NW * 32), smem, st, a));
+    PATS_CUDA_TRY(launch_chained(gnn_attention2_kernel<NJ, VMODE, NW, R>, dim3((unsigned)(2 * a.Bc * a.heads)), dim3(NW * 32), smem, st, a));
     return PATS_OK;
 }
 
@@ -1484,8 +1492,11 @@ int gnn_impl(const float *desc0, const float *desc1, int B, int D, int N, const 
                 // 65 rows = 9 blocks of 8: one pass per warp.  Measured (2800 points, 560 per launch): 9 warps 158 us, 5 warps 165 us, 4 warps 188 us, 3 warps 242 us
                 rc = av == 0 ? launch_attention2<3, 0, 9>(at, st, dev) : launch_attention<3, 1, false, 8, 4>(at, st, dev);
             else if (NJ <= 5 && dim >= 64 && dim <= 68)
-                // first generation, measured (tools/gnn_kernels.py, 89 windows per launch): 4 rows x 20 warps 206 us, 8 rows x 10 warps 232 us
-                rc = av == 0 ? launch_attention2<5, 1, 20>(at, st, dev) : launch_attention<5, 3, true, 4, 20>(at, st, dev);
+                // first generation, measured (tools/gnn_kernels.py, 89 windows per launch): 4 rows x 20 warps 206 us, 8 rows x 10 warps 232 us;
+                // packed generation, 300 windows x 18 launches (tools/ab_attention_rows.py): 8 x 20 10.7 ms, 12 x 13 (av 3) 12.2 ms, 16 x 10 (av 2) 14.6 ms
+                rc = av == 0 ? launch_attention2<5, 1, 20>(at, st, dev) : av == 2 ? launch_attention2<5, 1, 10, 16>(at, st, dev)
+                             : av == 3 ? launch_attention2<5, 1, 13, 12>(at, st, dev)
+                             : launch_attention<5, 3, true, 4, 20>(at, st, dev);
             else if (NJ <= 5 && DI <= 3)
                 rc = launch_attention<5, 3, false, 4, 8>(at, st, dev);
             else
