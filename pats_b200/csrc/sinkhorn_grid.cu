@@ -65,6 +65,89 @@ __device__ __forceinline__ void group_barrier(unsigned *ctr, unsigned &epoch, un
     __syncthreads();
 }
 
+// My column slice [c0, c1) of the G per-CTA partials of one problem: fin(j, total).  Few CTAs: a thread per column (coalesced
+// over j); many CTAs: a warp per column, lanes over the partials (lane-strided running sum, then the butterfly: a fixed order, so
+// the sum is deterministic).  The partial loads are L2 round trips: a warp issues those of TWO columns, up to eight per lane each,
+// before it uses the first -- issued one by one (5 per lane at 148 CTAs, 10 at 296) they were a quarter of an iteration of a
+// single large plan.
+template <class Fin>
+__device__ __forceinline__ void combine_slice(const float *partg, int npad, unsigned G, bool is_max, int c0, int c1, int w, int W, int lane,
+                                              int tid, int T, Fin &&fin) {
+#ifdef PATS_AB_SERIAL_COMBINE
+    if (G >= 16u) {
+        for (int j = c0 + w; j < c1; j += W) {
+            float t = is_max ? -INFINITY : 0.f;
+            for (unsigned q = lane; q < G; q += 32) {
+                const float x = __ldcg(partg + (size_t)q * npad + j);
+                t = is_max ? fmaxf(t, x) : t + x;
+            }
+            t = is_max ? warp_max(t) : warp_sum(t);
+            if (lane == 0) fin(j, t);
+        }
+    } else
+#endif
+    if (G >= 16u) {
+        const float idn = is_max ? -INFINITY : 0.f;
+        for (int j = c0 + w; j < c1; j += 2 * W) {
+            const int j2 = j + W;
+            const bool two = j2 < c1;
+            float t0 = idn, t1 = idn;
+            for (unsigned q0 = 0; q0 < G; q0 += 256u) {
+                float x0[8], x1[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const unsigned qq = q0 + lane + 32u * u;
+                    x0[u] = qq < G ? __ldcg(partg + (size_t)qq * npad + j) : idn;
+                    x1[u] = (two && qq < G) ? __ldcg(partg + (size_t)qq * npad + j2) : idn;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    t0 = is_max ? fmaxf(t0, x0[u]) : t0 + x0[u];
+                    t1 = is_max ? fmaxf(t1, x1[u]) : t1 + x1[u];
+                }
+            }
+            t0 = is_max ? warp_max(t0) : warp_sum(t0);
+            t1 = is_max ? warp_max(t1) : warp_sum(t1);
+            if (lane == 0) {
+                fin(j, t0);
+                if (two) fin(j2, t1);
+            }
+        }
+    } else {
+        for (int j = c0 + tid; j < c1; j += T) {
+            float t = __ldcg(partg + j);
+#pragma unroll 8
+            for (unsigned q = 1; q < G; ++q) {  // unrolled: the partial loads of a column are issued together
+                const float x = __ldcg(partg + (size_t)q * npad + j);
+                t = is_max ? fmaxf(t, x) : t + x;
+            }
+            fin(j, t);
+        }
+    }
+}
+
+// dst (shared memory)[0, n) <- src (global, written by other CTAs before the barrier)[0, n): eight loads per thread in flight
+template <int T>
+__device__ __forceinline__ void reload_vector(float *dst, const float *src, int n, int tid) {
+#ifdef PATS_AB_SERIAL_RELOAD
+    for (int j = tid; j < n; j += T) dst[j] = __ldcg(src + j);
+    return;
+#endif
+    for (int j0 = 0; j0 < n; j0 += 8 * T) {
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + tid + u * T;
+            x[u] = j < n ? __ldcg(src + j) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + tid + u * T;
+            if (j < n) dst[j] = x[u];
+        }
+    }
+}
+
 template <int CPL, int W>
 struct GridSmem {
     static constexpr int NC = 32 * CPL;  // padded core width
@@ -202,30 +285,8 @@ __global__ void __launch_bounds__(W * 32, OCC) sinkhorn_grid_kernel(GridArgs ga)
         }
     };
 
-    // my column slice of the G per-CTA partials: fin(j, total).  Few CTAs: a thread per column (coalesced over j);
-    // many CTAs: a warp per column, lanes over the partials (fixed butterfly order, so the sum is deterministic).
     auto combine = [&](const float *partg, bool is_max, auto &&fin) {
-        if (G >= 16u) {
-            for (int j = c0 + w; j < c1; j += W) {
-                float t = is_max ? -INFINITY : 0.f;
-                for (unsigned q = lane; q < G; q += 32) {
-                    const float x = __ldcg(partg + (size_t)q * ga.npad + j);
-                    t = is_max ? fmaxf(t, x) : t + x;
-                }
-                t = is_max ? warp_max(t) : warp_sum(t);
-                if (lane == 0) fin(j, t);
-            }
-        } else {
-            for (int j = c0 + tid; j < c1; j += T) {
-                float t = __ldcg(partg + j);
-#pragma unroll 8
-                for (unsigned q = 1; q < G; ++q) {  // unrolled: the partial loads of a column are issued together
-                    const float x = __ldcg(partg + (size_t)q * ga.npad + j);
-                    t = is_max ? fmaxf(t, x) : t + x;
-                }
-                fin(j, t);
-            }
-        }
+        combine_slice(partg, ga.npad, G, is_max, c0, c1, w, W, lane, tid, T, fin);
     };
 
     for (int p = grp; p < a.b; p += ga.groups) {
@@ -280,7 +341,7 @@ __global__ void __launch_bounds__(W * 32, OCC) sinkhorn_grid_kernel(GridArgs ga)
             group_barrier(ctr, epoch, G);
             combine(partg, true, [&](int j, float t) { __stcg(crg + j, finite_or_zero(t)); });
             group_barrier(ctr, epoch, G);
-            for (int j = tid; j < NC; j += T) bes[j] = __ldcg(crg + j);  // bes holds the column reference for this pass
+            reload_vector<T>(bes, crg, NC, tid);  // bes holds the column reference for this pass
             if (tid == 0) bes[NCP] = __ldcg(crg + NC);
             __syncthreads();
             // ---- v1 = log_nu - LSE_i (Z + u1): column sums of exp(Z + u1 - cref) -----------------------------------------
@@ -302,7 +363,8 @@ __global__ void __launch_bounds__(W * 32, OCC) sinkhorn_grid_kernel(GridArgs ga)
                 __stcg(beg + j, 1.f);
             });
             group_barrier(ctr, epoch, G);
-            for (int j = tid; j < NC; j += T) v1s[j] = __ldcg(v1g + j), bes[j] = 1.f;
+            reload_vector<T>(v1s, v1g, NC, tid);
+            for (int j = tid; j < NC; j += T) bes[j] = 1.f;
             if (tid == 0) v1s[NCP] = __ldcg(v1g + NC), bes[NCP] = 1.f;
             __syncthreads();
         }
@@ -390,7 +452,7 @@ __global__ void __launch_bounds__(W * 32, OCC) sinkhorn_grid_kernel(GridArgs ga)
                 __stcg(beg + j, be);
             });
             group_barrier(ctr, epoch, G);
-            for (int j = tid; j < NC; j += T) bes[j] = __ldcg(beg + j);
+            reload_vector<T>(bes, beg, NC, tid);
             if (tid == 0) bes[NCP] = __ldcg(beg + NC);
             __syncthreads();
         }
@@ -505,27 +567,7 @@ __global__ void __launch_bounds__(Q * RG * 32, 1) sinkhorn_gridq_kernel(GridArgs
     };
 
     auto combine = [&](const float *partg, bool is_max, auto &&fin) {
-        if (G >= 16u) {
-            for (int j = c0 + w; j < c1; j += W) {
-                float t = is_max ? -INFINITY : 0.f;
-                for (unsigned qq = lane; qq < G; qq += 32) {
-                    const float x = __ldcg(partg + (size_t)qq * ga.npad + j);
-                    t = is_max ? fmaxf(t, x) : t + x;
-                }
-                t = is_max ? warp_max(t) : warp_sum(t);
-                if (lane == 0) fin(j, t);
-            }
-        } else {
-            for (int j = c0 + tid; j < c1; j += T) {
-                float t = __ldcg(partg + j);
-#pragma unroll 8
-                for (unsigned qq = 1; qq < G; ++qq) {
-                    const float x = __ldcg(partg + (size_t)qq * ga.npad + j);
-                    t = is_max ? fmaxf(t, x) : t + x;
-                }
-                fin(j, t);
-            }
-        }
+        combine_slice(partg, ga.npad, G, is_max, c0, c1, w, W, lane, tid, T, fin);
     };
 
     // this lane's CPL elements of a row (the virtual dustbin row of log_optimal_transport is `fill`)
@@ -582,7 +624,7 @@ __global__ void __launch_bounds__(Q * RG * 32, 1) sinkhorn_gridq_kernel(GridArgs
             group_barrier(ctr, epoch, G);
             combine(partg, true, [&](int j, float t) { __stcg(crg + j, finite_or_zero(t)); });
             group_barrier(ctr, epoch, G);
-            for (int j = tid; j <= NCP; j += T) bes[j] = __ldcg(crg + j);  // bes holds the column reference for this pass
+            reload_vector<T>(bes, crg, NCP + 1, tid);  // bes holds the column reference for this pass
             __syncthreads();
             // ---- v1 = log_nu - LSE_i (Z + u1): column sums of exp(Z + u1 - cref) -------------------------------------------
             float cs[CPL], csl = 0.f;
@@ -606,7 +648,8 @@ __global__ void __launch_bounds__(Q * RG * 32, 1) sinkhorn_gridq_kernel(GridArgs
                 __stcg(beg + j, 1.f);
             });
             group_barrier(ctr, epoch, G);
-            for (int j = tid; j <= NCP; j += T) v1s[j] = __ldcg(v1g + j), bes[j] = 1.f;
+            reload_vector<T>(v1s, v1g, NCP + 1, tid);
+            for (int j = tid; j <= NCP; j += T) bes[j] = 1.f;
             __syncthreads();
         }
 
@@ -651,7 +694,7 @@ __global__ void __launch_bounds__(Q * RG * 32, 1) sinkhorn_gridq_kernel(GridArgs
                 __stcg(beg + j, be);
             });
             group_barrier(ctr, epoch, G);
-            for (int j = tid; j <= NCP; j += T) bes[j] = __ldcg(beg + j);
+            reload_vector<T>(bes, beg, NCP + 1, tid);
             __syncthreads();
         }
 

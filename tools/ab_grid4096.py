@@ -29,8 +29,17 @@ def main():
 
     lib = _lib.load()
     dev = torch.device("cuda:0")
-    out = {"parity": [], "timing": []}
+    out = {"library": os.environ.get("PATS_B200_LIB", "default"), "parity": [], "timing": []}
     N = 4096
+    if not os.environ.get("AB_TIMING_ONLY"):
+        parity(lib, M, dev, N, out)
+    timing(lib, M, dev, N, out)
+    if len(sys.argv) > 1:
+        with open(sys.argv[1], "w") as f:
+            json.dump(out, f, indent=1)
+
+
+def parity(lib, M, dev, N, out):
     # ---- log_optimal_transport (dustbin synthesised): b = 2, 40 iterations ----
     g = torch.Generator().manual_seed(8000 + N)
     b, iters = 2, 40
@@ -84,13 +93,17 @@ def main():
             out["parity"].append({"mode": "raw", "b": 1, "shape": [530, N + 1], "iters": iters, "variant": v, "max_abs_diff_vs_torch_lse": float((o - ref).abs().max()),
                                   "argmax_equal": bool(torch.equal(o.argmax(2), ref.argmax(2))), "finite": bool(torch.isfinite(o).all())})
             print(out["parity"][-1], flush=True)
+    lib.pats_sinkhorn_grid_variant(0)
+
+
+def timing(lib, M, dev, N, out):
     # ---- timing: bench.py's stress leg (one problem, 200 iterations) and b = 2 ----
     for b in (1, 2):
         g2 = torch.Generator().manual_seed(1234 + N)
         sc = (0.1 * torch.randn(b, N, N, generator=g2)).to(dev)
         nss = torch.exp((torch.rand(b, 1, N, generator=g2) * 2 - 1) * math.log(16.0)).to(dev)
         one = torch.tensor(1.0, device=dev)
-        for v in (0, 2, 0, 2):
+        for v in ((0, 2, 0, 2) if not os.environ.get("AB_TIMING_ONLY") else (0, 2)):
             lib.pats_sinkhorn_grid_variant(v)
             for _ in range(2):
                 M.log_optimal_transport(sc, one, nss, 200)
@@ -105,9 +118,25 @@ def main():
             out["timing"].append({"b": b, "iters": 200, "variant": v, "ms": round(ms, 4), "us_per_iteration": round(ms * 1e3 / 200, 2), "algorithmic_gbs": round(nbytes / ms / 1e6, 1)})
             print(out["timing"][-1], flush=True)
     lib.pats_sinkhorn_grid_variant(0)
-    if len(sys.argv) > 1:
-        with open(sys.argv[1], "w") as f:
-            json.dump(out, f, indent=1)
+    # ---- the other streaming shapes (same kernel family, shared exchange code): BASELINE configs[2], the 1025 x 1025 level-1 plan ----
+    for b, n, iters in ((32, 1536, 100), (1, 1024, 100), (8, 1024, 100)):
+        g2 = torch.Generator().manual_seed(77 + n + b)
+        sc = (0.1 * torch.randn(b, n, n, generator=g2)).to(dev)
+        nss = torch.exp((torch.rand(b, 1, n, generator=g2) * 2 - 1) * math.log(16.0)).to(dev)
+        one = torch.tensor(1.0, device=dev)
+        for _ in range(3):
+            M.log_optimal_transport(sc, one, nss, iters)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(7)]
+        for e0, e1 in ev:
+            e0.record()
+            M.log_optimal_transport(sc, one, nss, iters)
+            e1.record()
+        torch.cuda.synchronize()
+        ms = sorted(x.elapsed_time(y) for x, y in ev)[3]
+        nbytes = 4 * b * (n + 1) * (n + 1) * (iters + 2)
+        out["timing"].append({"b": b, "N": n, "iters": iters, "ms": round(ms, 4), "us_per_iteration": round(ms * 1e3 / iters, 2), "algorithmic_gbs": round(nbytes / ms / 1e6, 1)})
+        print(out["timing"][-1], flush=True)
+        del sc, nss
 
 
 if __name__ == "__main__":
