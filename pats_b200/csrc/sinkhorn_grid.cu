@@ -13,8 +13,9 @@
 //   * Iteration 1 is exact in the log domain (row log-sum-exp, then column max and column sum passes), as in the
 //     register-resident kernels; scalings are monitored and a problem that leaves [1e-13, 1e13] is flagged and
 //     re-solved by the log-domain kernel after this one.  No CPU path.
-//   Measured on B200 (tools/kernel_times.py): b = 32, 1537 x 1537, 100 iterations: 5.5 ms = 5.6 TB/s algorithmic =
-//   86 % of the measured HBM peak (the one-CTA-per-problem log-domain kernel needs > 1 s); 1025 x 1025, b = 1: 0.65 ms.
+//   Measured on B200 (tools/ab_grid4096.py): b = 32, 1537 x 1537, 100 iterations: 4.94 ms = 6.2 TB/s algorithmic =
+//   95 % of the measured HBM (copy) peak (5.5 ms before the exchange's loads were batched; the one-CTA-per-problem log-domain
+//   kernel needs > 1 s); 1025 x 1025, b = 1: 0.64 ms; 4097 x 4097, b = 1, 200 iterations: 3.36 ms (sinkhorn_gridq_kernel below).
 //   Variants that lost the A/B and were removed: register prefetch of the next row across the exchange (register
 //   pressure), a one-barrier exchange where every CTA sums all partials, 16 warps x 1 CTA per SM (kept as a hook).
 #include <atomic>
@@ -838,6 +839,11 @@ int launch_grid_cfg(const SinkArgs &a, cudaStream_t st) {
 }
 
 // rows split over Q warps: core width exactly 32 * CPL * Q columns, one CTA of Q * RG warps per SM
+#ifndef PATS_GRIDQ_CPL  // columns per lane, warps per row, row groups per CTA; measured: 32 x 4 x 4 3.49 ms, 16 x 8 x 4 (32 warps, 64 registers) 3.67 ms
+#define PATS_GRIDQ_CPL 32
+#define PATS_GRIDQ_Q 4
+#define PATS_GRIDQ_RG 4
+#endif
 template <int CPL, int Q, int RG>
 int launch_gridq_cfg(const SinkArgs &a, cudaStream_t st) {
     auto kern = sinkhorn_gridq_kernel<CPL, Q, RG>;
@@ -863,7 +869,9 @@ int launch_gridq_cfg(const SinkArgs &a, cudaStream_t st) {
     ga.rpc = (a.M + G - 1) / G;
     ga.slice = (a.N + G - 1) / G;
     ga.npad = (a.N + 3) & ~3;
-    ga.l2_prefetch = (size_t)a.b * a.M * a.N * sizeof(float) > ((size_t)64 << 20);
+    // one 4097 x 4097 plan (67 MB) stays in L2 between iterations: prefetching the next row measured 3.49 vs 3.36 ms without
+    // (profiles/r02_ab_gridq_configs.json); batches beyond L2 keep the prefetch of the one-warp-per-row kernel
+    ga.l2_prefetch = (size_t)a.b * a.M * a.N * sizeof(float) > ((size_t)128 << 20);
     const size_t vec = (size_t)a.b * ga.npad;
     const size_t floats = vec * (3 + (size_t)G);
     const size_t bytes = floats * sizeof(float) + 2 * (size_t)a.b * sizeof(unsigned);
@@ -894,7 +902,7 @@ int launch_grid(const SinkArgs &a, cudaStream_t st) {
     if (nc <= 1536) return launch_grid_cfg<48, 8, 2, true>(a, st);
     if (nc <= 2048) return launch_grid_cfg<64, 8, 1, true>(a, st);
     if (nc == 4096)  // BASELINE.json's stress size: four warps per row (exponentials kept); variant 2: one warp per row, exponentials recomputed
-        return (g_grid_variant & 2) ? launch_grid_cfg<128, 8, 1, false, true>(a, st) : launch_gridq_cfg<32, 4, 4>(a, st);
+        return (g_grid_variant & 2) ? launch_grid_cfg<128, 8, 1, false, true>(a, st) : launch_gridq_cfg<PATS_GRIDQ_CPL, PATS_GRIDQ_Q, PATS_GRIDQ_RG>(a, st);
     return launch_grid_cfg<128, 8, 1, false>(a, st);
 }
 

@@ -438,7 +438,7 @@ def test_full_size_marginals_and_subset_parity(M, dev, b, m, n, span):
     assert_plan_equal(out[idx].cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("N,iters", [(1536, 100), (1024, 100), (4096, 40)])  # 4096: BASELINE.json's stress size (clamp-free recompute sweep)
+@pytest.mark.parametrize("N,iters", [(1536, 100), (1024, 100), (4096, 40)])  # 4096: BASELINE.json's stress size (four warps per row)
 def test_large_plan_grid_kernel_vs_torch(M, lib, dev, N, iters):
     """BASELINE.json's synthetic kernel sizes (N=1536) and the 1024x1024-pair coarse plan (1024 -> 1025):
     grid-cooperative streaming kernel against a torch fp32 logsumexp restatement on the same device."""
@@ -457,6 +457,27 @@ def test_large_plan_grid_kernel_vs_torch(M, lib, dev, N, iters):
     ref = _torch_lse_sinkhorn(Z, lmu, lnu, iters) - norm[:, None, None]
     assert (out - ref).abs().max().item() <= TOL
     assert torch.equal(out.argmax(2), ref.argmax(2))
+
+
+def test_4096_column_kernels_vs_torch_in_every_mode(M, lib, dev):
+    """4096 core columns (BASELINE.json's stress size) has its own kernel -- a row split over four warps, sinkhorn_gridq_kernel -- and
+    the one-warp-per-row kernel behind pats_sinkhorn_grid_variant(2): both against the torch float32 logsumexp restatement in all
+    three modes (dustbin synthesised, b = 2, 40 iterations; dustbin in memory with 37 and 601 rows at row stride 4097; raw marginals
+    at 0 / 1 / 2 / 7 iterations).  The checks are tools/ab_grid4096.py's (profiles/r02_ab_grid4096.json is its record)."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import ab_grid4096 as A
+
+    out = {"parity": [], "timing": []}
+    try:
+        A.parity(lib, M, dev, 4096, out)
+    finally:
+        lib.pats_sinkhorn_grid_variant(0)
+    assert len(out["parity"]) == 14
+    for r in out["parity"]:
+        assert r["finite"] and r["argmax_equal"] and r["max_abs_diff_vs_torch_lse"] <= TOL, r
 
 
 # ---- grid-cooperative streaming kernel (plans beyond 512 x 512) ---------------------------------------------

@@ -98,7 +98,7 @@ def parity(lib, M, dev, N, out):
 
 def timing(lib, M, dev, N, out):
     # ---- timing: bench.py's stress leg (one problem, 200 iterations) and b = 2 ----
-    for b in (1, 2):
+    for b in ((1,) if os.environ.get("AB_ONLY4096") else (1, 2)):
         g2 = torch.Generator().manual_seed(1234 + N)
         sc = (0.1 * torch.randn(b, N, N, generator=g2)).to(dev)
         nss = torch.exp((torch.rand(b, 1, N, generator=g2) * 2 - 1) * math.log(16.0)).to(dev)
@@ -119,7 +119,7 @@ def timing(lib, M, dev, N, out):
             print(out["timing"][-1], flush=True)
     lib.pats_sinkhorn_grid_variant(0)
     # ---- the other streaming shapes (same kernel family, shared exchange code): BASELINE configs[2], the 1025 x 1025 level-1 plan ----
-    for b, n, iters in ((32, 1536, 100), (1, 1024, 100), (8, 1024, 100)):
+    for b, n, iters in (() if os.environ.get("AB_ONLY4096") else ((32, 1536, 100), (1, 1024, 100), (8, 1024, 100))):
         g2 = torch.Generator().manual_seed(77 + n + b)
         sc = (0.1 * torch.randn(b, n, n, generator=g2)).to(dev)
         nss = torch.exp((torch.rand(b, 1, n, generator=g2) * 2 - 1) * math.log(16.0)).to(dev)
