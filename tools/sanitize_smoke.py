@@ -68,6 +68,12 @@ M.log_optimal_transport2(s3[1:], one, ns3[1:], IT)
 # streaming (grid-cooperative) kernel and the generic log-domain kernel
 sb = (0.3 * torch.randn(2, 600, 600, generator=g)).to(dev)
 M.log_optimal_transport(sb, one, areas(2, 1, 600), 3)
+# 4096 core columns: a row split over four warps (named barriers within the quad), and the one-warp-per-row kernel it replaced
+sq = (0.3 * torch.randn(1, 40, 4097, generator=g)).to(dev)
+M.log_optimal_transport2(sq, one, areas(1, 1, 4096), 3)
+lib.pats_sinkhorn_grid_variant(2)
+M.log_optimal_transport2(sq, one, areas(1, 1, 4096), 3)
+lib.pats_sinkhorn_grid_variant(0)
 lib.pats_sinkhorn_force_generic(1)
 M.log_optimal_transport(s1, one, ns1, 2)
 lib.pats_sinkhorn_force_generic(0)
