@@ -66,8 +66,9 @@ int pats_sinkhorn_kernel_kind(int M, int N);
 /* CTAs per problem of the grid-cooperative kernel (0 = automatic: floor(SMs / b), at least one row per warp);
  * tests / A-B timing. */
 void pats_sinkhorn_grid_ctas_per_problem(int g);
-/* A-B hook of the grid-cooperative kernel: 1 = 16 warps x 1 CTA per SM instead of 8 warps x 2 CTAs per SM (plans up
- * to 1537 columns). */
+/* A-B hook of the grid-cooperative kernels, bits: 1 = 16 warps x 1 CTA per SM instead of 8 warps x 2 CTAs per SM (plans up
+ * to 1537 columns); 2 = exactly 4096 core columns: one warp per row with the exponentials recomputed instead of four warps
+ * per row with the exponentials kept (the default; same results to rounding, 1.7x faster on one 4097 x 4097 plan). */
 void pats_sinkhorn_grid_variant(int v);
 /* Force the generic log-domain kernel for every shape (tests: exercises the fallback path). */
 void pats_sinkhorn_force_generic(int on);
@@ -300,7 +301,8 @@ int pats_attentional_gnn_train_f32(const float *desc0, const float *desc1, int B
                                    float *workspace, long long workspace_floats, void *stream);
 void pats_gnn_precision(int passes);
 /* A/B switch: 0 = the packed-FP32 (fma.rn.f32x2) generation of the resident-key attention kernels (default), 1 = the first
- *   generation.  Same sums in the same order: bit-identical results. */
+ *   generation; 2 / 3 = the packed generation at the level-2 shape with 16 query rows x 10 warps / 12 rows x 13 warps instead of
+ *   8 x 20 (measured slower).  Same sums in the same order: bit-identical results. */
 void pats_gnn_attention_variant(int v);
 /* A/B switch: 0 = the TMA-fed, warp-specialised GEMM (operands pre-split into TF32 halves by their producers) in thread-block
  *                 clusters of two CTAs: two token blocks of one output block, each CTA loads half of the weight tile and multicasts
